@@ -1,0 +1,496 @@
+"""CPU oracle for the GP-NeRF progressive volume-rendering hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it; the product path (``gp-nerf_b200``) never does.
+
+It is a torch-CPU fp32 restatement of the reference's algorithm, function by
+function, each citing the ``/root/reference`` file:line it follows.  The
+reference is pure PyTorch, so the restatement uses the same ATen calls where
+only *values* matter (``F.grid_sample``, ``F.linear``, ``F.elu``) and spells the
+arithmetic out, op by op, on every chain that feeds an integer result (pixel
+mask, ray list, ``mask_at_box``, ``valid``), so that the CUDA kernels can follow
+the same IEEE-754 sequence and be compared bit for bit:
+
+* small-K matmuls (K = 3, 4) are "first product rounded, then one FMA per
+  further term, k ascending" – what ATen's CPU sgemm does on these shapes
+  (checked numerically, see oracle/gen_golden.py);
+* elementwise torch expressions are separate roundings (no FMA contraction);
+* ``x / python_float`` on CPU is a true IEEE division by the fp32 scalar.
+
+Parity pinning: the reference has no tests, golden vectors or fixtures
+(SURVEY.md §4, §8c).  The oracle is pinned instead against outputs of the
+reference's own functions imported in the build container
+(oracle/gen_golden.py → tests/golden/*.npz, committed).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------
+# arithmetic helpers
+# --------------------------------------------------------------------------
+
+
+def _fma(a, b, c):
+    """round_fp32(a*b + c) with one rounding (the product of two fp32 is exact
+    in fp64; the fp64 sum is then rounded once more to fp32 – double rounding
+    differs from a hardware FMA with probability ~2^-29 per op)."""
+    return (a.double() * b.double() + c.double()).float()
+
+
+def mm_seqfma(A, B):
+    """A[..., M, K] @ B[..., K, N] as ATen's CPU sgemm rounds it for tiny K:
+    acc = a0*b0 (rounded); acc = fma(ak, bk, acc) for k = 1..K-1."""
+    K = A.shape[-1]
+    acc = A[..., :, 0:1] * B[..., 0:1, :]
+    for k in range(1, K):
+        acc = _fma(A[..., :, k:k + 1], B[..., k:k + 1, :], acc)
+    return acc
+
+
+def norm3(x):
+    """sqrt(x0² ⊕ x1² ⊕ x2²) accumulated as one rounded product plus two FMAs,
+    correctly-rounded sqrt.  (torch.norm(dim=1) on CPU agrees on 99.3 % of
+    inputs and is 1 ulp off on the rest – recorded in tests/golden/README.)"""
+    acc = x[..., 0] * x[..., 0]
+    acc = _fma(x[..., 1], x[..., 1], acc)
+    acc = _fma(x[..., 2], x[..., 2], acc)
+    return torch.sqrt(acc)
+
+
+def t_vals(S, device="cpu"):
+    """linspace(0,1,S) as torch produces it (BaseRender.py:37)."""
+    return torch.linspace(0.0, 1.0, steps=S, device=device)
+
+
+# --------------------------------------------------------------------------
+# a7 (mask build) – libs/nerfheads/networks/SparseConvNet.py:135-141
+# --------------------------------------------------------------------------
+
+
+def build_masks3d(levels, threshold=0.1):
+    """Occupancy volume on the level-1 grid and the list of occupied voxels.
+
+    levels: list of [1, C, Dk, Hk, Wk].  Returns masks3d [D1,H1,W1] and
+    mask_xyz [N,3] float = (x,y,z) level-1 index × 2 (full-res voxel units)."""
+    size = levels[0].shape[-3:]
+    ups = []
+    for feat in levels:
+        chan_sum = feat[0].sum(dim=0)
+        ups.append(F.interpolate(chan_sum[None, None], size)[0, 0])   # nearest
+    masks3d = torch.stack(ups, 0).sum(0)
+    idx = torch.stack(torch.where(masks3d > threshold), 0).permute(1, 0)  # (d,h,w)
+    mask_xyz = idx.flip(-1).float() * 2.0
+    return masks3d, mask_xyz
+
+
+# --------------------------------------------------------------------------
+# a4 – libs/renders/demo_render.py:166-239
+# --------------------------------------------------------------------------
+
+
+def occupied_voxels_world(mask_xyz, voxel_size, bounds, R, Th):
+    """demo_render.py:167-168: voxel → SMPL frame → world."""
+    pts = mask_xyz * voxel_size + bounds[0, 0]
+    return mm_seqfma(pts, R[0].T.contiguous()) + Th[0, 0]
+
+
+def world_bounds_of(pts_world):
+    """demo_render.py:171-175."""
+    lo = pts_world.min(0)[0].clone()
+    hi = pts_world.max(0)[0].clone()
+    lo[2] -= 0.05
+    hi[2] += 0.05
+    return torch.stack([lo, hi], 0)
+
+
+def pixel_mask_from_voxels(pts_world, target_pose, target_K, W, Hh=None):
+    """demo_render.py:179-200 with W (hard-coded 512 there) as a parameter.
+    Returns the float mask [Hh*W] and the ascending flat pixel indices."""
+    Hh = W if Hh is None else Hh
+    pose = target_pose[0]
+    cam = mm_seqfma(pts_world, pose[:, :3].T.contiguous()) + pose[:, 3:].T
+    pix = mm_seqfma(cam, target_K[0].T.contiguous())
+    xy = pix[:, :2] / pix[:, 2:]
+    minx, miny = xy[:, 0].long(), xy[:, 1].long()          # truncation toward zero
+    maxx, maxy = minx + 1, miny + 1
+    minx, maxx = minx.clamp(0, W - 1), maxx.clamp(0, W - 1)
+    miny, maxy = miny.clamp(0, Hh - 1), maxy.clamp(0, Hh - 1)
+    idx = torch.cat([miny * W + minx, maxy * W + minx, miny * W + maxx, maxy * W + maxx], 0)
+    mask = torch.zeros(Hh * W)
+    mask[idx] = 1.0
+    pix_idx = torch.where(mask == 1)[0]
+    return mask, pix_idx
+
+
+def rays_bbox(pix_idx, W, target_pose, target_K_inv, can_bounds, neg_ray=False):
+    """demo_render.py:200-239: rays through the masked pixels, 6-plane AABB
+    test (exactly two hits), near/far.  Returns a dict; `keep` indexes pix_idx."""
+    pose = target_pose[0]
+    j = torch.div(pix_idx, W, rounding_mode="floor")
+    i = pix_idx - j * W
+    xy1 = torch.stack([i, j, torch.ones_like(i)], -1).float()
+    origin = mm_seqfma(-pose[:, :3].T.contiguous(), pose[:, 3:].contiguous()).view(-1)   # [3]
+    cam = mm_seqfma(xy1, target_K_inv[0].T.contiguous())
+    world = mm_seqfma(cam - pose[:, 3:].T, pose[:, :3].contiguous())
+    d = world - origin[None]
+    o = origin[None].expand(d.shape)
+    t = ((can_bounds[None] - o[:, None]) / d[:, None]).reshape(-1, 6)
+    p = t[..., None] * d[:, None] + o[:, None]                     # [R0,6,3]
+    lo, hi = can_bounds[0], can_bounds[1]
+    eps = 1e-6
+    inside = ((p[..., 0] >= (lo[0] - eps)) & (p[..., 0] <= (hi[0] + eps))
+              & (p[..., 1] >= (lo[1] - eps)) & (p[..., 1] <= (hi[1] + eps))
+              & (p[..., 2] >= (lo[2] - eps)) & (p[..., 2] <= (hi[2] + eps)))
+    at_box = inside.sum(-1) == 2
+    hits = p[at_box][inside[at_box]].reshape(-1, 2, 3)
+    o_k, d_k = o[at_box], d[at_box]
+    nrm = norm3(d_k)
+    d0 = norm3(hits[:, 0] - o_k) / nrm
+    d1 = norm3(hits[:, 1] - o_k) / nrm
+    if neg_ray:
+        d1 = -d1
+    return {
+        "rays_o": o_k.contiguous(), "rays_d": d_k.contiguous(),
+        "near": torch.min(d0, d1), "far": torch.max(d0, d1),
+        "mask_at_box": at_box, "ray_pix": pix_idx[at_box],
+    }
+
+
+# --------------------------------------------------------------------------
+# a3 – BaseRender.py:35-50 / demo_render.py:59-74
+# --------------------------------------------------------------------------
+
+
+def sampling_points(ray_o, ray_d, near, far, S, t_rand=None):
+    """ray_o/d [R,3], near/far [R] → pts [R,S,3], z [R,S].  `t_rand` [R,S] is
+    the host-drawn jitter of training mode (BaseRender.py:40-47)."""
+    t = t_vals(S).to(near)
+    z = near[:, None] * (1.0 - t) + far[:, None] * t
+    if t_rand is not None:
+        mids = 0.5 * (z[:, 1:] + z[:, :-1])
+        upper = torch.cat([mids, z[:, -1:]], -1)
+        lower = torch.cat([z[:, :1], mids], -1)
+        z = lower + (upper - lower) * t_rand
+    pts = ray_o[:, None] + ray_d[:, None] * z[..., None]
+    return pts, z
+
+
+# --------------------------------------------------------------------------
+# a6 – BaseRender.py:52-73 / demo_render.py:76-94
+# --------------------------------------------------------------------------
+
+
+def pts_to_can_pts(pts, R, Th):
+    """(p − Th)·R, pts [P,3]."""
+    return mm_seqfma(pts - Th.reshape(1, 3), R[0].contiguous())
+
+
+def grid_coords_of(pts_smpl, bounds, out_sh_dhw, voxel=0.005):
+    """Normalised (x,y,z) grid coordinates in [-1,1] w.r.t. the padded full-res
+    shape.  demo_render.py:86-94 (xyz order) and BaseRender.py:62-73 (dhw order,
+    swapped back) perform the same per-component arithmetic."""
+    xyz = pts_smpl - bounds[0, 0][None]
+    xyz = xyz / voxel
+    sh_xyz = torch.as_tensor(out_sh_dhw, dtype=torch.float32).flip(-1)
+    return xyz / sh_xyz * 2 - 1
+
+
+# --------------------------------------------------------------------------
+# a7 / a8 – demo_render.py:270-283, SparseConvNet.py:111-122
+# --------------------------------------------------------------------------
+
+
+def trilinear(vol, grid):
+    """vol [C,D,H,W], grid [P,3] (x,y,z) → [P,C]; align_corners, zeros padding."""
+    out = F.grid_sample(vol[None], grid[None, None, None], padding_mode="zeros", align_corners=True)
+    return out[0, :, 0, 0].permute(1, 0)
+
+
+def occupancy_valid(masks3d, grid):
+    """valid = where(trilinear(masks3d) > 0), ascending (demo_render.py:274-281)."""
+    occ = trilinear(masks3d[None], grid)[:, 0]
+    return torch.where(occ > 0)[0]
+
+
+def gather_levels(levels, grid):
+    """[P, 32·L] in level-major channel order (SparseConvNet.py:111-122)."""
+    return torch.cat([trilinear(lv[0], grid) for lv in levels], -1)
+
+
+# --------------------------------------------------------------------------
+# a9 – BaseRender.py:283-363 / demo_render.py:506-609
+# --------------------------------------------------------------------------
+
+
+def pack_cameras(src_poses, src_Ks, H, W):
+    """src_cameras [1,V,34] = (H, W, K 4×4, E 4×4) – BaseRender.py:233-247."""
+    V = src_poses.shape[1]
+    Eh = torch.eye(4).repeat(1, V, 1, 1)
+    Eh[:, :, :3, :4] = src_poses
+    Kh = torch.eye(4).repeat(1, V, 1, 1)
+    Kh[:, :, :3, :3] = src_Ks
+    cams = torch.ones(1, V, 34)
+    cams[:, :, 0] = H
+    cams[:, :, 1] = W
+    cams[:, :, 2:18] = Kh.reshape(1, V, 16)
+    cams[:, :, 18:] = Eh.reshape(1, V, 16)
+    return cams
+
+
+def project(xyz, cams, neg_ray=False):
+    """compute_projections (BaseRender.py:301-323): xyz [P,3] → pix [V,P,2],
+    in_front [V,P]."""
+    Kh = cams[:, 2:18].reshape(-1, 4, 4)
+    Eh = cams[:, 18:].reshape(-1, 4, 4)
+    KE = Kh.bmm(Eh)
+    xyz_h = torch.cat([xyz, torch.ones_like(xyz[:, :1])], -1)
+    proj = mm_seqfma(KE, xyz_h.t()[None].expand(KE.shape[0], -1, -1)).permute(0, 2, 1)  # [V,P,4]
+    pix = proj[..., :2] / proj[..., 2:3]
+    pix = torch.clamp(pix, min=-1e6, max=1e6)
+    in_front = proj[..., 2] < 0 if neg_ray else proj[..., 2] > 0
+    return pix, in_front
+
+
+def projector_compute(xyz, src_imgs01, cams, featmaps, neg_ray=False):
+    """Projector.compute (demo_render.py:560-609): xyz [P,3]; src_imgs01
+    [V,3,H,W] already ×0.5+0.5; featmaps [V,C,h,w].  Returns rgb_feat
+    [P,V,3+C] (RGB first) and mask [P,V] float."""
+    cams = cams[0]
+    h, w = cams[0][:2]
+    pix, in_front = project(xyz, cams, neg_ray)
+    resize = torch.stack([w - 1.0, h - 1.0])[None, None]
+    norm = 2 * pix / resize - 1.0                                       # [V,P,2]
+    rgb = F.grid_sample(src_imgs01, norm[:, :, None], align_corners=True)[..., 0]      # [V,3,P]
+    feat = F.grid_sample(featmaps, norm[:, :, None], align_corners=True)[..., 0]       # [V,C,P]
+    rgb_feat = torch.cat([rgb, feat], 1).permute(2, 0, 1).contiguous()                # [P,V,3+C]
+    inbound = ((pix[..., 0] <= w - 1.0) & (pix[..., 0] >= 0)
+               & (pix[..., 1] <= h - 1.0) & (pix[..., 1] >= 0))
+    mask = (inbound & in_front).float().permute(1, 0).contiguous()                     # [P,V]
+    return rgb_feat, mask
+
+
+# --------------------------------------------------------------------------
+# a10-a14 – libs/nerfheads/trainhead.py
+# --------------------------------------------------------------------------
+
+
+def mean_var(rgb_feat):
+    """fused_mean_variance (trainhead.py:20-24): population stats over views,
+    unmasked.  rgb_feat [P,V,Cf] → mean, var [P,Cf]."""
+    mean = rgb_feat.mean(1, keepdim=True)
+    var = ((rgb_feat - mean) ** 2).mean(1)
+    return mean[:, 0], var
+
+
+def _seq(x, w, prefix, acts):
+    """nn.Sequential of Linear/activation pairs keyed `prefix.{0,2,4,..}`."""
+    for n, act in enumerate(acts):
+        x = F.linear(x, w[f"{prefix}.{2 * n}.weight"], w[f"{prefix}.{2 * n}.bias"])
+        if act == "elu":
+            x = F.elu(x)
+        elif act == "relu":
+            x = F.relu(x)
+    return x
+
+
+def sigma_feat_of(vol_feat, w):
+    """NeRFSigmaHead.out_geometry_fc (trainhead.py:39-41): 128→64 + ELU."""
+    return _seq(vol_feat, w, "sigmahead.out_geometry_fc", ["elu"])
+
+
+def density_mlp(sigma_feat, mean, var, mask, w):
+    """NeRFRGBHead.out_geometry_fc on [sigma_feat | mean | var] and the
+    no-valid-view fill (trainhead.py:102-110, 133-137; demo_render.py:298-304).
+    Returns sigma [P]."""
+    x = torch.cat([sigma_feat, mean, var], -1)
+    sigma = _seq(x, w, "rgbhead.out_geometry_fc", ["elu", "elu", "elu", "relu"])[:, 0]
+    return sigma.masked_fill(mask.sum(1) < 1, 0.0)
+
+
+def color_mlp(rgb_feat, mean, var, w):
+    """Colour trunk of NeRFRGBHead.forward (trainhead.py:128-145).  rgb_feat
+    [P,V,Cf] → rgb [P,3]."""
+    V = rgb_feat.shape[1]
+    glob = torch.cat([mean, var], -1)[:, None].expand(-1, V, -1)
+    x = torch.cat([glob, rgb_feat], -1)
+    x = _seq(x, w, "rgbhead.base_fc", ["elu", "elu"])
+    x = x + _seq(x * 1.0 / V, w, "rgbhead.vis_fc", ["elu", "elu"])
+    return _seq(x.flatten(1, 2), w, "rgbhead.rgb_fc", ["elu", "elu", None]).sigmoid()
+
+
+# --------------------------------------------------------------------------
+# a13, a15, a16
+# --------------------------------------------------------------------------
+
+
+def alpha_valid(sigma):
+    """demo_render.py:312-317."""
+    alpha = 1.0 - torch.exp(-sigma)
+    return alpha, torch.where(alpha > 1e-14)[0]
+
+
+def composite_progressive(R, S, valid, valid1, alpha, rgb):
+    """demo_render.py:335-347: scatter to dense [R,S], exclusive cumprod of
+    (1−α+1e-10), weights, Σ w·rgb."""
+    hold_rgb = torch.zeros(R * S, 3)
+    hold_alpha = torch.zeros(R * S)
+    hold_rgb[valid[valid1]] = rgb
+    hold_alpha[valid] = alpha
+    hold_rgb = hold_rgb.view(R, S, 3)
+    hold_alpha = hold_alpha.view(R, S)
+    T = torch.cumprod(1.0 - hold_alpha + 1e-10, -1)[..., :-1]
+    T = torch.cat([torch.ones_like(T[..., :1]), T], -1)
+    weights = hold_alpha * T
+    return (weights[..., None] * hold_rgb).sum(1), weights
+
+
+def raw2outputs(raw, z_vals, neg=False):
+    """Renderer.raw2outputs (BaseRender.py:75-107) minus the unused mask."""
+    rgb, sigma = raw[:, :, :3], raw[:, :, 3]
+    if neg:
+        rgb, sigma = torch.flip(rgb, [1]), torch.flip(sigma, [1])
+    alpha = 1.0 - torch.exp(-sigma)
+    T = torch.cumprod(1.0 - alpha + 1e-10, -1)[:, :-1]
+    T = torch.cat([torch.ones_like(T[:, :1]), T], -1)
+    weights = alpha * T
+    rgb_map = (weights[..., None] * rgb).sum(1)
+    depth = (weights * z_vals).sum(-1)
+    acc = weights.sum(-1)
+    disp = 1.0 / torch.max(1e-10 * torch.ones_like(depth), depth / acc)
+    return rgb_map, disp, acc, weights, depth
+
+
+# --------------------------------------------------------------------------
+# whole-path drivers
+# --------------------------------------------------------------------------
+
+
+def _scene_common(scene):
+    H, W = scene["H"], scene["W"]
+    cams = pack_cameras(scene["src_poses"], scene["src_Ks"], H, W)
+    imgs01 = scene["src_imgs"][0] * 0.5 + 0.5                 # BaseRender.py:231
+    out_sh = [int(v) for v in scene["out_sh"][0]]
+    return cams, imgs01, out_sh
+
+
+@torch.no_grad()
+def render_progressive(scene, w, S=64, neg_ray=False, chunk=None, keep=False):
+    """Device-agnostic restatement of demo_render.Renderer.render_rays
+    (demo_render.py:96-365) downstream of the upstream producers, i.e. with
+    `levels`/`featmaps` supplied.  `chunk` bounds peak memory of the head stage
+    (points per pass, ascending order; results are order-identical).
+    Returns rgb_map [R,3], pred_img [H,W,3], mask_at_box [H*W] and – if `keep`
+    – every intermediate the parity tests compare."""
+    cams, imgs01, out_sh = _scene_common(scene)
+    W_img, H_img = scene["W"], scene["H"]
+    R_, Th, bounds = scene["R"], scene["Th"], scene["bounds"]
+    levels, featmaps = scene["levels"], scene["featmaps"]
+
+    masks3d, mask_xyz = build_masks3d(levels)
+    vox_world = occupied_voxels_world(mask_xyz, torch.tensor(VOXEL3), bounds, R_, Th)
+    can_bounds = world_bounds_of(vox_world)
+    pix_mask, pix_idx = pixel_mask_from_voxels(vox_world, scene["target_pose"], scene["target_K"], W_img, H_img)
+    rb = rays_bbox(pix_idx, W_img, scene["target_pose"], scene["target_K_inv"], can_bounds, neg_ray)
+    n_rays = rb["near"].shape[0]
+    pts, z = sampling_points(rb["rays_o"], rb["rays_d"], rb["near"], rb["far"], S)
+    pts = pts.reshape(-1, 3)
+    grid = grid_coords_of(pts_to_can_pts(pts, R_, Th), bounds, out_sh)
+    valid = occupancy_valid(masks3d, grid)
+
+    P1 = valid.shape[0]
+    chunk = P1 if not chunk else chunk
+    sig_l, rgbf_l, mean_l, var_l, mask_l, sfeat_l, vfeat_l = [], [], [], [], [], [], []
+    for s0 in range(0, max(P1, 1), max(chunk, 1)):
+        sel = valid[s0:s0 + chunk]
+        rgb_feat, mask = projector_compute(pts[sel], imgs01, cams, featmaps, neg_ray)
+        vol_feat = gather_levels(levels, grid[sel])
+        sfeat = sigma_feat_of(vol_feat, w)
+        mean, var = mean_var(rgb_feat)
+        sig_l.append(density_mlp(sfeat, mean, var, mask, w))
+        rgbf_l.append(rgb_feat); mean_l.append(mean); var_l.append(var); mask_l.append(mask)
+        if keep:
+            sfeat_l.append(sfeat); vfeat_l.append(vol_feat)
+    sigma = torch.cat(sig_l) if sig_l else torch.zeros(0)
+    alpha, valid1 = alpha_valid(sigma)
+    rgb_feat = torch.cat(rgbf_l); mean = torch.cat(mean_l); var = torch.cat(var_l)
+    rgb_l = []
+    P2 = valid1.shape[0]
+    for s0 in range(0, max(P2, 1), max(chunk, 1)):
+        sel = valid1[s0:s0 + chunk]
+        rgb_l.append(color_mlp(rgb_feat[sel], mean[sel], var[sel], w))
+    rgb = torch.cat(rgb_l) if rgb_l else torch.zeros(0, 3)
+    rgb_map, weights = composite_progressive(n_rays, S, valid, valid1, alpha, rgb)
+
+    pix_mask_final = torch.zeros(H_img * W_img, dtype=torch.bool)
+    pix_mask_final[rb["ray_pix"]] = True                     # demo_render.py:348-351
+    pred_img = torch.zeros(H_img * W_img, 3, dtype=torch.float64)
+    pred_img[rb["ray_pix"]] = rgb_map.double()
+    out = {"rgb_map": rgb_map, "pred_img": pred_img.view(H_img, W_img, 3),
+           "mask_at_box": pix_mask_final, "n_rays": n_rays, "P": n_rays * S, "P1": P1, "P2": P2}
+    if keep:
+        out.update({
+            "masks3d": masks3d, "mask_xyz": mask_xyz, "can_bounds": can_bounds,
+            "pix_mask": pix_mask, "pix_idx": pix_idx, "ray_pix": rb["ray_pix"],
+            "box_hit": rb["mask_at_box"], "rays_o": rb["rays_o"], "rays_d": rb["rays_d"],
+            "near": rb["near"], "far": rb["far"], "z_vals": z, "valid": valid, "valid1": valid1,
+            "sigma": sigma, "alpha": alpha, "rgb": rgb, "weights": weights,
+            "rgb_feat": rgb_feat, "mean": mean, "var": var, "mask": torch.cat(mask_l),
+            "sigma_feat": torch.cat(sfeat_l), "vol_feat": torch.cat(vfeat_l),
+        })
+    return out
+
+
+@torch.no_grad()
+def render_dense(scene, w, S=64, neg_ray=False, t_rand=None, chunk=2000, rays=None, keep=False):
+    """BaseRender.Renderer.render_rays/batchify_rays (BaseRender.py:110-184)
+    with the volume levels supplied: every sample point goes through both
+    heads, no compaction.  `rays` = (o,d,near,far) or taken from the scene."""
+    cams, imgs01, out_sh = _scene_common(scene)
+    R_, Th, bounds = scene["R"], scene["Th"], scene["bounds"]
+    levels, featmaps = scene["levels"], scene["featmaps"]
+    if rays is None:
+        rays = (scene["ray_o"][0], scene["ray_d"][0], scene["near"][0], scene["far"][0])
+    o, d, near, far = rays
+    V = cams.shape[1]
+    outs = {k: [] for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "alpha", "z_vals", "rgb_in_map")}
+    raws = []
+    for r0 in range(0, o.shape[0], chunk):
+        sl = slice(r0, r0 + chunk)
+        tr = None if t_rand is None else t_rand[sl]
+        pts, z = sampling_points(o[sl], d[sl], near[sl], far[sl], S, tr)
+        n = pts.shape[0]
+        pts = pts.reshape(-1, 3)
+        grid = grid_coords_of(pts_to_can_pts(pts, R_, Th), bounds, out_sh)
+        rgb_feat, mask = projector_compute(pts, imgs01, cams, featmaps, neg_ray)
+        sfeat = sigma_feat_of(gather_levels(levels, grid), w)
+        mean, var = mean_var(rgb_feat)
+        sigma = density_mlp(sfeat, mean, var, mask, w)
+        rgb = color_mlp(rgb_feat, mean, var, w)
+        raw = torch.cat([rgb, sigma[:, None]], -1).view(n, S, 4)
+        rgb_map, disp, acc, weights, depth = raw2outputs(raw, z, neg_ray)
+        rgb_in = rgb_feat[..., :3].reshape(n, S, V, 3)
+        rgb_in_map = (weights[..., None, None] * rgb_in).sum(1)
+        for k, v in (("rgb_map", rgb_map), ("disp_map", disp[:, None]), ("acc_map", acc[:, None]),
+                     ("depth_map", depth[:, None]), ("alpha", weights), ("z_vals", z),
+                     ("rgb_in_map", rgb_in_map.reshape(n, -1))):
+            outs[k].append(v)
+        if keep:
+            raws.append(raw)
+    ret = {k: torch.cat(v, 0) for k, v in outs.items()}
+    if keep:
+        ret["raw"] = torch.cat(raws, 0)
+    return ret
+
+
+VOXEL3 = [0.005, 0.005, 0.005]
+
+
+def psnr(a, b):
+    """libs/evaluators/if_nerf.py:29-32 (10·log10(1/mse))."""
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return 10.0 * math.log10(1.0 / max(mse, 1e-20))
