@@ -1,0 +1,206 @@
+// Library-wide plumbing: error reporting, device query and the ordered
+// stream-compaction passes shared by K1 (pixels→rays), K2 (occupancy) and K4
+// (density).  HBM-bound integer work: 1 bit/item in, 4 B/survivor out.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gpnerf {
+
+static thread_local char g_err[256] = "";
+
+void set_error(const char* what, cudaError_t err) {
+  if (err != cudaSuccess)
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(err));
+  else
+    snprintf(g_err, sizeof(g_err), "invalid argument: %s", what);
+}
+
+int check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(what, err);
+    return GPNERF_E_CUDA;
+  }
+  return GPNERF_OK;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached = n;
+  }
+  return cached;
+}
+
+static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+CompactWs carve_workspace(void* ws, int64_t n_items_max) {
+  int64_t n_words = div_up(n_items_max, 32);
+  int64_t n_tiles = div_up(n_words, kTileWords);
+  CompactWs c;
+  c.words = reinterpret_cast<uint32_t*>(ws);
+  int64_t words_padded = div_up(n_words, 64) * 64;
+  c.tile_sums = reinterpret_cast<int32_t*>(c.words + words_padded);
+  c.tile_offs = c.tile_sums + div_up(n_tiles, 64) * 64;
+  return c;
+}
+
+// --- pass B1: per-tile popcount ------------------------------------------
+__global__ void __launch_bounds__(256) compact_tile_sums(const uint32_t* __restrict__ words,
+                                                         const int32_t* n_src, int mult,
+                                                         long long n_const,
+                                                         int32_t* __restrict__ tile_sums) {
+  const long long n_items = live_count(n_src, mult, n_const);
+  const long long n_words = (n_items + 31) >> 5;
+  const long long n_tiles = (n_words + kTileWords - 1) / kTileWords;
+  __shared__ int warp_part[8];
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int local = 0;
+    for (int i = threadIdx.x; i < kTileWords; i += 256) {
+      long long w = tile * kTileWords + i;
+      if (w < n_words) local += __popc(__ldg(words + w));
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int k = 0; k < 8; ++k) s += warp_part[k];
+      tile_sums[tile] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// --- pass B2: single-CTA exclusive scan of the tile sums -------------------
+__global__ void __launch_bounds__(1024) compact_scan(const int32_t* __restrict__ tile_sums,
+                                                     const int32_t* n_src, int mult,
+                                                     long long n_const,
+                                                     int32_t* __restrict__ tile_offs,
+                                                     int32_t* __restrict__ out_count) {
+  const long long n_items = live_count(n_src, mult, n_const);
+  const long long n_words = (n_items + 31) >> 5;
+  const int n_tiles = (int)((n_words + kTileWords - 1) / kTileWords);
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < n_tiles; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = (i < n_tiles) ? tile_sums[i] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_tot[lane];
+      int wi = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    int carry = carry_s;
+    int excl = carry + warp_tot[wid] + incl - v;
+    if (i < n_tiles) tile_offs[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_count = carry_s;
+}
+
+// --- pass C: expand bit words into ascending indices -----------------------
+__global__ void __launch_bounds__(256) compact_expand(const uint32_t* __restrict__ words,
+                                                      const int32_t* __restrict__ tile_offs,
+                                                      const int32_t* n_src, int mult,
+                                                      long long n_const,
+                                                      int32_t* __restrict__ out_idx) {
+  const long long n_items = live_count(n_src, mult, n_const);
+  const long long n_words = (n_items + 31) >> 5;
+  const long long n_tiles = (n_words + kTileWords - 1) / kTileWords;
+  __shared__ int word_off[kTileWords];
+  __shared__ int warp_tot[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // each thread owns 4 consecutive words of the tile
+    const long long w0 = tile * kTileWords + threadIdx.x * 4;
+    uint32_t wv[4];
+    int cnt[4];
+    int tsum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      wv[k] = (w0 + k < n_words) ? __ldg(words + w0 + k) : 0u;
+      cnt[k] = __popc(wv[k]);
+      tsum += cnt[k];
+    }
+    int incl = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int k = 0; k < wid; ++k) wbase += warp_tot[k];
+    int run = tile_offs[tile] + wbase + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      word_off[threadIdx.x * 4 + k] = run;
+      run += cnt[k];
+    }
+    __syncthreads();
+    // a warp expands one word at a time: coalesced index writes
+    for (int wl = wid; wl < kTileWords; wl += 8) {
+      long long w = tile * kTileWords + wl;
+      if (w >= n_words) break;
+      uint32_t bits = __ldg(words + w);
+      if (bits == 0u) continue;
+      if ((bits >> lane) & 1u) {
+        int rank = __popc(bits & ((1u << lane) - 1u));
+        out_idx[word_off[wl] + rank] = (int32_t)(w * 32 + lane);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t n_const,
+                   int64_t n_items_max, int32_t* out_idx, int32_t* out_count, cudaStream_t st) {
+  int64_t n_words = div_up(n_items_max, 32);
+  int64_t n_tiles = div_up(n_words, kTileWords);
+  int grid = (int)(n_tiles < (int64_t)sm_count() * 8 ? (n_tiles > 0 ? n_tiles : 1) : sm_count() * 8);
+  compact_tile_sums<<<grid, 256, 0, st>>>(ws.words, n_src, mult, n_const, ws.tile_sums);
+  compact_scan<<<1, 1024, 0, st>>>(ws.tile_sums, n_src, mult, n_const, ws.tile_offs, out_count);
+  compact_expand<<<grid, 256, 0, st>>>(ws.words, ws.tile_offs, n_src, mult, n_const, out_idx);
+  return check_launch("compact");
+}
+
+}  // namespace gpnerf
+
+extern "C" {
+
+int gpnerf_abi_version(void) { return GPNERF_ABI_VERSION; }
+const char* gpnerf_last_error(void) { return gpnerf::g_err; }
+int gpnerf_sm_count(void) { return gpnerf::sm_count(); }
+
+int64_t gpnerf_workspace_bytes(int64_t n_items) {
+  if (n_items < 0) return GPNERF_E_ARG;
+  int64_t n_words = gpnerf::div_up(n_items, 32);
+  int64_t n_tiles = gpnerf::div_up(n_words, gpnerf::kTileWords);
+  return (gpnerf::div_up(n_words, 64) * 64 + 2 * gpnerf::div_up(n_tiles, 64) * 64 + 64) * 4;
+}
+
+}  // extern "C"

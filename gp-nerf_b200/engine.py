@@ -1,0 +1,282 @@
+"""Host-side driver of the hot path: owns the device buffers of one frame and
+issues the K0…K5 launches of libgpnerf_b200.so on torch's current stream.
+
+PyTorch is used for device memory and streams only; every computation on the
+path is a kernel of the C-ABI library (gpnerf_b200._lib).  Data-dependent
+sizes stay on the device (`counters`), so a frame is a sync-free launch
+sequence; the host reads the counters once, together with the image.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (CNT_P1, CNT_P2, CNT_PIX, CNT_RAYS, N_COUNTERS, PREC_BF16, PREC_FP32, Frame,
+                   HeadWeights, check, ptr, ptr_array)
+
+HEAD_KEYS = {
+    "geo": ("sigmahead.out_geometry_fc.0",),
+    "den": tuple(f"rgbhead.out_geometry_fc.{i}" for i in (0, 2, 4, 6)),
+    "base": tuple(f"rgbhead.base_fc.{i}" for i in (0, 2)),
+    "vis": tuple(f"rgbhead.vis_fc.{i}" for i in (0, 2)),
+    "rgb": tuple(f"rgbhead.rgb_fc.{i}" for i in (0, 2, 4)),
+}
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class Engine:
+    """Buffers + launch sequence for one target resolution / sample count."""
+
+    def __init__(self, H, W, n_samples, n_views, device="cuda:0", precision=PREC_FP32,
+                 rank=0, world=1, tile_px=64, max_rays=None, t_min=0.0, voxel_size=(0.005,) * 3,
+                 mask_threshold=0.1):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.GpnerfError("gpnerf_b200 runs on CUDA devices only (no CPU fallback)")
+        self.H, self.W, self.S, self.V = int(H), int(W), int(n_samples), int(n_views)
+        self.precision = int(precision)
+        self.rank, self.world, self.tile_px = int(rank), int(world), int(tile_px)
+        self.t_min = float(t_min)
+        self.voxel_size = tuple(float(v) for v in voxel_size)
+        self.mask_threshold = float(mask_threshold)
+        npx = self.H * self.W
+        if max_rays is None:
+            n_tiles = math.ceil(npx / self.tile_px)
+            max_rays = min(npx, math.ceil(n_tiles / self.world) * self.tile_px)
+        self.max_rays = int(max_rays)
+        self.max_pts = self.max_rays * self.S
+        if self.max_pts >= 2 ** 31:
+            raise _lib.GpnerfError("ray·sample count exceeds int32 indexing")
+        dev = self.device
+        f32, i32 = torch.float32, torch.int32
+
+        def buf(n, dt=f32):
+            return torch.empty(int(n), dtype=dt, device=dev)
+
+        self.counters = torch.zeros(N_COUNTERS, dtype=i32, device=dev)
+        self.can_bounds = buf(12)
+        self.pix_mask = buf(npx)
+        self.ray_pix = buf(npx, i32)
+        self.rays_o = buf(3)
+        self.rays_d = buf(max(npx, self.max_rays) * 3)
+        self.near = buf(max(npx, self.max_rays))
+        self.far = buf(max(npx, self.max_rays))
+        self.t_vals = torch.linspace(0.0, 1.0, steps=self.S, device="cpu").to(dev)  # BaseRender.py:37
+        self.valid = buf(self.max_pts, i32)
+        self.z_vals = buf(self.max_pts)
+        self.vol_feat = buf(self.max_pts * 128)
+        self.rgb_feat = buf(self.max_pts * self.V * 35)
+        self.mask = buf(self.max_pts * self.V)
+        self.meanvar = buf(self.max_pts * 70)
+        self.sigma = buf(self.max_pts)
+        self.alpha = buf(self.max_pts)
+        self.valid1 = buf(self.max_pts, i32)
+        self.rgb = buf(self.max_pts * 3)
+        self.rgb_map = buf(self.max_rays * 3)
+        self.pred_img = buf(npx * 3)
+        self.hit_mask = torch.empty(npx, dtype=torch.uint8, device=dev)
+        ws_bytes = self.lib.gpnerf_workspace_bytes(max(self.max_pts, npx))
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        # products of K0 (allocated on first upload)
+        self.levels_cl = None
+        self.chan_sums = None
+        self.masks3d = None
+        self.images_rgbx = None
+        self.featmaps_cl = None
+        self.level_dims = None
+        self._weights = None
+        self._weight_tensors = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ utils
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_weights(self, state_dict):
+        """Head weights keyed as in the reference state_dict (prefix
+        'nerfhead.' optional)."""
+        from .ops import pack_head_weights
+        hw, keep = pack_head_weights(state_dict, self.device, self.V)
+        if keep[2 * (1 + 4 + 2 + 2)].shape[1] != 32 * self.V:
+            raise _lib.GpnerfError("rgb_fc.0 expects 32·n_views input features")
+        self._weights, self._weight_tensors = hw, keep
+
+    # ------------------------------------------------------------- K0 uploads
+    def upload_products(self, levels, featmaps, src_imgs):
+        """levels: 4 × [1,32,D,H,W] fp32 (SparseConvTensor.dense() layout);
+        featmaps [V,32,h,w]; src_imgs [1,V,3,H,W] or [V,3,H,W] in [-1,1].
+        Tensors already on the device are used in place; host tensors are
+        copied (non-blocking when pinned)."""
+        dev, st = self.device, self._stream()
+        lv = [t.to(dev, non_blocking=True) for t in levels]
+        fm = featmaps.to(dev, non_blocking=True)
+        im = src_imgs.to(dev, non_blocking=True)
+        im = im[0] if im.dim() == 5 else im
+        dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
+        if self.level_dims != dims:
+            self.level_dims = dims
+            self.levels_cl = [torch.empty(d * h * w * 32, dtype=torch.float32, device=dev) for d, h, w in dims]
+            self.chan_sums = [torch.empty(d * h * w, dtype=torch.float32, device=dev) for d, h, w in dims]
+            self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
+        assert len(lv) == 4 and all(t.shape[1] == 32 and t.dtype == torch.float32 for t in lv)
+        for t, (d, h, w), cl, cs in zip(lv, dims, self.levels_cl, self.chan_sums):
+            check(self.lib.gpnerf_k0_level_to_channels_last(ptr(t.contiguous()), d, h, w, ptr(cl), ptr(cs), st),
+                  "k0_level_to_channels_last")
+        V, Cc, fh, fw = fm.shape
+        assert V == self.V and Cc == 32
+        if self.featmaps_cl is None or self.featmaps_cl.numel() != fm.numel():
+            self.featmaps_cl = torch.empty(fm.numel(), dtype=torch.float32, device=dev)
+        check(self.lib.gpnerf_k0_featmaps_to_channels_last(ptr(fm.contiguous()), V, fh, fw,
+                                                           ptr(self.featmaps_cl), st), "k0_featmaps")
+        _, _, ih, iw = im.shape
+        if self.images_rgbx is None or self.images_rgbx.numel() != V * ih * iw * 4:
+            self.images_rgbx = torch.empty(V * ih * iw * 4, dtype=torch.float32, device=dev)
+        check(self.lib.gpnerf_k0_images_to_rgbx(ptr(im.contiguous()), V, ih, iw, 1, ptr(self.images_rgbx), st),
+              "k0_images_to_rgbx")
+        self.src_hw, self.feat_hw = (ih, iw), (fh, fw)
+        self.launches += 6
+        self._keep_inputs = (lv, fm, im)     # keep alive until the stream drains
+
+    # ------------------------------------------------------------ frame setup
+    def make_frame(self, batch, neg_ray=False):
+        """Pack gpnerf_frame_t from the reference's batch dict (host-side
+        scalars; ZjumocapDataset.py:464-517).  K·E is formed with torch's bmm
+        exactly as Projector.compute_projections does (BaseRender.py:311-314)."""
+        f = Frame()
+
+        def cpu(x):
+            return x.detach().to("cpu", torch.float32)
+        Rm = cpu(batch["Rh"] if "Rh" in batch else batch["R"]).reshape(3, 3)
+        f.R[:] = Rm.flatten().tolist()
+        f.Th[:] = cpu(batch["Th"]).flatten().tolist()
+        f.bounds_min[:] = cpu(batch["bounds"])[0, 0].tolist()
+        f.voxel_size[:] = list(self.voxel_size)
+        osh = [int(v) for v in batch["out_sh"].reshape(-1, 3).max(0)[0].tolist()]
+        f.out_sh[:] = osh
+        for k in range(4):
+            f.level_dims[k][:] = list(self.level_dims[k])
+        f.target_pose[:] = cpu(batch["target_pose"]).reshape(12).tolist()
+        f.target_K[:] = cpu(batch["target_K"]).reshape(9).tolist()
+        f.target_K_inv[:] = cpu(batch["target_K_inv"]).reshape(9).tolist()
+        f.H, f.W = self.H, self.W
+        V = self.V
+        f.n_views = V
+        src_poses, src_Ks = cpu(batch["src_poses"]).reshape(V, 3, 4), cpu(batch["src_Ks"]).reshape(V, 3, 3)
+        Eh = torch.eye(4).repeat(V, 1, 1)
+        Eh[:, :3, :4] = src_poses
+        Kh = torch.eye(4).repeat(V, 1, 1)
+        Kh[:, :3, :3] = src_Ks
+        KE = Kh.bmm(Eh)
+        for v in range(V):
+            f.src_KE[v][:] = KE[v].flatten().tolist()
+        f.src_h, f.src_w = self.src_hw
+        f.feat_h, f.feat_w = self.feat_hw
+        f.n_samples = self.S
+        f.neg_ray = int(bool(neg_ray))
+        f.mask_threshold = self.mask_threshold
+        f.rank, f.world, f.tile_px = self.rank, self.world, self.tile_px
+        return f
+
+    # --------------------------------------------------------------- launches
+    def build_occupancy(self, frame):
+        st = self._stream()
+        cs = ptr_array(self.chan_sums)
+        check(self.lib.gpnerf_k0_build_masks3d(cs, C.byref(frame), ptr(self.masks3d), st), "k0_build_masks3d")
+        self.launches += 1
+
+    def render_progressive(self, frame, t_rand=None):
+        """demo_render.Renderer.render_rays downstream of the producers.
+        Leaves results in self.{rgb_map,pred_img,hit_mask,counters,...}."""
+        if self._weights is None:
+            raise _lib.GpnerfError("set_weights() has not been called")
+        L, st, fr = self.lib, self._stream(), C.byref(frame)
+        self.build_occupancy(frame)
+        check(L.gpnerf_k1_voxel_pixel_mask(ptr(self.masks3d), fr, ptr(self.can_bounds), ptr(self.pix_mask), st),
+              "k1_voxel_pixel_mask")
+        check(L.gpnerf_k1_rays_bbox(ptr(self.pix_mask), ptr(self.can_bounds), fr, ptr(self.ray_pix),
+                                    ptr(self.rays_o), ptr(self.rays_d), ptr(self.near), ptr(self.far),
+                                    ptr(self.counters), ptr(self.workspace), st), "k1_rays_bbox")
+        self.launches += 4 + 5
+        self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays)
+        check(L.gpnerf_k4_compact_alpha(ptr(self.sigma), self.max_pts, ptr(self.counters), ptr(self.alpha),
+                                        ptr(self.valid1), ptr(self.workspace), st), "k4_compact_alpha")
+        check(L.gpnerf_k3_color_mlp(ptr(self.rgb_feat), ptr(self.meanvar), ptr(self.valid1),
+                                    C.byref(self._weights), self.V, self.max_pts, ptr(self.counters), CNT_P2,
+                                    ptr(self.rgb), self.precision, st), "k3_color_mlp")
+        check(L.gpnerf_k5_composite(ptr(self.valid), ptr(self.alpha), ptr(self.rgb), ptr(self.ray_pix), fr,
+                                    self.max_rays, ptr(self.counters), C.c_float(self.t_min), ptr(self.rgb_map),
+                                    ptr(self.pred_img), ptr(self.hit_mask), st), "k5_composite")
+        self.launches += 4 + 1 + 3
+
+    def _heads(self, frame, masks3d, t_rand, n_rays_max):
+        """occupancy (or identity) compaction → gathers → density head."""
+        L, st, fr = self.lib, self._stream(), C.byref(frame)
+        n_pts_max = n_rays_max * self.S
+        check(L.gpnerf_k2_occupancy_compact(ptr(masks3d), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near),
+                                            ptr(self.far), ptr(self.t_vals), ptr(t_rand), fr, n_rays_max,
+                                            ptr(self.valid), ptr(self.z_vals), ptr(self.counters),
+                                            ptr(self.workspace), st), "k2_occupancy_compact")
+        lv = ptr_array(self.levels_cl)
+        check(L.gpnerf_k2_gather_volume(lv, 0, ptr(self.valid), ptr(self.rays_o), ptr(self.rays_d),
+                                        ptr(self.z_vals), None, fr, n_pts_max, ptr(self.counters),
+                                        ptr(self.vol_feat), st), "k2_gather_volume")
+        check(L.gpnerf_k2_project_gather_meanvar(ptr(self.images_rgbx), ptr(self.featmaps_cl), 0, ptr(self.valid),
+                                                 ptr(self.rays_o), ptr(self.rays_d), ptr(self.z_vals), None, fr,
+                                                 n_pts_max, ptr(self.counters), ptr(self.rgb_feat),
+                                                 ptr(self.mask), ptr(self.meanvar), st),
+              "k2_project_gather_meanvar")
+        check(L.gpnerf_k3_density_mlp(ptr(self.vol_feat), 0, ptr(self.meanvar), ptr(self.mask),
+                                      C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), CNT_P1,
+                                      ptr(self.sigma), None, self.precision, st), "k3_density_mlp")
+        self.launches += 4 + 1 + 1 + 1
+
+    def render_dense(self, frame, ray_o, ray_d, near, far, t_rand=None, neg_ray=False):
+        """BaseRender.Renderer.render_rays semantics: every sample of the given
+        rays goes through both heads (no occupancy / density compaction).
+        ray_o/ray_d [R,3] (shared origin not required by the reference, but the
+        dataset path always has one camera per batch; row 0 is used), near/far
+        [R].  Returns a dict of device tensors."""
+        if self._weights is None:
+            raise _lib.GpnerfError("set_weights() has not been called")
+        L, st = self.lib, self._stream()
+        R = int(ray_d.shape[0])
+        if R > self.max_rays:
+            raise _lib.GpnerfError(f"{R} rays exceed the engine capacity {self.max_rays}")
+        dev = self.device
+        self.rays_o.copy_(_f32(ray_o, dev).reshape(-1, 3)[0], non_blocking=True)
+        self.rays_d[: R * 3].copy_(_f32(ray_d, dev).reshape(-1), non_blocking=True)
+        self.near[:R].copy_(_f32(near, dev).reshape(-1), non_blocking=True)
+        self.far[:R].copy_(_f32(far, dev).reshape(-1), non_blocking=True)
+        self.counters[CNT_RAYS] = R
+        tr = None if t_rand is None else _f32(t_rand, dev).reshape(-1)
+        self._heads(frame, masks3d=None, t_rand=tr, n_rays_max=R)
+        n = R * self.S
+        # colour head on every point: valid (identity after the NULL-mask pass) indexes the P1 rows
+        check(L.gpnerf_k3_color_mlp(ptr(self.rgb_feat), ptr(self.meanvar), ptr(self.valid),
+                                    C.byref(self._weights), self.V, n, ptr(self.counters), CNT_P1, ptr(self.rgb),
+                                    self.precision, st), "k3_color_mlp")
+        raw = torch.cat([self.rgb[: n * 3].view(n, 3), self.sigma[:n].view(n, 1)], 1).contiguous()
+        rgb_in = self.rgb_feat[: n * self.V * 35].view(n, self.V, 35)[..., :3].contiguous()
+        out = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in
+               (("rgb_map", (R, 3)), ("disp_map", (R, 1)), ("acc_map", (R, 1)), ("depth_map", (R, 1)),
+                ("alpha", (R, self.S)), ("rgb_in_map", (R, self.V * 3)))}
+        check(L.gpnerf_k5_raw2outputs(ptr(raw), ptr(self.z_vals), ptr(rgb_in), R, self.S, self.V, int(neg_ray),
+                                      ptr(out["rgb_map"]), ptr(out["disp_map"]), ptr(out["acc_map"]),
+                                      ptr(out["depth_map"]), ptr(out["alpha"]), ptr(out["rgb_in_map"]), st),
+              "k5_raw2outputs")
+        out["z_vals"] = self.z_vals[:n].view(R, self.S).clone()
+        out["raw"] = raw.view(R, self.S, 4)
+        self.launches += 2
+        return out
+
+    def read_counters(self):
+        """One device→host sync: (n_pix, n_rays, P1, P2)."""
+        c = self.counters.cpu().tolist()
+        return {"n_pix": c[CNT_PIX], "n_rays": c[CNT_RAYS], "P1": c[CNT_P1], "P2": c[CNT_P2]}

@@ -1,0 +1,188 @@
+"""Tensor-level wrappers of the stand-alone C-ABI entry points – the operator
+granularity of the reference's modules (Projector.compute,
+SparseConvNet.forward's gather, fused_mean_variance, the head MLPs,
+Renderer.raw2outputs).  Inputs/outputs are torch CUDA tensors; all arithmetic
+happens in libgpnerf_b200.so.  No fallback: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import PREC_FP32, Frame, HeadWeights, check, ptr, ptr_array
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.GpnerfError("gpnerf_b200 ops take CUDA tensors only (no CPU fallback)")
+
+
+def _c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def level_to_channels_last(level):
+    """[1,32,D,H,W] → ([D*H*W*32], chan_sum [D*H*W])."""
+    _need_cuda(level)
+    lib = _lib.load()
+    _, ch, D, H, W = level.shape
+    assert ch == 32
+    out = torch.empty(D * H * W * 32, dtype=torch.float32, device=level.device)
+    cs = torch.empty(D * H * W, dtype=torch.float32, device=level.device)
+    check(lib.gpnerf_k0_level_to_channels_last(ptr(_c(level)), D, H, W, ptr(out), ptr(cs), _stream(level.device)),
+          "k0_level_to_channels_last")
+    return out, cs
+
+
+def featmaps_to_channels_last(featmaps):
+    _need_cuda(featmaps)
+    lib = _lib.load()
+    V, ch, h, w = featmaps.shape
+    assert ch == 32
+    out = torch.empty(V * h * w * 32, dtype=torch.float32, device=featmaps.device)
+    check(lib.gpnerf_k0_featmaps_to_channels_last(ptr(_c(featmaps)), V, h, w, ptr(out), _stream(featmaps.device)),
+          "k0_featmaps_to_channels_last")
+    return out
+
+
+def images_to_rgbx(src_imgs, unnormalize=True):
+    """[V,3,H,W] → [V*H*W*4] (RGB, pad); x*0.5+0.5 on the way if `unnormalize`."""
+    _need_cuda(src_imgs)
+    lib = _lib.load()
+    V, ch, H, W = src_imgs.shape
+    assert ch == 3
+    out = torch.empty(V * H * W * 4, dtype=torch.float32, device=src_imgs.device)
+    check(lib.gpnerf_k0_images_to_rgbx(ptr(_c(src_imgs)), V, H, W, int(bool(unnormalize)), ptr(out), _stream(src_imgs.device)),
+          "k0_images_to_rgbx")
+    return out
+
+
+def gather_volume(levels_cl, frame: Frame, points, normalised=False):
+    """SparseConvNet.forward's 4-level trilinear gather.  points [n,3] are
+    world points, or normalised (x,y,z) grid coordinates when `normalised`."""
+    _need_cuda(points, *levels_cl)
+    lib = _lib.load()
+    pts = _c(points).reshape(-1, 3)
+    n = pts.shape[0]
+    out = torch.empty((n, 128), dtype=torch.float32, device=pts.device)
+    if n:
+        check(lib.gpnerf_k2_gather_volume(ptr_array(levels_cl), 2 if normalised else 1, None, None, None, None,
+                                          ptr(pts), C.byref(frame), n, None, ptr(out), _stream(pts.device)),
+              "k2_gather_volume")
+    return out
+
+
+def project_gather_meanvar(images_rgbx, featmaps_cl, frame: Frame, points):
+    """Projector.compute + fused_mean_variance on explicit world points [n,3].
+    Returns rgb_feat [n,V,35], mask [n,V], meanvar [n,70]."""
+    _need_cuda(points, images_rgbx, featmaps_cl)
+    lib = _lib.load()
+    pts = _c(points).reshape(-1, 3)
+    n, V = pts.shape[0], frame.n_views
+    dev = pts.device
+    rgb_feat = torch.empty((n, V, 35), dtype=torch.float32, device=dev)
+    mask = torch.empty((n, V), dtype=torch.float32, device=dev)
+    meanvar = torch.empty((n, 70), dtype=torch.float32, device=dev)
+    if n:
+        check(lib.gpnerf_k2_project_gather_meanvar(ptr(images_rgbx), ptr(featmaps_cl), 1, None, None, None, None,
+                                                   ptr(pts), C.byref(frame), n, None, ptr(rgb_feat), ptr(mask),
+                                                   ptr(meanvar), _stream(dev)), "k2_project_gather_meanvar")
+    return rgb_feat, mask, meanvar
+
+
+def mean_variance(rgb_feat):
+    """fused_mean_variance: [..., V, 35] → meanvar [n,70]."""
+    _need_cuda(rgb_feat)
+    lib = _lib.load()
+    V = rgb_feat.shape[-2]
+    x = _c(rgb_feat).reshape(-1, V, 35)
+    n = x.shape[0]
+    out = torch.empty((n, 70), dtype=torch.float32, device=x.device)
+    if n:
+        check(lib.gpnerf_k2_mean_variance(ptr(x), V, n, ptr(out), _stream(x.device)), "k2_mean_variance")
+    return out
+
+
+def pack_head_weights(state_dict, device, n_views=3):
+    """HeadWeights struct (+ the tensors it points into) from reference-keyed
+    parameters."""
+    from .engine import HEAD_KEYS
+
+    def get(name):
+        for pre in ("", "nerfhead."):
+            if pre + name in state_dict:
+                return state_dict[pre + name].detach().to(device=device, dtype=torch.float32).contiguous()
+        raise KeyError(name)
+    hw, keep = HeadWeights(), []
+
+    def pair(name):
+        w, b = get(name + ".weight"), get(name + ".bias")
+        keep.extend([w, b])
+        return w.data_ptr(), b.data_ptr()
+    hw.geo_w, hw.geo_b = pair(HEAD_KEYS["geo"][0])
+    for field in ("den", "base", "vis", "rgb"):
+        for i, nme in enumerate(HEAD_KEYS[field]):
+            wp, bp = pair(nme)
+            getattr(hw, field + "_w")[i] = wp
+            getattr(hw, field + "_b")[i] = bp
+    return hw, keep
+
+
+def density_mlp(feat_in, meanvar, mask, weights: HeadWeights, precision=PREC_FP32, want_sigma_feat=False):
+    """feat_in [n,128] (volume features) or [n,64] (sigma_feat); returns σ [n]
+    (and sigma_feat [n,64])."""
+    _need_cuda(feat_in, meanvar, mask)
+    lib = _lib.load()
+    x = _c(feat_in)
+    n, k = x.shape
+    assert k in (128, 64)
+    V = mask.shape[-1]
+    dev = x.device
+    sigma = torch.empty(n, dtype=torch.float32, device=dev)
+    sfeat = torch.empty((n, 64), dtype=torch.float32, device=dev) if want_sigma_feat else None
+    if n:
+        check(lib.gpnerf_k3_density_mlp(ptr(x), 0 if k == 128 else 1, ptr(_c(meanvar)), ptr(_c(mask).reshape(n, V)),
+                                        C.byref(weights), V, n, None, 0, ptr(sigma), ptr(sfeat), precision,
+                                        _stream(dev)), "k3_density_mlp")
+    return (sigma, sfeat) if want_sigma_feat else sigma
+
+
+def color_mlp(rgb_feat, meanvar, weights: HeadWeights, precision=PREC_FP32):
+    """rgb_feat [n,V,35], meanvar [n,70] → rgb [n,3]."""
+    _need_cuda(rgb_feat, meanvar)
+    lib = _lib.load()
+    x = _c(rgb_feat)
+    n, V, _ = x.shape
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=x.device)
+    if n:
+        check(lib.gpnerf_k3_color_mlp(ptr(x), ptr(_c(meanvar)), None, C.byref(weights), V, n, None, 0, ptr(rgb),
+                                      precision, _stream(x.device)), "k3_color_mlp")
+    return rgb
+
+
+def raw2outputs(raw, z_vals, rgb_in=None, neg=False):
+    """Renderer.raw2outputs (+ rgb_in_map): raw [R,S,4], z_vals [R,S],
+    rgb_in [R,S,V,3] → rgb_map, disp, acc, weights, depth, rgb_in_map."""
+    _need_cuda(raw, z_vals, rgb_in)
+    lib = _lib.load()
+    raw, z = _c(raw), _c(z_vals)
+    R, S, _ = raw.shape
+    dev = raw.device
+    V = 0 if rgb_in is None else rgb_in.shape[2]
+    rgb_map = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    disp, acc, depth = (torch.empty(R, dtype=torch.float32, device=dev) for _ in range(3))
+    weights = torch.empty((R, S), dtype=torch.float32, device=dev)
+    rin = None if rgb_in is None else _c(rgb_in)
+    rin_map = None if rgb_in is None else torch.empty((R, V * 3), dtype=torch.float32, device=dev)
+    if R:
+        check(lib.gpnerf_k5_raw2outputs(ptr(raw), ptr(z), ptr(rin), R, S, V, int(bool(neg)), ptr(rgb_map), ptr(disp),
+                                        ptr(acc), ptr(depth), ptr(weights), ptr(rin_map), _stream(dev)),
+              "k5_raw2outputs")
+    return rgb_map, disp, acc, weights, depth, rin_map

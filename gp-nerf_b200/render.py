@@ -1,0 +1,234 @@
+"""Mirror of the reference's renderers behind the same plugin API.
+
+``build_render(cfg) -> Renderer`` and ``Renderer.render(batch) -> dict`` as in
+libs/renders/BaseRender.py:211-274,367-403 (dense training/validation path,
+``progressive=False``) and libs/renders/demo_render.py:429-498,635-671
+(progressive inference path, ``progressive=True``).  The hot path runs in
+libgpnerf_b200.so through :class:`gpnerf_b200.engine.Engine`.
+
+Upstream products.  The image encoder and the SMPL-code attention + sparse-conv
+volume encoder are outside the hot path.  ``render`` takes their
+outputs from ``batch['featmaps']`` / ``batch['levels']`` when present (synthetic
+benchmarks, tests); otherwise it runs ``self.encoder`` and the reference's own
+producer modules held by ``self.nerfhead.sigmahead`` (available when this file
+is used inside the reference tree with spconv installed).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import PREC_FP32
+from .engine import Engine
+
+
+class Projector:
+    """BaseRender.py:278-363 / demo_render.py:501-632 on the B200 kernels."""
+
+    def __init__(self, device, neg_ray=False):
+        self.device = device
+        self.neg_ray = neg_ray
+
+    @staticmethod
+    def _frame(train_cameras, featmaps, neg_ray):
+        cams = train_cameras.reshape(-1, 34).detach().cpu().float()
+        V = cams.shape[0]
+        f = _lib.Frame()
+        f.n_views = V
+        KE = cams[:, 2:18].reshape(V, 4, 4).bmm(cams[:, 18:].reshape(V, 4, 4))
+        for v in range(V):
+            f.src_KE[v][:] = KE[v].flatten().tolist()
+        f.src_h, f.src_w = int(cams[0, 0]), int(cams[0, 1])
+        f.feat_h, f.feat_w = int(featmaps.shape[-2]), int(featmaps.shape[-1])
+        f.neg_ray = int(bool(neg_ray))
+        f.n_samples = 1
+        return f
+
+    def compute(self, xyz, train_imgs, train_cameras, featmaps):
+        """xyz [R,S,3]; train_imgs [1,V,3,H,W] already in [0,1]; train_cameras
+        [1,V,34]; featmaps [V,C,h,w] → rgb_feat [R,S,V,35], mask [R,S,V,1]."""
+        assert train_imgs.shape[0] == 1 and train_cameras.shape[0] == 1   # BaseRender.py:336
+        f = self._frame(train_cameras, featmaps, self.neg_ray)
+        rgbx = ops.images_to_rgbx(train_imgs[0], unnormalize=False)
+        fm = ops.featmaps_to_channels_last(featmaps)
+        sh = xyz.shape[:2]
+        rgb_feat, mask, _ = ops.project_gather_meanvar(rgbx, fm, f, xyz.reshape(-1, 3))
+        return rgb_feat.view(*sh, f.n_views, 35), mask.view(*sh, f.n_views, 1)
+
+    def compute_smpl(self, smpl_xyz, train_cameras, featmaps):
+        """demo_render.py:612-632 → [1,6890,V,32]"""
+        f = self._frame(train_cameras, featmaps, self.neg_ray)
+        dummy = torch.zeros(f.n_views * f.src_h * f.src_w * 4, device=featmaps.device)
+        fm = ops.featmaps_to_channels_last(featmaps)
+        rgb_feat, _, _ = ops.project_gather_meanvar(dummy, fm, f, smpl_xyz.reshape(-1, 3))
+        return rgb_feat[..., 3:].reshape(*smpl_xyz.shape[:2], f.n_views, 32)
+
+
+class Renderer(nn.Module):
+    def __init__(self, encoder, nerfhead, is_train=True, neg_ray_train=False, neg_ray_val=False, n_rays=1024,
+                 n_samples=64, voxel_size=(0.005, 0.005, 0.005), chunk=64, mesh_th=-1, progressive=False,
+                 precision=PREC_FP32, t_min=0.0, rank=0, world=1, tile_px=64):
+        super().__init__()
+        self.encoder = encoder
+        self.nerfhead = nerfhead
+        self.is_train = is_train
+        self.neg_ray_train = neg_ray_train
+        self.neg_ray_val = neg_ray_val
+        self.n_rays = n_rays
+        self.n_samples = n_samples
+        self.voxel_size = np.array(voxel_size)
+        self.chunk = chunk            # kept for API compatibility; 180 GB of HBM needs no ray chunking
+        self.mesh_th = mesh_th
+        self.progressive = progressive
+        self.precision = precision
+        self.t_min = t_min
+        self.rank, self.world, self.tile_px = rank, world, tile_px
+        self._engine = None
+
+    # ------------------------------------------------------------------ engine
+    def engine_for(self, H, W, V, device, max_rays=None):
+        e = self._engine
+        key = (H, W, V, str(device), max_rays)
+        if e is None or e._key != key:
+            e = Engine(H, W, self.n_samples, V, device=device, precision=self.precision, rank=self.rank,
+                       world=self.world, tile_px=self.tile_px, t_min=self.t_min, max_rays=max_rays,
+                       voxel_size=tuple(float(v) for v in self.voxel_size))
+            e._key = key
+            self._engine = e
+        return e
+
+    def _upstream(self, batch):
+        """featmaps and dense levels: from the batch, or from the reference's
+        producer modules (demo_render.py:103-157, 442)."""
+        src_imgs = batch["src_imgs"]
+        if "featmaps" in batch:
+            featmaps = batch["featmaps"]
+        else:
+            if self.encoder is None:
+                raise _lib.GpnerfError("no encoder and no batch['featmaps']")
+            featmaps = self.encoder(src_imgs.squeeze(0))
+        if "levels" in batch:
+            return featmaps, batch["levels"]
+        sh = self.nerfhead.sigmahead
+        if not hasattr(sh, "xyzc_net"):
+            raise _lib.GpnerfError("no batch['levels'] and the sparse-conv producer (spconv) is unavailable")
+        import spconv  # noqa: F401  (reference dependency, only on this upstream branch)
+        device = featmaps.device
+        xyz = batch["feature"][..., :3]
+        R, Th = batch["Rh"].float(), batch["Th"].float()
+        smpl_xyz = torch.bmm(xyz, R.transpose(1, 2)) + Th
+        cams = self._pack_cameras(batch, src_imgs.shape[-2:], device)
+        code = sh.c(torch.arange(0, sh.c.num_embeddings, device=device))
+        feats = Projector(device).compute_smpl(smpl_xyz, cams, featmaps).flatten(0, 1)
+        fused = sh.xyzc_attn(code.unsqueeze(1), feats, feats)[0].squeeze(1)
+        coord = batch["coord"].view(-1, 3)
+        coord = torch.cat([torch.zeros_like(coord[:, :1]), coord], 1)
+        out_sh = batch["out_sh"].max(0)[0].tolist()
+        xyzc = spconv.SparseConvTensor(fused, coord, out_sh, 1)
+        levels = sh.xyzc_net(xyzc)          # grid_coords=None → the dense levels
+        return featmaps, levels
+
+    @staticmethod
+    def _pack_cameras(batch, img_size, device):
+        """src_cameras [1,V,34] – BaseRender.py:233-247"""
+        src_poses, src_Ks = batch["src_poses"], batch["src_Ks"]
+        V = src_poses.shape[1]
+        Eh = torch.eye(4, device=device).repeat(1, V, 1, 1)
+        Eh[:, :, :3, :4] = src_poses
+        Kh = torch.eye(4, device=device).repeat(1, V, 1, 1)
+        Kh[:, :, :3, :3] = src_Ks
+        cams = torch.ones((1, V, 34), device=device)
+        cams[:, :, 0] = img_size[0]
+        cams[:, :, 1] = img_size[1]
+        cams[:, :, 2:18] = Kh.reshape(1, V, -1)
+        cams[:, :, -16:] = Eh.reshape(1, V, -1)
+        return cams
+
+    def _neg_ray(self, batch):
+        """BaseRender.py:165-168"""
+        if "body_msk" in batch and batch["body_msk"].shape[-1] > self.n_rays:
+            return self.neg_ray_val
+        return self.neg_ray_train
+
+    # ------------------------------------------------------------------ render
+    def render(self, batch):
+        return self.render_progressive(batch) if self.progressive else self.render_dense(batch)
+
+    @torch.no_grad()
+    def render_progressive(self, batch):
+        """demo_render.Renderer.render: returns numpy rgb_map [R,3], pred_img
+        [H,W,3] (float64), mask_at_box [H*W] bool, time_slots, etime, rtime."""
+        device = batch["src_imgs"].device
+        torch.cuda.synchronize(device)
+        t0 = time.time()
+        featmaps, levels = self._upstream(batch)
+        torch.cuda.synchronize(device)
+        etime = time.time() - t0
+        t0 = time.time()
+        H, W = batch["src_imgs"].shape[-2:]
+        V = batch["src_imgs"].shape[1]
+        eng = self.engine_for(int(H), int(W), int(V), device)
+        eng.set_weights(self.nerfhead.hot_path_state())
+        eng.upload_products(levels, featmaps, batch["src_imgs"])
+        frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
+        eng.render_progressive(frame)
+        cnt = eng.read_counters()                     # the frame's single host sync
+        n = cnt["n_rays"]
+        rgb_map = eng.rgb_map[: n * 3].view(n, 3).cpu().numpy()
+        pred_img = eng.pred_img.view(H, W, 3).cpu().numpy().astype(np.float64)
+        mask_at_box = eng.hit_mask.cpu().numpy().astype(bool)
+        rtime = time.time() - t0
+        return {"rgb_map": rgb_map, "pred_img": pred_img, "mask_at_box": mask_at_box,
+                "time_slots": {"bc_render": rtime}, "etime": etime, "rtime": rtime, "counts": cnt}
+
+    def render_dense(self, batch):
+        """BaseRender.Renderer.render: rgb_map [1,R,3], disp/acc/depth [1,R,1],
+        alpha (=weights) [1,R,S], z_vals [1,R,S], rgb_in_map [1,R,3V]."""
+        device = batch["src_imgs"].device
+        featmaps, levels = self._upstream(batch)
+        H, W = batch["src_imgs"].shape[-2:]
+        V = batch["src_imgs"].shape[1]
+        rays_o, rays_d = batch["ray_o"], batch["ray_d"]
+        R = int(rays_o.shape[1])
+        eng = self.engine_for(int(H), int(W), int(V), device, max_rays=R)
+        eng.set_weights(self.nerfhead.hot_path_state())
+        eng.upload_products(levels, featmaps, batch["src_imgs"])
+        neg = self._neg_ray(batch)
+        frame = eng.make_frame(batch, neg_ray=neg)
+        t_rand = None
+        if self.is_train:          # BaseRender.py:40-47: jitter drawn on the CPU generator
+            t_rand = torch.rand((1, R, self.n_samples))
+        out = eng.render_dense(frame, rays_o[0], rays_d[0], batch["near"][0], batch["far"][0], t_rand, neg)
+        keys = ("rgb_map", "disp_map", "acc_map", "depth_map", "alpha", "z_vals", "rgb_in_map")
+        return {k: out[k].view(1, R, -1) for k in keys}
+
+
+def build_render(cfg, progressive=False):
+    """BaseRender.py:367-403 / demo_render.py:635-671.  `cfg.encoder.file` and
+    `cfg.head.file` keep their plugin meaning; a head file that cannot be
+    imported falls back to this package's NeRFHead mirror."""
+    from importlib import import_module as impm
+    try:
+        encoder = getattr(impm(cfg.encoder.file), "build_encoder")(cfg)
+    except Exception:
+        encoder = None            # feature maps must then come with the batch
+    try:
+        nerfhead = getattr(impm(cfg.head.file), "build_head")(cfg)
+        if not hasattr(nerfhead, "hot_path_state"):
+            raise ImportError
+    except Exception:
+        from .nerfhead import build_head
+        nerfhead = build_head(cfg)
+    neg_ray_train = "thuman" in cfg.dataset.train.name
+    neg_ray_val = "thuman" in cfg.dataset.test.name
+    is_train = nerfhead.training or (encoder is not None and encoder.training)
+    chunk = cfg.dataset.train.chunk if is_train else cfg.dataset.test.chunk
+    mesh_th = 1.0 / cfg.test.mesh_th if cfg.head.rgb.use_rgbhead is False else -1
+    return Renderer(encoder=encoder, nerfhead=nerfhead, is_train=False if progressive else is_train,
+                    neg_ray_train=neg_ray_train, neg_ray_val=neg_ray_val, n_rays=cfg.train.n_rays,
+                    n_samples=cfg.train.n_samples, voxel_size=cfg.dataset.voxel_size, chunk=chunk,
+                    mesh_th=mesh_th, progressive=progressive)

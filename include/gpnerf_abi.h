@@ -1,0 +1,223 @@
+/*
+ * gpnerf_abi.h – C ABI of libgpnerf_b200.so: the B200 (sm_100a) kernels of
+ * GP-NeRF's geometry-guided progressive volume-rendering hot path.
+ *
+ * The reference (sail-sg/GP-Nerf) has no native code and therefore no FFI; it
+ * reaches the GPU through ATen/cuBLAS/cuDNN calls issued from Python.  Each
+ * entry point below replaces the group of torch calls named in its comment
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - all tensors are dense, row-major, fp32 unless stated; indices are int32;
+ *  - nothing is allocated: the caller owns all buffers, sizes them for the
+ *    worst case (see gpnerf_workspace_bytes) and keeps them alive until the
+ *    stream has drained;
+ *  - data-dependent sizes (rays, surviving points) stay on the device in
+ *    `counters` (int32[GPNERF_N_COUNTERS]); kernels downstream read them there,
+ *    so a frame is one sync-free stream of launches;
+ *  - `stream` is a cudaStream_t passed as void*; functions are thread-safe when
+ *    called with distinct streams and buffers;
+ *  - return value: 0 = launched, <0 = GPNERF_E_* (never throws, never exits).
+ */
+#ifndef GPNERF_ABI_H
+#define GPNERF_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPNERF_ABI_VERSION 1
+#define GPNERF_MAX_VIEWS 8
+#define GPNERF_N_LEVELS 4
+#define GPNERF_LEVEL_CH 32 /* head.sigma.outdims = [32]*4, configs/default.py:92 */
+
+enum {
+  GPNERF_OK = 0,
+  GPNERF_E_ARG = -1,     /* bad argument (null pointer, size out of range)   */
+  GPNERF_E_CUDA = -2,    /* a CUDA runtime call failed; see gpnerf_last_error */
+  GPNERF_E_UNSUPPORTED = -3
+};
+
+/* slots of the device-side `counters` array */
+enum {
+  GPNERF_CNT_PIX = 0,   /* pixels set in the voxel-projection mask           */
+  GPNERF_CNT_RAYS = 1,  /* rays kept by the box test (this rank's share)     */
+  GPNERF_CNT_P1 = 2,    /* sample points surviving the occupancy test        */
+  GPNERF_CNT_P2 = 3,    /* points surviving the density test                 */
+  GPNERF_N_COUNTERS = 8
+};
+
+/* Per-frame constants, filled on the host.  Mirrors what render_rays reads
+ * from `batch` / `sp_input` (libs/renders/demo_render.py:96-113, 393-427). */
+typedef struct gpnerf_frame {
+  /* SMPL pose: p_smpl = (p_world - Th) · R          (BaseRender.py:52-60)  */
+  float R[9];              /* row-major 3x3 rotation matrix (batch['Rh'])   */
+  float Th[3];
+  float bounds_min[3];     /* batch['bounds'][0,0] – SMPL-frame min (x,y,z) */
+  float voxel_size[3];     /* cfg.dataset.voxel_size (0.005)                */
+  int32_t out_sh[3];       /* padded full-res volume shape (d,h,w)          */
+  int32_t level_dims[GPNERF_N_LEVELS][3]; /* (D,H,W) of every dense level   */
+  /* target camera                                   (demo_render.py:177-207) */
+  float target_pose[12];   /* 3x4 row-major [R|T], world→camera              */
+  float target_K[9];
+  float target_K_inv[9];
+  int32_t H, W;            /* target image size (reference hard-codes 512)   */
+  /* source views                                    (BaseRender.py:233-323) */
+  int32_t n_views;
+  float src_KE[GPNERF_MAX_VIEWS][16]; /* K(4x4)·E(4x4), row-major, per view  */
+  int32_t src_h, src_w;    /* source image size                              */
+  int32_t feat_h, feat_w;  /* encoder feature-map size                       */
+  /* sampling */
+  int32_t n_samples;       /* cfg.train.n_samples (64)                       */
+  int32_t neg_ray;         /* THuman convention (BaseRender.py:165-168)      */
+  float mask_threshold;    /* 0.1 (demo_render.py:155)                       */
+  /* ray sharding over ranks: pixel tiles of `tile_px` consecutive row-major
+   * pixels are dealt round-robin; rank r keeps tiles with tile % world == r */
+  int32_t rank, world, tile_px;
+} gpnerf_frame_t;
+
+/* Head weights, all device pointers, nn.Linear layout [out][in] row-major, as
+ * they sit in the reference state_dict (libs/nerfheads/trainhead.py:39-41,
+ * 85-110).  `rgb0` has 32·n_views input columns. */
+typedef struct gpnerf_head_weights {
+  const float *geo_w, *geo_b;                 /* sigmahead.out_geometry_fc.0   [64,128] */
+  const float *den_w[4], *den_b[4];           /* rgbhead.out_geometry_fc.{0,2,4,6}: [64,134] [32,64] [16,32] [1,16] */
+  const float *base_w[2], *base_b[2];         /* rgbhead.base_fc.{0,2}: [64,105] [32,64] */
+  const float *vis_w[2], *vis_b[2];           /* rgbhead.vis_fc.{0,2}:  [32,32] [32,32]  */
+  const float *rgb_w[3], *rgb_b[3];           /* rgbhead.rgb_fc.{0,2,4}: [32,32V] [16,32] [3,16] */
+} gpnerf_head_weights_t;
+
+int gpnerf_abi_version(void);
+const char *gpnerf_last_error(void);
+/* number of SMs of the current device (grid sizing is a multiple of it) */
+int gpnerf_sm_count(void);
+
+/* ---- K0: layout of the upstream products ------------------------------- */
+/* One dense level NCDHW → NDHWC (one 128-byte line per voxel) plus the
+ * per-voxel channel sum that SparseConvNet.encode reduces
+ * (libs/nerfheads/networks/SparseConvNet.py:135-136). */
+int gpnerf_k0_level_to_channels_last(const float *ncdhw, int D, int H, int W,
+                                     float *ndhwc, float *chan_sum, void *stream);
+/* masks3d on the level-1 grid = Σ_levels nearest-upsampled channel sums
+ * (SparseConvNet.py:137-139). */
+int gpnerf_k0_build_masks3d(const float *const chan_sum[GPNERF_N_LEVELS],
+                            const gpnerf_frame_t *frame_host, float *masks3d, void *stream);
+/* encoder maps [V,C=32,h,w] → [V,h,w,32]; images [V,3,H,W] → [V,H,W,4] (RGB,
+ * pad); with `unnormalize` the [-1,1] inputs become x*0.5+0.5 on the way
+ * (BaseRender.py:231), otherwise they are taken as already in [0,1]. */
+int gpnerf_k0_featmaps_to_channels_last(const float *nchw, int V, int h, int w, float *nhwc, void *stream);
+int gpnerf_k0_images_to_rgbx(const float *nchw, int V, int H, int W, int unnormalize, float *rgbx,
+                             void *stream);
+
+/* ---- K1: pixel mask, rays, box intersection ---------------------------- */
+/* demo_render.py:166-200: occupied voxels → world → can_bounds (min/max,
+ * z∓0.05) and the 4-neighbour pixel mask of their projection.
+ * can_bounds float[12]: [0..5] = (min xyz, max xyz), [6..11] = scratch for the
+ * ordered-int atomics; pix_mask float[H*W] (1.0 / 0.0). */
+int gpnerf_k1_voxel_pixel_mask(const float *masks3d, const gpnerf_frame_t *frame_host,
+                               float *can_bounds, float *pix_mask, void *stream);
+/* demo_render.py:200-239: rays through masked pixels, 6-plane test with
+ * exactly two hits, near/far.  Kept rays are written in ascending pixel order
+ * for this rank's tiles.  ray_pix int32[H*W], rays_d float[H*W*3], near/far
+ * float[H*W], rays_o float[3]; counters[PIX], counters[RAYS] are set. */
+int gpnerf_k1_rays_bbox(const float *pix_mask, const float *can_bounds,
+                        const gpnerf_frame_t *frame_host, int32_t *ray_pix, float *rays_o,
+                        float *rays_d, float *near, float *far, int32_t *counters,
+                        void *workspace, void *stream);
+
+/* ---- K2: occupancy test, gathers --------------------------------------- */
+/* demo_render.py:59-94, 270-283: sample S depths per ray (t_vals = linspace,
+ * optional jitter t_rand[R*S] or NULL), world→SMPL, trilinear tap of masks3d,
+ * valid = ascending flat indices (ray*S+sample) of points with tap > 0.
+ * If masks3d is NULL every point is kept (BaseRender semantics).
+ * n_rays_max bounds the grid; the live count is counters[RAYS].
+ * Outputs valid int32[n_rays_max*S], counters[P1]. */
+int gpnerf_k2_occupancy_compact(const float *masks3d, const float *rays_o, const float *rays_d,
+                                const float *near, const float *far, const float *t_vals,
+                                const float *t_rand, const gpnerf_frame_t *frame_host,
+                                int n_rays_max, int32_t *valid, float *z_vals,
+                                int32_t *counters, void *workspace, void *stream);
+/* Where the two gathers take their sample points from (`point_kind`):
+ *   0  ray-parametrised: flat index valid[i] → (ray, sample), p = o + d·z;
+ *      the live count is counters[P1] (n_points_max bounds the grid);
+ *   1  explicit world points[n][3]   – the Projector.compute(xyz, …) API;
+ *   2  explicit normalised grid coordinates[n][3] in [-1,1] – the
+ *      SparseConvNet.forward(x, grid_coords) API (volume gather only).
+ * For kinds 1/2 pass counters = NULL and n_points_max = n. */
+
+/* SparseConvNet.py:111-122: 4-level trilinear gather (align_corners, zeros);
+ * vol_feat float[n][128] level-major. */
+int gpnerf_k2_gather_volume(const float *const levels_ndhwc[GPNERF_N_LEVELS], int point_kind,
+                            const int32_t *valid, const float *rays_o, const float *rays_d,
+                            const float *z_vals, const float *points,
+                            const gpnerf_frame_t *frame_host, int n_points_max,
+                            const int32_t *counters, float *vol_feat, void *stream);
+/* Projector.compute + fused_mean_variance (demo_render.py:560-609,
+ * trainhead.py:20-24): rgb_feat float[n][V][35] (RGB first), mask
+ * float[n][V], meanvar float[n][70] = (mean 35 | var 35). */
+int gpnerf_k2_project_gather_meanvar(const float *images_rgbx, const float *featmaps_nhwc,
+                                     int point_kind, const int32_t *valid, const float *rays_o,
+                                     const float *rays_d, const float *z_vals, const float *points,
+                                     const gpnerf_frame_t *frame_host, int n_points_max,
+                                     const int32_t *counters, float *rgb_feat, float *mask,
+                                     float *meanvar, void *stream);
+/* fused_mean_variance alone (trainhead.py:20-24): rgb_feat [n][V][35] → [n][70] */
+int gpnerf_k2_mean_variance(const float *rgb_feat, int n_views, int n_points, float *meanvar,
+                            void *stream);
+
+/* ---- K3: heads ---------------------------------------------------------- */
+/* For both heads the live row count is counters[counter_slot], or exactly
+ * n_points_max when counters is NULL. */
+
+/* trainhead.py:39-41,61-76,102-110,133-137: sigma_feat = ELU(Linear 128→64);
+ * σ = ReLU(MLP 134→64→32→16→1 on [sigma_feat|mean|var]); σ = 0 where no view
+ * is valid.  input_kind 0: `feat_in` = vol_feat float[n][128];
+ * input_kind 1: `feat_in` = sigma_feat float[n][64] (NeRFRGBHead.forward API).
+ * sigma float[n]; sigma_feat_out float[n][64] or NULL.
+ * precision: 0 = fp32 CUDA cores (parity), 1 = bf16 tcgen05 tensor cores. */
+int gpnerf_k3_density_mlp(const float *feat_in, int input_kind, const float *meanvar,
+                          const float *mask, const gpnerf_head_weights_t *weights_host, int n_views,
+                          int n_points_max, const int32_t *counters, int counter_slot, float *sigma,
+                          float *sigma_feat_out, int precision, void *stream);
+/* trainhead.py:128-145 colour trunk on the rows listed in valid1 (indices into
+ * rgb_feat/meanvar; NULL = all rows in order); rgb float[rows][3] is written at
+ * those rows. */
+int gpnerf_k3_color_mlp(const float *rgb_feat, const float *meanvar, const int32_t *valid1,
+                        const gpnerf_head_weights_t *weights_host, int n_views, int n_points_max,
+                        const int32_t *counters, int counter_slot, float *rgb, int precision,
+                        void *stream);
+
+/* ---- K4: progressive step ---------------------------------------------- */
+/* demo_render.py:312-317: α = 1-exp(-σ); valid1 = ascending indices (into the
+ * P1 arrays) with α > 1e-14; counters[P2]. */
+int gpnerf_k4_compact_alpha(const float *sigma, int n_points_max, int32_t *counters,
+                            float *alpha, int32_t *valid1, void *workspace, void *stream);
+
+/* ---- K5: compositing ---------------------------------------------------- */
+/* demo_render.py:335-353: front-to-back compositing of the surviving samples
+ * of each ray (CSR over `valid`), T = exclusive Π(1-α+1e-10), Σ w·rgb; writes
+ * rgb_map float[R][3] and scatters into pred_img float[H*W][3] (pre-zeroed by
+ * the call) and hit_mask uint8[H*W].  t_min > 0 stops a ray once T < t_min. */
+int gpnerf_k5_composite(const int32_t *valid, const float *alpha, const float *rgb,
+                        const int32_t *ray_pix, const gpnerf_frame_t *frame_host, int n_rays_max,
+                        const int32_t *counters, float t_min, float *rgb_map, float *pred_img,
+                        uint8_t *hit_mask, void *stream);
+/* Renderer.raw2outputs (BaseRender.py:75-107,147): dense [R][S] path.
+ * raw float[R][S][4] (rgb,σ); rgb_in float[R][S][V][3] or NULL.  Outputs
+ * rgb_map[R][3], disp/acc/depth[R], weights[R][S], rgb_in_map[R][V][3]. */
+int gpnerf_k5_raw2outputs(const float *raw, const float *z_vals, const float *rgb_in, int n_rays,
+                          int n_samples, int n_views, int neg, float *rgb_map, float *disp,
+                          float *acc, float *depth, float *weights, float *rgb_in_map, void *stream);
+
+/* bytes of scratch `workspace` needed by the compaction passes for up to
+ * n_items flags */
+int64_t gpnerf_workspace_bytes(int64_t n_items);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPNERF_ABI_H */

@@ -53,13 +53,14 @@ def mm_seqfma(A, B):
 
 
 def norm3(x):
-    """sqrt(x0² ⊕ x1² ⊕ x2²) accumulated as one rounded product plus two FMAs,
-    correctly-rounded sqrt.  (torch.norm(dim=1) on CPU agrees on 99.3 % of
-    inputs and is 1 ulp off on the rest – recorded in tests/golden/README.)"""
+    """torch.norm(x, dim=-1) for 3-vectors as ATen's CPU kernel rounds it: x0²
+    rounded, two FMAs, then a correctly rounded sqrt (taken in fp64 and rounded
+    once more – torch.sqrt's vectorised fp32 kernel is NOT correctly rounded,
+    torch.norm's is)."""
     acc = x[..., 0] * x[..., 0]
     acc = _fma(x[..., 1], x[..., 1], acc)
     acc = _fma(x[..., 2], x[..., 2], acc)
-    return torch.sqrt(acc)
+    return torch.sqrt(acc.double()).float()
 
 
 def t_vals(S, device="cpu"):
