@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the GP-NeRF progressive render hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--scene zju|dense]
+                  [--precision fp32|bf16] [--impl ours|reference]
+
+One step = one 512×512 novel-view frame of the synthetic ZJU-Mocap-shaped
+scene (BASELINE.json configs[1]): layout of the upstream products (K0), pixel
+mask + rays + box test (K1), occupancy compaction + gathers (K2), density head
+(K3), progressive compaction (K4), colour head (K3), compositing (K5).  At N>1
+the frame's rays are sharded over the ranks by pixel tiles and the image is
+re-assembled by one NCCL all_gather (strong scaling of a single frame).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident
+in HBM; `e2e` goes through Renderer.render(batch) with pinned host inputs and
+a device→host read of the image.  `--impl reference` times the CPU oracle (the
+restatement of the reference's PyTorch path, oracle/gpnerf_oracle.py) on the
+host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rays/s"
+S_SAMPLES = 64
+VIEWS = 3
+RES = 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="zju", choices=["zju", "dense"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--tile-px", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# per-point algorithmic work of each stage (SURVEY.md §8d / DESIGN.md)
+def stage_work(counts, n_level_elems, V):
+    P, P1, P2 = counts["n_rays"] * S_SAMPLES, counts["P1"], counts["P2"]
+    return {
+        "k0_level_to_channels_last": ("hbm", 8.0 * n_level_elems / 4, "all 4 calls: 4 B read + 4 B written per element"),
+        "k2_occupancy_compact": ("hbm", 36.0 * P, "32 B tap + 4 B z per point"),
+        "k2_gather_volume": ("hbm", 4096.0 * P1, "4 levels x 8 corners x 32 ch x 4 B per point"),
+        "k2_project_gather_meanvar": ("hbm", V * 4 * 35 * 4.0 * P1, "V x 4 corners x 35 ch x 4 B per point"),
+        "k3_density_mlp": ("tensor", 38688.0 * P1, "38,688 FLOP per point"),
+        "k3_color_mlp": ("tensor", 72160.0 * P2, "72,160 FLOP per point"),
+        "k4_compact_alpha": ("hbm", 8.0 * P1, "4 B read + 4 B written per point"),
+        "k5_composite": ("hbm", 16.0 * P1, "16 B per surviving sample"),
+    }
+
+
+def cpu_reference_frames(scene, weights, min_seconds, max_frames):
+    """Time the CPU oracle (port of the reference's PyTorch path) on full frames."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gpnerf_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    times, out = [], None
+    t_all = time.perf_counter()
+    while len(times) < max_frames and (time.perf_counter() - t_all < min_seconds or not times):
+        t0 = time.perf_counter()
+        out = orc.render_progressive(scene, weights, S=S_SAMPLES, chunk=131072)
+        times.append(time.perf_counter() - t0)
+    return times, out
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own algorithm on the host cores."""
+    if rank != 0:
+        return
+    import gpnerf_b200  # noqa: F401
+    from gpnerf_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gpnerf_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    scene = synth.make_scene(args.scene if args.scene == "zju" else "zju", H=RES, W=RES, V=VIEWS, seed=42)
+    w = synth.make_head_weights(V=VIEWS, seed=42)
+    times, out = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        out = orc.render_progressive(scene, w, S=S_SAMPLES, chunk=131072)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    rays = out["n_rays"]
+    val = rays * len(times) / total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frames_per_s": len(times) / total,
+        "config": {"workload": f"zju-like synthetic frame, {RES}x{RES}, V={VIEWS}, S={S_SAMPLES} (BASELINE configs[1])",
+                   "rays": rays, "P1": out["P1"], "P2": out["P2"]},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "every step = the full frame through oracle/gpnerf_oracle.py "
+                                   "(torch CPU restatement of the reference; chunk 131072 points)"},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    import torch.distributed as dist
+    import gpnerf_b200  # noqa: F401
+    from gpnerf_b200 import shard, synth
+    from gpnerf_b200._lib import PREC_BF16, PREC_FP32
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Renderer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    prec = PREC_BF16 if args.precision == "bf16" else PREC_FP32
+
+    scene = synth.make_scene("zju", H=RES, W=RES, V=VIEWS, seed=42)
+    weights = synth.make_head_weights(V=VIEWS, seed=42)
+    head = NeRFHead(code_dim=32, n_views=VIEWS, precision=prec)
+    sd = head.state_dict()
+    sd.update({k: v for k, v in weights.items()})
+    head.load_state_dict(sd)
+    head = head.to(dev)
+    renderer = Renderer(None, head, is_train=False, n_samples=S_SAMPLES, progressive=True, precision=prec,
+                        rank=rank, world=world, tile_px=args.tile_px)
+    n_px = RES * RES
+
+    # ---- device-resident inputs for `value`
+    host_keys = ("levels", "featmaps", "src_imgs")
+    d_levels = [t.to(dev) for t in scene["levels"]]
+    d_feat, d_imgs = scene["featmaps"].to(dev), scene["src_imgs"].to(dev)
+    eng = renderer.engine_for(RES, RES, VIEWS, dev)
+    eng.set_weights(head.hot_path_state())
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_device():
+        eng.upload_products(d_levels, d_feat, d_imgs)
+        frame = eng.make_frame(scene)
+        eng.render_progressive(frame)
+        if world > 1:
+            return shard.gather_frame(eng.pred_img.view(n_px, 3), n_px, args.tile_px)
+        return eng.pred_img
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize(dev)
+    counts = eng.read_counters()
+    if world > 1:
+        tot = torch.tensor([counts["n_rays"], counts["P1"], counts["P2"]], device=dev)
+        dist.all_reduce(tot)
+        g_rays, g_p1, g_p2 = [int(v) for v in tot.tolist()]
+    else:
+        g_rays, g_p1, g_p2 = counts["n_rays"], counts["P1"], counts["P2"]
+
+    # ---- timed region: exactly K steps, device-timed, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launches
+    eng.timing = True
+    eng.stage_events = {}
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        step_device()
+        b.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    eng.timing = False
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    stage_ms = eng.stage_times_ms()
+    launches = (eng.launches - launches0) // args.steps
+    if world > 1:
+        t = torch.tensor([dev_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = g_rays / (ms_per_step * 1e-3)
+
+    # ---- e2e: Renderer.render(batch) with pinned host inputs, image read back
+    e2e = None
+    if not args.no_e2e:
+        batch = {k: v for k, v in scene.items() if torch.is_tensor(v)}
+        batch["levels"] = [t.pin_memory() for t in scene["levels"]]
+        batch["featmaps"] = scene["featmaps"].pin_memory()
+        batch["src_imgs"] = scene["src_imgs"].pin_memory()
+        h2d = sum(t.numel() * 4 for t in batch["levels"]) + batch["featmaps"].numel() * 4 + batch["src_imgs"].numel() * 4
+
+        def e2e_step():
+            b = dict(batch)
+            # render() takes its device from src_imgs; levels/featmaps stay on the host so that
+            # their copies happen inside the call
+            b["src_imgs"] = batch["src_imgs"].to(dev, non_blocking=True)
+            return renderer.render(b)          # gathers the tiles itself when world > 1
+        for _ in range(2):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        et = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([et], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            et = float(t.item())
+        e2e = {"value": g_rays * args.steps / et, "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(n_px * 3 * 4 + n_px + 32), "ms_per_step": 1e3 * et / args.steps,
+               "frames_per_s": args.steps / et,
+               "api": "gpnerf_b200.render.Renderer.render(batch) – levels/featmaps/src_imgs in pinned host memory"}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (this rank's share of the work)
+    pk = peaks()
+    n_level_elems = sum(t.numel() for t in scene["levels"]) * 4
+    work = stage_work(counts, n_level_elems, VIEWS)
+    timed = {k: v for k, v in stage_ms.items() if k in work}
+    top = max(timed, key=timed.get) if timed else None
+    roofline = None
+    if top:
+        bound, amount, what = work[top]
+        n_calls = 4 if top == "k0_level_to_channels_last" else 1
+        dur_s = timed[top] * n_calls * 1e-3
+        if bound == "hbm":
+            ach, peak, unit = amount / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = amount / dur_s / 1e12, pk["bf16_tflops"], "TFLOP/s"
+        roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                    "traffic": None, "algorithmic": what, "launch_ms": timed[top] * n_calls,
+                    "peak_source": pk["source"]}
+    stages_out = {}
+    for k, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
+        ent = {"ms": round(ms * (4 if k == "k0_level_to_channels_last" else 1), 4)}
+        if k in work:
+            bound, amount, _ = work[k]
+            dur = ent["ms"] * 1e-3
+            if bound == "hbm":
+                ent["GB/s"] = round(amount / dur / 1e9, 1); ent["frac_hbm"] = round(amount / dur / 1e9 / pk["hbm_gbs"], 4)
+            else:
+                ent["TFLOP/s"] = round(amount / dur / 1e12, 2); ent["frac_bf16"] = round(amount / dur / 1e12 / pk["bf16_tflops"], 4)
+        stages_out[k] = ent
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        times, o = cpu_reference_frames(scene, weights, min_seconds=10.0, max_frames=3)
+        cpu_baseline = {"value": o["n_rays"] * len(times) / sum(times), "unit": "rays/s",
+                        "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{len(times)} full frame(s) of the same scene through oracle/gpnerf_oracle.py "
+                                  f"({sum(times):.1f} s of CPU work)",
+                        "s_per_frame": sum(times) / len(times)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "frames_per_s": 1e3 / ms_per_step, "pixel_rays_per_s": n_px * 1e3 / ms_per_step,
+        "config": {"workload": f"zju-like synthetic frame {RES}x{RES}, V={VIEWS}, S={S_SAMPLES} "
+                               "(BASELINE configs[1], trainzju_valzju inference shape), progressive path",
+                   "rays": g_rays, "points": g_rays * S_SAMPLES, "P1": g_p1, "P2": g_p2,
+                   "l2": "256 MB flush between timed steps; inputs 135 MB > 126 MB L2",
+                   "sharding": f"pixel tiles of {args.tile_px}, round-robin over {world} rank(s); "
+                               "one NCCL all_gather of tiles per frame" if world > 1 else "single GPU",
+                   "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "stages_ms": stages_out, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,7 @@ class HeadWeights(C.Structure):
         ("base_w", C.c_void_p * 2), ("base_b", C.c_void_p * 2),
         ("vis_w", C.c_void_p * 2), ("vis_b", C.c_void_p * 2),
         ("rgb_w", C.c_void_p * 3), ("rgb_b", C.c_void_p * 3),
+        ("tc_image", C.c_void_p),
     ]
 
 
@@ -64,6 +65,8 @@ _SIGNATURES = {
     "gpnerf_k2_mean_variance": ([_P, _I, _I, _P, _P], C.c_int),
     "gpnerf_k3_density_mlp": ([_P, _I, _P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _P, _I, _P], C.c_int),
     "gpnerf_k3_color_mlp": ([_P, _P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _I, _P], C.c_int),
+    "gpnerf_k3_packed_weight_bytes": ([], C.c_int64),
+    "gpnerf_k3_pack_weights": ([C.POINTER(HeadWeights), _I, _P, _P], C.c_int),
     "gpnerf_k4_compact_alpha": ([_P, _I, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_composite": ([_P, _P, _P, _P, C.POINTER(Frame), _I, _P, C.c_float, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_raw2outputs": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(256) raw2outputs_kernel(const float* __restric
       rgb_map[(long long)r * 3 + 2] = cb;
       depth[r] = dsum;
       acc[r] = asum;
-      disp[r] = 1.0f / fmaxf(1e-10f, dsum / asum);
+      const float q = dsum / asum;                       // 0/0 → NaN on empty rays, as in the reference
+      disp[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));  // torch.max propagates NaN (BaseRender.py:101)
     }
   }
 }

@@ -26,8 +26,62 @@ HEAD_KEYS = {
 }
 
 
+# CUDA kernels launched by each C-ABI call (memsets not counted) – used for
+# bench.py's `gpu_launches`; keep in sync with csrc/.
+KERNELS_PER_CALL = {
+    "k0_level_to_channels_last": 1, "k0_featmaps_to_channels_last": 1, "k0_images_to_rgbx": 1,
+    "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 5, "k2_occupancy_compact": 4,
+    "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,
+    "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1,
+}
+
+
 def _f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def frame_from_batch(batch, H, W, n_views, n_samples, level_dims, src_hw, feat_hw,
+                     voxel_size=(0.005,) * 3, mask_threshold=0.1, neg_ray=False, rank=0, world=1,
+                     tile_px=64) -> Frame:
+    """Pack gpnerf_frame_t from the reference's batch dict (host-side scalars;
+    ZjumocapDataset.py:464-517).  K·E is formed with torch's bmm exactly as
+    Projector.compute_projections does (BaseRender.py:311-314).  Pure host
+    code: needs no GPU."""
+    f = Frame()
+
+    def cpu(x):
+        return x.detach().to("cpu", torch.float32)
+    Rm = cpu(batch["Rh"] if "Rh" in batch else batch["R"]).reshape(3, 3)
+    f.R[:] = Rm.flatten().tolist()
+    f.Th[:] = cpu(batch["Th"]).flatten().tolist()
+    f.bounds_min[:] = cpu(batch["bounds"])[0, 0].tolist()
+    f.voxel_size[:] = [float(v) for v in voxel_size]
+    f.out_sh[:] = [int(v) for v in batch["out_sh"].reshape(-1, 3).max(0)[0].tolist()]
+    for k in range(4):
+        f.level_dims[k][:] = [int(v) for v in level_dims[k]]
+    f.target_pose[:] = cpu(batch["target_pose"]).reshape(12).tolist()
+    f.target_K[:] = cpu(batch["target_K"]).reshape(9).tolist()
+    f.target_K_inv[:] = cpu(batch["target_K_inv"]).reshape(9).tolist()
+    f.H, f.W = int(H), int(W)
+    V = int(n_views)
+    if not 1 <= V <= _lib.MAX_VIEWS:
+        raise _lib.GpnerfError(f"n_views must be 1..{_lib.MAX_VIEWS}")
+    f.n_views = V
+    src_poses, src_Ks = cpu(batch["src_poses"]).reshape(V, 3, 4), cpu(batch["src_Ks"]).reshape(V, 3, 3)
+    Eh = torch.eye(4).repeat(V, 1, 1)
+    Eh[:, :3, :4] = src_poses
+    Kh = torch.eye(4).repeat(V, 1, 1)
+    Kh[:, :3, :3] = src_Ks
+    KE = Kh.bmm(Eh)
+    for v in range(V):
+        f.src_KE[v][:] = KE[v].flatten().tolist()
+    f.src_h, f.src_w = int(src_hw[0]), int(src_hw[1])
+    f.feat_h, f.feat_w = int(feat_hw[0]), int(feat_hw[1])
+    f.n_samples = int(n_samples)
+    f.neg_ray = int(bool(neg_ray))
+    f.mask_threshold = float(mask_threshold)
+    f.rank, f.world, f.tile_px = int(rank), int(world), int(tile_px)
+    return f
 
 
 class Engine:
@@ -94,8 +148,29 @@ class Engine:
         self._weights = None
         self._weight_tensors = None
         self.launches = 0
+        self.timing = False          # when set, CUDA events bracket every stage (bench.py)
+        self.stage_events = {}
 
     # ------------------------------------------------------------------ utils
+    def _tic(self, name):
+        if not self.timing:
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record(torch.cuda.current_stream(self.device))
+        self.stage_events.setdefault(name, []).append(ev)
+        return ev
+
+    def _toc(self, ev):
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.device))
+
+    def stage_times_ms(self, reset=True):
+        """Mean device time per stage (call after a synchronize)."""
+        out = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.stage_events.items() if v}
+        if reset:
+            self.stage_events = {}
+        return out
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -108,17 +183,23 @@ class Engine:
             raise _lib.GpnerfError("rgb_fc.0 expects 32·n_views input features")
         self._weights, self._weight_tensors = hw, keep
 
+    def _run(self, name, fn, *args):
+        ev = self._tic(name)
+        check(fn(*args), name)
+        self._toc(ev)
+        self.launches += KERNELS_PER_CALL[name]
+
     # ------------------------------------------------------------- K0 uploads
     def upload_products(self, levels, featmaps, src_imgs):
         """levels: 4 × [1,32,D,H,W] fp32 (SparseConvTensor.dense() layout);
         featmaps [V,32,h,w]; src_imgs [1,V,3,H,W] or [V,3,H,W] in [-1,1].
         Tensors already on the device are used in place; host tensors are
         copied (non-blocking when pinned)."""
-        dev, st = self.device, self._stream()
-        lv = [t.to(dev, non_blocking=True) for t in levels]
-        fm = featmaps.to(dev, non_blocking=True)
+        dev, st, L = self.device, self._stream(), self.lib
+        lv = [t.to(dev, non_blocking=True).contiguous() for t in levels]
+        fm = featmaps.to(dev, non_blocking=True).contiguous()
         im = src_imgs.to(dev, non_blocking=True)
-        im = im[0] if im.dim() == 5 else im
+        im = (im[0] if im.dim() == 5 else im).contiguous()
         dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
         if self.level_dims != dims:
             self.level_dims = dims
@@ -127,69 +208,32 @@ class Engine:
             self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
         assert len(lv) == 4 and all(t.shape[1] == 32 and t.dtype == torch.float32 for t in lv)
         for t, (d, h, w), cl, cs in zip(lv, dims, self.levels_cl, self.chan_sums):
-            check(self.lib.gpnerf_k0_level_to_channels_last(ptr(t.contiguous()), d, h, w, ptr(cl), ptr(cs), st),
-                  "k0_level_to_channels_last")
+            self._run("k0_level_to_channels_last", L.gpnerf_k0_level_to_channels_last, ptr(t), d, h, w, ptr(cl),
+                      ptr(cs), st)
         V, Cc, fh, fw = fm.shape
         assert V == self.V and Cc == 32
         if self.featmaps_cl is None or self.featmaps_cl.numel() != fm.numel():
             self.featmaps_cl = torch.empty(fm.numel(), dtype=torch.float32, device=dev)
-        check(self.lib.gpnerf_k0_featmaps_to_channels_last(ptr(fm.contiguous()), V, fh, fw,
-                                                           ptr(self.featmaps_cl), st), "k0_featmaps")
+        self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw,
+                  ptr(self.featmaps_cl), st)
         _, _, ih, iw = im.shape
         if self.images_rgbx is None or self.images_rgbx.numel() != V * ih * iw * 4:
             self.images_rgbx = torch.empty(V * ih * iw * 4, dtype=torch.float32, device=dev)
-        check(self.lib.gpnerf_k0_images_to_rgbx(ptr(im.contiguous()), V, ih, iw, 1, ptr(self.images_rgbx), st),
-              "k0_images_to_rgbx")
+        self._run("k0_images_to_rgbx", L.gpnerf_k0_images_to_rgbx, ptr(im), V, ih, iw, 1, ptr(self.images_rgbx), st)
         self.src_hw, self.feat_hw = (ih, iw), (fh, fw)
-        self.launches += 6
         self._keep_inputs = (lv, fm, im)     # keep alive until the stream drains
 
     # ------------------------------------------------------------ frame setup
     def make_frame(self, batch, neg_ray=False):
-        """Pack gpnerf_frame_t from the reference's batch dict (host-side
-        scalars; ZjumocapDataset.py:464-517).  K·E is formed with torch's bmm
-        exactly as Projector.compute_projections does (BaseRender.py:311-314)."""
-        f = Frame()
-
-        def cpu(x):
-            return x.detach().to("cpu", torch.float32)
-        Rm = cpu(batch["Rh"] if "Rh" in batch else batch["R"]).reshape(3, 3)
-        f.R[:] = Rm.flatten().tolist()
-        f.Th[:] = cpu(batch["Th"]).flatten().tolist()
-        f.bounds_min[:] = cpu(batch["bounds"])[0, 0].tolist()
-        f.voxel_size[:] = list(self.voxel_size)
-        osh = [int(v) for v in batch["out_sh"].reshape(-1, 3).max(0)[0].tolist()]
-        f.out_sh[:] = osh
-        for k in range(4):
-            f.level_dims[k][:] = list(self.level_dims[k])
-        f.target_pose[:] = cpu(batch["target_pose"]).reshape(12).tolist()
-        f.target_K[:] = cpu(batch["target_K"]).reshape(9).tolist()
-        f.target_K_inv[:] = cpu(batch["target_K_inv"]).reshape(9).tolist()
-        f.H, f.W = self.H, self.W
-        V = self.V
-        f.n_views = V
-        src_poses, src_Ks = cpu(batch["src_poses"]).reshape(V, 3, 4), cpu(batch["src_Ks"]).reshape(V, 3, 3)
-        Eh = torch.eye(4).repeat(V, 1, 1)
-        Eh[:, :3, :4] = src_poses
-        Kh = torch.eye(4).repeat(V, 1, 1)
-        Kh[:, :3, :3] = src_Ks
-        KE = Kh.bmm(Eh)
-        for v in range(V):
-            f.src_KE[v][:] = KE[v].flatten().tolist()
-        f.src_h, f.src_w = self.src_hw
-        f.feat_h, f.feat_w = self.feat_hw
-        f.n_samples = self.S
-        f.neg_ray = int(bool(neg_ray))
-        f.mask_threshold = self.mask_threshold
-        f.rank, f.world, f.tile_px = self.rank, self.world, self.tile_px
-        return f
+        return frame_from_batch(batch, H=self.H, W=self.W, n_views=self.V, n_samples=self.S,
+                                level_dims=self.level_dims, src_hw=self.src_hw, feat_hw=self.feat_hw,
+                                voxel_size=self.voxel_size, mask_threshold=self.mask_threshold,
+                                neg_ray=neg_ray, rank=self.rank, world=self.world, tile_px=self.tile_px)
 
     # --------------------------------------------------------------- launches
     def build_occupancy(self, frame):
-        st = self._stream()
-        cs = ptr_array(self.chan_sums)
-        check(self.lib.gpnerf_k0_build_masks3d(cs, C.byref(frame), ptr(self.masks3d), st), "k0_build_masks3d")
-        self.launches += 1
+        self._run("k0_build_masks3d", self.lib.gpnerf_k0_build_masks3d, ptr_array(self.chan_sums),
+                  C.byref(frame), ptr(self.masks3d), self._stream())
 
     def render_progressive(self, frame, t_rand=None):
         """demo_render.Renderer.render_rays downstream of the producers.
@@ -198,51 +242,43 @@ class Engine:
             raise _lib.GpnerfError("set_weights() has not been called")
         L, st, fr = self.lib, self._stream(), C.byref(frame)
         self.build_occupancy(frame)
-        check(L.gpnerf_k1_voxel_pixel_mask(ptr(self.masks3d), fr, ptr(self.can_bounds), ptr(self.pix_mask), st),
-              "k1_voxel_pixel_mask")
-        check(L.gpnerf_k1_rays_bbox(ptr(self.pix_mask), ptr(self.can_bounds), fr, ptr(self.ray_pix),
-                                    ptr(self.rays_o), ptr(self.rays_d), ptr(self.near), ptr(self.far),
-                                    ptr(self.counters), ptr(self.workspace), st), "k1_rays_bbox")
-        self.launches += 4 + 5
+        self._run("k1_voxel_pixel_mask", L.gpnerf_k1_voxel_pixel_mask, ptr(self.masks3d), fr,
+                  ptr(self.can_bounds), ptr(self.pix_mask), st)
+        self._run("k1_rays_bbox", L.gpnerf_k1_rays_bbox, ptr(self.pix_mask), ptr(self.can_bounds), fr,
+                  ptr(self.ray_pix), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near), ptr(self.far),
+                  ptr(self.counters), ptr(self.workspace), st)
         self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays)
-        check(L.gpnerf_k4_compact_alpha(ptr(self.sigma), self.max_pts, ptr(self.counters), ptr(self.alpha),
-                                        ptr(self.valid1), ptr(self.workspace), st), "k4_compact_alpha")
-        check(L.gpnerf_k3_color_mlp(ptr(self.rgb_feat), ptr(self.meanvar), ptr(self.valid1),
-                                    C.byref(self._weights), self.V, self.max_pts, ptr(self.counters), CNT_P2,
-                                    ptr(self.rgb), self.precision, st), "k3_color_mlp")
-        check(L.gpnerf_k5_composite(ptr(self.valid), ptr(self.alpha), ptr(self.rgb), ptr(self.ray_pix), fr,
-                                    self.max_rays, ptr(self.counters), C.c_float(self.t_min), ptr(self.rgb_map),
-                                    ptr(self.pred_img), ptr(self.hit_mask), st), "k5_composite")
-        self.launches += 4 + 1 + 3
+        self._run("k4_compact_alpha", L.gpnerf_k4_compact_alpha, ptr(self.sigma), self.max_pts,
+                  ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
+        self._run("k3_color_mlp", L.gpnerf_k3_color_mlp, ptr(self.rgb_feat), ptr(self.meanvar), ptr(self.valid1),
+                  C.byref(self._weights), self.V, self.max_pts, ptr(self.counters), CNT_P2, ptr(self.rgb),
+                  self.precision, st)
+        self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.valid), ptr(self.alpha), ptr(self.rgb),
+                  ptr(self.ray_pix), fr, self.max_rays, ptr(self.counters), C.c_float(self.t_min),
+                  ptr(self.rgb_map), ptr(self.pred_img), ptr(self.hit_mask), st)
 
     def _heads(self, frame, masks3d, t_rand, n_rays_max):
         """occupancy (or identity) compaction → gathers → density head."""
         L, st, fr = self.lib, self._stream(), C.byref(frame)
         n_pts_max = n_rays_max * self.S
-        check(L.gpnerf_k2_occupancy_compact(ptr(masks3d), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near),
-                                            ptr(self.far), ptr(self.t_vals), ptr(t_rand), fr, n_rays_max,
-                                            ptr(self.valid), ptr(self.z_vals), ptr(self.counters),
-                                            ptr(self.workspace), st), "k2_occupancy_compact")
-        lv = ptr_array(self.levels_cl)
-        check(L.gpnerf_k2_gather_volume(lv, 0, ptr(self.valid), ptr(self.rays_o), ptr(self.rays_d),
-                                        ptr(self.z_vals), None, fr, n_pts_max, ptr(self.counters),
-                                        ptr(self.vol_feat), st), "k2_gather_volume")
-        check(L.gpnerf_k2_project_gather_meanvar(ptr(self.images_rgbx), ptr(self.featmaps_cl), 0, ptr(self.valid),
-                                                 ptr(self.rays_o), ptr(self.rays_d), ptr(self.z_vals), None, fr,
-                                                 n_pts_max, ptr(self.counters), ptr(self.rgb_feat),
-                                                 ptr(self.mask), ptr(self.meanvar), st),
-              "k2_project_gather_meanvar")
-        check(L.gpnerf_k3_density_mlp(ptr(self.vol_feat), 0, ptr(self.meanvar), ptr(self.mask),
-                                      C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), CNT_P1,
-                                      ptr(self.sigma), None, self.precision, st), "k3_density_mlp")
-        self.launches += 4 + 1 + 1 + 1
+        self._run("k2_occupancy_compact", L.gpnerf_k2_occupancy_compact, ptr(masks3d), ptr(self.rays_o),
+                  ptr(self.rays_d), ptr(self.near), ptr(self.far), ptr(self.t_vals), ptr(t_rand), fr, n_rays_max,
+                  ptr(self.valid), ptr(self.z_vals), ptr(self.counters), ptr(self.workspace), st)
+        self._run("k2_gather_volume", L.gpnerf_k2_gather_volume, ptr_array(self.levels_cl), 0, ptr(self.valid),
+                  ptr(self.rays_o), ptr(self.rays_d), ptr(self.z_vals), None, fr, n_pts_max, ptr(self.counters),
+                  ptr(self.vol_feat), st)
+        self._run("k2_project_gather_meanvar", L.gpnerf_k2_project_gather_meanvar, ptr(self.images_rgbx),
+                  ptr(self.featmaps_cl), 0, ptr(self.valid), ptr(self.rays_o), ptr(self.rays_d), ptr(self.z_vals),
+                  None, fr, n_pts_max, ptr(self.counters), ptr(self.rgb_feat), ptr(self.mask), ptr(self.meanvar), st)
+        self._run("k3_density_mlp", L.gpnerf_k3_density_mlp, ptr(self.vol_feat), 0, ptr(self.meanvar),
+                  ptr(self.mask), C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), CNT_P1,
+                  ptr(self.sigma), None, self.precision, st)
 
     def render_dense(self, frame, ray_o, ray_d, near, far, t_rand=None, neg_ray=False):
         """BaseRender.Renderer.render_rays semantics: every sample of the given
         rays goes through both heads (no occupancy / density compaction).
-        ray_o/ray_d [R,3] (shared origin not required by the reference, but the
-        dataset path always has one camera per batch; row 0 is used), near/far
-        [R].  Returns a dict of device tensors."""
+        ray_o/ray_d [R,3] (one camera per batch as in the dataset path: row 0 of
+        ray_o is the shared origin), near/far [R].  Returns device tensors."""
         if self._weights is None:
             raise _lib.GpnerfError("set_weights() has not been called")
         L, st = self.lib, self._stream()
@@ -258,22 +294,19 @@ class Engine:
         tr = None if t_rand is None else _f32(t_rand, dev).reshape(-1)
         self._heads(frame, masks3d=None, t_rand=tr, n_rays_max=R)
         n = R * self.S
-        # colour head on every point: valid (identity after the NULL-mask pass) indexes the P1 rows
-        check(L.gpnerf_k3_color_mlp(ptr(self.rgb_feat), ptr(self.meanvar), ptr(self.valid),
-                                    C.byref(self._weights), self.V, n, ptr(self.counters), CNT_P1, ptr(self.rgb),
-                                    self.precision, st), "k3_color_mlp")
+        # colour head on every point (valid1 = NULL → all rows in order)
+        self._run("k3_color_mlp", L.gpnerf_k3_color_mlp, ptr(self.rgb_feat), ptr(self.meanvar), None,
+                  C.byref(self._weights), self.V, n, ptr(self.counters), CNT_P1, ptr(self.rgb), self.precision, st)
         raw = torch.cat([self.rgb[: n * 3].view(n, 3), self.sigma[:n].view(n, 1)], 1).contiguous()
         rgb_in = self.rgb_feat[: n * self.V * 35].view(n, self.V, 35)[..., :3].contiguous()
         out = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in
                (("rgb_map", (R, 3)), ("disp_map", (R, 1)), ("acc_map", (R, 1)), ("depth_map", (R, 1)),
                 ("alpha", (R, self.S)), ("rgb_in_map", (R, self.V * 3)))}
-        check(L.gpnerf_k5_raw2outputs(ptr(raw), ptr(self.z_vals), ptr(rgb_in), R, self.S, self.V, int(neg_ray),
-                                      ptr(out["rgb_map"]), ptr(out["disp_map"]), ptr(out["acc_map"]),
-                                      ptr(out["depth_map"]), ptr(out["alpha"]), ptr(out["rgb_in_map"]), st),
-              "k5_raw2outputs")
+        self._run("k5_raw2outputs", L.gpnerf_k5_raw2outputs, ptr(raw), ptr(self.z_vals), ptr(rgb_in), R, self.S,
+                  self.V, int(neg_ray), ptr(out["rgb_map"]), ptr(out["disp_map"]), ptr(out["acc_map"]),
+                  ptr(out["depth_map"]), ptr(out["alpha"]), ptr(out["rgb_in_map"]), st)
         out["z_vals"] = self.z_vals[:n].view(R, self.S).clone()
         out["raw"] = raw.view(R, self.S, 4)
-        self.launches += 2
         return out
 
     def read_counters(self):

@@ -95,8 +95,10 @@ class NeRFRGBHead(nn.Module):
     def _weights(self, device, n_views):
         sd = {"rgbhead." + k: v for k, v in self.state_dict().items()}
         dummy = torch.zeros(1, device=device)
-        sd["sigmahead.out_geometry_fc.0.weight"] = dummy      # not read when the input is sigma_feat
-        sd["sigmahead.out_geometry_fc.0.bias"] = dummy
+        if self.precision != PREC_FP32:
+            dummy = torch.zeros(64 * 128, device=device)      # the bf16 image packs it; never used here
+        sd["sigmahead.out_geometry_fc.0.weight"] = dummy.view(64, -1) if dummy.numel() > 1 else dummy
+        sd["sigmahead.out_geometry_fc.0.bias"] = dummy[:64] if dummy.numel() > 1 else dummy
         return ops.pack_head_weights(sd, device, n_views)
 
     def forward(self, rgb_feat, sigma_feat, mask):

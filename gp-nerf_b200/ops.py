@@ -110,9 +110,10 @@ def mean_variance(rgb_feat):
     return out
 
 
-def pack_head_weights(state_dict, device, n_views=3):
+def pack_head_weights(state_dict, device, n_views=3, tensor_core_image=True):
     """HeadWeights struct (+ the tensors it points into) from reference-keyed
-    parameters."""
+    parameters.  With `tensor_core_image` the bf16 UMMA operand image for the
+    tcgen05 path is packed on the device as well."""
     from .engine import HEAD_KEYS
 
     def get(name):
@@ -132,6 +133,13 @@ def pack_head_weights(state_dict, device, n_views=3):
             wp, bp = pair(nme)
             getattr(hw, field + "_w")[i] = wp
             getattr(hw, field + "_b")[i] = bp
+    dev = torch.device(device)
+    if tensor_core_image and dev.type == "cuda" and 1 <= n_views <= 4 and keep[0].numel() == 64 * 128:
+        lib = _lib.load()
+        image = torch.empty(lib.gpnerf_k3_packed_weight_bytes(), dtype=torch.uint8, device=dev)
+        check(lib.gpnerf_k3_pack_weights(C.byref(hw), n_views, ptr(image), _stream(dev)), "k3_pack_weights")
+        hw.tc_image = image.data_ptr()
+        keep.append(image)
     return hw, keep
 
 

@@ -176,11 +176,24 @@ class Renderer(nn.Module):
         eng.upload_products(levels, featmaps, batch["src_imgs"])
         frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
         eng.render_progressive(frame)
+        img_d, hit_d = eng.pred_img.view(H * W, 3), eng.hit_mask
+        if self.world > 1:
+            # the frame's only collective: one all_gather of this rank's pixel tiles (RGB + hit flag)
+            import torch.distributed as dist
+            from . import shard
+            if not dist.is_initialized():
+                raise _lib.GpnerfError("world > 1 needs an initialised torch.distributed process group")
+            both = torch.cat([img_d, hit_d.view(-1, 1).float()], 1)
+            both = shard.gather_frame(both, int(H * W), self.tile_px)
+            img_d, hit_d = both[:, :3].contiguous(), both[:, 3] > 0.5
         cnt = eng.read_counters()                     # the frame's single host sync
-        n = cnt["n_rays"]
-        rgb_map = eng.rgb_map[: n * 3].view(n, 3).cpu().numpy()
-        pred_img = eng.pred_img.view(H, W, 3).cpu().numpy().astype(np.float64)
-        mask_at_box = eng.hit_mask.cpu().numpy().astype(bool)
+        pred_img = img_d.view(H, W, 3).cpu().numpy().astype(np.float64)
+        mask_at_box = hit_d.cpu().numpy().astype(bool)
+        if self.world > 1:
+            rgb_map = pred_img.reshape(-1, 3)[mask_at_box].astype(np.float32)   # ascending pixel order
+        else:
+            n = cnt["n_rays"]
+            rgb_map = eng.rgb_map[: n * 3].view(n, 3).cpu().numpy()
         rtime = time.time() - t0
         return {"rgb_map": rgb_map, "pred_img": pred_img, "mask_at_box": mask_at_box,
                 "time_slots": {"bc_render": rtime}, "etime": etime, "rtime": rtime, "counts": cnt}

@@ -89,6 +89,10 @@ typedef struct gpnerf_head_weights {
   const float *base_w[2], *base_b[2];         /* rgbhead.base_fc.{0,2}: [64,105] [32,64] */
   const float *vis_w[2], *vis_b[2];           /* rgbhead.vis_fc.{0,2}:  [32,32] [32,32]  */
   const float *rgb_w[3], *rgb_b[3];           /* rgbhead.rgb_fc.{0,2,4}: [32,32V] [16,32] [3,16] */
+  /* bf16 UMMA-operand image of all of the above, produced by gpnerf_k3_pack_weights
+   * (gpnerf_k3_packed_weight_bytes() bytes, 128-byte aligned); only read when
+   * precision = 1, may be NULL otherwise. */
+  const void *tc_image;
 } gpnerf_head_weights_t;
 
 int gpnerf_abi_version(void);
@@ -190,6 +194,12 @@ int gpnerf_k3_color_mlp(const float *rgb_feat, const float *meanvar, const int32
                         const gpnerf_head_weights_t *weights_host, int n_views, int n_points_max,
                         const int32_t *counters, int counter_slot, float *rgb, int precision,
                         void *stream);
+
+/* Pack the fp32 head weights into the bf16 K-major operand layout the tcgen05
+ * kernels consume (once per weight update). n_views in 1..4. */
+int64_t gpnerf_k3_packed_weight_bytes(void);
+int gpnerf_k3_pack_weights(const gpnerf_head_weights_t *weights_host, int n_views, void *image,
+                           void *stream);
 
 /* ---- K4: progressive step ---------------------------------------------- */
 /* demo_render.py:312-317: α = 1-exp(-σ); valid1 = ascending indices (into the

@@ -1,0 +1,132 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol the header
+declares; argument validation; host-side frame packing and ray sharding
+(including a world_size-2 gloo run).  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from gpnerf_b200 import _lib, shard, synth
+from gpnerf_b200.engine import frame_from_batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "gpnerf_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpnerf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    names = header_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib_built, n), f"{n} declared in gpnerf_abi.h but not exported"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+    assert lib_built.gpnerf_abi_version() == 1
+
+
+def test_frame_struct_matches_header_size(lib_built):
+    # 4-byte fields only: R9 Th3 bmin3 vox3 out_sh3 dims12 pose12 K9 Kinv9 H W nv KE128 4 + 2 + thr + 3
+    assert C.sizeof(_lib.Frame) == 4 * (9 + 3 + 3 + 3 + 3 + 12 + 12 + 9 + 9 + 2 + 1 + 128 + 4 + 2 + 1 + 3)
+    assert C.sizeof(_lib.HeadWeights) == 8 * (2 + 8 + 4 + 4 + 6 + 1)
+
+
+def test_argument_validation_without_gpu(lib_built):
+    L = lib_built
+    assert L.gpnerf_workspace_bytes(-1) == -1
+    assert L.gpnerf_workspace_bytes(1 << 20) > (1 << 20) // 8
+    assert L.gpnerf_k0_level_to_channels_last(None, 1, 1, 1, None, None, None) == -1
+    assert b"invalid argument" in L.gpnerf_last_error()
+    f = _lib.Frame()
+    assert L.gpnerf_k1_voxel_pixel_mask(None, C.byref(f), None, None, None) == -1
+    assert L.gpnerf_k3_color_mlp(None, None, None, None, 3, 0, None, 0, None, 0, None) == -1
+
+
+def test_product_path_has_no_cpu_fallback(lib_built):
+    from gpnerf_b200 import ops
+    with pytest.raises(_lib.GpnerfError):
+        ops.mean_variance(torch.zeros(4, 3, 35))
+    if not torch.cuda.is_available():
+        from gpnerf_b200.engine import Engine
+        with pytest.raises(Exception):
+            Engine(32, 32, 8, 3, device="cpu")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "gp-nerf_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "gpnerf_oracle" not in src and "ref_import" not in src, fn
+
+
+def test_frame_from_batch():
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=3)
+    dims = [tuple(t.shape[-3:]) for t in scene["levels"]]
+    f = frame_from_batch(scene, 64, 64, 3, 16, dims, (64, 64), (16, 16), rank=1, world=2, tile_px=32)
+    assert list(f.out_sh) == scene["out_sh"][0].tolist()
+    assert [list(d) for d in f.level_dims] == [list(d) for d in dims]
+    assert list(f.R) == scene["R"].flatten().tolist()
+    Kh = torch.eye(4); Kh[:3, :3] = scene["src_Ks"][0, 1]
+    Eh = torch.eye(4); Eh[:3, :4] = scene["src_poses"][0, 1]
+    assert list(f.src_KE[1]) == (Kh @ Eh).flatten().tolist() or \
+        torch.allclose(torch.tensor(list(f.src_KE[1])), (Kh @ Eh).flatten(), rtol=0, atol=1e-4)
+    assert (f.rank, f.world, f.tile_px, f.n_samples, f.neg_ray) == (1, 2, 32, 16, 0)
+
+
+def test_tile_ownership_partitions_the_image():
+    n_px, tile = 64 * 64 + 5, 48
+    seen = torch.zeros(n_px, dtype=torch.int32)
+    for r in range(3):
+        idx = shard.local_pixel_index(n_px, tile, r, 3)
+        idx = idx[idx >= 0]
+        assert torch.all(shard.owner_of_pixel(idx, tile, 3) == r)
+        seen[idx] += 1
+    assert torch.all(seen == 1)
+
+
+def test_pack_unpack_roundtrip():
+    n_px, tile, world = 1000, 64, 4
+    full = torch.arange(n_px * 3, dtype=torch.float32).view(n_px, 3)
+    parts = []
+    for r in range(world):
+        own = shard.owner_of_pixel(torch.arange(n_px), tile, world) == r
+        local = torch.where(own[:, None], full, torch.zeros_like(full))
+        parts.append(shard.pack_local_tiles(local, n_px, tile, r, world))
+    out = shard.unpack_gathered_tiles(torch.stack(parts), n_px, tile, world)
+    assert torch.equal(out, full)
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import gpnerf_b200
+from gpnerf_b200 import shard
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+n_px, tile = 32 * 32, 64
+full = torch.arange(n_px * 3, dtype=torch.float32).view(n_px, 3) + 1
+own = shard.owner_of_pixel(torch.arange(n_px), tile, 2) == rank
+local = torch.where(own[:, None], full, torch.zeros_like(full))     # what this rank rendered
+out = shard.gather_frame(local, n_px, tile)
+assert torch.equal(out, full), "gathered frame differs"
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_frame_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
