@@ -1,0 +1,17 @@
+"""Drop-in for libs/renders/BaseRender.py (training / validation renderer).
+Copy or symlink into <reference>/libs/renders/ and run the reference's CLI with
+`render.file B200Render` (tools/train.py:143,167 resolve it by module name)."""
+import os
+import sys
+
+_REPO = os.environ.get("GPNERF_B200_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _REPO not in sys.path:
+    sys.path.insert(0, _REPO)
+
+import gpnerf_b200  # noqa: E402,F401
+from gpnerf_b200.render import Projector, Renderer  # noqa: E402,F401
+from gpnerf_b200.render import build_render as _build  # noqa: E402
+
+
+def build_render(cfg):
+    return _build(cfg, progressive=False)
