@@ -53,9 +53,9 @@ _SIGNATURES = {
     "gpnerf_last_error": ([], C.c_char_p),
     "gpnerf_sm_count": ([], C.c_int),
     "gpnerf_workspace_bytes": ([C.c_int64], C.c_int64),
-    "gpnerf_k0_level_to_channels_last": ([_P, _I, _I, _I, _P, _P, _P], C.c_int),
+    "gpnerf_k0_level_to_channels_last": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "gpnerf_k0_build_masks3d": ([C.POINTER(_P), C.POINTER(Frame), _P, _P], C.c_int),
-    "gpnerf_k0_featmaps_to_channels_last": ([_P, _I, _I, _I, _P, _P], C.c_int),
+    "gpnerf_k0_featmaps_to_channels_last": ([_P, _I, _I, _I, _I, _P, _P], C.c_int),
     "gpnerf_k0_images_to_rgbx": ([_P, _I, _I, _I, _I, _P, _P], C.c_int),
     "gpnerf_k1_voxel_pixel_mask": ([_P, C.POINTER(Frame), _P, _P, _P], C.c_int),
     "gpnerf_k1_rays_bbox": ([_P, _P, C.POINTER(Frame), _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
@@ -67,6 +67,10 @@ _SIGNATURES = {
     "gpnerf_k3_color_mlp": ([_P, _P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _I, _P], C.c_int),
     "gpnerf_k3_packed_weight_bytes": ([], C.c_int64),
     "gpnerf_k3_pack_weights": ([C.POINTER(HeadWeights), _I, _P, _P], C.c_int),
+    "gpnerf_k23_record_bytes": ([_I], C.c_int64),
+    "gpnerf_k23_gather_density_tc": ([C.POINTER(_P), _P, _P, _P, _P, _P, _P, C.POINTER(Frame), C.POINTER(HeadWeights),
+                                      _I, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k3_color_mlp_records": ([_P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _P], C.c_int),
     "gpnerf_k4_compact_alpha": ([_P, _I, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_composite": ([_P, _P, _P, _P, C.POINTER(Frame), _I, _P, C.c_float, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_raw2outputs": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),

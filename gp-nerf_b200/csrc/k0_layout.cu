@@ -7,41 +7,86 @@
 // transaction.  The same pass produces the per-voxel channel sum that
 // SparseConvNet.encode reduces into masks3d (SparseConvNet.py:135-139).
 // Pure HBM streaming: 4 B read + 4 B written per element.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gpnerf {
 
-// in: [32][n] (channel-first), out: [n][32]; optional chan_sum[n] = Σ_c in[c][v]
-// (c ascending).  Block (32,8), tile = 32 channels × 32 positions.
-__global__ void __launch_bounds__(256) to_channels_last_32(const float* __restrict__ in,
-                                                           long long n, long long batch_stride_in,
-                                                           float* __restrict__ out,
+// in: [32][n] (channel-first) → out: [n][32] as fp32 (128-byte lines) or bf16
+// (64-byte lines); optional chan_sum[n] = Σ_c in[c][v] (c ascending, fp32).
+// CTA = 256 threads, tile = 32 channels × 128 positions: float4 loads along the
+// positions (512 B per channel row), transposed through shared memory, 32 B
+// (bf16) or 64 B (fp32) stored per thread.
+template <bool BF16>
+__global__ void __launch_bounds__(256) to_channels_last_32(const float* __restrict__ in, long long n,
+                                                           long long batch_stride_in, void* __restrict__ out_v,
                                                            float* __restrict__ chan_sum) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const long long n_tiles = (n + 31) / 32;
+  constexpr int TV = 128, LD = TV + 4;
+  __shared__ __align__(16) float tile[32 * LD];
+  const int tid = threadIdx.x;
+  const long long n_tiles = (n + TV - 1) / TV;
   const float* src = in + (long long)blockIdx.y * batch_stride_in;
-  float* dst = out + (long long)blockIdx.y * n * 32;
+  const bool vec_ok = (n % 4 == 0);
   for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const long long v0 = t * 32;
+    const long long v0 = t * TV;
+    {
+      const int q = tid & 31;            // which float4 of the 128 positions
 #pragma unroll
-    for (int c = ty; c < 32; c += 8) {
-      long long v = v0 + tx;
-      tile[c][tx] = (v < n) ? __ldg(src + (long long)c * n + v) : 0.0f;
+      for (int i = 0; i < 4; ++i) {
+        const int c = (tid >> 5) + 8 * i;
+        const long long v = v0 + 4 * q;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* p = src + (long long)c * n + v;
+        if (vec_ok && v + 3 < n) {
+          x = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (v < n) x.x = __ldg(p);
+          if (v + 1 < n) x.y = __ldg(p + 1);
+          if (v + 2 < n) x.z = __ldg(p + 2);
+          if (v + 3 < n) x.w = __ldg(p + 3);
+        }
+        *reinterpret_cast<float4*>(&tile[c * LD + 4 * q]) = x;
+      }
     }
     __syncthreads();
-#pragma unroll
-    for (int vv = ty; vv < 32; vv += 8) {
-      long long v = v0 + vv;
-      if (v < n) dst[v * 32 + tx] = tile[tx][vv];
-    }
-    if (chan_sum != nullptr && ty == 0) {
-      long long v = v0 + tx;
+    {
+      const int vv = tid & 127, h = tid >> 7;     // position, channel half
+      const long long v = v0 + vv;
       if (v < n) {
-        float s = tile[0][tx];
+        float x[16];
 #pragma unroll
-        for (int c = 1; c < 32; ++c) s = xadd(s, tile[c][tx]);
-        chan_sum[v] = s;
+        for (int k = 0; k < 16; ++k) x[k] = tile[(h * 16 + k) * LD + vv];
+        if constexpr (BF16) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_v) +
+                                                ((long long)blockIdx.y * n + v) * 32 + h * 16);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            uint4 o;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(x[k * 8 + 0], x[k * 8 + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(x[k * 8 + 2], x[k * 8 + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(x[k * 8 + 4], x[k * 8 + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(x[k * 8 + 6], x[k * 8 + 7]);
+            o.x = *reinterpret_cast<uint32_t*>(&b0);
+            o.y = *reinterpret_cast<uint32_t*>(&b1);
+            o.z = *reinterpret_cast<uint32_t*>(&b2);
+            o.w = *reinterpret_cast<uint32_t*>(&b3);
+            dst[k] = o;
+          }
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) +
+                                                  ((long long)blockIdx.y * n + v) * 32 + h * 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+        }
+        if (chan_sum != nullptr && h == 0) {
+          float s = x[0];
+#pragma unroll
+          for (int k = 1; k < 16; ++k) s = xadd(s, x[k]);
+#pragma unroll
+          for (int k = 16; k < 32; ++k) s = xadd(s, tile[k * LD + vv]);
+          chan_sum[v] = s;
+        }
       }
     }
     __syncthreads();
@@ -113,12 +158,15 @@ using namespace gpnerf;
 
 extern "C" {
 
-int gpnerf_k0_level_to_channels_last(const float* ncdhw, int D, int H, int W, float* ndhwc,
+int gpnerf_k0_level_to_channels_last(const float* ncdhw, int D, int H, int W, int out_bf16, void* ndhwc,
                                      float* chan_sum, void* stream) {
   GPNERF_REQUIRE(ncdhw && ndhwc && D > 0 && H > 0 && W > 0);
   long long n = (long long)D * H * W;
-  dim3 grid(grid_for((n + 31) / 32, 1), 1), block(32, 8);
-  to_channels_last_32<<<grid, block, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, ndhwc, chan_sum);
+  dim3 grid(grid_for((n + 127) / 128, 1), 1);
+  if (out_bf16)
+    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, ndhwc, chan_sum);
+  else
+    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, ndhwc, chan_sum);
   return check_launch("k0_level_to_channels_last");
 }
 
@@ -136,12 +184,15 @@ int gpnerf_k0_build_masks3d(const float* const chan_sum[GPNERF_N_LEVELS],
   return check_launch("k0_build_masks3d");
 }
 
-int gpnerf_k0_featmaps_to_channels_last(const float* nchw, int V, int h, int w, float* nhwc,
+int gpnerf_k0_featmaps_to_channels_last(const float* nchw, int V, int h, int w, int out_bf16, void* nhwc,
                                         void* stream) {
   GPNERF_REQUIRE(nchw && nhwc && V > 0 && V <= GPNERF_MAX_VIEWS && h > 0 && w > 0);
   long long n = (long long)h * w;
-  dim3 grid(grid_for((n + 31) / 32, 1), V), block(32, 8);
-  to_channels_last_32<<<grid, block, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, nhwc, nullptr);
+  dim3 grid(grid_for((n + 127) / 128, 1), V);
+  if (out_bf16)
+    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, nhwc, nullptr);
+  else
+    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, nhwc, nullptr);
   return check_launch("k0_featmaps_to_channels_last");
 }
 

@@ -1,0 +1,399 @@
+// K2+K3 fused (bf16 tensor-core path): for each tile of 128 surviving sample
+// points, gather the 4-level geometry volume and the V source views, aggregate
+// mean/variance, and run the density head – without the gathered features ever
+// leaving the SM.
+//
+//   gather phase  (SparseConvNet.py:111-122, BaseRender.py:283-363,
+//                  trainhead.py:20-24): 4 lanes per point, 8 bf16 channels
+//                  (one 16-byte load) per lane and corner; fp32 accumulation;
+//                  each lane's result is exactly one 16-byte chunk of a UMMA
+//                  A operand, stored straight into shared memory.
+//   density phase (trainhead.py:39-41, 102-110, 133-137): four tcgen05.mma
+//                  rounds 128→64, 144→64, 64→32, 32→16 with TMEM accumulators,
+//                  16→1 + ReLU + no-valid-view fill on CUDA cores.
+// By-product: one 16·(9+5V)-byte bf16 record per point ([mean|var] and the V
+// per-view feature rows, already in operand order) for the colour head, which
+// only the points that survive the progressive step will read back.
+//
+// Volumes / feature maps are stored channel-last in bf16 (64-byte lines).
+// Index arithmetic is one affine map per point (FMAs): unlike the fp32 path this
+// kernel does not reproduce the reference's rounding sequence – the integer
+// results (which points exist) were fixed upstream by the exact K1/K2 kernels.
+// 256 threads, 2 CTAs/SM: one CTA's gather overlaps the other's MMA/epilogue.
+#include "tc_heads.cuh"
+
+namespace gpnerf {
+
+struct FusedArgs {
+  const __nv_bfloat16* lv[GPNERF_N_LEVELS];
+  const __nv_bfloat16* feat;     // [V][fh][fw][32]
+  const float4* rgbx;            // [V][H][W] (r,g,b,·) in [0,1]
+  const int32_t* valid;
+  const float *rays_o, *rays_d, *z_vals;
+  const int32_t* counters;
+  const uint8_t* image;          // packed weights
+  float* sigma;
+  uint4* rec;
+};
+
+struct FusedSmem {
+  static constexpr uint32_t IMG = 0;
+  static constexpr uint32_t A0 = ((DenImg::BYTES + 127) / 128) * 128;   // [128 x 128]; later [128 x 64] + [128 x 32]
+  static constexpr uint32_t A1 = A0 + op_bytes(128, 128);               // [128 x 144] = sigma_feat | G
+  static constexpr uint32_t MISC = A1 + op_bytes(128, 144);             // barriers, tmem slot, flags, transform
+  static constexpr uint32_t BYTES = MISC + 512;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xffff0000u);
+  f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xffff0000u);
+  f[4] = __uint_as_float(q.z << 16); f[5] = __uint_as_float(q.z & 0xffff0000u);
+  f[6] = __uint_as_float(q.w << 16); f[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  return q;
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+template <int V>
+__global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const __grid_constant__ gpnerf_frame_t f) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* img = smem + FusedSmem::IMG;
+  uint8_t* A0 = smem + FusedSmem::A0;
+  uint8_t* A1 = smem + FusedSmem::A1;
+  uint8_t* A2 = A0 + op_bytes(128, 64);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + FusedSmem::MISC);
+  uint64_t* bar_m = bar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+  float* xf = reinterpret_cast<float*>(smem + FusedSmem::MISC + 32);      // 12 floats: u = A·p + B
+  uint8_t* nvalid = smem + FusedSmem::MISC + 128;                         // 128 flags
+  const float* fl = reinterpret_cast<const float*>(img + DenImg::F32);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(bar_w, DenImg::BYTES);
+    bulk_g2s(img, a.image, DenImg::BYTES, bar_w);
+    // normalised volume coordinate u_c = ((p − Th)·R[:,c] − bmin_c) / (voxel_c · out_sh_c), c = x,y,z
+    for (int c = 0; c < 3; ++c) {
+      const double scale = 1.0 / ((double)f.voxel_size[c] * (double)f.out_sh[2 - c]);
+      double b = -(double)f.bounds_min[c];
+      for (int k = 0; k < 3; ++k) {
+        xf[c * 4 + k] = (float)((double)f.R[k * 3 + c] * scale);
+        b -= (double)f.Th[k] * (double)f.R[k * 3 + c];
+      }
+      xf[c * 4 + 3] = (float)(b * scale);
+    }
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  // G chunk 9 (operand columns 136..143) is padding: zero once, nothing overwrites it
+  if (tid < 128) *reinterpret_cast<uint4*>(A1 + chunk_off(tid, 17, op_sbo(144))) = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  mbar_wait(bar_w, 0);
+
+  const uint32_t a0 = smem_u32(A0), a1 = smem_u32(A1), a2 = smem_u32(A2), wimg = smem_u32(img);
+  const float ox = __ldg(a.rays_o), oy = __ldg(a.rays_o + 1), oz = __ldg(a.rays_o + 2);
+  const int S = f.n_samples;
+  const float sfx = (float)(f.feat_w - 1) / (float)(f.src_w - 1), sfy = (float)(f.feat_h - 1) / (float)(f.src_h - 1);
+  const float wm1 = (float)(f.src_w - 1), hm1 = (float)(f.src_h - 1);
+  const long long img_stride = (long long)f.src_h * f.src_w;
+  const long long map_stride = (long long)f.feat_h * f.feat_w * 32;
+  constexpr int RC = rec_chunks(V);
+  const int grp = tid >> 2, sub = tid & 3;
+  const int row = tid & 127, half = tid >> 7;
+  uint32_t phase = 0;
+  const int n = __ldg(a.counters + GPNERF_CNT_P1);
+  const int n_tiles = (n + 127) / 128;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long first = (long long)tile * 128;
+    const int n_valid = min(128, n - (int)first);
+    // =================== gather phase ===================
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 64 + grp;
+      const bool ok = r < n_valid;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (ok) {
+        const int q = __ldg(a.valid + first + r);
+        const int ray = q / S;
+        const float z = __ldg(a.z_vals + q);
+        px = fmaf(__ldg(a.rays_d + ray * 3 + 0), z, ox);
+        py = fmaf(__ldg(a.rays_d + ray * 3 + 1), z, oy);
+        pz = fmaf(__ldg(a.rays_d + ray * 3 + 2), z, oz);
+      }
+      // ---- 4-level trilinear gather → A0 chunk (level*4 + sub)
+      const float ux = fmaf(xf[0], px, fmaf(xf[1], py, fmaf(xf[2], pz, xf[3])));
+      const float uy = fmaf(xf[4], px, fmaf(xf[5], py, fmaf(xf[6], pz, xf[7])));
+      const float uz = fmaf(xf[8], px, fmaf(xf[9], py, fmaf(xf[10], pz, xf[11])));
+#pragma unroll
+      for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+        const int D = f.level_dims[l][0], H = f.level_dims[l][1], W = f.level_dims[l][2];
+        const float ix = ux * (float)(W - 1), iy = uy * (float)(H - 1), iz = uz * (float)(D - 1);
+        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+        const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)W + 1.0f);
+        const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)H + 1.0f);
+        const int z0 = (int)fminf(fmaxf(fz, -2.0f), (float)D + 1.0f);
+        const float wx1 = ix - fx, wx0 = 1.0f - wx1, wy1 = iy - fy, wy0 = 1.0f - wy1, wz1 = iz - fz, wz0 = 1.0f - wz1;
+        const bool fin = ok && (ix == ix) && (iy == iy) && (iz == iz);
+        uint4 q[8];
+        float w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int x = x0 + (c & 1), y = y0 + ((c >> 1) & 1), zz = z0 + (c >> 2);
+          const bool inb = fin && x >= 0 && x < W && y >= 0 && y < H && zz >= 0 && zz < D;
+          w[c] = inb ? ((c & 1) ? wx1 : wx0) * (((c >> 1) & 1) ? wy1 : wy0) * ((c >> 2) ? wz1 : wz0) : 0.0f;
+          const long long idx = inb ? (((long long)zz * H + y) * W + x) : 0;
+          q[c] = inb ? ldg16(a.lv[l] + idx * 32 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[8];
+          unpack8(q[c], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], w[c], acc[e]);
+        }
+        st_chunk(A0, chunk_off(r, l * 4 + sub, op_sbo(128)), acc);
+      }
+      // ---- V source views: projection, bilinear taps, mean / variance
+      float fv[V][8];
+      float cv[V][3];
+      int nv = 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float* KE = f.src_KE[v];
+        const float qx = fmaf(KE[0], px, fmaf(KE[1], py, fmaf(KE[2], pz, KE[3])));
+        const float qy = fmaf(KE[4], px, fmaf(KE[5], py, fmaf(KE[6], pz, KE[7])));
+        const float qz = fmaf(KE[8], px, fmaf(KE[9], py, fmaf(KE[10], pz, KE[11])));
+        const float inv = 1.0f / qz;
+        const float ux2 = fminf(fmaxf(qx * inv, -1e6f), 1e6f), uy2 = fminf(fmaxf(qy * inv, -1e6f), 1e6f);
+        const bool front = f.neg_ray ? (qz < 0.0f) : (qz > 0.0f);
+        const bool inbv = (ux2 <= wm1) && (ux2 >= 0.0f) && (uy2 <= hm1) && (uy2 >= 0.0f);
+        nv += (front && inbv) ? 1 : 0;
+        // feature map tap (align_corners: pixel p ↦ p·(Wm−1)/(w−1))
+        {
+          const float ix = ux2 * sfx, iy = uy2 * sfy;
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)f.feat_w + 1.0f);
+          const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)f.feat_h + 1.0f);
+          const float wx = ix - fx, wy = iy - fy;
+          const bool fin = ok && (ix == ix) && (iy == iy);
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          uint4 q[4];
+          float w[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int x = x0 + (c & 1), y = y0 + (c >> 1);
+            const bool inb = fin && x >= 0 && x < f.feat_w && y >= 0 && y < f.feat_h;
+            w[c] = inb ? ((c & 1) ? wx : 1.0f - wx) * ((c >> 1) ? wy : 1.0f - wy) : 0.0f;
+            q[c] = inb ? ldg16(a.feat + v * map_stride + ((long long)y * f.feat_w + x) * 32 + sub * 8)
+                       : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float t[8];
+            unpack8(q[c], t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(t[e], w[c], acc[e]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) fv[v][e] = acc[e];
+        }
+        // RGB tap (lane 0 of the group only)
+        cv[v][0] = cv[v][1] = cv[v][2] = 0.0f;
+        if (sub == 0) {
+          const float ix = ux2, iy = uy2;   // the image is sampled at its own resolution
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)f.src_w + 1.0f);
+          const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)f.src_h + 1.0f);
+          const float wx = ix - fx, wy = iy - fy;
+          const bool fin = ok && (ix == ix) && (iy == iy);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int x = x0 + (c & 1), y = y0 + (c >> 1);
+            if (fin && x >= 0 && x < f.src_w && y >= 0 && y < f.src_h) {
+              const float wgt = ((c & 1) ? wx : 1.0f - wx) * ((c >> 1) ? wy : 1.0f - wy);
+              const float4 t = __ldg(a.rgbx + v * img_stride + (long long)y * f.src_w + x);
+              cv[v][0] = fmaf(t.x, wgt, cv[v][0]);
+              cv[v][1] = fmaf(t.y, wgt, cv[v][1]);
+              cv[v][2] = fmaf(t.z, wgt, cv[v][2]);
+            }
+          }
+        }
+        if (ok) {
+          uint4* rp = a.rec + (first + r) * RC + 9 + v * 5;
+          rp[sub] = pack8(fv[v]);
+          if (sub == 0) {
+            const float t[8] = {cv[v][0], cv[v][1], cv[v][2], 0.f, 0.f, 0.f, 0.f, 0.f};
+            rp[4] = pack8(t);
+          }
+        }
+      }
+      {
+        const float inv_v = 1.0f / (float)V;
+        float mean[8], var[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float m = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) m += fv[v][e];
+          m *= inv_v;
+          float s = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) s = fmaf(fv[v][e] - m, fv[v][e] - m, s);
+          mean[e] = m;
+          var[e] = s * inv_v;
+        }
+        const uint4 qm = pack8(mean), qv = pack8(var);
+        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 8 + sub, op_sbo(144))) = qm;
+        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 12 + sub, op_sbo(144))) = qv;
+        if (ok) {
+          uint4* rp = a.rec + (first + r) * RC;
+          rp[sub] = qm;
+          rp[4 + sub] = qv;
+        }
+        if (sub == 0) {
+          float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float m = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) m += cv[v][c];
+            m *= inv_v;
+            float s = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) s = fmaf(cv[v][c] - m, cv[v][c] - m, s);
+            t[c] = m;
+            t[3 + c] = s * inv_v;
+          }
+          const uint4 qc = pack8(t);
+          *reinterpret_cast<uint4*>(A1 + chunk_off(r, 16, op_sbo(144))) = qc;
+          if (ok) a.rec[(first + r) * RC + 8] = qc;
+          nvalid[r] = (uint8_t)nv;
+        }
+      }
+    }
+    // =================== density phase ===================
+    // sigmahead.out_geometry_fc: [128 x 128] · Wgᵀ → 64, ELU → columns 0..63 of A1
+    round_sync();
+    if (tid == 0) issue_gemm(a0, op_sbo(128), wimg + DenImg::Wg, op_sbo(128), 128, 64, tmem, bar_m);
+    wait_round(bar_m, phase);
+    epi32_to_tile(t_row, half * 32, fl + DenImg::bg, A1, op_sbo(144), row, 0);
+    // out_geometry_fc.0: [128 x 144] → 64, ELU → A0 as [128 x 64]
+    round_sync();
+    if (tid == 0) issue_gemm(a1, op_sbo(144), wimg + DenImg::W0, op_sbo(144), 144, 64, tmem, bar_m);
+    wait_round(bar_m, phase);
+    epi32_to_tile(t_row, half * 32, fl + DenImg::b0, A0, op_sbo(64), row, 0);
+    // .2: [128 x 64] → 32, ELU → A2
+    round_sync();
+    if (tid == 0) issue_gemm(a0, op_sbo(64), wimg + DenImg::W1, op_sbo(64), 64, 32, tmem, bar_m);
+    wait_round(bar_m, phase);
+    epi16_to_tile(t_row, half * 16, fl + DenImg::b1, A2, op_sbo(32), row, 0);
+    // .4: [128 x 32] → 16, ELU ; .6 + ReLU + fill on CUDA cores
+    round_sync();
+    if (tid == 0) issue_gemm(a2, op_sbo(32), wimg + DenImg::W2, op_sbo(32), 32, 16, tmem, bar_m);
+    wait_round(bar_m, phase);
+    if (half == 0) {
+      uint32_t r16[16];
+      tmem_ld16(t_row, r16);
+      tmem_wait_ld();
+      float s = fl[DenImg::b3];
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        s = fmaf(elu_fast(__uint_as_float(r16[k]) + fl[DenImg::b2 + k]), fl[DenImg::w3 + k], s);
+      s = fmaxf(s, 0.0f);
+      if (row < n_valid) a.sigma[first + row] = (nvalid[row] < 1) ? 0.0f : s;
+    }
+    // the next gather phase rewrites A0/A1/nvalid: order it after every thread's
+    // reads of this tile (TMEM reads are fenced by the next round_sync)
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+}  // namespace gpnerf
+
+using namespace gpnerf;
+
+int gpnerf_color_mlp_tc_any(const float* rgb_feat, const float* meanvar, const void* rec, const int32_t* valid1,
+                            const gpnerf_head_weights_t* w, int n_views, int n_points_max,
+                            const int32_t* count_ptr, float* rgb, cudaStream_t st);
+
+template <int V>
+static int launch_fused(const FusedArgs& a, const gpnerf_frame_t* f, int n_points_max, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gather_density_tc<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FusedSmem::BYTES);
+    if (e != cudaSuccess) {
+      set_error("gather_density_tc smem attribute", e);
+      return GPNERF_E_CUDA;
+    }
+    attr_set = true;
+  }
+  int tiles = (n_points_max + 127) / 128;
+  int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+  gather_density_tc<V><<<grid, 256, FusedSmem::BYTES, st>>>(a, *f);
+  return check_launch("k23_gather_density_tc");
+}
+
+extern "C" {
+
+int64_t gpnerf_k23_record_bytes(int n_views) { return 16ll * rec_chunks(n_views); }
+
+int gpnerf_k23_gather_density_tc(const void* const levels_bf16[GPNERF_N_LEVELS], const void* featmaps_bf16,
+                                 const float* images_rgbx, const int32_t* valid, const float* rays_o,
+                                 const float* rays_d, const float* z_vals, const gpnerf_frame_t* f,
+                                 const gpnerf_head_weights_t* w, int n_points_max, const int32_t* counters,
+                                 float* sigma, void* records, void* stream) {
+  GPNERF_REQUIRE(levels_bf16 && featmaps_bf16 && images_rgbx && valid && rays_o && rays_d && z_vals && f && w &&
+                 counters && sigma && records && n_points_max > 0);
+  GPNERF_REQUIRE(w->tc_image != nullptr && f->n_samples > 0 && f->src_w > 1 && f->src_h > 1);
+  FusedArgs a;
+  for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+    GPNERF_REQUIRE(levels_bf16[l] != nullptr);
+    a.lv[l] = reinterpret_cast<const __nv_bfloat16*>(levels_bf16[l]);
+  }
+  a.feat = reinterpret_cast<const __nv_bfloat16*>(featmaps_bf16);
+  a.rgbx = reinterpret_cast<const float4*>(images_rgbx);
+  a.valid = valid; a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals;
+  a.counters = counters;
+  a.image = reinterpret_cast<const uint8_t*>(w->tc_image);
+  a.sigma = sigma;
+  a.rec = reinterpret_cast<uint4*>(records);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (f->n_views) {
+    case 1: return launch_fused<1>(a, f, n_points_max, st);
+    case 2: return launch_fused<2>(a, f, n_points_max, st);
+    case 3: return launch_fused<3>(a, f, n_points_max, st);
+    case 4: return launch_fused<4>(a, f, n_points_max, st);
+    default:
+      set_error("fused tcgen05 path supports 1..4 source views", cudaSuccess);
+      return GPNERF_E_UNSUPPORTED;
+  }
+}
+
+int gpnerf_k3_color_mlp_records(const void* records, const int32_t* valid1, const gpnerf_head_weights_t* w,
+                                int n_views, int n_points_max, const int32_t* counters, int counter_slot,
+                                float* rgb, void* stream) {
+  GPNERF_REQUIRE(records && w && rgb && n_points_max > 0 && counter_slot >= 0 && counter_slot < GPNERF_N_COUNTERS);
+  return gpnerf_color_mlp_tc_any(nullptr, nullptr, records, valid1, w, n_views, n_points_max,
+                                 counters ? counters + counter_slot : nullptr, rgb, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// Shared definitions of the tcgen05 head kernels: packed-weight image layout,
+// operand column orders, epilogue helpers.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gpnerf {
+using namespace tc;
+
+__host__ __device__ constexpr uint32_t op_sbo(int Kp) { return (uint32_t)(Kp / 8) * kLBO; }
+__host__ __device__ constexpr uint32_t op_bytes(int rows, int Kp) { return (uint32_t)(rows / 8) * op_sbo(Kp); }
+
+// ---------------------------------------------------------------------------
+// Operand column orders.  The gather kernels own 8 consecutive feature channels
+// per lane, i.e. exactly one 16-byte bf16 chunk; so the 32 feature channels
+// come first and the 3 RGB channels after them (the reference order is RGB
+// first, BaseRender.py:358).  Weights are packed with the same permutation, so
+// the products are unchanged.
+//   G tile (80 cols): mean_feat 32 | var_feat 32 | mean_rgb 3, var_rgb 3, 0, 0 | 0×8
+//   F tile (48 cols): feat 32 | rgb 3, 0×5 | 0×8
+// ---------------------------------------------------------------------------
+// column j of the G tile → index into the reference's [mean 35 | var 35] row (or -1)
+__host__ __device__ inline int gmap(int j) {
+  if (j < 32) return 3 + j;
+  if (j < 64) return 35 + 3 + (j - 32);
+  if (j < 67) return j - 64;
+  if (j < 70) return 35 + (j - 67);
+  return -1;
+}
+// column j of an F tile → index into the reference's [rgb 3 | feat 32] row (or -1)
+__host__ __device__ inline int fmap(int j) {
+  if (j < 32) return 3 + j;
+  if (j < 35) return j - 32;
+  return -1;
+}
+
+// ---------------------------------------------------------------------------
+// packed weight images (bf16 UMMA operands + fp32 biases / last layers)
+// ---------------------------------------------------------------------------
+struct DenImg {   // density head
+  static constexpr uint32_t Wg = 0;                                 // [64 x 128]
+  static constexpr uint32_t W0 = Wg + op_bytes(64, 128);            // [64 x 144] = sigma_feat 64 | G order 80
+  static constexpr uint32_t W1 = W0 + op_bytes(64, 144);            // [32 x 64]
+  static constexpr uint32_t W2 = W1 + op_bytes(32, 64);             // [16 x 32]
+  static constexpr uint32_t F32 = W2 + op_bytes(16, 32);            // floats below
+  static constexpr int bg = 0, b0 = 64, b1 = 128, b2 = 160, w3 = 176, b3 = 192, NF = 196;
+  static constexpr uint32_t BYTES = F32 + NF * 4;
+};
+static_assert(DenImg::BYTES % 16 == 0, "bulk copy needs 16-byte multiples");
+
+template <int V>
+struct ColImg {   // colour head; base_fc.0 split into its [mean|var] (G order) and per-view (F order) blocks
+  static constexpr uint32_t Wb0a = 0;                               // [64 x 80]
+  static constexpr uint32_t Wb0b = Wb0a + op_bytes(64, 80);         // [64 x 48]
+  static constexpr uint32_t Wb1 = Wb0b + op_bytes(64, 48);          // [32 x 64]
+  static constexpr uint32_t Wv0 = Wb1 + op_bytes(32, 64);           // [32 x 32]
+  static constexpr uint32_t Wv1 = Wv0 + op_bytes(32, 32);           // [32 x 32]
+  static constexpr uint32_t Wr0 = Wv1 + op_bytes(32, 32);           // [32 x 32V]
+  static constexpr uint32_t Wr1 = Wr0 + op_bytes(32, 32 * V);       // [16 x 32]
+  static constexpr uint32_t F32 = Wr1 + op_bytes(16, 32);
+  static constexpr int bb0 = 0, bb1 = 64, vb0 = 96, vb1 = 128, rb0 = 160, rb1 = 192, rw2 = 208, rb2 = 256, NF = 260;
+  static constexpr uint32_t BYTES = F32 + NF * 4;
+};
+
+constexpr uint32_t kColImgOffset = ((DenImg::BYTES + 127) / 128) * 128;
+constexpr uint32_t kImageBytes = kColImgOffset + ((ColImg<4>::BYTES + 127) / 128) * 128;
+
+// Colour-stage record written by the fused gather+density kernel, one per P1
+// point: the G tile's 9 non-zero chunks followed by 5 non-zero chunks per view.
+__host__ __device__ constexpr int rec_chunks(int V) { return 9 + 5 * V; }
+
+// ---------------------------------------------------------------------------
+// epilogue helpers
+// ---------------------------------------------------------------------------
+// accumulator columns [c0, c0+32) of this thread's row → bias + ELU → 4 bf16 chunks
+__device__ __forceinline__ void epi32_to_tile(uint32_t taddr, int c0, const float* __restrict__ bias, uint8_t* tile,
+                                              uint32_t sbo, int row, int kc0) {
+  uint32_t r[32];
+  tmem_ld32(taddr + c0, r);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = elu_fast(__uint_as_float(r[j * 8 + e]) + bias[c0 + j * 8 + e]);
+    st_chunk(tile, chunk_off(row, kc0 + (c0 >> 3) + j, sbo), v);
+  }
+}
+__device__ __forceinline__ void epi16_to_tile(uint32_t taddr, int c0, const float* __restrict__ bias, uint8_t* tile,
+                                              uint32_t sbo, int row, int kc0) {
+  uint32_t r[16];
+  tmem_ld16(taddr + c0, r);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = elu_fast(__uint_as_float(r[j * 8 + e]) + bias[c0 + j * 8 + e]);
+    st_chunk(tile, chunk_off(row, kc0 + (c0 >> 3) + j, sbo), v);
+  }
+}
+template <int N>
+__device__ __forceinline__ void epilogue_elu_to_tile(uint32_t taddr, const float* __restrict__ bias, uint8_t* tile,
+                                                     uint32_t sbo, int row, int kc0) {
+  static_assert(N % 32 == 0, "");
+#pragma unroll
+  for (int c = 0; c < N / 32; ++c) epi32_to_tile(taddr, c * 32, bias, tile, sbo, row, kc0);
+}
+
+// make the operand stores visible to the tensor core, order the TMEM reads
+// before the next MMAs, and meet
+__device__ __forceinline__ void round_sync() {
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+__device__ __forceinline__ void wait_round(uint64_t* bar, uint32_t& phase) {
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+  tc_fence_after();
+}
+
+// 8 fp32 of a reference-layout row picked through a column map → one chunk
+template <class Map>
+__device__ __forceinline__ void load_chunk_mapped(const float* __restrict__ row, int kc, Map map, float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int src = map(kc * 8 + j);
+    v[j] = (row != nullptr && src >= 0) ? __ldg(row + src) : 0.0f;
+  }
+}
+struct GMap {
+  __device__ __forceinline__ int operator()(int j) const { return gmap(j); }
+};
+struct FMap {
+  __device__ __forceinline__ int operator()(int j) const { return fmap(j); }
+};
+struct IdMap {
+  int kmax;
+  __device__ __forceinline__ int operator()(int j) const { return j < kmax ? j : -1; }
+};
+
+}  // namespace gpnerf

@@ -33,6 +33,7 @@ KERNELS_PER_CALL = {
     "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 5, "k2_occupancy_compact": 4,
     "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,
     "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1,
+    "k23_gather_density_tc": 1, "k3_color_mlp_records": 1,
 }
 
 
@@ -125,10 +126,20 @@ class Engine:
         self.t_vals = torch.linspace(0.0, 1.0, steps=self.S, device="cpu").to(dev)  # BaseRender.py:37
         self.valid = buf(self.max_pts, i32)
         self.z_vals = buf(self.max_pts)
-        self.vol_feat = buf(self.max_pts * 128)
-        self.rgb_feat = buf(self.max_pts * self.V * 35)
-        self.mask = buf(self.max_pts * self.V)
-        self.meanvar = buf(self.max_pts * 70)
+        self.bf16 = self.precision == PREC_BF16
+        if self.bf16:
+            # tensor-core path: gathered features stay on chip; one bf16 record per point for the colour head
+            if not 1 <= self.V <= 4:
+                raise _lib.GpnerfError("the bf16 tensor-core path supports 1..4 source views")
+            self.rec_bytes = int(self.lib.gpnerf_k23_record_bytes(self.V))
+            self.rec = torch.empty(self.max_pts * self.rec_bytes, dtype=torch.uint8, device=dev)
+            self.vol_feat = self.rgb_feat = self.mask = self.meanvar = None
+        else:
+            self.rec = None
+            self.vol_feat = buf(self.max_pts * 128)
+            self.rgb_feat = buf(self.max_pts * self.V * 35)
+            self.mask = buf(self.max_pts * self.V)
+            self.meanvar = buf(self.max_pts * 70)
         self.sigma = buf(self.max_pts)
         self.alpha = buf(self.max_pts)
         self.valid1 = buf(self.max_pts, i32)
@@ -203,18 +214,22 @@ class Engine:
         dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
         if self.level_dims != dims:
             self.level_dims = dims
-            self.levels_cl = [torch.empty(d * h * w * 32, dtype=torch.float32, device=dev) for d, h, w in dims]
+            cl_dt = torch.bfloat16 if self.bf16 else torch.float32
+            self.levels_cl = [torch.empty(d * h * w * 32, dtype=cl_dt, device=dev) for d, h, w in dims]
             self.chan_sums = [torch.empty(d * h * w, dtype=torch.float32, device=dev) for d, h, w in dims]
             self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
         assert len(lv) == 4 and all(t.shape[1] == 32 and t.dtype == torch.float32 for t in lv)
         for t, (d, h, w), cl, cs in zip(lv, dims, self.levels_cl, self.chan_sums):
-            self._run("k0_level_to_channels_last", L.gpnerf_k0_level_to_channels_last, ptr(t), d, h, w, ptr(cl),
+            self._run("k0_level_to_channels_last", L.gpnerf_k0_level_to_channels_last, ptr(t), d, h, w,
+                      int(self.bf16), ptr(cl),
                       ptr(cs), st)
         V, Cc, fh, fw = fm.shape
         assert V == self.V and Cc == 32
         if self.featmaps_cl is None or self.featmaps_cl.numel() != fm.numel():
-            self.featmaps_cl = torch.empty(fm.numel(), dtype=torch.float32, device=dev)
+            self.featmaps_cl = torch.empty(fm.numel(), dtype=torch.bfloat16 if self.bf16 else torch.float32,
+                                           device=dev)
         self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw,
+                  int(self.bf16),
                   ptr(self.featmaps_cl), st)
         _, _, ih, iw = im.shape
         if self.images_rgbx is None or self.images_rgbx.numel() != V * ih * iw * 4:
@@ -250,12 +265,20 @@ class Engine:
         self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays)
         self._run("k4_compact_alpha", L.gpnerf_k4_compact_alpha, ptr(self.sigma), self.max_pts,
                   ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
-        self._run("k3_color_mlp", L.gpnerf_k3_color_mlp, ptr(self.rgb_feat), ptr(self.meanvar), ptr(self.valid1),
-                  C.byref(self._weights), self.V, self.max_pts, ptr(self.counters), CNT_P2, ptr(self.rgb),
-                  self.precision, st)
+        self._color(ptr(self.valid1), self.max_pts, CNT_P2)
         self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.valid), ptr(self.alpha), ptr(self.rgb),
                   ptr(self.ray_pix), fr, self.max_rays, ptr(self.counters), C.c_float(self.t_min),
                   ptr(self.rgb_map), ptr(self.pred_img), ptr(self.hit_mask), st)
+
+    def _color(self, valid1_ptr, n_pts_max, slot):
+        L, st = self.lib, self._stream()
+        if self.bf16:
+            self._run("k3_color_mlp_records", L.gpnerf_k3_color_mlp_records, ptr(self.rec), valid1_ptr,
+                      C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), slot, ptr(self.rgb), st)
+        else:
+            self._run("k3_color_mlp", L.gpnerf_k3_color_mlp, ptr(self.rgb_feat), ptr(self.meanvar), valid1_ptr,
+                      C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), slot, ptr(self.rgb),
+                      self.precision, st)
 
     def _heads(self, frame, masks3d, t_rand, n_rays_max):
         """occupancy (or identity) compaction → gathers → density head."""
@@ -264,6 +287,12 @@ class Engine:
         self._run("k2_occupancy_compact", L.gpnerf_k2_occupancy_compact, ptr(masks3d), ptr(self.rays_o),
                   ptr(self.rays_d), ptr(self.near), ptr(self.far), ptr(self.t_vals), ptr(t_rand), fr, n_rays_max,
                   ptr(self.valid), ptr(self.z_vals), ptr(self.counters), ptr(self.workspace), st)
+        if self.bf16:
+            self._run("k23_gather_density_tc", L.gpnerf_k23_gather_density_tc, ptr_array(self.levels_cl),
+                      ptr(self.featmaps_cl), ptr(self.images_rgbx), ptr(self.valid), ptr(self.rays_o),
+                      ptr(self.rays_d), ptr(self.z_vals), fr, C.byref(self._weights), n_pts_max,
+                      ptr(self.counters), ptr(self.sigma), ptr(self.rec), st)
+            return
         self._run("k2_gather_volume", L.gpnerf_k2_gather_volume, ptr_array(self.levels_cl), 0, ptr(self.valid),
                   ptr(self.rays_o), ptr(self.rays_d), ptr(self.z_vals), None, fr, n_pts_max, ptr(self.counters),
                   ptr(self.vol_feat), st)
@@ -295,10 +324,15 @@ class Engine:
         self._heads(frame, masks3d=None, t_rand=tr, n_rays_max=R)
         n = R * self.S
         # colour head on every point (valid1 = NULL → all rows in order)
-        self._run("k3_color_mlp", L.gpnerf_k3_color_mlp, ptr(self.rgb_feat), ptr(self.meanvar), None,
-                  C.byref(self._weights), self.V, n, ptr(self.counters), CNT_P1, ptr(self.rgb), self.precision, st)
+        self._color(None, n, CNT_P1)
         raw = torch.cat([self.rgb[: n * 3].view(n, 3), self.sigma[:n].view(n, 1)], 1).contiguous()
-        rgb_in = self.rgb_feat[: n * self.V * 35].view(n, self.V, 35)[..., :3].contiguous()
+        if self.bf16:     # per-view RGB sits in chunk 4 of each view block of the record
+            rc = self.rec_bytes // 2
+            recs = self.rec[: n * self.rec_bytes].view(torch.bfloat16).view(n, rc)
+            cols = [(9 + 5 * v + 4) * 8 + c for v in range(self.V) for c in range(3)]
+            rgb_in = recs[:, cols].float().view(n, self.V, 3).contiguous()
+        else:
+            rgb_in = self.rgb_feat[: n * self.V * 35].view(n, self.V, 35)[..., :3].contiguous()
         out = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in
                (("rgb_map", (R, 3)), ("disp_map", (R, 1)), ("acc_map", (R, 1)), ("depth_map", (R, 1)),
                 ("alpha", (R, self.S)), ("rgb_in_map", (R, self.V * 3)))}

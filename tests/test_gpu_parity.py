@@ -285,3 +285,23 @@ def test_progressive_bf16_psnr(H, S, seed):
     assert float((img - o["pred_img"]).abs().max()) < 0.05
     assert _psnr_delta_vs_pseudo_gt(img, o["pred_img"]) < 0.05
     assert orc.psnr(img, o["pred_img"]) > 45.0
+
+
+def test_dense_render_bf16_vs_oracle():
+    from gpnerf_b200._lib import PREC_BF16
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=17, with_rays=True)
+    w = synth.make_head_weights(V=3, seed=117, random_bias=True)
+    S, R = 32, 700
+    sel = torch.arange(R) * (scene["ray_o"].shape[1] // R)
+    rays = tuple(scene[k][0][sel] for k in ("ray_o", "ray_d", "near", "far"))
+    want = orc.render_dense(scene, w, S=S, rays=rays, chunk=300, keep=True)
+    eng = Engine(64, 64, S, 3, device=DEV, max_rays=R, precision=PREC_BF16)
+    eng.set_weights(w)
+    d = stages.to_dev(scene, DEV)
+    eng.upload_products(d["levels"], d["featmaps"], d["src_imgs"])
+    got = eng.render_dense(eng.make_frame(scene), *rays)
+    torch.cuda.synchronize()
+    assert torch.equal(got["z_vals"].cpu(), want["z_vals"])
+    assert float((got["rgb_map"].cpu() - want["rgb_map"]).abs().max()) < 0.03
+    assert float((got["acc_map"].cpu() - want["acc_map"]).abs().max()) < 0.03
+    assert float((got["rgb_in_map"].cpu().view(want["rgb_in_map"].shape) - want["rgb_in_map"]).abs().max()) < 0.03
