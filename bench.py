@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="zju", choices=["zju", "dense"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--tile-px", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -117,6 +117,12 @@ def stage_work(counts, n_level_elems, V):
         "k2_project_gather_meanvar": ("hbm", V * 4 * 35 * 4.0 * P1, "V x 4 corners x 35 ch x 4 B per point"),
         "k3_density_mlp": ("tensor", 38688.0 * P1, "38,688 FLOP per point"),
         "k3_color_mlp": ("tensor", 72160.0 * P2, "72,160 FLOP per point"),
+        # bf16 path: gathers (bf16 storage: 4 levels x 8 corners x 64 B + V x 4 x (64 B + 16 B RGBx)) fused
+        # with the density head; 16*(9+5V) B record written per point
+        "k23_gather_density_tc": ("hbm", (2048.0 + V * 320.0 + 16.0 * (9 + 5 * V)) * P1,
+                                  "gather-bound fused kernel: 2,048 B volume + 320 B/view images read, "
+                                  "16(9+5V) B record written per point (bf16 storage); also 38,688 FLOP/point"),
+        "k3_color_mlp_records": ("tensor", 72160.0 * P2, "72,160 FLOP per point"),
         "k4_compact_alpha": ("hbm", 8.0 * P1, "4 B read + 4 B written per point"),
         "k5_composite": ("hbm", 16.0 * P1, "16 B per surviving sample"),
     }

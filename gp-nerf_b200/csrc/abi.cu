@@ -51,27 +51,24 @@ CompactWs carve_workspace(void* ws, int64_t n_items_max) {
   return c;
 }
 
-// --- pass B1: per-tile popcount ------------------------------------------
-__global__ void __launch_bounds__(256) compact_tile_sums(const uint32_t* __restrict__ words,
-                                                         const int32_t* n_src, int mult,
-                                                         long long n_const,
-                                                         int32_t* __restrict__ tile_sums) {
+// --- pass B1: per-tile popcount (tile = kTileWords words, one per thread) ------
+__global__ void __launch_bounds__(kTileWords) compact_tile_sums(const uint32_t* __restrict__ words,
+                                                                const int32_t* n_src, int mult,
+                                                                long long n_const,
+                                                                int32_t* __restrict__ tile_sums) {
   const long long n_items = live_count(n_src, mult, n_const);
   const long long n_words = (n_items + 31) >> 5;
   const long long n_tiles = (n_words + kTileWords - 1) / kTileWords;
-  __shared__ int warp_part[8];
+  __shared__ int warp_part[kTileWords / 32];
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    int local = 0;
-    for (int i = threadIdx.x; i < kTileWords; i += 256) {
-      long long w = tile * kTileWords + i;
-      if (w < n_words) local += __popc(__ldg(words + w));
-    }
+    const long long w = tile * kTileWords + threadIdx.x;
+    int local = (w < n_words) ? __popc(__ldg(words + w)) : 0;
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = local;
     __syncthreads();
     if (threadIdx.x == 0) {
       int s = 0;
-      for (int k = 0; k < 8; ++k) s += warp_part[k];
+      for (int k = 0; k < kTileWords / 32; ++k) s += warp_part[k];
       tile_sums[tile] = s;
     }
     __syncthreads();
@@ -123,30 +120,24 @@ __global__ void __launch_bounds__(1024) compact_scan(const int32_t* __restrict__
 }
 
 // --- pass C: expand bit words into ascending indices -----------------------
-__global__ void __launch_bounds__(256) compact_expand(const uint32_t* __restrict__ words,
-                                                      const int32_t* __restrict__ tile_offs,
-                                                      const int32_t* n_src, int mult,
-                                                      long long n_const,
-                                                      int32_t* __restrict__ out_idx) {
+__global__ void __launch_bounds__(kTileWords) compact_expand(const uint32_t* __restrict__ words,
+                                                             const int32_t* __restrict__ tile_offs,
+                                                             const int32_t* n_src, int mult,
+                                                             long long n_const,
+                                                             int32_t* __restrict__ out_idx) {
   const long long n_items = live_count(n_src, mult, n_const);
   const long long n_words = (n_items + 31) >> 5;
   const long long n_tiles = (n_words + kTileWords - 1) / kTileWords;
+  constexpr int NW = kTileWords / 32;
   __shared__ int word_off[kTileWords];
-  __shared__ int warp_tot[8];
+  __shared__ uint32_t word_bits[kTileWords];
+  __shared__ int warp_tot[NW];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // each thread owns 4 consecutive words of the tile
-    const long long w0 = tile * kTileWords + threadIdx.x * 4;
-    uint32_t wv[4];
-    int cnt[4];
-    int tsum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      wv[k] = (w0 + k < n_words) ? __ldg(words + w0 + k) : 0u;
-      cnt[k] = __popc(wv[k]);
-      tsum += cnt[k];
-    }
-    int incl = tsum;
+    const long long w = tile * kTileWords + threadIdx.x;
+    const uint32_t bits = (w < n_words) ? __ldg(words + w) : 0u;
+    const int cnt = __popc(bits);
+    int incl = cnt;
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
@@ -155,22 +146,16 @@ __global__ void __launch_bounds__(256) compact_expand(const uint32_t* __restrict
     __syncthreads();
     int wbase = 0;
     for (int k = 0; k < wid; ++k) wbase += warp_tot[k];
-    int run = tile_offs[tile] + wbase + incl - tsum;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      word_off[threadIdx.x * 4 + k] = run;
-      run += cnt[k];
-    }
+    word_off[threadIdx.x] = tile_offs[tile] + wbase + incl - cnt;
+    word_bits[threadIdx.x] = bits;
     __syncthreads();
     // a warp expands one word at a time: coalesced index writes
-    for (int wl = wid; wl < kTileWords; wl += 8) {
-      long long w = tile * kTileWords + wl;
-      if (w >= n_words) break;
-      uint32_t bits = __ldg(words + w);
-      if (bits == 0u) continue;
-      if ((bits >> lane) & 1u) {
-        int rank = __popc(bits & ((1u << lane) - 1u));
-        out_idx[word_off[wl] + rank] = (int32_t)(w * 32 + lane);
+    for (int wl = wid; wl < kTileWords; wl += NW) {
+      const uint32_t b = word_bits[wl];
+      if (b == 0u) continue;
+      if ((b >> lane) & 1u) {
+        const int rank = __popc(b & ((1u << lane) - 1u));
+        out_idx[word_off[wl] + rank] = (int32_t)((tile * kTileWords + wl) * 32 + lane);
       }
     }
     __syncthreads();
@@ -182,9 +167,9 @@ int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t 
   int64_t n_words = div_up(n_items_max, 32);
   int64_t n_tiles = div_up(n_words, kTileWords);
   int grid = (int)(n_tiles < (int64_t)sm_count() * 8 ? (n_tiles > 0 ? n_tiles : 1) : sm_count() * 8);
-  compact_tile_sums<<<grid, 256, 0, st>>>(ws.words, n_src, mult, n_const, ws.tile_sums);
+  compact_tile_sums<<<grid, kTileWords, 0, st>>>(ws.words, n_src, mult, n_const, ws.tile_sums);
   compact_scan<<<1, 1024, 0, st>>>(ws.tile_sums, n_src, mult, n_const, ws.tile_offs, out_count);
-  compact_expand<<<grid, 256, 0, st>>>(ws.words, ws.tile_offs, n_src, mult, n_const, out_idx);
+  compact_expand<<<grid, kTileWords, 0, st>>>(ws.words, ws.tile_offs, n_src, mult, n_const, out_idx);
   return check_launch("compact");
 }
 

@@ -135,12 +135,12 @@ __device__ __forceinline__ Tri trilinear_setup(Vec3 g, int D, int H, int W) {
 // ---------------------------------------------------------------------------
 // Ordered stream compaction (ascending index order, deterministic):
 //   producer kernel  : one ballot word per 32 items            → words[]
-//   compact_tile_sums: popcount per tile of 1024 words          → tile_sums[]
+//   compact_tile_sums: popcount per tile of 256 words           → tile_sums[]
 //   compact_scan     : single-CTA exclusive scan of tile sums   → tile_offs[], total
 //   compact_expand   : per tile, scan words and write indices   → out[]
 // The live item count may sit on the device (n_src[0]*mult) or be a constant.
 // ---------------------------------------------------------------------------
-constexpr int kTileWords = 1024;
+constexpr int kTileWords = 256;
 
 struct CompactWs {
   uint32_t* words;
