@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--tile-px", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -211,7 +212,7 @@ def main():
     head.load_state_dict(sd)
     head = head.to(dev)
     renderer = Renderer(None, head, is_train=False, n_samples=S_SAMPLES, progressive=True, precision=prec,
-                        rank=rank, world=world, tile_px=args.tile_px)
+                        rank=rank, world=world, tile_px=args.tile_px, use_cuda_graph=not args.no_graph)
     n_px = RES * RES
 
     # ---- device-resident inputs for `value`
@@ -222,10 +223,19 @@ def main():
     eng.set_weights(head.hot_path_state())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step_device():
+    eng.set_static_inputs(d_levels, d_feat, d_imgs)
+    eng.upload_products(d_levels, d_feat, d_imgs)
+    frame = eng.make_frame(scene)
+
+    def step_eager():
         eng.upload_products(d_levels, d_feat, d_imgs)
-        frame = eng.make_frame(scene)
         eng.render_progressive(frame)
+
+    def step_device():
+        if args.no_graph:
+            step_eager()
+        else:
+            eng.run_progressive_graphed(frame)      # K0…K5 as one CUDA-graph launch
         if world > 1:
             return shard.gather_frame(eng.pred_img.view(n_px, 3), n_px, args.tile_px)
         return eng.pred_img
@@ -245,8 +255,6 @@ def main():
     # ---- timed region: exactly K steps, device-timed, L2 flushed between steps
     sampler = ClockSampler(local_rank)
     launches0 = eng.launches
-    eng.timing = True
-    eng.stage_events = {}
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
@@ -264,10 +272,18 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
-    eng.timing = False
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    stage_ms = eng.stage_times_ms()
     launches = (eng.launches - launches0) // args.steps
+    # per-stage device times: CUDA events cannot sit inside a graph replay, so the same steps are
+    # re-issued kernel by kernel (same stream, same L2 flush) right after the timed region
+    eng.timing = True
+    eng.stage_events = {}
+    for _ in range(min(args.steps, 10)):
+        flush.zero_()
+        step_eager()
+    torch.cuda.synchronize(dev)
+    eng.timing = False
+    stage_ms = eng.stage_times_ms()
     if world > 1:
         t = torch.tensor([dev_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -368,6 +384,9 @@ def main():
                    "l2": "256 MB flush between timed steps; inputs 135 MB > 126 MB L2",
                    "sharding": f"pixel tiles of {args.tile_px}, round-robin over {world} rank(s); "
                                "one NCCL all_gather of tiles per frame" if world > 1 else "single GPU",
+                   "launch": "eager, one launch per kernel" if args.no_graph else
+                             "one CUDA-graph replay per frame (frame constants through a pinned buffer)",
+                   "stages_ms_from": "eager re-issue of the same steps with CUDA events around every stage",
                    "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         "stages_ms": stages_out, "cpu_baseline": cpu_baseline,

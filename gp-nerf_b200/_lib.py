@@ -31,6 +31,7 @@ class Frame(C.Structure):
         ("src_h", C.c_int32), ("src_w", C.c_int32), ("feat_h", C.c_int32), ("feat_w", C.c_int32),
         ("n_samples", C.c_int32), ("neg_ray", C.c_int32), ("mask_threshold", C.c_float),
         ("rank", C.c_int32), ("world", C.c_int32), ("tile_px", C.c_int32),
+        ("reserved_", C.c_int32 * 2), ("self_dev", C.c_uint64),
     ]
 
 

@@ -48,6 +48,23 @@ struct Vec3 {
   float x, y, z;
 };
 
+// Every kernel that reads per-frame constants copies gpnerf_frame_t into shared
+// memory first: from the device-resident copy when frame.self_dev is set (so a
+// captured CUDA graph sees the values of the *current* frame on replay), else
+// from its by-value kernel parameter.  Must be reached by all threads.
+__device__ __forceinline__ void load_frame(gpnerf_frame_t* dst, const gpnerf_frame_t& param) {
+  const uint32_t* src = param.self_dev ? reinterpret_cast<const uint32_t*>(param.self_dev)
+                                       : reinterpret_cast<const uint32_t*>(&param);
+  const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+  const int nth = blockDim.x * blockDim.y;
+  for (int i = tid; i < (int)(sizeof(gpnerf_frame_t) / 4); i += nth) reinterpret_cast<uint32_t*>(dst)[i] = src[i];
+  __syncthreads();
+}
+#define GPNERF_LOAD_FRAME(param)        \
+  __shared__ gpnerf_frame_t f_shared__; \
+  gpnerf::load_frame(&f_shared__, param); \
+  const gpnerf_frame_t& f = f_shared__;
+
 // Depth of sample s on a ray (BaseRender.py:37-48): z = near·(1−t) + far·t,
 // optionally jittered inside its stratum with a host-drawn t_rand.
 __device__ __forceinline__ float plain_depth(float near, float far, const float* __restrict__ t_vals, int s) {

@@ -23,9 +23,10 @@ __global__ void init_bounds(unsigned* enc) {
 
 // demo_render.py:166-200.  One thread per level-1 voxel.
 __global__ void __launch_bounds__(256) voxel_pixel_mask(const float* __restrict__ masks3d,
-                                                        const __grid_constant__ gpnerf_frame_t f,
+                                                        const __grid_constant__ gpnerf_frame_t fparam,
                                                         unsigned* __restrict__ enc_bounds,
                                                         float* __restrict__ pix_mask) {
+  GPNERF_LOAD_FRAME(fparam)
   const int D = f.level_dims[0][0], H = f.level_dims[0][1], W = f.level_dims[0][2];
   const long long n = (long long)D * H * W;
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -180,10 +181,11 @@ __device__ __forceinline__ RayBox ray_through_pixel(int p, const gpnerf_frame_t&
 // one thread per pixel: flag = in voxel mask ∧ exactly-two-hits ∧ owned tile
 __global__ void __launch_bounds__(256) ray_flags(const float* __restrict__ pix_mask,
                                                  const float* __restrict__ can_bounds,
-                                                 const __grid_constant__ gpnerf_frame_t f,
+                                                 const __grid_constant__ gpnerf_frame_t fparam,
                                                  uint32_t* __restrict__ words,
                                                  int32_t* __restrict__ counters,
                                                  float* __restrict__ rays_o) {
+  GPNERF_LOAD_FRAME(fparam)
   const int n = f.H * f.W;
   const int n_warp_items = (n + 31) & ~31;
   float o[3];
@@ -207,11 +209,12 @@ __global__ void __launch_bounds__(256) ray_flags(const float* __restrict__ pix_m
 
 __global__ void __launch_bounds__(256) ray_finalize(const int32_t* __restrict__ ray_pix,
                                                     const float* __restrict__ can_bounds,
-                                                    const __grid_constant__ gpnerf_frame_t f,
+                                                    const __grid_constant__ gpnerf_frame_t fparam,
                                                     const int32_t* __restrict__ counters,
                                                     float* __restrict__ rays_d,
                                                     float* __restrict__ near,
                                                     float* __restrict__ far) {
+  GPNERF_LOAD_FRAME(fparam)
   const int n = __ldg(counters + GPNERF_CNT_RAYS);
   float o[3];
   camera_origin(f, o);

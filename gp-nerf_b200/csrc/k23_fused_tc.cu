@@ -61,7 +61,8 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 template <int V>
-__global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const __grid_constant__ gpnerf_frame_t f) {
+__global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const __grid_constant__ gpnerf_frame_t fparam) {
+  GPNERF_LOAD_FRAME(fparam)
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* img = smem + FusedSmem::IMG;
   uint8_t* A0 = smem + FusedSmem::A0;

@@ -23,10 +23,11 @@ __global__ void __launch_bounds__(256) occupancy_flags(const float* __restrict__
                                                        const float* __restrict__ far,
                                                        const float* __restrict__ t_vals,
                                                        const float* __restrict__ t_rand,
-                                                       const __grid_constant__ gpnerf_frame_t f,
+                                                       const __grid_constant__ gpnerf_frame_t fparam,
                                                        const int32_t* __restrict__ counters,
                                                        uint32_t* __restrict__ words,
                                                        float* __restrict__ z_vals) {
+  GPNERF_LOAD_FRAME(fparam)
   const int S = f.n_samples;
   const long long n = (long long)__ldg(counters + GPNERF_CNT_RAYS) * S;
   const long long n_pad = (n + 31) & ~31ll;
@@ -91,9 +92,10 @@ __device__ __forceinline__ Vec3 fetch_world_point(const PointSrc& ps, long long 
 }
 
 __global__ void __launch_bounds__(256) gather_volume(LevelPtrs lv, PointSrc ps,
-                                                     const __grid_constant__ gpnerf_frame_t f,
+                                                     const __grid_constant__ gpnerf_frame_t fparam,
                                                      const int32_t* __restrict__ count_ptr, int n_const,
                                                      float* __restrict__ vol_feat) {
+  GPNERF_LOAD_FRAME(fparam)
   const int n = count_ptr ? __ldg(count_ptr) : n_const;
   const int sub = threadIdx.x & 7;  // which float4 of the 128-byte line
   const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -174,8 +176,9 @@ __device__ __forceinline__ float4 bil_tap(const float* __restrict__ base, int pi
 template <int V>
 __global__ void __launch_bounds__(256) project_gather_meanvar(
     const float* __restrict__ images_rgbx, const float* __restrict__ featmaps, PointSrc ps,
-    const __grid_constant__ gpnerf_frame_t f, const int32_t* __restrict__ count_ptr, int n_const,
+    const __grid_constant__ gpnerf_frame_t fparam, const int32_t* __restrict__ count_ptr, int n_const,
     float* __restrict__ rgb_feat, float* __restrict__ mask, float* __restrict__ meanvar) {
+  GPNERF_LOAD_FRAME(fparam)
   const int n = count_ptr ? __ldg(count_ptr) : n_const;
   const int sub = threadIdx.x & 7;
   const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;

@@ -71,7 +71,7 @@ class Projector:
 class Renderer(nn.Module):
     def __init__(self, encoder, nerfhead, is_train=True, neg_ray_train=False, neg_ray_val=False, n_rays=1024,
                  n_samples=64, voxel_size=(0.005, 0.005, 0.005), chunk=64, mesh_th=-1, progressive=False,
-                 precision=PREC_FP32, t_min=0.0, rank=0, world=1, tile_px=64):
+                 precision=PREC_FP32, t_min=0.0, rank=0, world=1, tile_px=64, use_cuda_graph=True):
         super().__init__()
         self.encoder = encoder
         self.nerfhead = nerfhead
@@ -87,6 +87,7 @@ class Renderer(nn.Module):
         self.precision = precision
         self.t_min = t_min
         self.rank, self.world, self.tile_px = rank, world, tile_px
+        self.use_cuda_graph = use_cuda_graph
         self._engine = None
 
     # ------------------------------------------------------------------ engine
@@ -100,6 +101,14 @@ class Renderer(nn.Module):
             e._key = key
             self._engine = e
         return e
+
+    def _sync_weights(self, eng):
+        """(Re)pack the head weights for the kernels when they changed."""
+        sd = self.nerfhead.hot_path_state()
+        ver = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        if getattr(eng, "_weights_ver", None) != ver:
+            eng.set_weights(sd)
+            eng._weights_ver = ver
 
     def _upstream(self, batch):
         """featmaps and dense levels: from the batch, or from the reference's
@@ -172,10 +181,18 @@ class Renderer(nn.Module):
         H, W = batch["src_imgs"].shape[-2:]
         V = batch["src_imgs"].shape[1]
         eng = self.engine_for(int(H), int(W), int(V), device)
-        eng.set_weights(self.nerfhead.hot_path_state())
-        eng.upload_products(levels, featmaps, batch["src_imgs"])
-        frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
-        eng.render_progressive(frame)
+        self._sync_weights(eng)
+        if self.use_cuda_graph:
+            # inputs land in static device buffers; the whole frame is one graph launch
+            eng.copy_into_static_inputs(levels, featmaps, batch["src_imgs"])
+            if eng.level_dims is None:
+                eng.upload_products(*eng._static_inputs)      # first frame: learn the shapes
+            frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
+            eng.run_progressive_graphed(frame)
+        else:
+            eng.upload_products(levels, featmaps, batch["src_imgs"])
+            frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
+            eng.render_progressive(frame)
         img_d, hit_d = eng.pred_img.view(H * W, 3), eng.hit_mask
         if self.world > 1:
             # the frame's only collective: one all_gather of this rank's pixel tiles (RGB + hit flag)
@@ -208,7 +225,7 @@ class Renderer(nn.Module):
         rays_o, rays_d = batch["ray_o"], batch["ray_d"]
         R = int(rays_o.shape[1])
         eng = self.engine_for(int(H), int(W), int(V), device, max_rays=R)
-        eng.set_weights(self.nerfhead.hot_path_state())
+        self._sync_weights(eng)
         eng.upload_products(levels, featmaps, batch["src_imgs"])
         neg = self._neg_ray(batch)
         frame = eng.make_frame(batch, neg_ray=neg)

@@ -78,6 +78,13 @@ typedef struct gpnerf_frame {
   /* ray sharding over ranks: pixel tiles of `tile_px` consecutive row-major
    * pixels are dealt round-robin; rank r keeps tiles with tile % world == r */
   int32_t rank, world, tile_px;
+  int32_t reserved_[2];
+  /* Optional DEVICE address of a copy of this very struct.  When non-zero the
+   * kernels read the per-frame values (pose, cameras, bounds …) from there
+   * instead of from their by-value launch parameter, so a CUDA graph captured
+   * once replays with the values of the current frame; shapes (H, W, dims,
+   * n_views, n_samples) must not change between capture and replay. */
+  uint64_t self_dev;
 } gpnerf_frame_t;
 
 /* Head weights, all device pointers, nn.Linear layout [out][in] row-major, as

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib_built):
 
 def test_frame_struct_matches_header_size(lib_built):
     # 4-byte fields only: R9 Th3 bmin3 vox3 out_sh3 dims12 pose12 K9 Kinv9 H W nv KE128 4 + 2 + thr + 3
-    assert C.sizeof(_lib.Frame) == 4 * (9 + 3 + 3 + 3 + 3 + 12 + 12 + 9 + 9 + 2 + 1 + 128 + 4 + 2 + 1 + 3)
+    assert C.sizeof(_lib.Frame) == 4 * (9 + 3 + 3 + 3 + 3 + 12 + 12 + 9 + 9 + 2 + 1 + 128 + 4 + 2 + 1 + 3 + 2 + 2)
     assert C.sizeof(_lib.HeadWeights) == 8 * (2 + 8 + 4 + 4 + 6 + 1)
 
 
