@@ -237,7 +237,7 @@ def main():
         else:
             eng.run_progressive_graphed(frame)      # K0…K5 as one CUDA-graph launch
         if world > 1:
-            return shard.gather_frame(eng.pred_img.view(n_px, 3), n_px, args.tile_px)
+            return shard.gather_frame(eng.pred_img.view(n_px, 3), RES, args.tile_px)
         return eng.pred_img
 
     for _ in range(max(args.warmup, 3)):

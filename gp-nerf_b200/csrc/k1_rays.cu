@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(256) ray_flags(const float* __restrict__ pix_m
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_warp_items; p += gridDim.x * blockDim.x) {
     bool masked = (p < n) && (__ldg(pix_mask + p) == 1.0f);
     bool keep = false;
-    if (masked && ((p / f.tile_px) % f.world == f.rank)) keep = ray_through_pixel(p, f, cb, o).hit;
+    // diagonal tile deal (gpnerf_b200/shard.py): owner = (tile + row of the tile's first pixel) % world
+    const int tile = p / f.tile_px;
+    if (masked && ((tile + (tile * f.tile_px) / f.W) % f.world == f.rank)) keep = ray_through_pixel(p, f, cb, o).hit;
     unsigned mb = __ballot_sync(0xffffffffu, masked);
     unsigned kb = __ballot_sync(0xffffffffu, keep);
     if ((threadIdx.x & 31) == 0) {

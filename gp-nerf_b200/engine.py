@@ -274,8 +274,11 @@ class Engine:
         self._static_inputs = (lv, fm, im)
         self._graph = None
 
-    def copy_into_static_inputs(self, levels, featmaps, src_imgs):
-        """Host (pinned) or device tensors → the static input buffers."""
+    def copy_into_static_inputs(self, levels, featmaps, src_imgs, sharded_upload=False):
+        """Host (pinned) or device tensors → the static input buffers.  With
+        `sharded_upload` (world > 1, host inputs replicated on every rank) each
+        rank uploads 1/world of every tensor and the slices are all-gathered
+        over NVLink (shard.all_gather_sharded_upload)."""
         im = src_imgs[0] if src_imgs.dim() == 5 else src_imgs
         cur = self._static_inputs
         same = (cur is not None and [tuple(t.shape) for t in cur[0]] == [tuple(t.shape) for t in levels]
@@ -284,10 +287,17 @@ class Engine:
             self.set_static_inputs(levels, featmaps, src_imgs)
             return
         lv, fm, imd = self._static_inputs
-        for d, s in zip(lv, levels):
-            d.copy_(s, non_blocking=True)
-        fm.copy_(featmaps, non_blocking=True)
-        imd.copy_(im, non_blocking=True)
+        pairs = list(zip(lv, levels)) + [(fm, featmaps), (imd, im)]
+        if sharded_upload and self.world > 1:
+            from .shard import all_gather_sharded_upload
+            for d, s in pairs:
+                if s.is_cuda:
+                    d.copy_(s, non_blocking=True)
+                else:
+                    all_gather_sharded_upload(s, d)
+        else:
+            for d, s in pairs:
+                d.copy_(s, non_blocking=True)
 
     def run_progressive_graphed(self, frame):
         """K0…K5 of one frame as ONE CUDA-graph launch.  The graph is captured

@@ -102,6 +102,11 @@ class Renderer(nn.Module):
             self._engine = e
         return e
 
+    @staticmethod
+    def _dist_ready():
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+
     def _sync_weights(self, eng):
         """(Re)pack the head weights for the kernels when they changed."""
         sd = self.nerfhead.hot_path_state()
@@ -184,7 +189,8 @@ class Renderer(nn.Module):
         self._sync_weights(eng)
         if self.use_cuda_graph:
             # inputs land in static device buffers; the whole frame is one graph launch
-            eng.copy_into_static_inputs(levels, featmaps, batch["src_imgs"])
+            eng.copy_into_static_inputs(levels, featmaps, batch["src_imgs"],
+                                        sharded_upload=self.world > 1 and self._dist_ready())
             if eng.level_dims is None:
                 eng.upload_products(*eng._static_inputs)      # first frame: learn the shapes
             frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
@@ -201,7 +207,7 @@ class Renderer(nn.Module):
             if not dist.is_initialized():
                 raise _lib.GpnerfError("world > 1 needs an initialised torch.distributed process group")
             both = torch.cat([img_d, hit_d.view(-1, 1).float()], 1)
-            both = shard.gather_frame(both, int(H * W), self.tile_px)
+            both = shard.gather_frame(both, int(W), self.tile_px)
             img_d, hit_d = both[:, :3].contiguous(), both[:, 3] > 0.5
         cnt = eng.read_counters()                     # the frame's single host sync
         pred_img = img_d.view(H, W, 3).cpu().numpy().astype(np.float64)

@@ -76,7 +76,8 @@ typedef struct gpnerf_frame {
   int32_t neg_ray;         /* THuman convention (BaseRender.py:165-168)      */
   float mask_threshold;    /* 0.1 (demo_render.py:155)                       */
   /* ray sharding over ranks: pixel tiles of `tile_px` consecutive row-major
-   * pixels are dealt round-robin; rank r keeps tiles with tile % world == r */
+   * pixels are dealt diagonally; rank r keeps the tiles t with
+   * (t + (t*tile_px)/W) % world == r */
   int32_t rank, world, tile_px;
   int32_t reserved_[2];
   /* Optional DEVICE address of a copy of this very struct.  When non-zero the

@@ -81,25 +81,37 @@ def test_frame_from_batch():
 
 
 def test_tile_ownership_partitions_the_image():
-    n_px, tile = 64 * 64 + 5, 48
-    seen = torch.zeros(n_px, dtype=torch.int32)
-    for r in range(3):
-        idx = shard.local_pixel_index(n_px, tile, r, 3)
-        idx = idx[idx >= 0]
-        assert torch.all(shard.owner_of_pixel(idx, tile, 3) == r)
-        seen[idx] += 1
-    assert torch.all(seen == 1)
+    n_px, width, tile = 64 * 64, 64, 16
+    for world in (2, 3, 4, 8):
+        plan = shard.TilePlan(n_px, width, tile, world, "cpu")
+        seen = torch.zeros(n_px, dtype=torch.int32)
+        counts = []
+        for r in range(world):
+            idx = plan.local_idx[r]
+            idx = idx[idx >= 0]
+            assert torch.all(shard.owner_of_pixel(idx, tile, width, world) == r)
+            seen[idx] += 1
+            counts.append(int(idx.numel()))
+        assert torch.all(seen == 1)
+        assert max(counts) - min(counts) <= 2 * tile
+        # a centred vertical band (the subject) is spread over every rank, not over a few strips
+        cols = torch.arange(n_px) % width
+        band = (cols >= 24) & (cols < 40)
+        per_rank = [int(((shard.owner_of_pixel(torch.arange(n_px), tile, width, world) == r) & band).sum())
+                    for r in range(world)]
+        assert min(per_rank) > 0.5 * max(per_rank)
 
 
 def test_pack_unpack_roundtrip():
-    n_px, tile, world = 1000, 64, 4
+    n_px, width, tile, world = 40 * 25, 40, 8, 4
+    plan = shard.TilePlan(n_px, width, tile, world, "cpu")
     full = torch.arange(n_px * 3, dtype=torch.float32).view(n_px, 3)
+    owner = shard.owner_of_pixel(torch.arange(n_px), tile, width, world)
     parts = []
     for r in range(world):
-        own = shard.owner_of_pixel(torch.arange(n_px), tile, world) == r
-        local = torch.where(own[:, None], full, torch.zeros_like(full))
-        parts.append(shard.pack_local_tiles(local, n_px, tile, r, world))
-    out = shard.unpack_gathered_tiles(torch.stack(parts), n_px, tile, world)
+        local = torch.where((owner == r)[:, None], full, torch.zeros_like(full))
+        parts.append(plan.pack(local, r))
+    out = plan.unpack(torch.cat(parts, 0))
     assert torch.equal(out, full)
 
 
@@ -110,11 +122,11 @@ import gpnerf_b200
 from gpnerf_b200 import shard
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank = dist.get_rank()
-n_px, tile = 32 * 32, 64
+width, n_px, tile = 32, 32 * 32, 8
 full = torch.arange(n_px * 3, dtype=torch.float32).view(n_px, 3) + 1
-own = shard.owner_of_pixel(torch.arange(n_px), tile, 2) == rank
+own = shard.owner_of_pixel(torch.arange(n_px), tile, width, 2) == rank
 local = torch.where(own[:, None], full, torch.zeros_like(full))     # what this rank rendered
-out = shard.gather_frame(local, n_px, tile)
+out = shard.gather_frame(local, width, tile)
 assert torch.equal(out, full), "gathered frame differs"
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)

@@ -97,12 +97,15 @@ def test_sharded_render_equals_single_gpu():
     ref, _ = stages.run_engine_progressive(scene, w, S)
     full = ref.pred_img.view(-1, 3).clone()
     n_px = 128 * 128
-    parts, rays = [], 0
+    plan = shard.TilePlan(n_px, 128, tile, world, DEV)
+    parts, rays, per_rank = [], 0, []
     for r in range(world):
         eng, _ = stages.run_engine_progressive(scene, w, S, rank=r, world=world, tile_px=tile)
-        rays += eng.read_counters()["n_rays"]
-        parts.append(shard.pack_local_tiles(eng.pred_img.view(-1, 3), n_px, tile, r, world))
-    out = shard.unpack_gathered_tiles(torch.stack(parts), n_px, tile, world)
+        per_rank.append(eng.read_counters()["n_rays"])
+        rays += per_rank[-1]
+        parts.append(plan.pack(eng.pred_img.view(-1, 3), r))
+    out = plan.unpack(torch.cat(parts, 0))
+    assert min(per_rank) > 0.4 * max(per_rank)        # the diagonal deal balances the subject's rays
     assert rays == ref.read_counters()["n_rays"]
     assert torch.equal(out, full)            # per-ray math does not depend on the sharding
 
