@@ -54,10 +54,10 @@ _SIGNATURES = {
     "gpnerf_last_error": ([], C.c_char_p),
     "gpnerf_sm_count": ([], C.c_int),
     "gpnerf_workspace_bytes": ([C.c_int64], C.c_int64),
-    "gpnerf_k0_level_to_channels_last": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
+    "gpnerf_k0_level_to_channels_last": ([_P, _I, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "gpnerf_k0_build_masks3d": ([C.POINTER(_P), C.POINTER(Frame), _P, _P], C.c_int),
-    "gpnerf_k0_featmaps_to_channels_last": ([_P, _I, _I, _I, _I, _P, _P], C.c_int),
-    "gpnerf_k0_images_to_rgbx": ([_P, _I, _I, _I, _I, _P, _P], C.c_int),
+    "gpnerf_k0_featmaps_to_channels_last": ([_P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
+    "gpnerf_k0_images_to_rgbx": ([_P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
     "gpnerf_k1_voxel_pixel_mask": ([_P, C.POINTER(Frame), _P, _P, _P], C.c_int),
     "gpnerf_k1_rays_bbox": ([_P, _P, C.POINTER(Frame), _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k2_occupancy_compact": ([_P, _P, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P, _P, _P], C.c_int),

@@ -18,9 +18,27 @@ namespace gpnerf {
 // CTA = 256 threads, tile = 32 channels × 128 positions: float4 loads along the
 // positions (512 B per channel row), transposed through shared memory, 32 B
 // (bf16) or 64 B (fp32) stored per thread.
+// Where position v = (z*H + y)*W + x of batch b lands in the output: dense, or
+// inside a one-element zero border (pad) so that gathers need no bounds tests.
+struct OutMap {
+  int H, W;                 // source extents of the two fastest dims
+  long long sz, sy, off;    // output strides of z and y, offset of (0,0,0)
+  long long batch;          // output positions per batch entry
+  int pad;
+  __device__ __forceinline__ long long operator()(long long b, long long v) const {
+    if (!pad) return b * batch + v;
+    const int x = (int)(v % W);
+    const long long t = v / W;
+    const int y = (int)(t % H);
+    const long long z = t / H;
+    return b * batch + z * sz + (long long)y * sy + x + off;
+  }
+};
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) to_channels_last_32(const float* __restrict__ in, long long n,
-                                                           long long batch_stride_in, void* __restrict__ out_v,
+                                                           long long batch_stride_in, OutMap om,
+                                                           void* __restrict__ out_v,
                                                            float* __restrict__ chan_sum) {
   constexpr int TV = 128, LD = TV + 4;
   __shared__ __align__(16) float tile[32 * LD];
@@ -59,7 +77,7 @@ __global__ void __launch_bounds__(256) to_channels_last_32(const float* __restri
         for (int k = 0; k < 16; ++k) x[k] = tile[(h * 16 + k) * LD + vv];
         if constexpr (BF16) {
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_v) +
-                                                ((long long)blockIdx.y * n + v) * 32 + h * 16);
+                                                om(blockIdx.y, v) * 32 + h * 16);
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             uint4 o;
@@ -75,7 +93,7 @@ __global__ void __launch_bounds__(256) to_channels_last_32(const float* __restri
           }
         } else {
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) +
-                                                  ((long long)blockIdx.y * n + v) * 32 + h * 16);
+                                                  om(blockIdx.y, v) * 32 + h * 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dst[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
         }
@@ -124,7 +142,7 @@ __global__ void __launch_bounds__(256) build_masks3d(MaskArgs a, float* __restri
 // [V][3][H][W] in [-1,1] → [V][H][W][4] = (x·0.5+0.5, 0); separate mul/add like
 // the reference's `src_imgs * 0.5 + 0.5` (BaseRender.py:231).
 __global__ void __launch_bounds__(256) images_to_rgbx(const float* __restrict__ in, int V,
-                                                      long long hw, int unnormalize,
+                                                      long long hw, int unnormalize, OutMap om,
                                                       float4* __restrict__ out) {
   const long long n = (long long)V * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -141,7 +159,7 @@ __global__ void __launch_bounds__(256) images_to_rgbx(const float* __restrict__ 
       o.z = xadd(xmul(o.z, 0.5f), 0.5f);
     }
     o.w = 0.0f;
-    out[i] = o;
+    out[om(v, p)] = o;
   }
 }
 
@@ -158,15 +176,26 @@ using namespace gpnerf;
 
 extern "C" {
 
-int gpnerf_k0_level_to_channels_last(const float* ncdhw, int D, int H, int W, int out_bf16, void* ndhwc,
-                                     float* chan_sum, void* stream) {
+static OutMap make_map(int H, int W, int pad, int pad_z, long long n) {
+  OutMap om;
+  om.H = H; om.W = W; om.pad = pad;
+  om.sy = W + 2;
+  om.sz = (long long)(H + 2) * (W + 2);
+  om.off = (pad_z ? om.sz : 0) + om.sy + 1;
+  om.batch = pad ? 0 : n;   // callers set the padded batch stride
+  return om;
+}
+
+int gpnerf_k0_level_to_channels_last(const float* ncdhw, int D, int H, int W, int out_bf16, int pad,
+                                     void* ndhwc, float* chan_sum, void* stream) {
   GPNERF_REQUIRE(ncdhw && ndhwc && D > 0 && H > 0 && W > 0);
   long long n = (long long)D * H * W;
   dim3 grid(grid_for((n + 127) / 128, 1), 1);
+  OutMap om = make_map(H, W, pad, 1, n);
   if (out_bf16)
-    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, ndhwc, chan_sum);
+    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
   else
-    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, ndhwc, chan_sum);
+    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
   return check_launch("k0_level_to_channels_last");
 }
 
@@ -184,24 +213,30 @@ int gpnerf_k0_build_masks3d(const float* const chan_sum[GPNERF_N_LEVELS],
   return check_launch("k0_build_masks3d");
 }
 
-int gpnerf_k0_featmaps_to_channels_last(const float* nchw, int V, int h, int w, int out_bf16, void* nhwc,
-                                        void* stream) {
+int gpnerf_k0_featmaps_to_channels_last(const float* nchw, int V, int h, int w, int out_bf16, int pad,
+                                        void* nhwc, void* stream) {
   GPNERF_REQUIRE(nchw && nhwc && V > 0 && V <= GPNERF_MAX_VIEWS && h > 0 && w > 0);
   long long n = (long long)h * w;
   dim3 grid(grid_for((n + 127) / 128, 1), V);
+  OutMap om = make_map(h, w, pad, 0, n);
+  if (pad) om.batch = (long long)(h + 2) * (w + 2);
   if (out_bf16)
-    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, nhwc, nullptr);
+    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, om, nhwc, nullptr);
   else
-    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, nhwc, nullptr);
+    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, om, nhwc, nullptr);
   return check_launch("k0_featmaps_to_channels_last");
 }
 
-int gpnerf_k0_images_to_rgbx(const float* nchw, int V, int H, int W, int unnormalize, float* rgbx,
-                             void* stream) {
+int gpnerf_k0_images_to_rgbx(const float* nchw, int V, int H, int W, int unnormalize, int pad,
+                             float* rgbx, void* stream) {
   GPNERF_REQUIRE(nchw && rgbx && V > 0 && V <= GPNERF_MAX_VIEWS && H > 0 && W > 0);
   long long hw = (long long)H * W;
   images_to_rgbx<<<grid_for(V * hw, 256), 256, 0, (cudaStream_t)stream>>>(
-      nchw, V, hw, unnormalize, reinterpret_cast<float4*>(rgbx));
+      nchw, V, hw, unnormalize, [&] {
+        OutMap om = make_map(H, W, pad, 0, hw);
+        if (pad) om.batch = (long long)(H + 2) * (W + 2);
+        return om;
+      }(), reinterpret_cast<float4*>(rgbx));
   return check_launch("k0_images_to_rgbx");
 }
 

@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
   const int S = f.n_samples;
   const float sfx = (float)(f.feat_w - 1) / (float)(f.src_w - 1), sfy = (float)(f.feat_h - 1) / (float)(f.src_h - 1);
   const float wm1 = (float)(f.src_w - 1), hm1 = (float)(f.src_h - 1);
-  const long long img_stride = (long long)f.src_h * f.src_w;
-  const long long map_stride = (long long)f.feat_h * f.feat_w * 32;
+  const long long img_stride_p = (long long)(f.src_h + 2) * (f.src_w + 2);          // padded image, float4 units
+  const long long map_stride_q = (long long)(f.feat_h + 2) * (f.feat_w + 2) * 4;    // padded map, uint4 units
   constexpr int RC = rec_chunks(V);
   const int grp = tid >> 2, sub = tid & 3;
   const int row = tid & 127, half = tid >> 7;
@@ -141,24 +141,28 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
       const float uz = fmaf(xf[8], px, fmaf(xf[9], py, fmaf(xf[10], pz, xf[11])));
 #pragma unroll
       for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+        // the level is stored inside a one-voxel zero border: after clamping the continuous index to
+        // [-1, size] all 8 corners are addressable and out-of-range corners read zeros (= zeros padding)
         const int D = f.level_dims[l][0], H = f.level_dims[l][1], W = f.level_dims[l][2];
-        const float ix = ux * (float)(W - 1), iy = uy * (float)(H - 1), iz = uz * (float)(D - 1);
-        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-        const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)W + 1.0f);
-        const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)H + 1.0f);
-        const int z0 = (int)fminf(fmaxf(fz, -2.0f), (float)D + 1.0f);
-        const float wx1 = ix - fx, wx0 = 1.0f - wx1, wy1 = iy - fy, wy0 = 1.0f - wy1, wz1 = iz - fz, wz0 = 1.0f - wz1;
-        const bool fin = ok && (ix == ix) && (iy == iy) && (iz == iz);
+        const float ix = fminf(fmaxf(ux * (float)(W - 1), -1.0f), (float)W);
+        const float iy = fminf(fmaxf(uy * (float)(H - 1), -1.0f), (float)H);
+        const float iz = fminf(fmaxf(uz * (float)(D - 1), -1.0f), (float)D);
+        const int x0 = min((int)floorf(ix), W - 1), y0 = min((int)floorf(iy), H - 1), z0 = min((int)floorf(iz), D - 1);
+        const float wx1 = ix - (float)x0, wx0 = 1.0f - wx1, wy1 = iy - (float)y0, wy0 = 1.0f - wy1;
+        const float wz1 = iz - (float)z0, wz0 = 1.0f - wz1;
+        const int dy = (W + 2) * 4, dz = (H + 2) * dy;               // strides in uint4 (16 B) units
+        const uint4* p0 = reinterpret_cast<const uint4*>(a.lv[l]) + ((z0 + 1) * dz + (y0 + 1) * dy + (x0 + 1) * 4 + sub);
         uint4 q[8];
-        float w[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int x = x0 + (c & 1), y = y0 + ((c >> 1) & 1), zz = z0 + (c >> 2);
-          const bool inb = fin && x >= 0 && x < W && y >= 0 && y < H && zz >= 0 && zz < D;
-          w[c] = inb ? ((c & 1) ? wx1 : wx0) * (((c >> 1) & 1) ? wy1 : wy0) * ((c >> 2) ? wz1 : wz0) : 0.0f;
-          const long long idx = inb ? (((long long)zz * H + y) * W + x) : 0;
-          q[c] = inb ? ldg16(a.lv[l] + idx * 32 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
-        }
+        q[0] = __ldg(p0);
+        q[1] = __ldg(p0 + 4);
+        q[2] = __ldg(p0 + dy);
+        q[3] = __ldg(p0 + dy + 4);
+        q[4] = __ldg(p0 + dz);
+        q[5] = __ldg(p0 + dz + 4);
+        q[6] = __ldg(p0 + dz + dy);
+        q[7] = __ldg(p0 + dz + dy + 4);
+        const float w00 = wy0 * wz0, w10 = wy1 * wz0, w01 = wy0 * wz1, w11 = wy1 * wz1;
+        const float w[8] = {wx0 * w00, wx1 * w00, wx0 * w10, wx1 * w10, wx0 * w01, wx1 * w01, wx0 * w11, wx1 * w11};
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
         }
         st_chunk(A0, chunk_off(r, l * 4 + sub, op_sbo(128)), acc);
       }
-      // ---- V source views: projection, bilinear taps, mean / variance
+      // ---- V source views: projection, bilinear taps (maps stored inside a zero border), mean / variance
       float fv[V][8];
       float cv[V][3];
       int nv = 0;
@@ -180,29 +184,25 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
         const float qy = fmaf(KE[4], px, fmaf(KE[5], py, fmaf(KE[6], pz, KE[7])));
         const float qz = fmaf(KE[8], px, fmaf(KE[9], py, fmaf(KE[10], pz, KE[11])));
         const float inv = 1.0f / qz;
-        const float ux2 = fminf(fmaxf(qx * inv, -1e6f), 1e6f), uy2 = fminf(fmaxf(qy * inv, -1e6f), 1e6f);
+        const float ux2 = qx * inv, uy2 = qy * inv;
         const bool front = f.neg_ray ? (qz < 0.0f) : (qz > 0.0f);
         const bool inbv = (ux2 <= wm1) && (ux2 >= 0.0f) && (uy2 <= hm1) && (uy2 >= 0.0f);
         nv += (front && inbv) ? 1 : 0;
-        // feature map tap (align_corners: pixel p ↦ p·(Wm−1)/(w−1))
-        {
-          const float ix = ux2 * sfx, iy = uy2 * sfy;
-          const float fx = floorf(ix), fy = floorf(iy);
-          const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)f.feat_w + 1.0f);
-          const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)f.feat_h + 1.0f);
-          const float wx = ix - fx, wy = iy - fy;
-          const bool fin = ok && (ix == ix) && (iy == iy);
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        {  // feature map tap (align_corners: pixel p ↦ p·(Wm−1)/(w−1))
+          const float ix = fminf(fmaxf(ux2 * sfx, -1.0f), (float)f.feat_w);
+          const float iy = fminf(fmaxf(uy2 * sfy, -1.0f), (float)f.feat_h);
+          const int x0 = min((int)floorf(ix), f.feat_w - 1), y0 = min((int)floorf(iy), f.feat_h - 1);
+          const float wx = ix - (float)x0, wy = iy - (float)y0;
+          const int dy = (f.feat_w + 2) * 4;
+          const uint4* p0 = reinterpret_cast<const uint4*>(a.feat) + v * map_stride_q +
+                            ((y0 + 1) * dy + (x0 + 1) * 4 + sub);
           uint4 q[4];
-          float w[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int x = x0 + (c & 1), y = y0 + (c >> 1);
-            const bool inb = fin && x >= 0 && x < f.feat_w && y >= 0 && y < f.feat_h;
-            w[c] = inb ? ((c & 1) ? wx : 1.0f - wx) * ((c >> 1) ? wy : 1.0f - wy) : 0.0f;
-            q[c] = inb ? ldg16(a.feat + v * map_stride + ((long long)y * f.feat_w + x) * 32 + sub * 8)
-                       : make_uint4(0u, 0u, 0u, 0u);
-          }
+          q[0] = __ldg(p0);
+          q[1] = __ldg(p0 + 4);
+          q[2] = __ldg(p0 + dy);
+          q[3] = __ldg(p0 + dy + 4);
+          const float w[4] = {(1.0f - wx) * (1.0f - wy), wx * (1.0f - wy), (1.0f - wx) * wy, wx * wy};
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float t[8];
@@ -213,26 +213,17 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
 #pragma unroll
           for (int e = 0; e < 8; ++e) fv[v][e] = acc[e];
         }
-        // RGB tap (lane 0 of the group only)
-        cv[v][0] = cv[v][1] = cv[v][2] = 0.0f;
-        if (sub == 0) {
-          const float ix = ux2, iy = uy2;   // the image is sampled at its own resolution
-          const float fx = floorf(ix), fy = floorf(iy);
-          const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)f.src_w + 1.0f);
-          const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)f.src_h + 1.0f);
-          const float wx = ix - fx, wy = iy - fy;
-          const bool fin = ok && (ix == ix) && (iy == iy);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int x = x0 + (c & 1), y = y0 + (c >> 1);
-            if (fin && x >= 0 && x < f.src_w && y >= 0 && y < f.src_h) {
-              const float wgt = ((c & 1) ? wx : 1.0f - wx) * ((c >> 1) ? wy : 1.0f - wy);
-              const float4 t = __ldg(a.rgbx + v * img_stride + (long long)y * f.src_w + x);
-              cv[v][0] = fmaf(t.x, wgt, cv[v][0]);
-              cv[v][1] = fmaf(t.y, wgt, cv[v][1]);
-              cv[v][2] = fmaf(t.z, wgt, cv[v][2]);
-            }
-          }
+        {  // RGB tap at the image's own resolution (same addresses in the 4 lanes: one broadcast load)
+          const float ix = fminf(fmaxf(ux2, -1.0f), (float)f.src_w), iy = fminf(fmaxf(uy2, -1.0f), (float)f.src_h);
+          const int x0 = min((int)floorf(ix), f.src_w - 1), y0 = min((int)floorf(iy), f.src_h - 1);
+          const float wx = ix - (float)x0, wy = iy - (float)y0;
+          const int dy = f.src_w + 2;
+          const float4* p0 = a.rgbx + v * img_stride_p + ((y0 + 1) * dy + (x0 + 1));
+          const float4 t0 = __ldg(p0), t1 = __ldg(p0 + 1), t2 = __ldg(p0 + dy), t3 = __ldg(p0 + dy + 1);
+          const float w0 = (1.0f - wx) * (1.0f - wy), w1 = wx * (1.0f - wy), w2 = (1.0f - wx) * wy, w3 = wx * wy;
+          cv[v][0] = fmaf(t3.x, w3, fmaf(t2.x, w2, fmaf(t1.x, w1, t0.x * w0)));
+          cv[v][1] = fmaf(t3.y, w3, fmaf(t2.y, w2, fmaf(t1.y, w1, t0.y * w0)));
+          cv[v][2] = fmaf(t3.z, w3, fmaf(t2.z, w2, fmaf(t1.z, w1, t0.z * w0)));
         }
         if (ok) {
           uint4* rp = a.rec + (first + r) * RC + 9 + v * 5;

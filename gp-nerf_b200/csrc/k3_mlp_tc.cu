@@ -299,10 +299,18 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
         long long src = -1;
         if (r < n_valid) src = valid1 ? (long long)__ldg(valid1 + first + r) : first + r;
         if constexpr (FROM_REC) {
-          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-          for (int c = csub; c < RC + 1 + V; c += 4) {
-            // c < RC: a stored chunk; the remaining 1 + V tasks zero the padding chunks
-            uint4 q = zero;
+          // RC stored chunks + (1 + V) padding chunks to zero; all loads are issued before the stores
+          constexpr int NT = (RC + 1 + V + 3) / 4;
+          uint4 q[NT];
+#pragma unroll
+          for (int it = 0; it < NT; ++it) {
+            const int c = csub + 4 * it;
+            q[it] = (c < RC && src >= 0) ? __ldg(rec + src * RC + c) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int it = 0; it < NT; ++it) {
+            const int c = csub + 4 * it;
+            if (c >= RC + 1 + V) continue;
             uint8_t* dst;
             if (c < 9) {
               dst = G + chunk_off(r, c, op_sbo(80));
@@ -314,8 +322,7 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
             } else {
               dst = F + (c - RC - 1) * F_STRIDE + chunk_off(r, 5, op_sbo(48));
             }
-            if (c < RC && src >= 0) q = __ldg(rec + src * RC + c);
-            *reinterpret_cast<uint4*>(dst) = q;
+            *reinterpret_cast<uint4*>(dst) = q[it];
           }
         } else {
           const float* mrow = src >= 0 ? meanvar + src * 70 : nullptr;

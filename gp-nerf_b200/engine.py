@@ -223,27 +223,33 @@ class Engine:
         dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
         if self.level_dims != dims:
             self.level_dims = dims
-            cl_dt = torch.bfloat16 if self.bf16 else torch.float32
-            self.levels_cl = [torch.empty(d * h * w * 32, dtype=cl_dt, device=dev) for d, h, w in dims]
+            # bf16 path: channel-last bf16 inside a zero border (allocated zeroed once; K0 only ever
+            # writes the interior), so the fused gather needs no bounds tests
+            if self.bf16:
+                self.levels_cl = [torch.zeros((d + 2) * (h + 2) * (w + 2) * 32, dtype=torch.bfloat16, device=dev)
+                                  for d, h, w in dims]
+            else:
+                self.levels_cl = [torch.empty(d * h * w * 32, dtype=torch.float32, device=dev) for d, h, w in dims]
             self.chan_sums = [torch.empty(d * h * w, dtype=torch.float32, device=dev) for d, h, w in dims]
             self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
         assert len(lv) == 4 and all(t.shape[1] == 32 and t.dtype == torch.float32 for t in lv)
+        pad = int(self.bf16)
         for t, (d, h, w), cl, cs in zip(lv, dims, self.levels_cl, self.chan_sums):
             self._run("k0_level_to_channels_last", L.gpnerf_k0_level_to_channels_last, ptr(t), d, h, w,
-                      int(self.bf16), ptr(cl),
-                      ptr(cs), st)
+                      int(self.bf16), pad, ptr(cl), ptr(cs), st)
         V, Cc, fh, fw = fm.shape
         assert V == self.V and Cc == 32
-        if self.featmaps_cl is None or self.featmaps_cl.numel() != fm.numel():
-            self.featmaps_cl = torch.empty(fm.numel(), dtype=torch.bfloat16 if self.bf16 else torch.float32,
-                                           device=dev)
+        n_fm = V * (fh + 2 * pad) * (fw + 2 * pad) * 32
+        if self.featmaps_cl is None or self.featmaps_cl.numel() != n_fm:
+            self.featmaps_cl = torch.zeros(n_fm, dtype=torch.bfloat16 if self.bf16 else torch.float32, device=dev)
         self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw,
-                  int(self.bf16),
-                  ptr(self.featmaps_cl), st)
+                  int(self.bf16), pad, ptr(self.featmaps_cl), st)
         _, _, ih, iw = im.shape
-        if self.images_rgbx is None or self.images_rgbx.numel() != V * ih * iw * 4:
-            self.images_rgbx = torch.empty(V * ih * iw * 4, dtype=torch.float32, device=dev)
-        self._run("k0_images_to_rgbx", L.gpnerf_k0_images_to_rgbx, ptr(im), V, ih, iw, 1, ptr(self.images_rgbx), st)
+        n_im = V * (ih + 2 * pad) * (iw + 2 * pad) * 4
+        if self.images_rgbx is None or self.images_rgbx.numel() != n_im:
+            self.images_rgbx = torch.zeros(n_im, dtype=torch.float32, device=dev)
+        self._run("k0_images_to_rgbx", L.gpnerf_k0_images_to_rgbx, ptr(im), V, ih, iw, 1, pad,
+                  ptr(self.images_rgbx), st)
         self.src_hw, self.feat_hw = (ih, iw), (fh, fw)
         self._keep_inputs = (lv, fm, im)     # keep alive until the stream drains
 

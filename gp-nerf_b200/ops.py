@@ -36,7 +36,7 @@ def level_to_channels_last(level):
     assert ch == 32
     out = torch.empty(D * H * W * 32, dtype=torch.float32, device=level.device)
     cs = torch.empty(D * H * W, dtype=torch.float32, device=level.device)
-    check(lib.gpnerf_k0_level_to_channels_last(ptr(_c(level)), D, H, W, 0, ptr(out), ptr(cs), _stream(level.device)),
+    check(lib.gpnerf_k0_level_to_channels_last(ptr(_c(level)), D, H, W, 0, 0, ptr(out), ptr(cs), _stream(level.device)),
           "k0_level_to_channels_last")
     return out, cs
 
@@ -47,7 +47,7 @@ def featmaps_to_channels_last(featmaps):
     V, ch, h, w = featmaps.shape
     assert ch == 32
     out = torch.empty(V * h * w * 32, dtype=torch.float32, device=featmaps.device)
-    check(lib.gpnerf_k0_featmaps_to_channels_last(ptr(_c(featmaps)), V, h, w, 0, ptr(out), _stream(featmaps.device)),
+    check(lib.gpnerf_k0_featmaps_to_channels_last(ptr(_c(featmaps)), V, h, w, 0, 0, ptr(out), _stream(featmaps.device)),
           "k0_featmaps_to_channels_last")
     return out
 
@@ -59,7 +59,7 @@ def images_to_rgbx(src_imgs, unnormalize=True):
     V, ch, H, W = src_imgs.shape
     assert ch == 3
     out = torch.empty(V * H * W * 4, dtype=torch.float32, device=src_imgs.device)
-    check(lib.gpnerf_k0_images_to_rgbx(ptr(_c(src_imgs)), V, H, W, int(bool(unnormalize)), ptr(out), _stream(src_imgs.device)),
+    check(lib.gpnerf_k0_images_to_rgbx(ptr(_c(src_imgs)), V, H, W, int(bool(unnormalize)), 0, ptr(out), _stream(src_imgs.device)),
           "k0_images_to_rgbx")
     return out
 

@@ -112,8 +112,11 @@ int gpnerf_sm_count(void);
 /* One dense level NCDHW → NDHWC (one line per voxel: 128 B fp32, or 64 B bf16
  * when out_bf16 – the storage the tensor-core path gathers from) plus the
  * fp32 per-voxel channel sum that SparseConvNet.encode reduces
- * (libs/nerfheads/networks/SparseConvNet.py:135-136). */
-int gpnerf_k0_level_to_channels_last(const float *ncdhw, int D, int H, int W, int out_bf16,
+ * (libs/nerfheads/networks/SparseConvNet.py:135-136).
+ * With `pad` the output is written inside a one-voxel border,
+ * [D+2][H+2][W+2][32], which the caller zeroes once: gathers from it need no
+ * bounds tests (the border is grid_sample's zeros padding). */
+int gpnerf_k0_level_to_channels_last(const float *ncdhw, int D, int H, int W, int out_bf16, int pad,
                                      void *ndhwc, float *chan_sum, void *stream);
 /* masks3d on the level-1 grid = Σ_levels nearest-upsampled channel sums
  * (SparseConvNet.py:137-139). */
@@ -122,10 +125,10 @@ int gpnerf_k0_build_masks3d(const float *const chan_sum[GPNERF_N_LEVELS],
 /* encoder maps [V,C=32,h,w] → [V,h,w,32]; images [V,3,H,W] → [V,H,W,4] (RGB,
  * pad); with `unnormalize` the [-1,1] inputs become x*0.5+0.5 on the way
  * (BaseRender.py:231), otherwise they are taken as already in [0,1]. */
-int gpnerf_k0_featmaps_to_channels_last(const float *nchw, int V, int h, int w, int out_bf16,
-                                        void *nhwc, void *stream);
-int gpnerf_k0_images_to_rgbx(const float *nchw, int V, int H, int W, int unnormalize, float *rgbx,
-                             void *stream);
+int gpnerf_k0_featmaps_to_channels_last(const float *nchw, int V, int h, int w, int out_bf16, int pad,
+                                        void *nhwc, void *stream);   /* pad: [V][h+2][w+2][32] */
+int gpnerf_k0_images_to_rgbx(const float *nchw, int V, int H, int W, int unnormalize, int pad,
+                             float *rgbx, void *stream);              /* pad: [V][H+2][W+2][4]  */
 
 /* ---- K1: pixel mask, rays, box intersection ---------------------------- */
 /* demo_render.py:166-200: occupied voxels → world → can_bounds (min/max,

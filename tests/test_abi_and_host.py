@@ -41,7 +41,7 @@ def test_argument_validation_without_gpu(lib_built):
     L = lib_built
     assert L.gpnerf_workspace_bytes(-1) == -1
     assert L.gpnerf_workspace_bytes(1 << 20) > (1 << 20) // 8
-    assert L.gpnerf_k0_level_to_channels_last(None, 1, 1, 1, 0, None, None, None) == -1
+    assert L.gpnerf_k0_level_to_channels_last(None, 1, 1, 1, 0, 0, None, None, None) == -1
     assert b"invalid argument" in L.gpnerf_last_error()
     f = _lib.Frame()
     assert L.gpnerf_k1_voxel_pixel_mask(None, C.byref(f), None, None, None) == -1

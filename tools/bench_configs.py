@@ -1,0 +1,122 @@
+"""Device timings of the other BASELINE.json configurations (not bench lines:
+bench.py measures configs[1]).  Prints one JSON line per configuration.
+
+  python tools/bench_configs.py [dense512] [zju1024] [zju512_fp32] [thu512]
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import torch  # noqa: E402
+
+import gpnerf_b200  # noqa: F401,E402
+from gpnerf_b200 import synth  # noqa: E402
+from gpnerf_b200._lib import PREC_BF16, PREC_FP32  # noqa: E402
+from gpnerf_b200.engine import Engine  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def timed(fn, steps=10, warmup=3):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / steps
+
+
+def progressive(tag, H, S, V, precision, seed=42, graph=True):
+    scene = synth.make_scene("zju", H=H, W=H, V=V, seed=seed)
+    w = synth.make_head_weights(V=V, seed=seed)
+    eng = Engine(H, H, S, V, device=DEV, precision=precision)
+    eng.set_weights(w)
+    lv = [t.to(DEV) for t in scene["levels"]]
+    fm, im = scene["featmaps"].to(DEV), scene["src_imgs"].to(DEV)
+    eng.set_static_inputs(lv, fm, im)
+    eng.upload_products(lv, fm, im)
+    frame = eng.make_frame(scene)
+
+    def step():
+        if graph:
+            eng.run_progressive_graphed(frame)
+        else:
+            eng.upload_products(lv, fm, im)
+            eng.render_progressive(frame)
+    ms = timed(step)
+    c = eng.read_counters()
+    eng.timing = True
+    eng.stage_events = {}
+    for _ in range(5):
+        eng.upload_products(lv, fm, im)
+        eng.render_progressive(frame)
+    torch.cuda.synchronize()
+    st = {k: round(v, 4) for k, v in sorted(eng.stage_times_ms().items(), key=lambda kv: -kv[1])}
+    print(json.dumps({"config": tag, "H": H, "S": S, "V": V, "precision": "bf16" if precision else "fp32",
+                      "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "rays": c["n_rays"],
+                      "rays_per_s": c["n_rays"] * 1e3 / ms, "points": c["n_rays"] * S, "P1": c["P1"], "P2": c["P2"],
+                      "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30, "stages_ms": st}), flush=True)
+
+
+def dense(tag, H, S, V, precision, seed=42):
+    """BaseRender semantics on a full frame: every pixel's ray, every sample
+    through both heads (BASELINE configs[0]'s dense worst case)."""
+    scene = synth.make_scene("dense", H=H, W=H, V=V, seed=seed)
+    w = synth.make_head_weights(V=V, seed=seed)
+    R = scene["ray_o"].shape[1]
+    eng = Engine(H, H, S, V, device=DEV, precision=precision, max_rays=R)
+    eng.set_weights(w)
+    lv = [t.to(DEV) for t in scene["levels"]]
+    fm, im = scene["featmaps"].to(DEV), scene["src_imgs"].to(DEV)
+    rays = tuple(scene[k][0].to(DEV) for k in ("ray_o", "ray_d", "near", "far"))
+    eng.upload_products(lv, fm, im)
+    frame = eng.make_frame(scene)
+
+    def step():
+        eng.upload_products(lv, fm, im)
+        return eng.render_dense(frame, *rays)
+    ms = timed(step, steps=5, warmup=2)
+    eng.timing = True
+    eng.stage_events = {}
+    for _ in range(3):
+        out = step()
+    torch.cuda.synchronize()
+    st = {k: round(v, 4) for k, v in sorted(eng.stage_times_ms().items(), key=lambda kv: -kv[1])}
+    print(json.dumps({"config": tag, "H": H, "S": S, "V": V, "precision": "bf16" if precision else "fp32",
+                      "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "rays": R, "rays_per_s": R * 1e3 / ms,
+                      "points": R * S, "points_per_s": R * S * 1e3 / ms,
+                      "rgb_mean": float(out["rgb_map"].mean()), "acc_mean": float(out["acc_map"].mean()),
+                      "finite": bool(torch.isfinite(out["rgb_map"]).all()),
+                      "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30, "stages_ms": st}), flush=True)
+
+
+CONFIGS = {
+    "zju512_fp32": lambda: progressive("zju512_fp32 (configs[1] geometry, fp32 parity heads)", 512, 64, 3, PREC_FP32,
+                                       graph=False),
+    "thu512": lambda: progressive("trainthu_valzju shape (configs[2]): same hot-path tensors, other seed", 512, 64, 3,
+                                  PREC_BF16, seed=1234),
+    "dense512": lambda: dense("dense 512x512 BaseRender path (worst case, no compaction)", 512, 64, 3, PREC_BF16),
+    "zju1024": lambda: progressive("1024x1024, S=128, V=4 (configs[4] single-GPU share)", 1024, 128, 4, PREC_BF16),
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CONFIGS)
+    for n in names:
+        t0 = time.time()
+        try:
+            CONFIGS[n]()
+        except Exception as e:   # keep going, report
+            print(json.dumps({"config": n, "error": repr(e)}), flush=True)
+        torch.cuda.empty_cache()
+        print(f"# {n}: {time.time() - t0:.1f} s wall", file=sys.stderr, flush=True)
