@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
       }
       if (row < n_valid) {
         const long long dst = valid1 ? (long long)__ldg(valid1 + first + row) : first + row;
-        rgb[dst * 3 + 0] = 1.0f / (1.0f + __expf(-o0));
-        rgb[dst * 3 + 1] = 1.0f / (1.0f + __expf(-o1));
-        rgb[dst * 3 + 2] = 1.0f / (1.0f + __expf(-o2));
+        rgb[dst * 3 + 0] = sigmoid_fast(o0);
+        rgb[dst * 3 + 1] = sigmoid_fast(o1);
+        rgb[dst * 3 + 2] = sigmoid_fast(o2);
       }
     }
   }

@@ -167,7 +167,20 @@ __device__ __forceinline__ void st_chunk(uint8_t* tile, uint32_t off, const floa
 }
 
 // ELU for activations that are about to be rounded to bf16
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }
+// (one FMUL + MUFU.EX2 with flush-to-zero: the denormal-preserving __expf costs three more
+// instructions per element, and these epilogues are issue bound)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu_fast(float x) {
+  const float e = ex2_ftz(x * 1.4426950408889634f) - 1.0f;
+  return x > 0.0f ? x : e;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return __frcp_rn(1.0f + ex2_ftz(-1.4426950408889634f * x));
+}
 
 }  // namespace tc
 }  // namespace gpnerf
