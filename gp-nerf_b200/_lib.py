@@ -75,6 +75,7 @@ _SIGNATURES = {
     "gpnerf_k4_compact_alpha": ([_P, _I, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_composite": ([_P, _P, _P, _P, C.POINTER(Frame), _I, _P, C.c_float, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_raw2outputs": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k5_raw2outputs_bwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -188,6 +188,119 @@ __global__ void __launch_bounds__(256) raw2outputs_kernel(const float* __restric
   }
 }
 
+
+// Backward of raw2outputs (training path).  With G_j = ∂L/∂w_j collected from
+// every consumer of the weights (rgb_map, depth, acc, disp, the returned
+// weights themselves, rgb_in_map):
+//   ∂L/∂c_j = w_j · g_rgb
+//   ∂L/∂σ_j = (1−α_j) · [ G_j·T_j − (Σ_{k>j} G_k·w_k) / (1−α_j+1e-10) ]
+// One warp per ray: forward product-scan recomputed, suffix sums by a reverse
+// shuffle scan, 32 samples at a time (two passes over the ray).
+__global__ void __launch_bounds__(256) raw2outputs_bwd_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z_vals, const float* __restrict__ rgb_in, int n_rays,
+    int S, int V, int neg, const float* __restrict__ g_rgb_map, const float* __restrict__ g_disp,
+    const float* __restrict__ g_acc, const float* __restrict__ g_depth, const float* __restrict__ g_weights,
+    const float* __restrict__ g_rgb_in_map, float* __restrict__ d_raw) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_rays; r += n_warps) {
+    const float gr = g_rgb_map ? __ldg(g_rgb_map + r * 3) : 0.f, gg = g_rgb_map ? __ldg(g_rgb_map + r * 3 + 1) : 0.f,
+                gb = g_rgb_map ? __ldg(g_rgb_map + r * 3 + 2) : 0.f;
+    float gd = g_depth ? __ldg(g_depth + r) : 0.f, ga = g_acc ? __ldg(g_acc + r) : 0.f;
+    // pass 1: forward sums needed by disp = 1 / max(1e-10, depth/acc)
+    if (g_disp != nullptr) {
+      float T = 1.0f, dsum = 0.f, asum = 0.f;
+      for (int base = 0; base < S; base += 32) {
+        const int j = base + lane, s = neg ? (S - 1 - j) : j;
+        float a = 0.f, z = 0.f;
+        if (j < S) {
+          a = xsub(1.0f, expf(-__ldg(raw + ((long long)r * S + s) * 4 + 3)));
+          z = __ldg(z_vals + (long long)r * S + j);
+        }
+        float incl = xadd(xsub(1.0f, a), 1e-10f);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl *= t;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float w = a * (T * excl);
+        dsum += w * z;
+        asum += w;
+        T *= __shfl_sync(0xffffffffu, incl, 31);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      }
+      const float q = dsum / asum;
+      if (q > 1e-10f) {             // disp = acc/depth ; the clamped / NaN branch has zero gradient
+        const float gq = -__ldg(g_disp + r) / (q * q);
+        gd += gq / asum;
+        ga += -gq * dsum / (asum * asum);
+      }
+    }
+    // pass 2: chunks in reverse order, carrying the suffix sum Σ_{k>j} G_k w_k; the transmittance at a
+    // chunk start is the product of the factors of all earlier chunks, recomputed per chunk (S/32 ≤ 8)
+    float suffix = 0.f;
+    const int n_chunks = (S + 31) / 32;
+    for (int ch = n_chunks - 1; ch >= 0; --ch) {
+      float T0 = 1.0f;
+      for (int c2 = 0; c2 < ch; ++c2) {
+        const int j = c2 * 32 + lane, s = neg ? (S - 1 - j) : j;
+        float fct = 1.0f;
+        if (j < S) fct = xadd(xsub(1.0f, xsub(1.0f, expf(-__ldg(raw + ((long long)r * S + s) * 4 + 3)))), 1e-10f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fct *= __shfl_xor_sync(0xffffffffu, fct, o);
+        T0 *= fct;
+      }
+      const int j = ch * 32 + lane, s = neg ? (S - 1 - j) : j;
+      float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, G = 0.f;
+      if (j < S) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(raw + ((long long)r * S + s) * 4));
+        a = xsub(1.0f, expf(-q.w));
+        cr = q.x; cg = q.y; cb = q.z;
+        G = gr * cr + gg * cg + gb * cb + gd * __ldg(z_vals + (long long)r * S + j) + ga;
+        if (g_weights) G += __ldg(g_weights + (long long)r * S + j);
+        if (g_rgb_in_map && rgb_in) {
+          const float* ri = rgb_in + ((long long)r * S + j) * V * 3;
+          const float* gi = g_rgb_in_map + (long long)r * V * 3;
+          for (int k = 0; k < V * 3; ++k) G += __ldg(gi + k) * __ldg(ri + k);
+        }
+      }
+      const float fct = xadd(xsub(1.0f, a), 1e-10f);
+      float incl = fct;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= t;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float Tj = T0 * excl, w = a * Tj;
+      // inclusive suffix sum of G·w inside the chunk (reverse scan), plus the carry of later chunks
+      float gw = G * w, suf = gw;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += t;
+      }
+      const float after = suf - gw + suffix;          // Σ_{k>j} G_k w_k
+      if (j < S) {
+        float* o = d_raw + ((long long)r * S + s) * 4;
+        o[0] = w * gr;
+        o[1] = w * gg;
+        o[2] = w * gb;
+        o[3] = (1.0f - a) * (G * Tj - after / fct);
+      }
+      suffix += __shfl_sync(0xffffffffu, suf, 0);
+    }
+  }
+}
+
 }  // namespace gpnerf
 
 using namespace gpnerf;
@@ -237,6 +350,20 @@ int gpnerf_k5_raw2outputs(const float* raw, const float* z_vals, const float* rg
                                                              n_views, neg, rgb_map, disp, acc, depth,
                                                              weights, rgb_in_map);
   return check_launch("k5_raw2outputs");
+}
+
+int gpnerf_k5_raw2outputs_bwd(const float* raw, const float* z_vals, const float* rgb_in, int n_rays,
+                              int n_samples, int n_views, int neg, const float* g_rgb_map, const float* g_disp,
+                              const float* g_acc, const float* g_depth, const float* g_weights,
+                              const float* g_rgb_in_map, float* d_raw, void* stream) {
+  GPNERF_REQUIRE(raw && z_vals && d_raw && n_rays > 0 && n_samples > 0);
+  GPNERF_REQUIRE(n_views >= 0 && n_views <= GPNERF_MAX_VIEWS && (g_rgb_in_map == nullptr || rgb_in != nullptr));
+  long long blocks = ((long long)n_rays * 32 + 255) / 256;
+  int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : sm_count() * 8);
+  raw2outputs_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, z_vals, rgb_in, n_rays, n_samples, n_views,
+                                                                 neg, g_rgb_map, g_disp, g_acc, g_depth, g_weights,
+                                                                 g_rgb_in_map, d_raw);
+  return check_launch("k5_raw2outputs_bwd");
 }
 
 }  // extern "C"

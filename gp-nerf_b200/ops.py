@@ -194,3 +194,40 @@ def raw2outputs(raw, z_vals, rgb_in=None, neg=False):
                                         ptr(acc), ptr(depth), ptr(weights), ptr(rin_map), _stream(dev)),
               "k5_raw2outputs")
     return rgb_map, disp, acc, weights, depth, rin_map
+
+
+class _Raw2OutputsFn(torch.autograd.Function):
+    """Renderer.raw2outputs under autograd: both directions are library kernels
+    (gpnerf_k5_raw2outputs / gpnerf_k5_raw2outputs_bwd).  Differentiable in
+    `raw`; z_vals and rgb_in are treated as constants (they carry no parameters
+    in the reference's training graph, BaseRender.py:110-157)."""
+
+    @staticmethod
+    def forward(ctx, raw, z_vals, rgb_in, neg):
+        outs = raw2outputs(raw, z_vals, rgb_in, neg)
+        ctx.save_for_backward(raw.detach(), z_vals.detach(), rgb_in.detach() if rgb_in is not None else None)
+        ctx.neg = bool(neg)
+        ctx.mark_non_differentiable(*[o for o in outs[5:] if o is not None and rgb_in is None])
+        return outs if rgb_in is not None else outs[:5]
+
+    @staticmethod
+    def backward(ctx, g_rgb_map, g_disp, g_acc, g_weights, g_depth, g_rin=None):
+        raw, z, rin = ctx.saved_tensors
+        lib = _lib.load()
+        raw, z = _c(raw), _c(z)
+        R, S, _ = raw.shape
+        V = 0 if rin is None else rin.shape[2]
+        d_raw = torch.empty_like(raw)
+
+        def g(t):
+            return None if t is None else _c(t)
+        check(lib.gpnerf_k5_raw2outputs_bwd(ptr(raw), ptr(z), ptr(None if rin is None else _c(rin)), R, S, V,
+                                            int(ctx.neg), ptr(g(g_rgb_map)), ptr(g(g_disp)), ptr(g(g_acc)),
+                                            ptr(g(g_depth)), ptr(g(g_weights)), ptr(g(g_rin)), ptr(d_raw),
+                                            _stream(raw.device)), "k5_raw2outputs_bwd")
+        return d_raw, None, None, None
+
+
+def raw2outputs_autograd(raw, z_vals, rgb_in=None, neg=False):
+    """Differentiable raw2outputs: (rgb_map, disp, acc, weights, depth[, rgb_in_map])."""
+    return _Raw2OutputsFn.apply(raw, z_vals, rgb_in, neg)

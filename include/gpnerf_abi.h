@@ -259,6 +259,16 @@ int gpnerf_k5_raw2outputs(const float *raw, const float *z_vals, const float *rg
                           int n_samples, int n_views, int neg, float *rgb_map, float *disp,
                           float *acc, float *depth, float *weights, float *rgb_in_map, void *stream);
 
+/* Backward of gpnerf_k5_raw2outputs (training, BaseRender.py:75-107 under
+ * autograd): upstream gradients of rgb_map [R][3], disp/acc/depth [R], weights
+ * [R][S], rgb_in_map [R][3V] (any may be NULL = zero) → d_raw float[R][S][4]
+ * (∂L/∂rgb, ∂L/∂σ per sample). */
+int gpnerf_k5_raw2outputs_bwd(const float *raw, const float *z_vals, const float *rgb_in, int n_rays,
+                              int n_samples, int n_views, int neg, const float *g_rgb_map,
+                              const float *g_disp, const float *g_acc, const float *g_depth,
+                              const float *g_weights, const float *g_rgb_in_map, float *d_raw,
+                              void *stream);
+
 /* bytes of scratch `workspace` needed by the compaction passes for up to
  * n_items flags */
 int64_t gpnerf_workspace_bytes(int64_t n_items);

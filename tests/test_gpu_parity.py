@@ -339,3 +339,31 @@ def test_cuda_graph_replay_tracks_new_pose():
     torch.cuda.synchronize()
     assert eager.read_counters() == imgs[1][1]
     assert torch.equal(eager.pred_img, imgs[1][0])
+
+
+@pytest.mark.parametrize("neg", [False, True])
+def test_raw2outputs_backward_vs_torch_autograd(fn, neg):
+    """Training path: gradient of every raw2outputs output w.r.t. raw against
+    torch autograd through the oracle (BaseRender.py:75-107,147)."""
+    gen = torch.Generator().manual_seed(5)
+    raw0 = torch.cat([fn["rgb_out"], fn["sigma_out"] * 3.0], -1)
+    rgb_in = fn["rgb_feat"][..., :3].contiguous()
+    R, S = raw0.shape[:2]
+    gs = [torch.randn(R, 3, generator=gen), torch.randn(R, generator=gen) * 0.1, torch.randn(R, generator=gen),
+          torch.randn(R, S, generator=gen), torch.randn(R, generator=gen), torch.randn(R, 9, generator=gen)]
+    # oracle
+    raw_c = raw0.clone().requires_grad_(True)
+    o_rgb, o_disp, o_acc, o_w, o_depth = orc.raw2outputs(raw_c, fn["z"], neg)
+    o_rin = (o_w[..., None, None] * rgb_in).sum(1).reshape(R, -1)
+    loss = (o_rgb * gs[0]).sum() + (o_disp * gs[1]).sum() + (o_acc * gs[2]).sum() + (o_w * gs[3]).sum() \
+        + (o_depth * gs[4]).sum() + (o_rin * gs[5]).sum()
+    loss.backward()
+    # kernels
+    raw_g = raw0.clone().to(DEV).requires_grad_(True)
+    rgb_map, disp, acc, w, depth, rin = ops.raw2outputs_autograd(raw_g, fn["z"].to(DEV), rgb_in.to(DEV), neg)
+    loss_g = (rgb_map * gs[0].to(DEV)).sum() + (disp * gs[1].to(DEV)).sum() + (acc * gs[2].to(DEV)).sum() \
+        + (w * gs[3].to(DEV)).sum() + (depth * gs[4].to(DEV)).sum() + (rin * gs[5].to(DEV)).sum()
+    loss_g.backward()
+    ref, got = raw_c.grad, raw_g.grad.cpu()
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 1e-4 * max(1.0, scale)
