@@ -72,6 +72,15 @@ _SIGNATURES = {
     "gpnerf_k23_gather_density_tc": ([C.POINTER(_P), _P, _P, _P, _P, _P, _P, C.POINTER(Frame), C.POINTER(HeadWeights),
                                       _I, _P, _P, _P, _P], C.c_int),
     "gpnerf_k3_color_mlp_records": ([_P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _P], C.c_int),
+    "gpnerf_k2_gather_volume_bwd": ([C.POINTER(_P), _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),
+    "gpnerf_k2_project_gather_bwd": ([_P, _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),
+    "gpnerf_k6_linear": ([_P, _I, _I, C.c_float, _P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I,
+                          C.c_longlong, _P], C.c_int),
+    "gpnerf_k6_grad_weights": ([_P, _I, _I, C.c_float, _P, _I, _I, _P, _I, _P, _I, _P, C.c_longlong, _P], C.c_int),
+    "gpnerf_k6_assemble_raw": ([_P, _P, _P, _I, C.c_longlong, _P, _P], C.c_int),
+    "gpnerf_k6_raw_grad_split": ([_P, _P, _P, _P, _I, C.c_longlong, _P, _P, _P], C.c_int),
+    "gpnerf_k6_meanvar_bwd": ([_P, _P, _P, _I, C.c_longlong, _P, _P], C.c_int),
+    "gpnerf_k6_from_channels_last": ([_P, _I, C.c_longlong, _P, _P], C.c_int),
     "gpnerf_k4_compact_alpha": ([_P, _I, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_composite": ([_P, _P, _P, _P, C.POINTER(Frame), _I, _P, C.c_float, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_raw2outputs": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),

@@ -279,6 +279,88 @@ __global__ void __launch_bounds__(256) mean_variance(const float* __restrict__ r
   }
 }
 
+// ---------------------------------------------------------------------------
+// Backward of the two gathers (training): grid_sample's gradient w.r.t. its
+// input = scatter-add of weight·upstream into the sampled corners.  Same point
+// sources, same weights (trilinear_setup / bilinear_setup) as the forward
+// kernels above; 16-byte vector atomics into channel-last fp32 gradient
+// buffers (sums are order-dependent at the ulp level, like torch's).
+// ---------------------------------------------------------------------------
+struct LevelGradPtrs {
+  float* p[GPNERF_N_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) scatter_volume_bwd(LevelGradPtrs lg, PointSrc ps,
+                                                          const __grid_constant__ gpnerf_frame_t fparam,
+                                                          const int32_t* __restrict__ count_ptr, int n_const,
+                                                          const float* __restrict__ d_vol_feat) {
+  GPNERF_LOAD_FRAME(fparam)
+  const int n = count_ptr ? __ldg(count_ptr) : n_const;
+  const int sub = threadIdx.x & 7;
+  const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
+  for (long long i = group; i < n; i += n_groups) {
+    const Vec3 wp = fetch_world_point(ps, i);
+    const Vec3 g = (ps.kind == 2) ? wp : world_to_grid(f, wp);
+#pragma unroll
+    for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+      const int D = f.level_dims[l][0], H = f.level_dims[l][1], W = f.level_dims[l][2];
+      const Tri t = trilinear_setup(g, D, H, W);
+      const float4 d = ld4(d_vol_feat + i * 128 + l * 32 + sub * 4);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if ((t.inb >> c) & 1u) {
+          long long idx = ((long long)(t.z0 + (c >> 2)) * H + (t.y0 + ((c >> 1) & 1))) * W + (t.x0 + (c & 1));
+          const float w = t.w[c];
+          atomicAdd(reinterpret_cast<float4*>(lg.p[l] + idx * 32 + sub * 4),
+                    make_float4(d.x * w, d.y * w, d.z * w, d.w * w));
+        }
+      }
+    }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) scatter_features_bwd(float* __restrict__ d_featmaps, PointSrc ps,
+                                                            const __grid_constant__ gpnerf_frame_t fparam,
+                                                            const int32_t* __restrict__ count_ptr, int n_const,
+                                                            const float* __restrict__ d_rgb_feat) {
+  GPNERF_LOAD_FRAME(fparam)
+  const int n = count_ptr ? __ldg(count_ptr) : n_const;
+  const int sub = threadIdx.x & 7;
+  const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) >> 3;
+  const float wm1 = xsub((float)f.src_w, 1.0f), hm1 = xsub((float)f.src_h, 1.0f);
+  const long long map_stride = (long long)f.feat_h * f.feat_w * 32;
+  for (long long i = group; i < n; i += n_groups) {
+    const Vec3 pt = fetch_world_point(ps, i);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float* KE = f.src_KE[v];
+      float qx = dot4(KE[0], pt.x, KE[1], pt.y, KE[2], pt.z, KE[3], 1.0f);
+      float qy = dot4(KE[4], pt.x, KE[5], pt.y, KE[6], pt.z, KE[7], 1.0f);
+      float qz = dot4(KE[8], pt.x, KE[9], pt.y, KE[10], pt.z, KE[11], 1.0f);
+      float px = fminf(fmaxf(xdiv(qx, qz), -1e6f), 1e6f);
+      float py = fminf(fmaxf(xdiv(qy, qz), -1e6f), 1e6f);
+      float nx = xsub(xdiv(xmul(2.0f, px), wm1), 1.0f);
+      float ny = xsub(xdiv(xmul(2.0f, py), hm1), 1.0f);
+      const Bil b = bilinear_setup(nx, ny, f.feat_w, f.feat_h);
+      const float* dr = d_rgb_feat + (i * V + v) * 35 + 3 + sub * 4;
+      const float4 d = make_float4(__ldg(dr), __ldg(dr + 1), __ldg(dr + 2), __ldg(dr + 3));
+      float* base = d_featmaps + v * map_stride + sub * 4;
+      const float wts[4] = {b.nw, b.ne, b.sw, b.se};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if ((b.inb >> c) & 1u) {
+          const long long idx = ((long long)(b.y0 + (c >> 1)) * f.feat_w + (b.x0 + (c & 1))) * 32;
+          const float w = wts[c];
+          atomicAdd(reinterpret_cast<float4*>(base + idx), make_float4(d.x * w, d.y * w, d.z * w, d.w * w));
+        }
+      }
+    }
+  }
+}
+
 static int persistent_grid(int ctas_per_sm) { return sm_count() * ctas_per_sm; }
 
 }  // namespace gpnerf
@@ -367,6 +449,50 @@ int gpnerf_k2_mean_variance(const float* rgb_feat, int n_views, int n_points, fl
   int grid = (int)(blocks < (long long)persistent_grid(8) ? blocks : persistent_grid(8));
   mean_variance<<<grid, 256, 0, (cudaStream_t)stream>>>(rgb_feat, n_views, n_points, meanvar);
   return check_launch("k2_mean_variance");
+}
+
+int gpnerf_k2_gather_volume_bwd(float* const d_levels_ndhwc[GPNERF_N_LEVELS], int point_kind, const int32_t* valid,
+                                const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                                const gpnerf_frame_t* f, int n_points_max, const int32_t* counters,
+                                const float* d_vol_feat, void* stream) {
+  GPNERF_REQUIRE(d_levels_ndhwc && f && d_vol_feat && n_points_max > 0);
+  PointSrc ps;
+  GPNERF_REQUIRE(make_point_src(&ps, point_kind, valid, rays_o, rays_d, z_vals, points, f));
+  LevelGradPtrs lg;
+  for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+    GPNERF_REQUIRE(d_levels_ndhwc[l] != nullptr);
+    lg.p[l] = d_levels_ndhwc[l];
+  }
+  long long blocks = ((long long)n_points_max * 8 + 255) / 256;
+  int grid = (int)(blocks < (long long)persistent_grid(8) ? blocks : persistent_grid(8));
+  scatter_volume_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(lg, ps, *f, counters ? counters + GPNERF_CNT_P1 : nullptr,
+                                                             n_points_max, d_vol_feat);
+  return check_launch("k2_gather_volume_bwd");
+}
+
+int gpnerf_k2_project_gather_bwd(float* d_featmaps_nhwc, int point_kind, const int32_t* valid, const float* rays_o,
+                                 const float* rays_d, const float* z_vals, const float* points,
+                                 const gpnerf_frame_t* f, int n_points_max, const int32_t* counters,
+                                 const float* d_rgb_feat, void* stream) {
+  GPNERF_REQUIRE(d_featmaps_nhwc && f && d_rgb_feat && n_points_max > 0);
+  PointSrc ps;
+  GPNERF_REQUIRE(point_kind != 2 && make_point_src(&ps, point_kind, valid, rays_o, rays_d, z_vals, points, f));
+  const int32_t* cp = counters ? counters + GPNERF_CNT_P1 : nullptr;
+  long long blocks = ((long long)n_points_max * 8 + 255) / 256;
+  int grid = (int)(blocks < (long long)persistent_grid(8) ? blocks : persistent_grid(8));
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_V(VV)                                                                                         \
+  case VV:                                                                                                   \
+    scatter_features_bwd<VV><<<grid, 256, 0, st>>>(d_featmaps_nhwc, ps, *f, cp, n_points_max, d_rgb_feat);   \
+    break;
+  switch (f->n_views) {
+    LAUNCH_V(1) LAUNCH_V(2) LAUNCH_V(3) LAUNCH_V(4) LAUNCH_V(5) LAUNCH_V(6) LAUNCH_V(7) LAUNCH_V(8)
+    default:
+      set_error("n_views out of range", cudaSuccess);
+      return GPNERF_E_ARG;
+  }
+#undef LAUNCH_V
+  return check_launch("k2_project_gather_bwd");
 }
 
 }  // extern "C"

@@ -269,6 +269,51 @@ int gpnerf_k5_raw2outputs_bwd(const float *raw, const float *z_vals, const float
                               const float *g_weights, const float *g_rgb_in_map, float *d_raw,
                               void *stream);
 
+/* ---- K6: training path (layer-wise fp32; BASELINE configs[3]) ------------- */
+/* Backward of the gathers: scatter-add of the weighted upstream gradients into
+ * channel-last fp32 gradient buffers (caller zeroes them). Same point sources
+ * as the forward gathers. d_vol_feat float[n][128]; d_rgb_feat float[n][V][35]
+ * (only the 32 feature channels propagate: the images carry no gradient). */
+int gpnerf_k2_gather_volume_bwd(float *const d_levels_ndhwc[GPNERF_N_LEVELS], int point_kind,
+                                const int32_t *valid, const float *rays_o, const float *rays_d,
+                                const float *z_vals, const float *points,
+                                const gpnerf_frame_t *frame_host, int n_points_max,
+                                const int32_t *counters, const float *d_vol_feat, void *stream);
+int gpnerf_k2_project_gather_bwd(float *d_featmaps_nhwc, int point_kind, const int32_t *valid,
+                                 const float *rays_o, const float *rays_d, const float *z_vals,
+                                 const float *points, const gpnerf_frame_t *frame_host,
+                                 int n_points_max, const int32_t *counters, const float *d_rgb_feat,
+                                 void *stream);
+/* Y[p][0..N) = epi(X'[p][0..K)·B + bias) for p < P, rows strided by ldx / ldy;
+ * X' = in_scale·X, times ELU'(in_aux) element-wise when in_aux is given (in_aux
+ * = the saved ELU output the incoming gradient has to pass through);
+ * B[k][n] = w_is_kn ? W[k*ldw+n] : W[n*ldw+k] (nn.Linear layout → forward; its
+ * transpose → ∂L/∂X).  epilogue: 0 none, 1 ELU, 2 ReLU, 3 sigmoid, 4 multiply
+ * by ELU'(aux[p][n]).  add_pre / add_post add the previous content of Y before
+ * / after the epilogue. */
+int gpnerf_k6_linear(const float *X, int ldx, int K, float in_scale, const float *in_aux,
+                     int ld_in_aux, const float *W, int ldw, int w_is_kn, int N, const float *bias,
+                     int epilogue, const float *aux, int ld_aux, float *Y, int ldy, int add_pre,
+                     int add_post, long long P, void *stream);
+/* dW[n*ldw+k] += Σ_p dY'[p][n]·X[p][k]·in_scale ; db[n] += Σ_p dY'[p][n] (db may
+ * be NULL); dY' = dY ⊙ ELU'(dy_aux) when dy_aux is given */
+int gpnerf_k6_grad_weights(const float *X, int ldx, int K, float in_scale, const float *dY, int ldy,
+                           int N, const float *dy_aux, int ld_dy_aux, float *dW, int ldw, float *db,
+                           long long P, void *stream);
+/* raw[p] = (rgb[p], σ[p]) with σ = s_relu[p], forced to 0 where Σ_v mask[p][v] < 1
+ * (trainhead.py:136-137,162); and the matching split of ∂L/∂raw into the
+ * pre-sigmoid / pre-ReLU gradients */
+int gpnerf_k6_assemble_raw(const float *rgb, const float *s_relu, const float *mask, int n_views,
+                           long long P, float *raw, void *stream);
+int gpnerf_k6_raw_grad_split(const float *d_raw, const float *rgb, const float *s_relu,
+                             const float *mask, int n_views, long long P, float *d_rgb_pre,
+                             float *d_s_pre, void *stream);
+/* fused_mean_variance backward: d_rgb_feat += dmean/V + dvar·2(x−mean)/V */
+int gpnerf_k6_meanvar_bwd(const float *rgb_feat, const float *meanvar, const float *d_meanvar,
+                          int n_views, long long P, float *d_rgb_feat, void *stream);
+/* [batch][n][32] channel-last → [batch][32][n] (gradients back to NC(D)HW) */
+int gpnerf_k6_from_channels_last(const float *nxc, int batch, long long n, float *cxn, void *stream);
+
 /* bytes of scratch `workspace` needed by the compaction passes for up to
  * n_items flags */
 int64_t gpnerf_workspace_bytes(int64_t n_items);

@@ -367,3 +367,91 @@ def test_raw2outputs_backward_vs_torch_autograd(fn, neg):
     ref, got = raw_c.grad, raw_g.grad.cpu()
     scale = float(ref.abs().max())
     assert float((got - ref).abs().max()) < 1e-4 * max(1.0, scale)
+
+
+# ------------------------------------------------------------ training path
+def _oracle_dense_differentiable(scene, w, rays, S, t_rand, levels, featmaps):
+    """The dense render composed from the oracle's functions with autograd on
+    (oracle.render_dense itself runs under no_grad)."""
+    cams, imgs01, out_sh = orc._scene_common(scene)
+    o, d, near, far = rays
+    pts, z = orc.sampling_points(o, d, near, far, S, t_rand)
+    n = pts.shape[0]
+    pts = pts.reshape(-1, 3)
+    grid = orc.grid_coords_of(orc.pts_to_can_pts(pts, scene["R"], scene["Th"]), scene["bounds"], out_sh)
+    rgb_feat, mask = orc.projector_compute(pts, imgs01, cams, featmaps, False)
+    sfeat = orc.sigma_feat_of(orc.gather_levels(levels, grid), w)
+    mean, var = orc.mean_var(rgb_feat)
+    sigma = orc.density_mlp(sfeat, mean, var, mask, w)
+    rgb = orc.color_mlp(rgb_feat, mean, var, w)
+    raw = torch.cat([rgb, sigma[:, None]], -1).view(n, S, 4)
+    rgb_map, disp, acc, weights, depth = orc.raw2outputs(raw, z, False)
+    rin = (weights[..., None, None] * rgb_feat[..., :3].reshape(n, S, -1, 3)).sum(1).reshape(n, -1)
+    return rgb_map, disp, acc, weights, depth, rin
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+def test_training_step_forward_backward_vs_torch_autograd(jitter):
+    """BASELINE configs[3] in miniature: forward + backward of the dense render
+    through our kernels vs torch autograd through the oracle: gradients of all
+    head parameters, of the encoder feature maps and of the 4 volume levels."""
+    from gpnerf_b200.train import PARAM_KEYS, render_dense_autograd
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=19, with_rays=True)
+    w0 = synth.make_head_weights(V=3, seed=119, random_bias=True)
+    S, R = 16, 600
+    sel = torch.arange(R) * (scene["ray_o"].shape[1] // R)
+    rays = tuple(scene[k][0][sel] for k in ("ray_o", "ray_d", "near", "far"))
+    gen = torch.Generator().manual_seed(7)
+    t_rand = torch.rand(R, S, generator=gen) if jitter else None
+    cot = [torch.randn(R, 3, generator=gen), torch.randn(R, generator=gen) * 0.05, torch.randn(R, generator=gen),
+           torch.randn(R, S, generator=gen) * 0.3, torch.randn(R, generator=gen), torch.randn(R, 9, generator=gen) * 0.3]
+
+    # ---- oracle + torch autograd (CPU)
+    w_c = {k: v.clone().requires_grad_(True) for k, v in w0.items()}
+    lv_c = [t.clone().requires_grad_(True) for t in scene["levels"]]
+    fm_c = scene["featmaps"].clone().requires_grad_(True)
+    outs_c = _oracle_dense_differentiable(scene, w_c, rays, S, t_rand, lv_c, fm_c)
+    sum((o * c).sum() for o, c in zip(outs_c, cot)).backward()
+
+    # ---- kernels (GPU)
+    eng = Engine(64, 64, S, 3, device=DEV, max_rays=R)
+    w_g = {k: v.clone().to(DEV).requires_grad_(True) for k, v in w0.items()}
+    lv_g = [t.clone().to(DEV).requires_grad_(True) for t in scene["levels"]]
+    fm_g = scene["featmaps"].clone().to(DEV).requires_grad_(True)
+    eng.set_weights(w0)
+    eng.upload_products([t.detach() for t in lv_g], fm_g.detach(), scene["src_imgs"].to(DEV))
+    frame = eng.make_frame(scene)
+    out = render_dense_autograd(eng, frame, rays, lv_g, fm_g, scene["src_imgs"].to(DEV), w_g, t_rand=t_rand)
+    got = (out["rgb_map"], out["disp_map"][:, 0], out["acc_map"][:, 0], out["alpha"], out["depth_map"][:, 0],
+           out["rgb_in_map"])
+    for a, b, name in zip(got, outs_c, ("rgb_map", "disp", "acc", "weights", "depth", "rgb_in_map")):
+        ok = ~torch.isnan(b)
+        assert float((a.detach().cpu()[ok] - b.detach()[ok]).abs().max()) < 1e-3, name
+    # disp is NaN on empty rays (0/0) in both: keep it out of the loss there
+    cot_g = [c.to(DEV) for c in cot]
+    finite = ~torch.isnan(got[1].detach())
+    loss = sum((o * c).sum() for o, c in zip((got[0], got[2], got[3], got[4], got[5]),
+                                             (cot_g[0], cot_g[2], cot_g[3], cot_g[4], cot_g[5])))
+    loss = loss + (got[1][finite] * cot_g[1][finite]).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    # the CPU side must treat the NaN rows the same way
+    if not bool(finite.all()):
+        for t in list(w_c.values()) + lv_c + [fm_c]:
+            t.grad = None
+        outs_c = _oracle_dense_differentiable(scene, w_c, rays, S, t_rand, lv_c, fm_c)
+        fin_c = finite.cpu()
+        lc = sum((o * c).sum() for o, c in zip((outs_c[0], outs_c[2], outs_c[3], outs_c[4], outs_c[5]),
+                                               (cot[0], cot[2], cot[3], cot[4], cot[5])))
+        (lc + (outs_c[1][fin_c] * cot[1][fin_c]).sum()).backward()
+
+    def close(a, b, name, rel=2e-3):
+        scale = max(float(b.abs().max()), 1e-6)
+        err = float((a - b).abs().max())
+        assert err <= rel * scale, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+    for key in PARAM_KEYS:
+        for suf in (".weight", ".bias"):
+            close(w_g[key + suf].grad.cpu(), w_c[key + suf].grad, key + suf)
+    close(fm_g.grad.cpu(), fm_c.grad, "featmaps")
+    for i in range(4):
+        close(lv_g[i].grad.cpu(), lv_c[i].grad, f"level{i}")
