@@ -8,13 +8,16 @@
 // SparseConvNet.encode reduces into masks3d (SparseConvNet.py:135-139).
 // Pure HBM streaming: 4 B read + 4 B written per element.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace gpnerf {
 
-// in: [32][n] (channel-first) → out: [n][32] as fp32 (128-byte lines) or bf16
-// (64-byte lines); optional chan_sum[n] = Σ_c in[c][v] (c ascending, fp32).
+// in: [32][n] (channel-first) → out: [n][32] as fp32 (128-byte lines) or as
+// 16-bit bf16 / fp16 (64-byte lines; fp16 saturates at ±65504 and is what the
+// fused tensor-core kernel interpolates with HFMA2); optional
+// chan_sum[n] = Σ_c in[c][v] (c ascending, fp32).
 // CTA = 256 threads, tile = 32 channels × 128 positions: float4 loads along the
 // positions (512 B per channel row), transposed through shared memory, 32 B
 // (bf16) or 64 B (fp32) stored per thread.
@@ -35,7 +38,8 @@ struct OutMap {
   }
 };
 
-template <bool BF16>
+// FMT: 0 fp32, 1 bf16, 2 fp16
+template <int FMT>
 __global__ void __launch_bounds__(256) to_channels_last_32(const float* __restrict__ in, long long n,
                                                            long long batch_stride_in, OutMap om,
                                                            void* __restrict__ out_v,
@@ -75,7 +79,25 @@ __global__ void __launch_bounds__(256) to_channels_last_32(const float* __restri
         float x[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = tile[(h * 16 + k) * LD + vv];
-        if constexpr (BF16) {
+        if constexpr (FMT == 2) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out_v) + om(blockIdx.y, v) * 32 + h * 16);
+          float y[16];    // saturated copy: x itself still feeds the exact channel sum below
+#pragma unroll
+          for (int k = 0; k < 16; ++k) y[k] = fminf(fmaxf(x[k], -65504.0f), 65504.0f);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            uint4 o;
+            __half2 b0 = __floats2half2_rn(y[k * 8 + 0], y[k * 8 + 1]);
+            __half2 b1 = __floats2half2_rn(y[k * 8 + 2], y[k * 8 + 3]);
+            __half2 b2 = __floats2half2_rn(y[k * 8 + 4], y[k * 8 + 5]);
+            __half2 b3 = __floats2half2_rn(y[k * 8 + 6], y[k * 8 + 7]);
+            o.x = *reinterpret_cast<uint32_t*>(&b0);
+            o.y = *reinterpret_cast<uint32_t*>(&b1);
+            o.z = *reinterpret_cast<uint32_t*>(&b2);
+            o.w = *reinterpret_cast<uint32_t*>(&b3);
+            dst[k] = o;
+          }
+        } else if constexpr (FMT == 1) {
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_v) +
                                                 om(blockIdx.y, v) * 32 + h * 16);
 #pragma unroll
@@ -186,16 +208,19 @@ static OutMap make_map(int H, int W, int pad, int pad_z, long long n) {
   return om;
 }
 
-int gpnerf_k0_level_to_channels_last(const float* ncdhw, int D, int H, int W, int out_bf16, int pad,
+int gpnerf_k0_level_to_channels_last(const float* ncdhw, int D, int H, int W, int storage, int pad,
                                      void* ndhwc, float* chan_sum, void* stream) {
   GPNERF_REQUIRE(ncdhw && ndhwc && D > 0 && H > 0 && W > 0);
   long long n = (long long)D * H * W;
   dim3 grid(grid_for((n + 127) / 128, 1), 1);
   OutMap om = make_map(H, W, pad, 1, n);
-  if (out_bf16)
-    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
+  GPNERF_REQUIRE(storage >= 0 && storage <= 2);
+  if (storage == 2)
+    to_channels_last_32<2><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
+  else if (storage == 1)
+    to_channels_last_32<1><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
   else
-    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
+    to_channels_last_32<0><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
   return check_launch("k0_level_to_channels_last");
 }
 
@@ -213,17 +238,20 @@ int gpnerf_k0_build_masks3d(const float* const chan_sum[GPNERF_N_LEVELS],
   return check_launch("k0_build_masks3d");
 }
 
-int gpnerf_k0_featmaps_to_channels_last(const float* nchw, int V, int h, int w, int out_bf16, int pad,
+int gpnerf_k0_featmaps_to_channels_last(const float* nchw, int V, int h, int w, int storage, int pad,
                                         void* nhwc, void* stream) {
   GPNERF_REQUIRE(nchw && nhwc && V > 0 && V <= GPNERF_MAX_VIEWS && h > 0 && w > 0);
   long long n = (long long)h * w;
   dim3 grid(grid_for((n + 127) / 128, 1), V);
   OutMap om = make_map(h, w, pad, 0, n);
   if (pad) om.batch = (long long)(h + 2) * (w + 2);
-  if (out_bf16)
-    to_channels_last_32<true><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, om, nhwc, nullptr);
+  GPNERF_REQUIRE(storage >= 0 && storage <= 2);
+  if (storage == 2)
+    to_channels_last_32<2><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, om, nhwc, nullptr);
+  else if (storage == 1)
+    to_channels_last_32<1><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, om, nhwc, nullptr);
   else
-    to_channels_last_32<false><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, om, nhwc, nullptr);
+    to_channels_last_32<0><<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, n, 32 * n, om, nhwc, nullptr);
   return check_launch("k0_featmaps_to_channels_last");
 }
 

@@ -1,21 +1,27 @@
-// K2+K3 fused (bf16 tensor-core path): for each tile of 128 surviving sample
-// points, gather the 4-level geometry volume and the V source views, aggregate
+// K2+K3 fused (tensor-core path): for each tile of 128 surviving sample points,
+// gather the 4-level geometry volume and the V source views, aggregate
 // mean/variance, and run the density head – without the gathered features ever
 // leaving the SM.
 //
-//   gather phase  (SparseConvNet.py:111-122, BaseRender.py:283-363,
-//                  trainhead.py:20-24): 4 lanes per point, 8 bf16 channels
-//                  (one 16-byte load) per lane and corner; fp32 accumulation;
-//                  each lane's result is exactly one 16-byte chunk of a UMMA
-//                  A operand, stored straight into shared memory.
-//   density phase (trainhead.py:39-41, 102-110, 133-137): four tcgen05.mma
-//                  rounds 128→64, 144→64, 64→32, 32→16 with TMEM accumulators,
-//                  16→1 + ReLU + no-valid-view fill on CUDA cores.
+//   plan phase    one thread per (point, {levels | views}): sample position, world→grid
+//                 transform, per-level corner offset + fractions, per-view projection,
+//                 in-front/in-bounds test, tap offsets + fractions.  16 bytes per level and
+//                 per view, parked in the (still unused) sigma_feat columns of the A1 tile.
+//   gather phase  (SparseConvNet.py:111-122, BaseRender.py:283-363, trainhead.py:20-24):
+//                 4 lanes per point, 8 channels (one 16-byte load) per lane and corner.
+//                 Volumes and feature maps are stored channel-last in FP16 inside a zero
+//                 border; the interpolation is HFMA2 on the packed pairs (no unpacking,
+//                 11-bit mantissa: finer than the bf16 the result is rounded to anyway).
+//                 Each lane's result is exactly one 16-byte chunk of a UMMA A operand,
+//                 stored straight into shared memory.  RGB taps: lane v takes view v.
+//   density phase (trainhead.py:39-41, 102-110, 133-137): four tcgen05.mma rounds
+//                 128→64 (fp16 × fp16), 144→64, 64→32, 32→16 (bf16) with TMEM accumulators,
+//                 biases folded into the GEMMs, activations kept times log2(e)
+//                 (tc_common.cuh, elu_scaled); 16→1 + ReLU + no-valid-view fill on CUDA cores.
 // By-product: one 16·(9+5V)-byte bf16 record per point ([mean|var] and the V
 // per-view feature rows, already in operand order) for the colour head, which
 // only the points that survive the progressive step will read back.
 //
-// Volumes / feature maps are stored channel-last in bf16 (64-byte lines).
 // Index arithmetic is one affine map per point (FMAs): unlike the fp32 path this
 // kernel does not reproduce the reference's rounding sequence – the integer
 // results (which points exist) were fixed upstream by the exact K1/K2 kernels.
@@ -25,9 +31,9 @@
 namespace gpnerf {
 
 struct FusedArgs {
-  const __nv_bfloat16* lv[GPNERF_N_LEVELS];
-  const __nv_bfloat16* feat;     // [V][fh][fw][32]
-  const float4* rgbx;            // [V][H][W] (r,g,b,·) in [0,1]
+  const __half* lv[GPNERF_N_LEVELS];
+  const __half* feat;            // [V][fh+2][fw+2][32]
+  const float4* rgbx;            // [V][H+2][W+2] (r,g,b,·) in [0,1]
   const int32_t* valid;
   const float *rays_o, *rays_d, *z_vals;
   const int32_t* counters;
@@ -38,18 +44,13 @@ struct FusedArgs {
 
 struct FusedSmem {
   static constexpr uint32_t IMG = 0;
-  static constexpr uint32_t A0 = ((DenImg::BYTES + 127) / 128) * 128;   // [128 x 128]; later [128 x 64] + [128 x 32]
-  static constexpr uint32_t A1 = A0 + op_bytes(128, 128);               // [128 x 144] = sigma_feat | G
+  static constexpr uint32_t A0 = ((DenImg::BYTES + 127) / 128) * 128;   // [128 x 128] fp16; later [128 x 64] + [128 x 32]
+  static constexpr uint32_t A1 = A0 + op_bytes(128, 128);               // [128 x 144] = sigma_feat | G ; plan in cols 0..63
   static constexpr uint32_t MISC = A1 + op_bytes(128, 144);             // barriers, tmem slot, flags, transform
   static constexpr uint32_t BYTES = MISC + 512;
 };
+static_assert(2 * (FusedSmem::BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 
-__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
-  f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xffff0000u);
-  f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xffff0000u);
-  f[4] = __uint_as_float(q.z << 16); f[5] = __uint_as_float(q.z & 0xffff0000u);
-  f[6] = __uint_as_float(q.w << 16); f[7] = __uint_as_float(q.w & 0xffff0000u);
-}
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   uint4 q;
   q.x = pack_bf16x2(v[0], v[1]);
@@ -58,7 +59,16 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   q.w = pack_bf16x2(v[6], v[7]);
   return q;
 }
-__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 dup_h2(float w) { return __float2half2_rn(w); }
+// acc += q (8 fp16 channels) * w
+__device__ __forceinline__ void hfma8(__half2 (&acc)[4], const uint4& q, __half2 w) {
+  acc[0] = __hfma2(as_h2(q.x), w, acc[0]);
+  acc[1] = __hfma2(as_h2(q.y), w, acc[1]);
+  acc[2] = __hfma2(as_h2(q.z), w, acc[2]);
+  acc[3] = __hfma2(as_h2(q.w), w, acc[3]);
+}
 
 template <int V>
 __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const __grid_constant__ gpnerf_frame_t fparam) {
@@ -105,13 +115,15 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
   mbar_wait(bar_w, 0);
 
   const uint32_t a0 = smem_u32(A0), a1 = smem_u32(A1), a2 = smem_u32(A2), wimg = smem_u32(img);
+  const uint32_t ones = a1 + 8 * 2 * kLBO;          // last K block of A1: (mean/var rgb, 1, 1 | 0×8)
   const float ox = __ldg(a.rays_o), oy = __ldg(a.rays_o + 1), oz = __ldg(a.rays_o + 2);
   const int S = f.n_samples;
   const float sfx = (float)(f.feat_w - 1) / (float)(f.src_w - 1), sfy = (float)(f.feat_h - 1) / (float)(f.src_h - 1);
   const float wm1 = (float)(f.src_w - 1), hm1 = (float)(f.src_h - 1);
-  const long long img_stride_p = (long long)(f.src_h + 2) * (f.src_w + 2);          // padded image, float4 units
-  const long long map_stride_q = (long long)(f.feat_h + 2) * (f.feat_w + 2) * 4;    // padded map, uint4 units
+  const int img_stride_p = (f.src_h + 2) * (f.src_w + 2);          // padded image, float4 units
+  const int map_stride_q = (f.feat_h + 2) * (f.feat_w + 2) * 4;    // padded map, uint4 units
   constexpr int RC = rec_chunks(V);
+  constexpr uint32_t SBO1 = op_sbo(144);
   const int grp = tid >> 2, sub = tid & 3;
   const int row = tid & 127, half = tid >> 7;
   uint32_t phase = 0;
@@ -121,37 +133,90 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long first = (long long)tile * 128;
     const int n_valid = min(128, n - (int)first);
-    // =================== gather phase ===================
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int r = pass * 64 + grp;
-      const bool ok = r < n_valid;
+    // =================== plan phase ===================
+    // thread (row, half): half 0 plans the 4 volume levels of point `row`, half 1 its V views.
+    // Plan entry = 16 bytes in chunk kc of the row's (unused until the first epilogue) sigma_feat
+    // columns of A1: kc = level, or 4 + view.  Rows past the tile's end plan all-zero taps at offset 0
+    // (the zero border), so the gather phase needs no row guard.
+    {
+      const bool ok = row < n_valid;
       float px = 0.f, py = 0.f, pz = 0.f;
       if (ok) {
-        const int q = __ldg(a.valid + first + r);
+        const int q = __ldg(a.valid + first + row);
         const int ray = q / S;
         const float z = __ldg(a.z_vals + q);
         px = fmaf(__ldg(a.rays_d + ray * 3 + 0), z, ox);
         py = fmaf(__ldg(a.rays_d + ray * 3 + 1), z, oy);
         pz = fmaf(__ldg(a.rays_d + ray * 3 + 2), z, oz);
       }
-      // ---- 4-level trilinear gather → A0 chunk (level*4 + sub)
-      const float ux = fmaf(xf[0], px, fmaf(xf[1], py, fmaf(xf[2], pz, xf[3])));
-      const float uy = fmaf(xf[4], px, fmaf(xf[5], py, fmaf(xf[6], pz, xf[7])));
-      const float uz = fmaf(xf[8], px, fmaf(xf[9], py, fmaf(xf[10], pz, xf[11])));
+      uint8_t* prow = A1 + chunk_off(row, 0, SBO1);
+      if (half == 0) {
+        const float ux = fmaf(xf[0], px, fmaf(xf[1], py, fmaf(xf[2], pz, xf[3])));
+        const float uy = fmaf(xf[4], px, fmaf(xf[5], py, fmaf(xf[6], pz, xf[7])));
+        const float uz = fmaf(xf[8], px, fmaf(xf[9], py, fmaf(xf[10], pz, xf[11])));
+#pragma unroll
+        for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+          // the level is stored inside a one-voxel zero border: after clamping the continuous index to
+          // [-1, size] all 8 corners are addressable and out-of-range corners read zeros (= zeros padding)
+          const int D = f.level_dims[l][0], H = f.level_dims[l][1], W = f.level_dims[l][2];
+          const float ix = fminf(fmaxf(ux * (float)(W - 1), -1.0f), (float)W);
+          const float iy = fminf(fmaxf(uy * (float)(H - 1), -1.0f), (float)H);
+          const float iz = fminf(fmaxf(uz * (float)(D - 1), -1.0f), (float)D);
+          const int x0 = min((int)floorf(ix), W - 1), y0 = min((int)floorf(iy), H - 1), z0 = min((int)floorf(iz), D - 1);
+          const int dy = (W + 2) * 4, dz = (H + 2) * dy;               // strides in uint4 (16 B) units
+          uint4 e;
+          e.x = ok ? (uint32_t)((z0 + 1) * dz + (y0 + 1) * dy + (x0 + 1) * 4) : 0u;
+          e.y = __float_as_uint(ix - (float)x0);
+          e.z = __float_as_uint(iy - (float)y0);
+          e.w = __float_as_uint(iz - (float)z0);
+          *reinterpret_cast<uint4*>(prow + l * kLBO) = e;
+        }
+      } else {
+        int nv = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float* KE = f.src_KE[v];
+          const float qx = fmaf(KE[0], px, fmaf(KE[1], py, fmaf(KE[2], pz, KE[3])));
+          const float qy = fmaf(KE[4], px, fmaf(KE[5], py, fmaf(KE[6], pz, KE[7])));
+          const float qz = fmaf(KE[8], px, fmaf(KE[9], py, fmaf(KE[10], pz, KE[11])));
+          const float inv = 1.0f / qz;
+          const float ux2 = qx * inv, uy2 = qy * inv;
+          const bool front = f.neg_ray ? (qz < 0.0f) : (qz > 0.0f);
+          const bool inbv = (ux2 <= wm1) && (ux2 >= 0.0f) && (uy2 <= hm1) && (uy2 >= 0.0f);
+          nv += (front && inbv) ? 1 : 0;
+          uint4 e;
+          {  // feature map tap (align_corners: pixel p ↦ p·(Wm−1)/(w−1)); map stored inside a zero border
+            const float ix = fminf(fmaxf(ux2 * sfx, -1.0f), (float)f.feat_w);
+            const float iy = fminf(fmaxf(uy2 * sfy, -1.0f), (float)f.feat_h);
+            const int x0 = min((int)floorf(ix), f.feat_w - 1), y0 = min((int)floorf(iy), f.feat_h - 1);
+            e.x = ok ? (uint32_t)(v * map_stride_q + (y0 + 1) * (f.feat_w + 2) * 4 + (x0 + 1) * 4) : 0u;
+            e.z = pack_f16x2(ix - (float)x0, iy - (float)y0);
+          }
+          {  // RGB tap at the image's own resolution
+            const float ix = fminf(fmaxf(ux2, -1.0f), (float)f.src_w), iy = fminf(fmaxf(uy2, -1.0f), (float)f.src_h);
+            const int x0 = min((int)floorf(ix), f.src_w - 1), y0 = min((int)floorf(iy), f.src_h - 1);
+            e.y = ok ? (uint32_t)(v * img_stride_p + (y0 + 1) * (f.src_w + 2) + (x0 + 1)) : 0u;
+            e.w = pack_f16x2(ix - (float)x0, iy - (float)y0);
+          }
+          *reinterpret_cast<uint4*>(prow + (4 + v) * kLBO) = e;
+        }
+        nvalid[row] = (uint8_t)nv;
+      }
+    }
+    __syncthreads();
+    // =================== gather phase ===================
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 64 + grp;
+      const bool ok = r < n_valid;
+      const uint8_t* prow = A1 + chunk_off(r, 0, SBO1);
+      // ---- 4-level trilinear gather → A0 chunk (level*4 + sub), fp16
 #pragma unroll
       for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
-        // the level is stored inside a one-voxel zero border: after clamping the continuous index to
-        // [-1, size] all 8 corners are addressable and out-of-range corners read zeros (= zeros padding)
-        const int D = f.level_dims[l][0], H = f.level_dims[l][1], W = f.level_dims[l][2];
-        const float ix = fminf(fmaxf(ux * (float)(W - 1), -1.0f), (float)W);
-        const float iy = fminf(fmaxf(uy * (float)(H - 1), -1.0f), (float)H);
-        const float iz = fminf(fmaxf(uz * (float)(D - 1), -1.0f), (float)D);
-        const int x0 = min((int)floorf(ix), W - 1), y0 = min((int)floorf(iy), H - 1), z0 = min((int)floorf(iz), D - 1);
-        const float wx1 = ix - (float)x0, wx0 = 1.0f - wx1, wy1 = iy - (float)y0, wy0 = 1.0f - wy1;
-        const float wz1 = iz - (float)z0, wz0 = 1.0f - wz1;
-        const int dy = (W + 2) * 4, dz = (H + 2) * dy;               // strides in uint4 (16 B) units
-        const uint4* p0 = reinterpret_cast<const uint4*>(a.lv[l]) + ((z0 + 1) * dz + (y0 + 1) * dy + (x0 + 1) * 4 + sub);
+        const uint4 e = *reinterpret_cast<const uint4*>(prow + l * kLBO);
+        const int W = f.level_dims[l][2], H = f.level_dims[l][1];
+        const int dy = (W + 2) * 4, dz = (H + 2) * dy;
+        const uint4* p0 = reinterpret_cast<const uint4*>(a.lv[l]) + (e.x + sub);
         uint4 q[8];
         q[0] = __ldg(p0);
         q[1] = __ldg(p0 + 4);
@@ -161,77 +226,64 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
         q[5] = __ldg(p0 + dz + 4);
         q[6] = __ldg(p0 + dz + dy);
         q[7] = __ldg(p0 + dz + dy + 4);
+        const float wx1 = __uint_as_float(e.y), wy1 = __uint_as_float(e.z), wz1 = __uint_as_float(e.w);
+        const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
         const float w00 = wy0 * wz0, w10 = wy1 * wz0, w01 = wy0 * wz1, w11 = wy1 * wz1;
-        const float w[8] = {wx0 * w00, wx1 * w00, wx0 * w10, wx1 * w10, wx0 * w01, wx1 * w01, wx0 * w11, wx1 * w11};
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float v[8];
-          unpack8(q[c], v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], w[c], acc[e]);
-        }
-        st_chunk(A0, chunk_off(r, l * 4 + sub, op_sbo(128)), acc);
+        __half2 acc[4] = {dup_h2(0.f), dup_h2(0.f), dup_h2(0.f), dup_h2(0.f)};
+        hfma8(acc, q[0], dup_h2(wx0 * w00));
+        hfma8(acc, q[1], dup_h2(wx1 * w00));
+        hfma8(acc, q[2], dup_h2(wx0 * w10));
+        hfma8(acc, q[3], dup_h2(wx1 * w10));
+        hfma8(acc, q[4], dup_h2(wx0 * w01));
+        hfma8(acc, q[5], dup_h2(wx1 * w01));
+        hfma8(acc, q[6], dup_h2(wx0 * w11));
+        hfma8(acc, q[7], dup_h2(wx1 * w11));
+        *reinterpret_cast<uint4*>(A0 + chunk_off(r, l * 4 + sub, op_sbo(128))) =
+            make_uint4(as_u32(acc[0]), as_u32(acc[1]), as_u32(acc[2]), as_u32(acc[3]));
       }
-      // ---- V source views: projection, bilinear taps (maps stored inside a zero border), mean / variance
+      // ---- V source views: feature taps by all 4 lanes (8 channels each), mean / variance
       float fv[V][8];
-      float cv[V][3];
-      int nv = 0;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float* KE = f.src_KE[v];
-        const float qx = fmaf(KE[0], px, fmaf(KE[1], py, fmaf(KE[2], pz, KE[3])));
-        const float qy = fmaf(KE[4], px, fmaf(KE[5], py, fmaf(KE[6], pz, KE[7])));
-        const float qz = fmaf(KE[8], px, fmaf(KE[9], py, fmaf(KE[10], pz, KE[11])));
-        const float inv = 1.0f / qz;
-        const float ux2 = qx * inv, uy2 = qy * inv;
-        const bool front = f.neg_ray ? (qz < 0.0f) : (qz > 0.0f);
-        const bool inbv = (ux2 <= wm1) && (ux2 >= 0.0f) && (uy2 <= hm1) && (uy2 >= 0.0f);
-        nv += (front && inbv) ? 1 : 0;
-        {  // feature map tap (align_corners: pixel p ↦ p·(Wm−1)/(w−1))
-          const float ix = fminf(fmaxf(ux2 * sfx, -1.0f), (float)f.feat_w);
-          const float iy = fminf(fmaxf(uy2 * sfy, -1.0f), (float)f.feat_h);
-          const int x0 = min((int)floorf(ix), f.feat_w - 1), y0 = min((int)floorf(iy), f.feat_h - 1);
-          const float wx = ix - (float)x0, wy = iy - (float)y0;
-          const int dy = (f.feat_w + 2) * 4;
-          const uint4* p0 = reinterpret_cast<const uint4*>(a.feat) + v * map_stride_q +
-                            ((y0 + 1) * dy + (x0 + 1) * 4 + sub);
-          uint4 q[4];
-          q[0] = __ldg(p0);
-          q[1] = __ldg(p0 + 4);
-          q[2] = __ldg(p0 + dy);
-          q[3] = __ldg(p0 + dy + 4);
-          const float w[4] = {(1.0f - wx) * (1.0f - wy), wx * (1.0f - wy), (1.0f - wx) * wy, wx * wy};
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint4 e = *reinterpret_cast<const uint4*>(prow + (4 + v) * kLBO);
+        const int dy = (f.feat_w + 2) * 4;
+        const uint4* p0 = reinterpret_cast<const uint4*>(a.feat) + (e.x + sub);
+        uint4 q[4];
+        q[0] = __ldg(p0);
+        q[1] = __ldg(p0 + 4);
+        q[2] = __ldg(p0 + dy);
+        q[3] = __ldg(p0 + dy + 4);
+        const float2 wf = __half22float2(as_h2(e.z));
+        const float wx = wf.x, wy = wf.y;
+        __half2 acc[4] = {dup_h2(0.f), dup_h2(0.f), dup_h2(0.f), dup_h2(0.f)};
+        hfma8(acc, q[0], dup_h2((1.0f - wx) * (1.0f - wy)));
+        hfma8(acc, q[1], dup_h2(wx * (1.0f - wy)));
+        hfma8(acc, q[2], dup_h2((1.0f - wx) * wy));
+        hfma8(acc, q[3], dup_h2(wx * wy));
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float t[8];
-            unpack8(q[c], t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(t[e], w[c], acc[e]);
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) fv[v][e] = acc[e];
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(acc[j]);
+          fv[v][2 * j] = t.x;
+          fv[v][2 * j + 1] = t.y;
         }
-        {  // RGB tap at the image's own resolution (same addresses in the 4 lanes: one broadcast load)
-          const float ix = fminf(fmaxf(ux2, -1.0f), (float)f.src_w), iy = fminf(fmaxf(uy2, -1.0f), (float)f.src_h);
-          const int x0 = min((int)floorf(ix), f.src_w - 1), y0 = min((int)floorf(iy), f.src_h - 1);
-          const float wx = ix - (float)x0, wy = iy - (float)y0;
-          const int dy = f.src_w + 2;
-          const float4* p0 = a.rgbx + v * img_stride_p + ((y0 + 1) * dy + (x0 + 1));
-          const float4 t0 = __ldg(p0), t1 = __ldg(p0 + 1), t2 = __ldg(p0 + dy), t3 = __ldg(p0 + dy + 1);
-          const float w0 = (1.0f - wx) * (1.0f - wy), w1 = wx * (1.0f - wy), w2 = (1.0f - wx) * wy, w3 = wx * wy;
-          cv[v][0] = fmaf(t3.x, w3, fmaf(t2.x, w2, fmaf(t1.x, w1, t0.x * w0)));
-          cv[v][1] = fmaf(t3.y, w3, fmaf(t2.y, w2, fmaf(t1.y, w1, t0.y * w0)));
-          cv[v][2] = fmaf(t3.z, w3, fmaf(t2.z, w2, fmaf(t1.z, w1, t0.z * w0)));
-        }
+        if (ok) a.rec[(first + r) * RC + 9 + v * 5 + sub] = pack8(fv[v]);
+      }
+      // ---- RGB taps: lane `sub` takes view `sub` (fp32 images, fp32 arithmetic)
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (sub < V) {
+        const uint4 e = *reinterpret_cast<const uint4*>(prow + (4 + sub) * kLBO);
+        const int dy = f.src_w + 2;
+        const float4* p0 = a.rgbx + e.y;
+        const float4 t0 = __ldg(p0), t1 = __ldg(p0 + 1), t2 = __ldg(p0 + dy), t3 = __ldg(p0 + dy + 1);
+        const float2 wr = __half22float2(as_h2(e.w));
+        const float wx = wr.x, wy = wr.y;
+        const float w0 = (1.0f - wx) * (1.0f - wy), w1 = wx * (1.0f - wy), w2 = (1.0f - wx) * wy, w3 = wx * wy;
+        c0 = fmaf(t3.x, w3, fmaf(t2.x, w2, fmaf(t1.x, w1, t0.x * w0)));
+        c1 = fmaf(t3.y, w3, fmaf(t2.y, w2, fmaf(t1.y, w1, t0.y * w0)));
+        c2 = fmaf(t3.z, w3, fmaf(t2.z, w2, fmaf(t1.z, w1, t0.z * w0)));
         if (ok) {
-          uint4* rp = a.rec + (first + r) * RC + 9 + v * 5;
-          rp[sub] = pack8(fv[v]);
-          if (sub == 0) {
-            const float t[8] = {cv[v][0], cv[v][1], cv[v][2], 0.f, 0.f, 0.f, 0.f, 0.f};
-            rp[4] = pack8(t);
-          }
+          const float t[8] = {c0, c1, c2, 0.f, 0.f, 0.f, 0.f, 0.f};
+          a.rec[(first + r) * RC + 9 + sub * 5 + 4] = pack8(t);
         }
       }
       {
@@ -250,53 +302,59 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
           var[e] = s * inv_v;
         }
         const uint4 qm = pack8(mean), qv = pack8(var);
-        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 8 + sub, op_sbo(144))) = qm;
-        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 12 + sub, op_sbo(144))) = qv;
+        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 8 + sub, SBO1)) = qm;
+        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 12 + sub, SBO1)) = qv;
         if (ok) {
           uint4* rp = a.rec + (first + r) * RC;
           rp[sub] = qm;
           rp[4 + sub] = qv;
         }
+        // RGB mean / variance over the views: butterfly over the point's 4 lanes (lanes >= V hold 0)
+        float m0 = c0, m1 = c1, m2 = c2;
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+          m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+          m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        }
+        m0 *= inv_v; m1 *= inv_v; m2 *= inv_v;
+        const bool mine = sub < V;
+        float s0 = mine ? (c0 - m0) * (c0 - m0) : 0.f, s1 = mine ? (c1 - m1) * (c1 - m1) : 0.f;
+        float s2 = mine ? (c2 - m2) * (c2 - m2) : 0.f;
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
         if (sub == 0) {
-          float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float m = 0.f;
-#pragma unroll
-            for (int v = 0; v < V; ++v) m += cv[v][c];
-            m *= inv_v;
-            float s = 0.f;
-#pragma unroll
-            for (int v = 0; v < V; ++v) s = fmaf(cv[v][c] - m, cv[v][c] - m, s);
-            t[c] = m;
-            t[3 + c] = s * inv_v;
-          }
+          // columns 70, 71 of the G tile are the constant 1.0 that carries the layers' biases
+          const float t[8] = {m0, m1, m2, s0 * inv_v, s1 * inv_v, s2 * inv_v, 1.0f, 1.0f};
           const uint4 qc = pack8(t);
-          *reinterpret_cast<uint4*>(A1 + chunk_off(r, 16, op_sbo(144))) = qc;
+          *reinterpret_cast<uint4*>(A1 + chunk_off(r, 16, SBO1)) = qc;
           if (ok) a.rec[(first + r) * RC + 8] = qc;
-          nvalid[r] = (uint8_t)nv;
         }
       }
     }
     // =================== density phase ===================
-    // sigmahead.out_geometry_fc: [128 x 128] · Wgᵀ → 64, ELU → columns 0..63 of A1
+    // sigmahead.out_geometry_fc: [128 x 128] · Wgᵀ → 64, ELU → columns 0..63 of A1 (over the plan)
     round_sync();
-    if (tid == 0) issue_gemm(a0, op_sbo(128), wimg + DenImg::Wg, op_sbo(128), 128, 64, tmem, bar_m);
+    if (tid == 0) issue_gemm_bias(a0, op_sbo(128), wimg + DenImg::Wg, 128, 64, ones, SBO1, tmem, bar_m, kFmtF16);
     wait_round(bar_m, phase);
-    epi32_to_tile(t_row, half * 32, fl + DenImg::bg, A1, op_sbo(144), row, 0);
+    epi32_to_tile(t_row, half * 32, A1, SBO1, row, 0);
     // out_geometry_fc.0: [128 x 144] → 64, ELU → A0 as [128 x 64]
     round_sync();
-    if (tid == 0) issue_gemm(a1, op_sbo(144), wimg + DenImg::W0, op_sbo(144), 144, 64, tmem, bar_m);
+    if (tid == 0) issue_gemm(a1, SBO1, wimg + DenImg::W0, SBO1, 144, 64, tmem, bar_m);
     wait_round(bar_m, phase);
-    epi32_to_tile(t_row, half * 32, fl + DenImg::b0, A0, op_sbo(64), row, 0);
+    epi32_to_tile(t_row, half * 32, A0, op_sbo(64), row, 0);
     // .2: [128 x 64] → 32, ELU → A2
     round_sync();
-    if (tid == 0) issue_gemm(a0, op_sbo(64), wimg + DenImg::W1, op_sbo(64), 64, 32, tmem, bar_m);
+    if (tid == 0) issue_gemm_bias(a0, op_sbo(64), wimg + DenImg::W1, 64, 32, ones, SBO1, tmem, bar_m);
     wait_round(bar_m, phase);
-    epi16_to_tile(t_row, half * 16, fl + DenImg::b1, A2, op_sbo(32), row, 0);
+    epi16_to_tile(t_row, half * 16, A2, op_sbo(32), row, 0);
     // .4: [128 x 32] → 16, ELU ; .6 + ReLU + fill on CUDA cores
     round_sync();
-    if (tid == 0) issue_gemm(a2, op_sbo(32), wimg + DenImg::W2, op_sbo(32), 32, 16, tmem, bar_m);
+    if (tid == 0) issue_gemm_bias(a2, op_sbo(32), wimg + DenImg::W2, 32, 16, ones, SBO1, tmem, bar_m);
     wait_round(bar_m, phase);
     if (half == 0) {
       uint32_t r16[16];
@@ -304,12 +362,11 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
       tmem_wait_ld();
       float s = fl[DenImg::b3];
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        s = fmaf(elu_fast(__uint_as_float(r16[k]) + fl[DenImg::b2 + k]), fl[DenImg::w3 + k], s);
+      for (int k = 0; k < 16; ++k) s = fmaf(elu_scaled(__uint_as_float(r16[k])), fl[DenImg::w3 + k], s);
       s = fmaxf(s, 0.0f);
       if (row < n_valid) a.sigma[first + row] = (nvalid[row] < 1) ? 0.0f : s;
     }
-    // the next gather phase rewrites A0/A1/nvalid: order it after every thread's
+    // the next plan phase rewrites A1/nvalid: order it after every thread's
     // reads of this tile (TMEM reads are fenced by the next round_sync)
     __syncthreads();
   }
@@ -348,20 +405,20 @@ extern "C" {
 
 int64_t gpnerf_k23_record_bytes(int n_views) { return 16ll * rec_chunks(n_views); }
 
-int gpnerf_k23_gather_density_tc(const void* const levels_bf16[GPNERF_N_LEVELS], const void* featmaps_bf16,
+int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], const void* featmaps_f16,
                                  const float* images_rgbx, const int32_t* valid, const float* rays_o,
                                  const float* rays_d, const float* z_vals, const gpnerf_frame_t* f,
                                  const gpnerf_head_weights_t* w, int n_points_max, const int32_t* counters,
                                  float* sigma, void* records, void* stream) {
-  GPNERF_REQUIRE(levels_bf16 && featmaps_bf16 && images_rgbx && valid && rays_o && rays_d && z_vals && f && w &&
+  GPNERF_REQUIRE(levels_f16 && featmaps_f16 && images_rgbx && valid && rays_o && rays_d && z_vals && f && w &&
                  counters && sigma && records && n_points_max > 0);
   GPNERF_REQUIRE(w->tc_image != nullptr && f->n_samples > 0 && f->src_w > 1 && f->src_h > 1);
   FusedArgs a;
   for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
-    GPNERF_REQUIRE(levels_bf16[l] != nullptr);
-    a.lv[l] = reinterpret_cast<const __nv_bfloat16*>(levels_bf16[l]);
+    GPNERF_REQUIRE(levels_f16[l] != nullptr);
+    a.lv[l] = reinterpret_cast<const __half*>(levels_f16[l]);
   }
-  a.feat = reinterpret_cast<const __nv_bfloat16*>(featmaps_bf16);
+  a.feat = reinterpret_cast<const __half*>(featmaps_f16);
   a.rgbx = reinterpret_cast<const float4*>(images_rgbx);
   a.valid = valid; a.rays_o = rays_o; a.rays_d = rays_d; a.z_vals = z_vals;
   a.counters = counters;

@@ -20,21 +20,46 @@
 
 namespace gpnerf {
 
-// W fp32 [N][ldw] → bf16 operand [N x Kp] at dst; column j of the operand is
-// W[:, colmap(j)] (or 0 when colmap(j) < 0)
+// W fp32 [N][ldw] → 16-bit operand [N x Kp] at dst.  Column j of the operand is
+//   scale · W[:, colmap(j)]            colmap(j) >= 0   (scale applies to columns j >= scaled_from only)
+//   0                                  colmap(j) == kZero
+//   bf16 hi / lo halves of c · bias    colmap(j) == kBiasHi / kBiasLo
+// stored as fp16 for j < n_f16_cols and as bf16 otherwise.
+constexpr int kZero = -1, kBiasHi = -2, kBiasLo = -3;
 template <class Map>
-__device__ void pack_operand(uint8_t* dst, const float* __restrict__ W, int N, int ldw, int Kp, Map colmap) {
+__device__ void pack_operand(uint8_t* dst, const float* __restrict__ W, const float* __restrict__ bias, int N,
+                             int ldw, int Kp, float scale, int scaled_from, int n_f16_cols, Map colmap) {
   const uint32_t sbo = op_sbo(Kp);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * Kp; i += gridDim.x * blockDim.x) {
     int n = i / Kp, k = i - n * Kp;
     const int src = colmap(k);
-    float v = (src >= 0) ? __ldg(W + (long long)n * ldw + src) : 0.0f;
-    *reinterpret_cast<__nv_bfloat16*>(dst + chunk_off(n, k >> 3, sbo) + (k & 7) * 2) = __float2bfloat16_rn(v);
+    float v = 0.0f;
+    if (src >= 0) {
+      v = (k >= scaled_from ? scale : 1.0f) * __ldg(W + (long long)n * ldw + src);
+    } else if (src == kBiasHi || src == kBiasLo) {
+      const float b = kLog2e * __ldg(bias + n);
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      v = (src == kBiasHi) ? hi : b - hi;
+    }
+    uint8_t* at = dst + chunk_off(n, k >> 3, sbo) + (k & 7) * 2;
+    if (k < n_f16_cols)
+      *reinterpret_cast<__half*>(at) = __float2half_rn(v);
+    else
+      *reinterpret_cast<__nv_bfloat16*>(at) = __float2bfloat16_rn(v);
   }
 }
-__device__ void pack_floats(float* dst, const float* __restrict__ src, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
+__device__ void pack_floats(float* dst, const float* __restrict__ src, int n, float scale) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = scale * __ldg(src + i);
 }
+// identity columns [0, K) followed by a bias K block (ones in columns K+6, K+7 of the A side)
+struct IdBiasMap {
+  int K;
+  __device__ __forceinline__ int operator()(int j) const {
+    return j < K ? j : (j == K + kBiasColHi ? kBiasHi : (j == K + kBiasColLo ? kBiasLo : kZero));
+  }
+};
+// G-tile order with the bias in the tile's constant-one columns 70, 71
+__device__ __forceinline__ int gmap_bias(int j) { return j == 70 ? kBiasHi : (j == 71 ? kBiasLo : gmap(j)); }
 
 struct RawW {
   const float *geo_w, *geo_b, *den_w[4], *den_b[4], *base_w[2], *base_b[2], *vis_w[2], *vis_b[2], *rgb_w[3], *rgb_b[3];
@@ -43,41 +68,32 @@ struct RawW {
 template <int V>
 __device__ void pack_color(uint8_t* c, const RawW& w) {
   using I = ColImg<V>;
-  pack_operand(c + I::Wb0a, w.base_w[0], 64, 105, 80, [](int j) { return gmap(j); });
-  pack_operand(c + I::Wb0b, w.base_w[0], 64, 105, 48, [](int j) { int s = fmap(j); return s < 0 ? -1 : 70 + s; });
-  pack_operand(c + I::Wb1, w.base_w[1], 32, 64, 64, IdMap{64});
-  pack_operand(c + I::Wv0, w.vis_w[0], 32, 32, 32, IdMap{32});
-  pack_operand(c + I::Wv1, w.vis_w[1], 32, 32, 32, IdMap{32});
-  pack_operand(c + I::Wr0, w.rgb_w[0], 32, 32 * V, 32 * V, IdMap{32 * V});
-  pack_operand(c + I::Wr1, w.rgb_w[1], 16, 32, 32, IdMap{32});
+  pack_operand(c + I::Wb0a, w.base_w[0], w.base_b[0], 64, 105, 80, kLog2e, 0, 0, [](int j) { return gmap_bias(j); });
+  pack_operand(c + I::Wb0b, w.base_w[0], nullptr, 64, 105, 48, kLog2e, 0, 0,
+               [](int j) { int s = fmap(j); return s < 0 ? kZero : 70 + s; });
+  pack_operand(c + I::Wb1, w.base_w[1], w.base_b[1], 32, 64, 80, 1.0f, 0, 0, IdBiasMap{64});
+  pack_operand(c + I::Wv0, w.vis_w[0], w.vis_b[0], 32, 32, 48, 1.0f, 0, 0, IdBiasMap{32});
+  pack_operand(c + I::Wv1, w.vis_w[1], w.vis_b[1], 32, 32, 48, 1.0f, 0, 0, IdBiasMap{32});
+  pack_operand(c + I::Wr0, w.rgb_w[0], w.rgb_b[0], 32, 32 * V, 32 * V + 16, 1.0f, 0, 0, IdBiasMap{32 * V});
+  pack_operand(c + I::Wr1, w.rgb_w[1], w.rgb_b[1], 16, 32, 48, 1.0f, 0, 0, IdBiasMap{32});
   float* f = reinterpret_cast<float*>(c + I::F32);
-  pack_floats(f + I::bb0, w.base_b[0], 64);
-  pack_floats(f + I::bb1, w.base_b[1], 32);
-  pack_floats(f + I::vb0, w.vis_b[0], 32);
-  pack_floats(f + I::vb1, w.vis_b[1], 32);
-  pack_floats(f + I::rb0, w.rgb_b[0], 32);
-  pack_floats(f + I::rb1, w.rgb_b[1], 16);
-  pack_floats(f + I::rw2, w.rgb_w[2], 48);
-  pack_floats(f + I::rb2, w.rgb_b[2], 3);
+  pack_floats(f + I::rw2, w.rgb_w[2], 48, 1.0f / kLog2e);
+  pack_floats(f + I::rb2, w.rgb_b[2], 3, 1.0f);
 }
 
 __global__ void pack_weights_kernel(RawW w, int V, uint8_t* image) {
   uint8_t* d = image;
-  pack_operand(d + DenImg::Wg, w.geo_w, 64, 128, 128, IdMap{128});
-  pack_operand(d + DenImg::W0, w.den_w[0], 64, 134, 144, [](int j) {
-    if (j < 64) return j;
-    int s = gmap(j - 64);
-    return s < 0 ? -1 : 64 + s;
+  pack_operand(d + DenImg::Wg, w.geo_w, w.geo_b, 64, 128, 144, kLog2e, 0, 128, IdBiasMap{128});
+  pack_operand(d + DenImg::W0, w.den_w[0], w.den_b[0], 64, 134, 144, kLog2e, 64, 0, [](int j) {
+    if (j < 64) return j;                       // sigma_feat columns: inputs arrive scaled, weights as they are
+    int s = gmap_bias(j - 64);
+    return s >= 0 ? 64 + s : s;
   });
-  pack_operand(d + DenImg::W1, w.den_w[1], 32, 64, 64, IdMap{64});
-  pack_operand(d + DenImg::W2, w.den_w[2], 16, 32, 32, IdMap{32});
+  pack_operand(d + DenImg::W1, w.den_w[1], w.den_b[1], 32, 64, 80, 1.0f, 0, 0, IdBiasMap{64});
+  pack_operand(d + DenImg::W2, w.den_w[2], w.den_b[2], 16, 32, 48, 1.0f, 0, 0, IdBiasMap{32});
   float* f = reinterpret_cast<float*>(d + DenImg::F32);
-  pack_floats(f + DenImg::bg, w.geo_b, 64);
-  pack_floats(f + DenImg::b0, w.den_b[0], 64);
-  pack_floats(f + DenImg::b1, w.den_b[1], 32);
-  pack_floats(f + DenImg::b2, w.den_b[2], 16);
-  pack_floats(f + DenImg::w3, w.den_w[3], 16);
-  pack_floats(f + DenImg::b3, w.den_b[3], 1);
+  pack_floats(f + DenImg::w3, w.den_w[3], 16, 1.0f / kLog2e);
+  pack_floats(f + DenImg::b3, w.den_b[3], 1, 1.0f);
   uint8_t* c = image + kColImgOffset;
   switch (V) {
     case 1: pack_color<1>(c, w); break;
@@ -153,7 +169,7 @@ __global__ void __launch_bounds__(128, 2) density_mlp_tc(const float* __restrict
           for (int it = 0; it < 4; ++it) {
             const int kc = it * 4 + csub;
             load_chunk_mapped(frow, kc, IdMap{128}, v);
-            st_chunk(A0, chunk_off(r, kc, op_sbo(128)), v);
+            st_chunk_f16(A0, chunk_off(r, kc, op_sbo(128)), v);      // the Wg operand pair is fp16
           }
         } else {
 #pragma unroll
@@ -165,17 +181,20 @@ __global__ void __launch_bounds__(128, 2) density_mlp_tc(const float* __restrict
         }
         for (int kc = csub; kc < 10; kc += 4) {       // [mean|var] in G order → columns 64..143
           load_chunk_mapped(mrow, kc, GMap(), v);
+          if (kc == 8) v[kBiasColHi] = v[kBiasColLo] = 1.0f;    // the tile's constant-one columns
           st_chunk(A1, chunk_off(r, 8 + kc, op_sbo(144)), v);
         }
       }
     }
     const int row = tid;
+    const uint32_t ones = a1 + 8 * 2 * kLBO;          // last K block of A1: (…, 1, 1 | 0×8)
     if (input_kind == 0) {
       // sigmahead.out_geometry_fc: [128 x 128] · Wgᵀ → 64, ELU → columns 0..63 of A1
       round_sync();
-      if (tid == 0) issue_gemm(a0, op_sbo(128), wimg + DenImg::Wg, op_sbo(128), 128, 64, tmem, bar_m);
+      if (tid == 0)
+        issue_gemm_bias(a0, op_sbo(128), wimg + DenImg::Wg, 128, 64, ones, op_sbo(144), tmem, bar_m, kFmtF16);
       wait_round(bar_m, phase);
-      epilogue_elu_to_tile<64>(t_row, fl + DenImg::bg, A1, op_sbo(144), row, 0);
+      epilogue_elu_to_tile<64>(t_row, A1, op_sbo(144), row, 0);
     }
     if (sigma_feat_out != nullptr && input_kind == 0 && row < n_valid) {
       // module API only: sigma_feat as the bf16 values the next layer consumes
@@ -186,8 +205,8 @@ __global__ void __launch_bounds__(128, 2) density_mlp_tc(const float* __restrict
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 f2 = __bfloat1622float2(h[e]);
-          o[kc * 8 + e * 2] = f2.x;
-          o[kc * 8 + e * 2 + 1] = f2.y;
+          o[kc * 8 + e * 2] = f2.x * (1.0f / kLog2e);          // activations are kept times log2(e)
+          o[kc * 8 + e * 2 + 1] = f2.y * (1.0f / kLog2e);
         }
       }
     }
@@ -195,15 +214,15 @@ __global__ void __launch_bounds__(128, 2) density_mlp_tc(const float* __restrict
     round_sync();
     if (tid == 0) issue_gemm(a1, op_sbo(144), wimg + DenImg::W0, op_sbo(144), 144, 64, tmem, bar_m);
     wait_round(bar_m, phase);
-    epilogue_elu_to_tile<64>(t_row, fl + DenImg::b0, A0, op_sbo(64), row, 0);
+    epilogue_elu_to_tile<64>(t_row, A0, op_sbo(64), row, 0);
     // .2: [128 x 64] → 32, ELU → A2 as [128 x 32]
     round_sync();
-    if (tid == 0) issue_gemm(a0, op_sbo(64), wimg + DenImg::W1, op_sbo(64), 64, 32, tmem, bar_m);
+    if (tid == 0) issue_gemm_bias(a0, op_sbo(64), wimg + DenImg::W1, 64, 32, ones, op_sbo(144), tmem, bar_m);
     wait_round(bar_m, phase);
-    epilogue_elu_to_tile<32>(t_row, fl + DenImg::b1, A2, op_sbo(32), row, 0);
+    epilogue_elu_to_tile<32>(t_row, A2, op_sbo(32), row, 0);
     // .4: [128 x 32] → 16, ELU ; .6: 16 → 1 on CUDA cores, ReLU, no-valid-view fill
     round_sync();
-    if (tid == 0) issue_gemm(a2, op_sbo(32), wimg + DenImg::W2, op_sbo(32), 32, 16, tmem, bar_m);
+    if (tid == 0) issue_gemm_bias(a2, op_sbo(32), wimg + DenImg::W2, 32, 16, ones, op_sbo(144), tmem, bar_m);
     wait_round(bar_m, phase);
     {
       uint32_t r[16];
@@ -211,7 +230,7 @@ __global__ void __launch_bounds__(128, 2) density_mlp_tc(const float* __restrict
       tmem_wait_ld();
       float s = fl[DenImg::b3];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) s = fmaf(elu_fast(__uint_as_float(r[k]) + fl[DenImg::b2 + k]), fl[DenImg::w3 + k], s);
+      for (int k = 0; k < 16; ++k) s = fmaf(elu_scaled(__uint_as_float(r[k])), fl[DenImg::w3 + k], s);
       s = fmaxf(s, 0.0f);
       if (row < n_valid) {
         float nv = 0.0f;
@@ -234,7 +253,8 @@ struct ColSmem {
   static constexpr uint32_t G = ((ColImg<V>::BYTES + 127) / 128) * 128;  // [128 x 80] mean|var ; later Y_v / Z
   static constexpr uint32_t H = G + op_bytes(128, 80);                   // [128 x 64] base_fc hidden
   static constexpr uint32_t F = H + op_bytes(128, 64);                   // V x [128 x 48] ; later Xs_v / flat
-  static constexpr uint32_t BAR = F + V * op_bytes(128, 48);
+  static constexpr uint32_t ONES = F + V * op_bytes(128, 48);            // [128 x 16] constant (…, 1, 1 | 0×8): bias block
+  static constexpr uint32_t BAR = ONES + op_bytes(128, 16);
   static constexpr uint32_t BYTES = BAR + 64;
   static constexpr uint32_t TMEM_COLS = (V <= 2) ? 64 : 128;
 };
@@ -281,6 +301,13 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
   mbar_wait(bar_w, 0);
 
   const uint32_t g_a = smem_u32(G), h_a = smem_u32(Hb), f_a = smem_u32(F), wimg = smem_u32(img);
+  const uint32_t ones = smem_u32(smem + S::ONES);
+  constexpr uint32_t ONES_SBO = op_sbo(16);
+  if (tid < 128) {     // written once: made visible to the tensor core by the first round_sync
+    uint8_t* o = smem + S::ONES;
+    *reinterpret_cast<uint4*>(o + chunk_off(tid, 0, ONES_SBO)) = make_uint4(0u, 0u, 0u, 0x3F803F80u);   // bf16 1.0 in columns 6, 7
+    *reinterpret_cast<uint4*>(o + chunk_off(tid, 1, ONES_SBO)) = make_uint4(0u, 0u, 0u, 0u);
+  }
   constexpr uint32_t F_STRIDE = op_bytes(128, 48);     // per-view feature operand
   constexpr uint32_t X_STRIDE = op_bytes(128, 32);     // per-view [128 x 32] operand
   constexpr int RC = rec_chunks(V);
@@ -288,16 +315,33 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
   const int n = count_ptr ? __ldg(count_ptr) : n_const;
   const int n_tiles = (n + 127) / 128;
   const float inv_v = 1.0f / (float)V;
+  // source row (record index) of tile row r, -1 past the end
+  auto src_of = [&](long long first_row, int r) -> int {
+    if (first_row + r >= n) return -1;
+    return valid1 ? __ldg(valid1 + first_row + r) : (int)(first_row + r);
+  };
+  // rows this thread stages: r = (warp + 8 j) * 8 + (lane & 7), j = 0, 1.  Their source indices are
+  // fetched one tile ahead and their records are pulled into L2 while the current tile computes.
+  int src_cur[2], src_nxt[2] = {-1, -1};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) src_cur[j] = src_of((long long)blockIdx.x * 128, (warp + 8 * j) * 8 + (lane & 7));
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long first = (long long)tile * 128;
     const int n_valid = min(128, n - (int)first);
+    const bool has_next = tile + (int)gridDim.x < n_tiles;
+    if (has_next) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        src_nxt[j] = src_of((long long)(tile + gridDim.x) * 128, (warp + 8 * j) * 8 + (lane & 7));
+    }
     // ---- stage G (80 cols) and F_v (48 cols); lanes = 8 rows x 4 chunks
     {
       const int rsub = lane & 7, csub = lane >> 3;
-      for (int rg = warp; rg < 16; rg += 8) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int rg = warp + 8 * j;
         const int r = rg * 8 + rsub;
-        long long src = -1;
-        if (r < n_valid) src = valid1 ? (long long)__ldg(valid1 + first + r) : first + r;
+        const long long src = src_cur[j];     // 64-bit for the row offsets below
         if constexpr (FROM_REC) {
           // RC stored chunks + (1 + V) padding chunks to zero; all loads are issued before the stores
           constexpr int NT = (RC + 1 + V + 3) / 4;
@@ -330,6 +374,7 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
           float v[8];
           for (int kc = csub; kc < 10; kc += 4) {
             load_chunk_mapped(mrow, kc, GMap(), v);
+            if (kc == 8) v[kBiasColHi] = v[kBiasColLo] = 1.0f;      // constant-one columns 70, 71 (base_fc.0 bias)
             st_chunk(G, chunk_off(r, kc, op_sbo(80)), v);
           }
           for (int t = csub; t < 6 * V; t += 4) {
@@ -356,17 +401,28 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
         umma_commit(bar_m);
       }
       wait_round(bar_m, phase);
-      epi32_to_tile(t_row, half * 32, fl + I::bb0, Hb, op_sbo(64), row, 0);
+      epi32_to_tile(t_row, half * 32, Hb, op_sbo(64), row, 0);
       // base_fc.2: 64 → 32, ELU ; keep x_v in registers
       round_sync();
-      if (tid == 0) issue_gemm(h_a, op_sbo(64), wimg + I::Wb1, op_sbo(64), 64, 32, tmem, bar_m);
+      if (tid == 0) issue_gemm_bias(h_a, op_sbo(64), wimg + I::Wb1, 64, 32, ones, ONES_SBO, tmem, bar_m);
       wait_round(bar_m, phase);
       {
         uint32_t r[16];
         tmem_ld16(t_row + half * 16, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[vw][k] = elu_fast(__uint_as_float(r[k]) + fl[I::bb1 + half * 16 + k]);
+        for (int k = 0; k < 16; ++k) x[vw][k] = elu_scaled(__uint_as_float(r[k]));
+      }
+    }
+    if constexpr (FROM_REC) {
+      if (has_next) {     // pull the next tile's records into L2 (one 128-byte line per lane of the row quad)
+        const int csub = lane >> 3;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (src_nxt[j] >= 0 && csub * 128 < RC * 16) {
+            const char* p = reinterpret_cast<const char*>(rec + (long long)src_nxt[j] * RC) + csub * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          }
       }
     }
     // all F_v consumed → reuse F for Xs_v = x_v / V (vis_fc input, trainhead.py:140)
@@ -383,24 +439,30 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
     round_sync();
     if (tid == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 32);
-      for (int vw = 0; vw < V; ++vw)
+      for (int vw = 0; vw < V; ++vw) {
         for (int k16 = 0; k16 < 2; ++k16)
           umma_bf16(tmem + vw * 32, make_smem_desc(f_a + vw * X_STRIDE + k16 * 2 * kLBO, kLBO, op_sbo(32)),
-                    make_smem_desc(wimg + I::Wv0 + k16 * 2 * kLBO, kLBO, op_sbo(32)), idesc, k16 > 0);
+                    make_smem_desc(wimg + I::Wv0 + k16 * 2 * kLBO, kLBO, op_sbo(48)), idesc, k16 > 0);
+        umma_bf16(tmem + vw * 32, make_smem_desc(ones, kLBO, ONES_SBO),
+                  make_smem_desc(wimg + I::Wv0 + 2 * 2 * kLBO, kLBO, op_sbo(48)), idesc, 1u);
+      }
       umma_commit(bar_m);
     }
     wait_round(bar_m, phase);
 #pragma unroll
     for (int vw = 0; vw < V; ++vw)   // Y_v → G region (G and H are free now)
-      epi16_to_tile(t_row + vw * 32, half * 16, fl + I::vb0, G + vw * X_STRIDE, op_sbo(32), row, 0);
+      epi16_to_tile(t_row + vw * 32, half * 16, G + vw * X_STRIDE, op_sbo(32), row, 0);
     // vis_fc.2, residual, flatten view-major → flat [128 x 32V] in F
     round_sync();
     if (tid == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 32);
-      for (int vw = 0; vw < V; ++vw)
+      for (int vw = 0; vw < V; ++vw) {
         for (int k16 = 0; k16 < 2; ++k16)
           umma_bf16(tmem + vw * 32, make_smem_desc(g_a + vw * X_STRIDE + k16 * 2 * kLBO, kLBO, op_sbo(32)),
-                    make_smem_desc(wimg + I::Wv1 + k16 * 2 * kLBO, kLBO, op_sbo(32)), idesc, k16 > 0);
+                    make_smem_desc(wimg + I::Wv1 + k16 * 2 * kLBO, kLBO, op_sbo(48)), idesc, k16 > 0);
+        umma_bf16(tmem + vw * 32, make_smem_desc(ones, kLBO, ONES_SBO),
+                  make_smem_desc(wimg + I::Wv1 + 2 * 2 * kLBO, kLBO, op_sbo(48)), idesc, 1u);
+      }
       umma_commit(bar_m);
     }
     wait_round(bar_m, phase);
@@ -414,18 +476,18 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          v[e] = x[vw][j * 8 + e] + elu_fast(__uint_as_float(r[j * 8 + e]) + fl[I::vb1 + half * 16 + j * 8 + e]);
+          v[e] = x[vw][j * 8 + e] + elu_scaled(__uint_as_float(r[j * 8 + e]));
         st_chunk(F, chunk_off(row, vw * 4 + half * 2 + j, op_sbo(32 * V)), v);
       }
     }
     // rgb_fc.0: 32V → 32, ELU → Z in G
     round_sync();
-    if (tid == 0) issue_gemm(f_a, op_sbo(32 * V), wimg + I::Wr0, op_sbo(32 * V), 32 * V, 32, tmem, bar_m);
+    if (tid == 0) issue_gemm_bias(f_a, op_sbo(32 * V), wimg + I::Wr0, 32 * V, 32, ones, ONES_SBO, tmem, bar_m);
     wait_round(bar_m, phase);
-    epi16_to_tile(t_row, half * 16, fl + I::rb0, G, op_sbo(32), row, 0);
+    epi16_to_tile(t_row, half * 16, G, op_sbo(32), row, 0);
     // rgb_fc.2: 32 → 16, ELU ; rgb_fc.4: 16 → 3 on CUDA cores ; sigmoid
     round_sync();
-    if (tid == 0) issue_gemm(g_a, op_sbo(32), wimg + I::Wr1, op_sbo(32), 32, 16, tmem, bar_m);
+    if (tid == 0) issue_gemm_bias(g_a, op_sbo(32), wimg + I::Wr1, 32, 16, ones, ONES_SBO, tmem, bar_m);
     wait_round(bar_m, phase);
     if (half == 0) {
       uint32_t r[16];
@@ -434,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
       float o0 = fl[I::rb2], o1 = fl[I::rb2 + 1], o2 = fl[I::rb2 + 2];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const float h = elu_fast(__uint_as_float(r[k]) + fl[I::rb1 + k]);
+        const float h = elu_scaled(__uint_as_float(r[k]));
         o0 = fmaf(h, fl[I::rw2 + k], o0);
         o1 = fmaf(h, fl[I::rw2 + 16 + k], o1);
         o2 = fmaf(h, fl[I::rw2 + 32 + k], o2);
@@ -446,6 +508,8 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
         rgb[dst * 3 + 2] = sigmoid_fast(o2);
       }
     }
+    src_cur[0] = src_nxt[0];
+    src_cur[1] = src_nxt[1];
   }
   tc_fence_before();
   __syncthreads();

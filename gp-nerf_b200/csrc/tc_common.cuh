@@ -10,6 +10,7 @@
 // core-matrix reads are both bank-conflict free.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,10 +34,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep, do not poll
       : "memory");
   return ok;
 }
@@ -44,7 +45,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 50000000u) __trap();
+    if (++spins > 4000000u) __trap();
   }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -113,14 +114,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;  // descriptor version
   return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
-// instruction descriptor for kind::f16: bf16 x bf16 → fp32, both K-major
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// instruction descriptor for kind::f16: (bf16 | fp16) x (bf16 | fp16) → fp32, both K-major
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1;
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
   return (1u << 4)                         // c_format  = F32
-         | (1u << 7)                       // a_format  = BF16
-         | (1u << 10)                      // b_format  = BF16
+         | (fmt << 7)                      // a_format
+         | (fmt << 10)                     // b_format
          | ((uint32_t)(N >> 3) << 17)      // n_dim
          | ((uint32_t)(M >> 4) << 24);     // m_dim
 }
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return make_idesc(M, N, kFmtBF16); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -147,6 +150,24 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_addr, uint32_t a_sbo, uint
   }
   umma_commit(bar);
 }
+// Same with the layer's bias folded in: B is [N x (Kp+16)], its last K block holds the bias (hi, lo
+// bf16 split) in columns 6 and 7; `ones_addr` is a [128 x 16] bf16 A block whose columns 6, 7 are 1.0
+// and whose columns 8..15 are zero (columns 0..5 meet zeros in B).  `fmt` is the format of the first
+// Kp columns of A and B (the bias block is always bf16).
+__device__ __forceinline__ void issue_gemm_bias(uint32_t a_addr, uint32_t a_sbo, uint32_t b_addr, int Kp, int N,
+                                                uint32_t ones_addr, uint32_t ones_sbo, uint32_t tmem_d,
+                                                uint64_t* bar, uint32_t fmt = kFmtBF16) {
+  const uint32_t idesc = make_idesc(128, N, fmt);
+  const uint32_t b_sbo = (uint32_t)((Kp + 16) / 8) * kLBO;
+  for (int k16 = 0; k16 < Kp / 16; ++k16) {
+    const uint64_t ad = make_smem_desc(a_addr + k16 * 2 * kLBO, kLBO, a_sbo);
+    const uint64_t bd = make_smem_desc(b_addr + k16 * 2 * kLBO, kLBO, b_sbo);
+    umma_bf16(tmem_d, ad, bd, idesc, k16 > 0 ? 1u : 0u);
+  }
+  umma_bf16(tmem_d, make_smem_desc(ones_addr, kLBO, ones_sbo),
+            make_smem_desc(b_addr + (Kp / 16) * 2 * kLBO, kLBO, b_sbo), make_idesc_bf16(128, N), 1u);
+  umma_commit(bar);
+}
 
 // byte offset of the 16-byte chunk holding k = 8*kc .. 8*kc+7 of row r
 __device__ __forceinline__ uint32_t chunk_off(int r, int kc, uint32_t sbo) {
@@ -166,6 +187,19 @@ __device__ __forceinline__ void st_chunk(uint8_t* tile, uint32_t off, const floa
   *reinterpret_cast<uint4*>(tile + off) = q;
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st_chunk_f16(uint8_t* tile, uint32_t off, const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_f16x2(v[0], v[1]);
+  q.y = pack_f16x2(v[2], v[3]);
+  q.z = pack_f16x2(v[4], v[5]);
+  q.w = pack_f16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + off) = q;
+}
+
 // ELU for activations that are about to be rounded to bf16
 // (one FMUL + MUFU.EX2 with flush-to-zero: the denormal-preserving __expf costs three more
 // instructions per element, and these epilogues are issue bound)
@@ -177,6 +211,17 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 __device__ __forceinline__ float elu_fast(float x) {
   const float e = ex2_ftz(x * 1.4426950408889634f) - 1.0f;
   return x > 0.0f ? x : e;
+}
+// The head kernels keep every hidden activation multiplied by c = log2(e): the first layer's
+// weights and all biases are packed pre-scaled (the bias sits in the B operand, see
+// issue_gemm_bias), so the accumulator already holds y = c·(W·a + b) and
+//     c·ELU(y / c) = y > 0 ? y : c·2^y − c
+// is MUFU.EX2 + FFMA + compare/select: no bias add, no pre-multiply.  The last (CUDA-core) layer of
+// each head is packed with its weights divided by c.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float elu_scaled(float y) {
+  const float e = fmaf(ex2_ftz(y), kLog2e, -kLog2e);
+  return y > 0.0f ? y : e;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) {
   return __frcp_rn(1.0f + ex2_ftz(-1.4426950408889634f * x));

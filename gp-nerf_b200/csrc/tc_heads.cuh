@@ -16,9 +16,14 @@ __host__ __device__ constexpr uint32_t op_bytes(int rows, int Kp) { return (uint
 // come first and the 3 RGB channels after them (the reference order is RGB
 // first, BaseRender.py:358).  Weights are packed with the same permutation, so
 // the products are unchanged.
-//   G tile (80 cols): mean_feat 32 | var_feat 32 | mean_rgb 3, var_rgb 3, 0, 0 | 0×8
+//   G tile (80 cols): mean_feat 32 | var_feat 32 | mean_rgb 3, var_rgb 3, 1, 1 | 0×8
 //   F tile (48 cols): feat 32 | rgb 3, 0×5 | 0×8
+// Columns 70, 71 of the G tile are the constant 1.0: the layers that read the G
+// tile carry their bias (bf16 hi + lo) in those two columns of the weight
+// operand, and the tile's last K block (columns 64..79) doubles as the "ones"
+// A block of issue_gemm_bias for the other layers of the density head.
 // ---------------------------------------------------------------------------
+constexpr int kBiasColHi = 6, kBiasColLo = 7;   // position of the ones inside a bias K block
 // column j of the G tile → index into the reference's [mean 35 | var 35] row (or -1)
 __host__ __device__ inline int gmap(int j) {
   if (j < 32) return 3 + j;
@@ -37,28 +42,30 @@ __host__ __device__ inline int fmap(int j) {
 // ---------------------------------------------------------------------------
 // packed weight images (bf16 UMMA operands + fp32 biases / last layers)
 // ---------------------------------------------------------------------------
+// Scaling (tc_common.cuh, elu_scaled): operands that multiply raw gathered features are packed
+// times c = log2(e), every bias times c, the CUDA-core last layers divided by c.
 struct DenImg {   // density head
-  static constexpr uint32_t Wg = 0;                                 // [64 x 128]
-  static constexpr uint32_t W0 = Wg + op_bytes(64, 128);            // [64 x 144] = sigma_feat 64 | G order 80
-  static constexpr uint32_t W1 = W0 + op_bytes(64, 144);            // [32 x 64]
-  static constexpr uint32_t W2 = W1 + op_bytes(32, 64);             // [16 x 32]
-  static constexpr uint32_t F32 = W2 + op_bytes(16, 32);            // floats below
-  static constexpr int bg = 0, b0 = 64, b1 = 128, b2 = 160, w3 = 176, b3 = 192, NF = 196;
+  static constexpr uint32_t Wg = 0;                                 // [64 x 144] = c·Wg as FP16 (128) | bias block
+  static constexpr uint32_t W0 = Wg + op_bytes(64, 144);            // [64 x 144] = sigma_feat 64 | G order 80 (bias in 70,71)
+  static constexpr uint32_t W1 = W0 + op_bytes(64, 144);            // [32 x 80]  = 64 | bias block
+  static constexpr uint32_t W2 = W1 + op_bytes(32, 80);             // [16 x 48]  = 32 | bias block
+  static constexpr uint32_t F32 = W2 + op_bytes(16, 48);            // floats below
+  static constexpr int w3 = 0, b3 = 16, NF = 20;                    // w3 / c, b3
   static constexpr uint32_t BYTES = F32 + NF * 4;
 };
 static_assert(DenImg::BYTES % 16 == 0, "bulk copy needs 16-byte multiples");
 
 template <int V>
 struct ColImg {   // colour head; base_fc.0 split into its [mean|var] (G order) and per-view (F order) blocks
-  static constexpr uint32_t Wb0a = 0;                               // [64 x 80]
-  static constexpr uint32_t Wb0b = Wb0a + op_bytes(64, 80);         // [64 x 48]
-  static constexpr uint32_t Wb1 = Wb0b + op_bytes(64, 48);          // [32 x 64]
-  static constexpr uint32_t Wv0 = Wb1 + op_bytes(32, 64);           // [32 x 32]
-  static constexpr uint32_t Wv1 = Wv0 + op_bytes(32, 32);           // [32 x 32]
-  static constexpr uint32_t Wr0 = Wv1 + op_bytes(32, 32);           // [32 x 32V]
-  static constexpr uint32_t Wr1 = Wr0 + op_bytes(32, 32 * V);       // [16 x 32]
-  static constexpr uint32_t F32 = Wr1 + op_bytes(16, 32);
-  static constexpr int bb0 = 0, bb1 = 64, vb0 = 96, vb1 = 128, rb0 = 160, rb1 = 192, rw2 = 208, rb2 = 256, NF = 260;
+  static constexpr uint32_t Wb0a = 0;                               // [64 x 80]  c·W, bias in columns 70, 71
+  static constexpr uint32_t Wb0b = Wb0a + op_bytes(64, 80);         // [64 x 48]  c·W
+  static constexpr uint32_t Wb1 = Wb0b + op_bytes(64, 48);          // [32 x 80]  = 64 | bias block
+  static constexpr uint32_t Wv0 = Wb1 + op_bytes(32, 80);           // [32 x 48]
+  static constexpr uint32_t Wv1 = Wv0 + op_bytes(32, 48);           // [32 x 48]
+  static constexpr uint32_t Wr0 = Wv1 + op_bytes(32, 48);           // [32 x (32V+16)]
+  static constexpr uint32_t Wr1 = Wr0 + op_bytes(32, 32 * V + 16);  // [16 x 48]
+  static constexpr uint32_t F32 = Wr1 + op_bytes(16, 48);
+  static constexpr int rw2 = 0, rb2 = 48, NF = 52;                  // rgb_fc.4 weights / c, bias
   static constexpr uint32_t BYTES = F32 + NF * 4;
 };
 
@@ -72,9 +79,8 @@ __host__ __device__ constexpr int rec_chunks(int V) { return 9 + 5 * V; }
 // ---------------------------------------------------------------------------
 // epilogue helpers
 // ---------------------------------------------------------------------------
-// accumulator columns [c0, c0+32) of this thread's row → bias + ELU → 4 bf16 chunks
-__device__ __forceinline__ void epi32_to_tile(uint32_t taddr, int c0, const float* __restrict__ bias, uint8_t* tile,
-                                              uint32_t sbo, int row, int kc0) {
+// accumulator columns [c0, c0+32) of this thread's row → scaled ELU → 4 bf16 chunks
+__device__ __forceinline__ void epi32_to_tile(uint32_t taddr, int c0, uint8_t* tile, uint32_t sbo, int row, int kc0) {
   uint32_t r[32];
   tmem_ld32(taddr + c0, r);
   tmem_wait_ld();
@@ -82,12 +88,11 @@ __device__ __forceinline__ void epi32_to_tile(uint32_t taddr, int c0, const floa
   for (int j = 0; j < 4; ++j) {
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = elu_fast(__uint_as_float(r[j * 8 + e]) + bias[c0 + j * 8 + e]);
+    for (int e = 0; e < 8; ++e) v[e] = elu_scaled(__uint_as_float(r[j * 8 + e]));
     st_chunk(tile, chunk_off(row, kc0 + (c0 >> 3) + j, sbo), v);
   }
 }
-__device__ __forceinline__ void epi16_to_tile(uint32_t taddr, int c0, const float* __restrict__ bias, uint8_t* tile,
-                                              uint32_t sbo, int row, int kc0) {
+__device__ __forceinline__ void epi16_to_tile(uint32_t taddr, int c0, uint8_t* tile, uint32_t sbo, int row, int kc0) {
   uint32_t r[16];
   tmem_ld16(taddr + c0, r);
   tmem_wait_ld();
@@ -95,16 +100,15 @@ __device__ __forceinline__ void epi16_to_tile(uint32_t taddr, int c0, const floa
   for (int j = 0; j < 2; ++j) {
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = elu_fast(__uint_as_float(r[j * 8 + e]) + bias[c0 + j * 8 + e]);
+    for (int e = 0; e < 8; ++e) v[e] = elu_scaled(__uint_as_float(r[j * 8 + e]));
     st_chunk(tile, chunk_off(row, kc0 + (c0 >> 3) + j, sbo), v);
   }
 }
 template <int N>
-__device__ __forceinline__ void epilogue_elu_to_tile(uint32_t taddr, const float* __restrict__ bias, uint8_t* tile,
-                                                     uint32_t sbo, int row, int kc0) {
+__device__ __forceinline__ void epilogue_elu_to_tile(uint32_t taddr, uint8_t* tile, uint32_t sbo, int row, int kc0) {
   static_assert(N % 32 == 0, "");
 #pragma unroll
-  for (int c = 0; c < N / 32; ++c) epi32_to_tile(taddr, c * 32, bias, tile, sbo, row, kc0);
+  for (int c = 0; c < N / 32; ++c) epi32_to_tile(taddr, c * 32, tile, sbo, row, kc0);
 }
 
 // make the operand stores visible to the tensor core, order the TMEM reads

@@ -223,10 +223,10 @@ class Engine:
         dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
         if self.level_dims != dims:
             self.level_dims = dims
-            # bf16 path: channel-last bf16 inside a zero border (allocated zeroed once; K0 only ever
-            # writes the interior), so the fused gather needs no bounds tests
+            # tensor-core path: channel-last fp16 inside a zero border (allocated zeroed once; K0 only
+            # ever writes the interior), so the fused gather needs no bounds tests
             if self.bf16:
-                self.levels_cl = [torch.zeros((d + 2) * (h + 2) * (w + 2) * 32, dtype=torch.bfloat16, device=dev)
+                self.levels_cl = [torch.zeros((d + 2) * (h + 2) * (w + 2) * 32, dtype=torch.float16, device=dev)
                                   for d, h, w in dims]
             else:
                 self.levels_cl = [torch.empty(d * h * w * 32, dtype=torch.float32, device=dev) for d, h, w in dims]
@@ -234,16 +234,17 @@ class Engine:
             self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
         assert len(lv) == 4 and all(t.shape[1] == 32 and t.dtype == torch.float32 for t in lv)
         pad = int(self.bf16)
+        storage = 2 if self.bf16 else 0      # 0 fp32 lines, 2 fp16 lines (HFMA2 interpolation)
         for t, (d, h, w), cl, cs in zip(lv, dims, self.levels_cl, self.chan_sums):
             self._run("k0_level_to_channels_last", L.gpnerf_k0_level_to_channels_last, ptr(t), d, h, w,
-                      int(self.bf16), pad, ptr(cl), ptr(cs), st)
+                      storage, pad, ptr(cl), ptr(cs), st)
         V, Cc, fh, fw = fm.shape
         assert V == self.V and Cc == 32
         n_fm = V * (fh + 2 * pad) * (fw + 2 * pad) * 32
         if self.featmaps_cl is None or self.featmaps_cl.numel() != n_fm:
-            self.featmaps_cl = torch.zeros(n_fm, dtype=torch.bfloat16 if self.bf16 else torch.float32, device=dev)
+            self.featmaps_cl = torch.zeros(n_fm, dtype=torch.float16 if self.bf16 else torch.float32, device=dev)
         self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw,
-                  int(self.bf16), pad, ptr(self.featmaps_cl), st)
+                  storage, pad, ptr(self.featmaps_cl), st)
         _, _, ih, iw = im.shape
         n_im = V * (ih + 2 * pad) * (iw + 2 * pad) * 4
         if self.images_rgbx is None or self.images_rgbx.numel() != n_im:

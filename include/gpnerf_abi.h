@@ -109,14 +109,15 @@ const char *gpnerf_last_error(void);
 int gpnerf_sm_count(void);
 
 /* ---- K0: layout of the upstream products ------------------------------- */
-/* One dense level NCDHW → NDHWC (one line per voxel: 128 B fp32, or 64 B bf16
- * when out_bf16 – the storage the tensor-core path gathers from) plus the
+/* One dense level NCDHW → NDHWC (one line per voxel; `storage`: 0 = 128 B fp32,
+ * 1 = 64 B bf16, 2 = 64 B fp16 saturated at ±65504 – the storage the
+ * tensor-core path gathers from and interpolates with HFMA2) plus the
  * fp32 per-voxel channel sum that SparseConvNet.encode reduces
  * (libs/nerfheads/networks/SparseConvNet.py:135-136).
  * With `pad` the output is written inside a one-voxel border,
  * [D+2][H+2][W+2][32], which the caller zeroes once: gathers from it need no
  * bounds tests (the border is grid_sample's zeros padding). */
-int gpnerf_k0_level_to_channels_last(const float *ncdhw, int D, int H, int W, int out_bf16, int pad,
+int gpnerf_k0_level_to_channels_last(const float *ncdhw, int D, int H, int W, int storage, int pad,
                                      void *ndhwc, float *chan_sum, void *stream);
 /* masks3d on the level-1 grid = Σ_levels nearest-upsampled channel sums
  * (SparseConvNet.py:137-139). */
@@ -125,7 +126,7 @@ int gpnerf_k0_build_masks3d(const float *const chan_sum[GPNERF_N_LEVELS],
 /* encoder maps [V,C=32,h,w] → [V,h,w,32]; images [V,3,H,W] → [V,H,W,4] (RGB,
  * pad); with `unnormalize` the [-1,1] inputs become x*0.5+0.5 on the way
  * (BaseRender.py:231), otherwise they are taken as already in [0,1]. */
-int gpnerf_k0_featmaps_to_channels_last(const float *nchw, int V, int h, int w, int out_bf16, int pad,
+int gpnerf_k0_featmaps_to_channels_last(const float *nchw, int V, int h, int w, int storage, int pad,
                                         void *nhwc, void *stream);   /* pad: [V][h+2][w+2][32] */
 int gpnerf_k0_images_to_rgbx(const float *nchw, int V, int H, int W, int unnormalize, int pad,
                              float *rgbx, void *stream);              /* pad: [V][H+2][W+2][4]  */
@@ -218,15 +219,16 @@ int gpnerf_k3_pack_weights(const gpnerf_head_weights_t *weights_host, int n_view
 /* Gathers (SparseConvNet.py:111-122, BaseRender.py:283-363), mean/variance
  * (trainhead.py:20-24) and the density head (trainhead.py:39-41,102-110,
  * 133-137) in one kernel: gathered features go straight into the shared-memory
- * operand tiles of the tcgen05 GEMM chain.  Inputs are the bf16 channel-last
- * products of K0 (out_bf16 = 1) and the fp32 RGBx images; points are the
+ * operand tiles of the tcgen05 GEMM chain.  Inputs are the fp16 channel-last
+ * zero-bordered products of K0 (storage = 2, pad = 1) and the padded fp32 RGBx
+ * images; points are the
  * ray-parametrised survivors `valid` (count = counters[P1]).  Outputs σ
  * float[P1] and one bf16 record of gpnerf_k23_record_bytes(V) bytes per point
  * ([mean|var] and the V per-view rows in operand order) for
  * gpnerf_k3_color_mlp_records.  n_views in 1..4. */
 int64_t gpnerf_k23_record_bytes(int n_views);
-int gpnerf_k23_gather_density_tc(const void *const levels_bf16[GPNERF_N_LEVELS],
-                                 const void *featmaps_bf16, const float *images_rgbx,
+int gpnerf_k23_gather_density_tc(const void *const levels_f16[GPNERF_N_LEVELS],
+                                 const void *featmaps_f16, const float *images_rgbx,
                                  const int32_t *valid, const float *rays_o, const float *rays_d,
                                  const float *z_vals, const gpnerf_frame_t *frame_host,
                                  const gpnerf_head_weights_t *weights_host, int n_points_max,
