@@ -7,9 +7,19 @@
 One step = one 512×512 novel-view frame of the synthetic ZJU-Mocap-shaped
 scene (BASELINE.json configs[1]): layout of the upstream products (K0), pixel
 mask + rays + box test (K1), occupancy compaction + gathers (K2), density head
-(K3), progressive compaction (K4), colour head (K3), compositing (K5).  At N>1
-the frame's rays are sharded over the ranks by pixel tiles and the image is
-re-assembled by one NCCL all_gather (strong scaling of a single frame).
+(K3), progressive compaction (K4), colour head (K3), compositing (K5).
+
+At N>1 (`--shard`):
+  frames (default)  one frame per GPU and step – a sweep of N novel views of the
+                    scene (rank r renders the ring camera at 45° + 360°·r/N);
+                    every finished pixel tile is written by K5 straight into slot
+                    r of rank 0's image buffer over NVLink (peer memory, no NCCL
+                    on the data path).  Per-GPU work is fixed: weak scaling.
+  tiles             ONE frame, its pixel tiles dealt over the ranks; K5 writes each
+                    tile into every rank's image (all ranks hold the full frame).
+                    Strong scaling of a 0.8 ms frame: the replicated K0/K1 passes
+                    bound it.
+`--collective nccl` replaces the peer-memory writes by one NCCL all_gather.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident
 in HBM; `e2e` goes through Renderer.render(batch) with pinned host inputs and
@@ -48,6 +58,8 @@ def parse():
     ap.add_argument("--scene", default="zju", choices=["zju", "dense"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--tile-px", type=int, default=64)
+    ap.add_argument("--shard", default="frames", choices=["frames", "tiles"])
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
@@ -113,6 +125,8 @@ def stage_work(counts, n_level_elems, V):
     P, P1, P2 = counts["n_rays"] * S_SAMPLES, counts["P1"], counts["P2"]
     return {
         "k0_level_to_channels_last": ("hbm", 8.0 * n_level_elems / 4, "all 4 calls: 4 B read + 4 B written per element"),
+        "k0_products_to_f16": ("hbm", 6.0 * n_level_elems / 4 + 4.0 * n_level_elems / 4 / 32,
+                               "4 B read + 2 B written per element, 4 B channel sum per voxel"),
         "k2_occupancy_compact": ("hbm", 36.0 * P, "32 B tap + 4 B z per point"),
         "k2_gather_volume": ("hbm", 4096.0 * P1, "4 levels x 8 corners x 32 ch x 4 B per point"),
         "k2_project_gather_meanvar": ("hbm", V * 4 * 35 * 4.0 * P1, "V x 4 corners x 35 ch x 4 B per point"),
@@ -168,7 +182,7 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": len(times) / total,
         "config": {"workload": f"zju-like synthetic frame, {RES}x{RES}, V={VIEWS}, S={S_SAMPLES} (BASELINE configs[1])",
                    "rays": rays, "P1": out["P1"], "P2": out["P2"]},
@@ -205,6 +219,9 @@ def main():
     prec = PREC_BF16 if args.precision == "bf16" else PREC_FP32
 
     scene = synth.make_scene("zju", H=RES, W=RES, V=VIEWS, seed=42)
+    frames_mode = world > 1 and args.shard == "frames"
+    if frames_mode:          # rank r renders its own novel view of the sweep
+        scene = synth.retarget(scene, 45.0 + 360.0 * rank / world)
     weights = synth.make_head_weights(V=VIEWS, seed=42)
     head = NeRFHead(code_dim=32, n_views=VIEWS, precision=prec)
     sd = head.state_dict()
@@ -212,7 +229,8 @@ def main():
     head.load_state_dict(sd)
     head = head.to(dev)
     renderer = Renderer(None, head, is_train=False, n_samples=S_SAMPLES, progressive=True, precision=prec,
-                        rank=rank, world=world, tile_px=args.tile_px, use_cuda_graph=not args.no_graph)
+                        rank=rank, world=world, tile_px=args.tile_px, use_cuda_graph=not args.no_graph,
+                        shard=args.shard, collective=args.collective)
     n_px = RES * RES
 
     # ---- device-resident inputs for `value`
@@ -236,9 +254,13 @@ def main():
             step_eager()
         else:
             eng.run_progressive_graphed(frame)      # K0…K5 as one CUDA-graph launch
-        if world > 1:
+        if world > 1 and eng.exchange is None:          # --collective nccl
+            if frames_mode:
+                out = torch.empty(world * n_px, 3, device=dev)
+                dist.all_gather_into_tensor(out, eng.pred_img.view(n_px, 3))
+                return out
             return shard.gather_frame(eng.pred_img.view(n_px, 3), RES, args.tile_px)
-        return eng.pred_img
+        return eng.result_image()
 
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
@@ -251,6 +273,18 @@ def main():
         g_rays, g_p1, g_p2 = [int(v) for v in tot.tolist()]
     else:
         g_rays, g_p1, g_p2 = counts["n_rays"], counts["P1"], counts["P2"]
+    # did the tiles written by the peers land?  (hit flags in rank 0's buffers vs. the ranks' ray counts)
+    peer_check = None
+    if world > 1:
+        mine = torch.tensor([counts["n_rays"]], device=dev, dtype=torch.long)
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
+        if eng.exchange is not None and rank == 0:
+            if frames_mode:
+                ok = all(int(eng.exchange.hit_mask(slot=r).sum()) == int(per_rank[r]) for r in range(world))
+            else:
+                ok = int(eng.exchange.hit_mask().sum()) == g_rays
+            peer_check = "ok" if ok else "MISMATCH"
 
     # ---- timed region: exactly K steps, device-timed, L2 flushed between steps
     sampler = ClockSampler(local_rank)
@@ -385,15 +419,21 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None,
+        "scaling": "weak" if (frames_mode or world == 1) else "strong", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "frames_per_s": 1e3 / ms_per_step, "pixel_rays_per_s": n_px * 1e3 / ms_per_step,
         "config": {"workload": f"zju-like synthetic frame {RES}x{RES}, V={VIEWS}, S={S_SAMPLES} "
                                "(BASELINE configs[1], trainzju_valzju inference shape), progressive path",
                    "rays": g_rays, "points": g_rays * S_SAMPLES, "P1": g_p1, "P2": g_p2,
                    "l2": "256 MB flush between timed steps; inputs 135 MB > 126 MB L2",
-                   "sharding": f"pixel tiles of {args.tile_px}, round-robin over {world} rank(s); "
-                               "one NCCL all_gather of tiles per frame" if world > 1 else "single GPU",
+                   "sharding": ("single GPU" if world == 1 else
+                                (f"one frame per GPU and step (sweep of {world} novel views), images gathered on rank 0"
+                                 if frames_mode else
+                                 f"one frame, pixel tiles of {args.tile_px} dealt diagonally over {world} ranks") +
+                                ("; K5 writes the tiles into the peers' images over NVLink (CUDA-IPC peer memory, "
+                                 "arrival flags; no NCCL on the data path)" if eng.exchange is not None else
+                                 "; one NCCL all_gather per step")),
+                   "peer_check": peer_check,
                    "launch": "eager, one launch per kernel" if args.no_graph else
                              "one CUDA-graph replay per frame (frame constants through a pinned buffer)",
                    "stages_ms_from": "eager re-issue of the same steps with CUDA events around every stage",

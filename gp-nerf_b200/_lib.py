@@ -35,6 +35,18 @@ class Frame(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class Peer(C.Structure):
+    """gpnerf_peer_t"""
+    _fields_ = [
+        ("n_dst", C.c_int32), ("n_flag", C.c_int32), ("seq", C.c_int32), ("reserved_", C.c_int32),
+        ("dst_img", C.c_uint64 * MAX_PEERS), ("dst_hit", C.c_uint64 * MAX_PEERS),
+        ("dst_flag", C.c_uint64 * MAX_PEERS), ("ticket", C.c_uint64),
+    ]
+
+
 class HeadWeights(C.Structure):
     """gpnerf_head_weights_t"""
     _fields_ = [
@@ -55,12 +67,15 @@ _SIGNATURES = {
     "gpnerf_sm_count": ([], C.c_int),
     "gpnerf_workspace_bytes": ([C.c_int64], C.c_int64),
     "gpnerf_k0_level_to_channels_last": ([_P, _I, _I, _I, _I, _I, _P, _P, _P], C.c_int),
+    "gpnerf_k0_products_to_f16": ([C.POINTER(_P), C.POINTER(C.c_int32 * 3), _P, _I, _I, _I, C.POINTER(_P),
+                                   C.POINTER(_P), _P, _P], C.c_int),
     "gpnerf_k0_build_masks3d": ([C.POINTER(_P), C.POINTER(Frame), _P, _P], C.c_int),
     "gpnerf_k0_featmaps_to_channels_last": ([_P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
     "gpnerf_k0_images_to_rgbx": ([_P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
     "gpnerf_k1_voxel_pixel_mask": ([_P, C.POINTER(Frame), _P, _P, _P], C.c_int),
-    "gpnerf_k1_rays_bbox": ([_P, _P, C.POINTER(Frame), _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
-    "gpnerf_k2_occupancy_compact": ([_P, _P, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k1_rays_bbox": ([_P, _P, C.POINTER(Frame), _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k2_occupancy_compact": ([_P, _P, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P, _P, _P, _P],
+                                    C.c_int),
     "gpnerf_k2_gather_volume": ([C.POINTER(_P), _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),
     "gpnerf_k2_project_gather_meanvar": ([_P, _P, _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k2_mean_variance": ([_P, _I, _I, _P, _P], C.c_int),
@@ -82,7 +97,13 @@ _SIGNATURES = {
     "gpnerf_k6_meanvar_bwd": ([_P, _P, _P, _I, C.c_longlong, _P, _P], C.c_int),
     "gpnerf_k6_from_channels_last": ([_P, _I, C.c_longlong, _P, _P], C.c_int),
     "gpnerf_k4_compact_alpha": ([_P, _I, _P, _P, _P, _P, _P], C.c_int),
-    "gpnerf_k5_composite": ([_P, _P, _P, _P, C.POINTER(Frame), _I, _P, C.c_float, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k5_composite": ([_P, _P, _P, _P, _P, C.POINTER(Frame), C.c_float, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_peer_wait": ([_P, _I, _I, _P, _P], C.c_int),
+    "gpnerf_peer_handle_bytes": ([], C.c_int),
+    "gpnerf_peer_alloc": ([C.c_int64, C.POINTER(_P), _P], C.c_int),
+    "gpnerf_peer_open": ([_P, C.POINTER(_P)], C.c_int),
+    "gpnerf_peer_close": ([_P], C.c_int),
+    "gpnerf_peer_free": ([_P], C.c_int),
     "gpnerf_k5_raw2outputs": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k5_raw2outputs_bwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
 }
@@ -111,7 +132,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = restype
-    if lib.gpnerf_abi_version() != 1:
+    if lib.gpnerf_abi_version() != 2:
         raise GpnerfError("libgpnerf_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(1024) compact_scan(const int32_t* __restrict__
                                                      const int32_t* n_src, int mult,
                                                      long long n_const,
                                                      int32_t* __restrict__ tile_offs,
-                                                     int32_t* __restrict__ out_count) {
+                                                     int32_t* __restrict__ out_count, int row_len,
+                                                     int32_t* __restrict__ row_begin) {
   const long long n_items = live_count(n_src, mult, n_const);
   const long long n_words = (n_items + 31) >> 5;
   const int n_tiles = (int)((n_words + kTileWords - 1) / kTileWords);
@@ -116,7 +117,10 @@ __global__ void __launch_bounds__(1024) compact_scan(const int32_t* __restrict__
     if (threadIdx.x == 1023) carry_s = excl + v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out_count = carry_s;
+  if (threadIdx.x == 0) {
+    *out_count = carry_s;
+    if (row_begin != nullptr) row_begin[(n_items + row_len - 1) / row_len] = carry_s;   // CSR sentinel
+  }
 }
 
 // --- pass C: expand bit words into ascending indices -----------------------
@@ -124,7 +128,8 @@ __global__ void __launch_bounds__(kTileWords) compact_expand(const uint32_t* __r
                                                              const int32_t* __restrict__ tile_offs,
                                                              const int32_t* n_src, int mult,
                                                              long long n_const,
-                                                             int32_t* __restrict__ out_idx) {
+                                                             int32_t* __restrict__ out_idx, int row_len,
+                                                             int32_t* __restrict__ row_begin) {
   const long long n_items = live_count(n_src, mult, n_const);
   const long long n_words = (n_items + 31) >> 5;
   const long long n_tiles = (n_words + kTileWords - 1) / kTileWords;
@@ -152,24 +157,31 @@ __global__ void __launch_bounds__(kTileWords) compact_expand(const uint32_t* __r
     // a warp expands one word at a time: coalesced index writes
     for (int wl = wid; wl < kTileWords; wl += NW) {
       const uint32_t b = word_bits[wl];
+      const unsigned item = (unsigned)((tile * kTileWords + wl) * 32 + lane);     // item counts stay below 2^31
+      const int rank = __popc(b & ((1u << lane) - 1u));
+      if (row_begin != nullptr && item < (unsigned)n_items && item % (unsigned)row_len == 0u)
+        row_begin[item / (unsigned)row_len] = word_off[wl] + rank;
       if (b == 0u) continue;
-      if ((b >> lane) & 1u) {
-        const int rank = __popc(b & ((1u << lane) - 1u));
-        out_idx[word_off[wl] + rank] = (int32_t)((tile * kTileWords + wl) * 32 + lane);
-      }
+      if ((b >> lane) & 1u) out_idx[word_off[wl] + rank] = (int32_t)item;
     }
     __syncthreads();
   }
 }
 
 int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t n_const,
-                   int64_t n_items_max, int32_t* out_idx, int32_t* out_count, cudaStream_t st) {
+                   int64_t n_items_max, int32_t* out_idx, int32_t* out_count, cudaStream_t st, int row_len,
+                   int32_t* row_begin) {
+  if (row_begin == nullptr || row_len <= 0) {
+    row_begin = nullptr;
+    row_len = 1;
+  }
   int64_t n_words = div_up(n_items_max, 32);
   int64_t n_tiles = div_up(n_words, kTileWords);
   int grid = (int)(n_tiles < (int64_t)sm_count() * 8 ? (n_tiles > 0 ? n_tiles : 1) : sm_count() * 8);
   compact_tile_sums<<<grid, kTileWords, 0, st>>>(ws.words, n_src, mult, n_const, ws.tile_sums);
-  compact_scan<<<1, 1024, 0, st>>>(ws.tile_sums, n_src, mult, n_const, ws.tile_offs, out_count);
-  compact_expand<<<grid, kTileWords, 0, st>>>(ws.words, ws.tile_offs, n_src, mult, n_const, out_idx);
+  compact_scan<<<1, 1024, 0, st>>>(ws.tile_sums, n_src, mult, n_const, ws.tile_offs, out_count, row_len, row_begin);
+  compact_expand<<<grid, kTileWords, 0, st>>>(ws.words, ws.tile_offs, n_src, mult, n_const, out_idx, row_len,
+                                              row_begin);
   return check_launch("compact");
 }
 

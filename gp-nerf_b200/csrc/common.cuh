@@ -165,9 +165,13 @@ struct CompactWs {
   int32_t* tile_offs;
 };
 CompactWs carve_workspace(void* ws, int64_t n_items_max);
-// launches the three passes; out_count_slot receives the total
+// launches the three passes; out_count_slot receives the total.  With `row_begin` the items are also
+// seen as rows of `row_len` consecutive items (a ray's samples, a tile's pixels) and
+// row_begin[r] = number of survivors before row r (CSR offsets, row_begin[n_rows] = total) comes out of
+// the same passes.
 int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t n_const,
-                   int64_t n_items_max, int32_t* out_idx, int32_t* out_count, cudaStream_t st);
+                   int64_t n_items_max, int32_t* out_idx, int32_t* out_count, cudaStream_t st,
+                   int row_len = 0, int32_t* row_begin = nullptr);
 
 __device__ __forceinline__ long long live_count(const int32_t* n_src, int mult, long long n_const) {
   return n_src ? (long long)__ldg(n_src) * mult : n_const;

@@ -7,6 +7,8 @@
 // transaction.  The same pass produces the per-voxel channel sum that
 // SparseConvNet.encode reduces into masks3d (SparseConvNet.py:135-139).
 // Pure HBM streaming: 4 B read + 4 B written per element.
+#include <string.h>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -133,6 +135,111 @@ __global__ void __launch_bounds__(256) to_channels_last_32(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------
+// One launch for everything the tensor-core path gathers from: the 4 dense
+// levels and the V encoder maps, channel-first fp32 → channel-last fp16 inside
+// a zero border, plus the per-voxel channel sums of the levels.
+//   tile = 32 channels × 256 positions, 256 threads
+//   load : warp w reads channels w, w+8, w+16, w+24 – two float4 per lane and
+//          channel (1 KB contiguous per warp instruction), 8 loads in flight
+//   smem : idx(c, p) = c·256 + (p ^ ((c >> 3) << 3)): float4 writes along p and
+//          the 8-channel reads of the store phase are both conflict-free
+//   store: 4 lanes per voxel, 16 B each → 8 voxels = 512 contiguous bytes per
+//          warp instruction
+// ---------------------------------------------------------------------------
+constexpr int kMaxJobs = GPNERF_N_LEVELS + 1;
+struct LayoutJob {
+  const float* src;      // [batch][32][n]
+  __half* dst;           // [batch][(D+2)][(H+2)][(W+2)][32] (pad_z) or [batch][(H+2)][(W+2)][32]
+  float* chan_sum;       // [n] or NULL
+  unsigned n, H, W;      // positions per batch entry, extents of the two fastest dims
+  unsigned sz, sy, off;  // padded strides of z, y and offset of element (0,0,0), in voxels
+  unsigned batch, batch_stride_out;   // entries, padded voxels per entry
+  unsigned tile0, tiles_per_batch;    // first global tile of the job, tiles per batch entry
+};
+struct LayoutJobs {
+  LayoutJob j[kMaxJobs];
+  int n_jobs;
+  unsigned n_tiles;
+};
+
+__global__ void __launch_bounds__(256) products_to_channels_last_f16(const __grid_constant__ LayoutJobs jobs) {
+  constexpr int TP = 256;
+  __shared__ __align__(16) float tile[32 * TP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (unsigned t = blockIdx.x; t < jobs.n_tiles; t += gridDim.x) {
+    int ji = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxJobs; ++k)
+      if (k < jobs.n_jobs && t >= jobs.j[k].tile0) ji = k;
+    const LayoutJob& J = jobs.j[ji];
+    const unsigned lt = t - J.tile0;
+    const unsigned b = lt / J.tiles_per_batch;
+    const unsigned v0 = (lt - b * J.tiles_per_batch) * TP;
+    const float* src = J.src + (size_t)b * 32 * J.n;
+    const bool vec_ok = (J.n % 4 == 0);
+    // ---- load phase
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = warp + 8 * i;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const unsigned p = hf * 128 + 4 * lane;
+        const unsigned v = v0 + p;
+        const float* g = src + (size_t)c * J.n + v;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec_ok && v + 3 < J.n) {
+          x = __ldg(reinterpret_cast<const float4*>(g));
+        } else {
+          if (v < J.n) x.x = __ldg(g);
+          if (v + 1 < J.n) x.y = __ldg(g + 1);
+          if (v + 2 < J.n) x.z = __ldg(g + 2);
+          if (v + 3 < J.n) x.w = __ldg(g + 3);
+        }
+        *reinterpret_cast<float4*>(&tile[c * TP + (p ^ ((c >> 3) << 3))]) = x;
+      }
+    }
+    __syncthreads();
+    // ---- channel sums (exact: c ascending, one rounding per add)
+    if (J.chan_sum != nullptr && v0 + tid < J.n) {
+      float sum = tile[tid];
+#pragma unroll
+      for (int c = 1; c < 32; ++c) sum = xadd(sum, tile[c * TP + (tid ^ ((c >> 3) << 3))]);
+      J.chan_sum[v0 + tid] = sum;
+    }
+    // ---- store phase: warp w owns positions [32w, 32w+32), 8 voxels per step
+    {
+      const int i = lane >> 2, j = lane & 3;
+      __half* dst = J.dst + (size_t)b * J.batch_stride_out * 32;
+#pragma unroll
+      for (int step = 0; step < 4; ++step) {
+        const unsigned p = warp * 32 + step * 8 + i;
+        const unsigned v = v0 + p;
+        if (v < J.n) {
+          float y[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = 8 * j + k;
+            y[k] = fminf(fmaxf(tile[c * TP + (p ^ (j << 3))], -65504.0f), 65504.0f);
+          }
+          const unsigned x = v % J.W, r = v / J.W;
+          const unsigned yy = r % J.H, zz = r / J.H;
+          const size_t o = (size_t)zz * J.sz + (size_t)yy * J.sy + x + J.off;
+          uint4 q;
+          __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+          __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
+          q.x = *reinterpret_cast<uint32_t*>(&h0);
+          q.y = *reinterpret_cast<uint32_t*>(&h1);
+          q.z = *reinterpret_cast<uint32_t*>(&h2);
+          q.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(dst + o * 32 + j * 8) = q;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 struct MaskArgs {
   const float* cs[GPNERF_N_LEVELS];
   int dims[GPNERF_N_LEVELS][3];
@@ -222,6 +329,44 @@ int gpnerf_k0_level_to_channels_last(const float* ncdhw, int D, int H, int W, in
   else
     to_channels_last_32<0><<<grid, 256, 0, (cudaStream_t)stream>>>(ncdhw, n, 0, om, ndhwc, chan_sum);
   return check_launch("k0_level_to_channels_last");
+}
+
+int gpnerf_k0_products_to_f16(const float* const levels[GPNERF_N_LEVELS], const int32_t level_dims[GPNERF_N_LEVELS][3],
+                              const float* featmaps, int V, int fh, int fw, void* const levels_out[GPNERF_N_LEVELS],
+                              float* const chan_sums[GPNERF_N_LEVELS], void* featmaps_out, void* stream) {
+  GPNERF_REQUIRE(levels && level_dims && levels_out && chan_sums);
+  GPNERF_REQUIRE(featmaps == nullptr || (featmaps_out && V > 0 && V <= GPNERF_MAX_VIEWS && fh > 0 && fw > 0));
+  LayoutJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  unsigned tile = 0;
+  int nj = 0;
+  for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+    GPNERF_REQUIRE(levels[l] && levels_out[l] && chan_sums[l]);
+    const int D = level_dims[l][0], H = level_dims[l][1], W = level_dims[l][2];
+    GPNERF_REQUIRE(D > 0 && H > 0 && W > 0 && (long long)(D + 2) * (H + 2) * (W + 2) < (1ll << 31));
+    LayoutJob& J = jobs.j[nj++];
+    J.src = levels[l]; J.dst = reinterpret_cast<__half*>(levels_out[l]); J.chan_sum = chan_sums[l];
+    J.n = (unsigned)D * H * W; J.H = H; J.W = W;
+    J.sy = W + 2; J.sz = (unsigned)(H + 2) * (W + 2); J.off = J.sz + J.sy + 1;
+    J.batch = 1; J.batch_stride_out = 0;
+    J.tile0 = tile; J.tiles_per_batch = (J.n + 255) / 256;
+    tile += J.tiles_per_batch;
+  }
+  if (featmaps != nullptr) {
+    LayoutJob& J = jobs.j[nj++];
+    J.src = featmaps; J.dst = reinterpret_cast<__half*>(featmaps_out); J.chan_sum = nullptr;
+    J.n = (unsigned)fh * fw; J.H = fh; J.W = fw;
+    J.sy = fw + 2; J.sz = 0; J.off = J.sy + 1;
+    J.batch = V; J.batch_stride_out = (unsigned)(fh + 2) * (fw + 2);
+    J.tile0 = tile; J.tiles_per_batch = (J.n + 255) / 256;
+    tile += J.tiles_per_batch * V;
+  }
+  jobs.n_jobs = nj;
+  jobs.n_tiles = tile;
+  const int cap = sm_count() * 8;
+  const int grid = (int)(tile < (unsigned)cap ? tile : (unsigned)cap);
+  products_to_channels_last_f16<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
+  return check_launch("k0_products_to_f16");
 }
 
 int gpnerf_k0_build_masks3d(const float* const chan_sum[GPNERF_N_LEVELS],

@@ -272,7 +272,7 @@ int gpnerf_k1_voxel_pixel_mask(const float* masks3d, const gpnerf_frame_t* f, fl
 
 int gpnerf_k1_rays_bbox(const float* pix_mask, const float* can_bounds, const gpnerf_frame_t* f,
                         int32_t* ray_pix, float* rays_o, float* rays_d, float* near, float* far,
-                        int32_t* counters, void* workspace, void* stream) {
+                        int32_t* counters, void* workspace, int32_t* tile_ray_begin, void* stream) {
   GPNERF_REQUIRE(pix_mask && can_bounds && ray_pix && rays_o && rays_d && near && far && counters &&
                  workspace && check_frame(f));
   cudaStream_t st = (cudaStream_t)stream;
@@ -286,7 +286,7 @@ int gpnerf_k1_rays_bbox(const float* pix_mask, const float* can_bounds, const gp
   long long blocks = (n + 255) / 256;
   int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : sm_count() * 8);
   ray_flags<<<grid, 256, 0, st>>>(pix_mask, can_bounds, *f, ws.words, counters, rays_o);
-  int rc = compact_launch(ws, nullptr, 1, n, n, ray_pix, counters + GPNERF_CNT_RAYS, st);
+  int rc = compact_launch(ws, nullptr, 1, n, n, ray_pix, counters + GPNERF_CNT_RAYS, st, f->tile_px, tile_ray_begin);
   if (rc != GPNERF_OK) return rc;
   ray_finalize<<<grid, 256, 0, st>>>(ray_pix, can_bounds, *f, counters, rays_d, near, far);
   return check_launch("k1_rays_bbox");

@@ -70,6 +70,19 @@ __device__ __forceinline__ void hfma8(__half2 (&acc)[4], const uint4& q, __half2
   acc[3] = __hfma2(as_h2(q.w), w, acc[3]);
 }
 
+// Operand-tile store for the gather lanes.  Lane L = 4·i + sub holds chunk (kc0 + sub) of row (row8 + i),
+// i = 0..7.  All K chunks of one row fall into the same 4 banks (LBO = 128 B), so storing from this lane
+// order is a 4-way conflict in every quarter-warp; after an 8x4 → 4x8 lane transpose (4 shuffles) every
+// quarter-warp writes one chunk column of 8 consecutive rows = 128 contiguous bytes.
+__device__ __forceinline__ void st_chunk_rows8(uint8_t* tile, uint32_t sbo, int row8, int kc0, uint4 v, int lane) {
+  const int src = (lane & 7) * 4 + (lane >> 3);
+  v.x = __shfl_sync(0xffffffffu, v.x, src);
+  v.y = __shfl_sync(0xffffffffu, v.y, src);
+  v.z = __shfl_sync(0xffffffffu, v.z, src);
+  v.w = __shfl_sync(0xffffffffu, v.w, src);
+  *reinterpret_cast<uint4*>(tile + chunk_off(row8 + (lane & 7), kc0 + (lane >> 3), sbo)) = v;
+}
+
 template <int V>
 __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const __grid_constant__ gpnerf_frame_t fparam) {
   GPNERF_LOAD_FRAME(fparam)
@@ -130,6 +143,24 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
   const int n = __ldg(a.counters + GPNERF_CNT_P1);
   const int n_tiles = (n + 127) / 128;
 
+  // Sample position of this thread's plan row, fetched one tile ahead: valid → (ray, z) → p is a chain of
+  // two dependent global loads that would otherwise sit at the head of every tile.
+  auto fetch_q = [&](long long first_row) -> int {
+    return (first_row + row < n) ? __ldg(a.valid + first_row + row) : -1;
+  };
+  auto fetch_point = [&](int q, float& px, float& py, float& pz) {
+    px = py = pz = 0.f;
+    if (q >= 0) {
+      const int ray = q / S;
+      const float z = __ldg(a.z_vals + q);
+      px = fmaf(__ldg(a.rays_d + ray * 3 + 0), z, ox);
+      py = fmaf(__ldg(a.rays_d + ray * 3 + 1), z, oy);
+      pz = fmaf(__ldg(a.rays_d + ray * 3 + 2), z, oz);
+    }
+  };
+  float px, py, pz;
+  fetch_point(fetch_q((long long)blockIdx.x * 128), px, py, pz);
+
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long first = (long long)tile * 128;
     const int n_valid = min(128, n - (int)first);
@@ -140,15 +171,6 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
     // (the zero border), so the gather phase needs no row guard.
     {
       const bool ok = row < n_valid;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (ok) {
-        const int q = __ldg(a.valid + first + row);
-        const int ray = q / S;
-        const float z = __ldg(a.z_vals + q);
-        px = fmaf(__ldg(a.rays_d + ray * 3 + 0), z, ox);
-        py = fmaf(__ldg(a.rays_d + ray * 3 + 1), z, oy);
-        pz = fmaf(__ldg(a.rays_d + ray * 3 + 2), z, oz);
-      }
       uint8_t* prow = A1 + chunk_off(row, 0, SBO1);
       if (half == 0) {
         const float ux = fmaf(xf[0], px, fmaf(xf[1], py, fmaf(xf[2], pz, xf[3])));
@@ -204,6 +226,7 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
       }
     }
     __syncthreads();
+    const int q_next = fetch_q((long long)(tile + gridDim.x) * 128);     // lands during the gather phase
     // =================== gather phase ===================
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -238,8 +261,8 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
         hfma8(acc, q[5], dup_h2(wx1 * w01));
         hfma8(acc, q[6], dup_h2(wx0 * w11));
         hfma8(acc, q[7], dup_h2(wx1 * w11));
-        *reinterpret_cast<uint4*>(A0 + chunk_off(r, l * 4 + sub, op_sbo(128))) =
-            make_uint4(as_u32(acc[0]), as_u32(acc[1]), as_u32(acc[2]), as_u32(acc[3]));
+        st_chunk_rows8(A0, op_sbo(128), r & ~7, l * 4,
+                       make_uint4(as_u32(acc[0]), as_u32(acc[1]), as_u32(acc[2]), as_u32(acc[3])), tid & 31);
       }
       // ---- V source views: feature taps by all 4 lanes (8 channels each), mean / variance
       float fv[V][8];
@@ -302,8 +325,8 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
           var[e] = s * inv_v;
         }
         const uint4 qm = pack8(mean), qv = pack8(var);
-        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 8 + sub, SBO1)) = qm;
-        *reinterpret_cast<uint4*>(A1 + chunk_off(r, 12 + sub, SBO1)) = qv;
+        st_chunk_rows8(A1, SBO1, r & ~7, 8, qm, tid & 31);
+        st_chunk_rows8(A1, SBO1, r & ~7, 12, qv, tid & 31);
         if (ok) {
           uint4* rp = a.rec + (first + r) * RC;
           rp[sub] = qm;
@@ -336,6 +359,7 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
         }
       }
     }
+    fetch_point(q_next, px, py, pz);                                     // lands during the density phase
     // =================== density phase ===================
     // sigmahead.out_geometry_fc: [128 x 128] · Wgᵀ → 64, ELU → columns 0..63 of A1 (over the plan)
     round_sync();

@@ -373,7 +373,7 @@ int gpnerf_k2_occupancy_compact(const float* masks3d, const float* rays_o, const
                                 const float* near, const float* far, const float* t_vals,
                                 const float* t_rand, const gpnerf_frame_t* f, int n_rays_max,
                                 int32_t* valid, float* z_vals, int32_t* counters, void* workspace,
-                                void* stream) {
+                                int32_t* ray_pt_begin, void* stream) {
   GPNERF_REQUIRE(rays_o && rays_d && near && far && t_vals && f && valid && z_vals && counters && workspace);
   GPNERF_REQUIRE(n_rays_max > 0 && f->n_samples > 0 && (long long)n_rays_max * f->n_samples < (1ll << 31));
   cudaStream_t st = (cudaStream_t)stream;
@@ -384,7 +384,7 @@ int gpnerf_k2_occupancy_compact(const float* masks3d, const float* rays_o, const
   occupancy_flags<<<grid, 256, 0, st>>>(masks3d, rays_o, rays_d, near, far, t_vals, t_rand, *f,
                                         counters, ws.words, z_vals);
   return compact_launch(ws, counters + GPNERF_CNT_RAYS, f->n_samples, 0, n_max, valid,
-                        counters + GPNERF_CNT_P1, st);
+                        counters + GPNERF_CNT_P1, st, f->n_samples, ray_pt_begin);
 }
 
 static int make_point_src(PointSrc* ps, int point_kind, const int32_t* valid, const float* rays_o,

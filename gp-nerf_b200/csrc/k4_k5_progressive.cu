@@ -11,6 +11,8 @@
 //     skipping them is exact.  Reads 16 B per surviving sample.
 //   raw2outputs      : BaseRender.py:75-107,147 dense [R][S] variant with the
 //     auxiliary maps the training loss consumes.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace gpnerf {
@@ -33,80 +35,144 @@ __global__ void __launch_bounds__(256) alpha_flags(const float* __restrict__ sig
   }
 }
 
-__device__ __forceinline__ int lower_bound(const int32_t* __restrict__ a, int n, int key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(a + mid) < key) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
+// One CTA per pixel tile of this rank (frame.rank/world/tile_px: the diagonal deal of K1), one warp
+// per ray of the tile.  `tile_ray_begin` / `ray_pt_begin` are the CSR offsets the two compactions leave
+// behind (rays of a tile, surviving points of a ray), so nothing is searched.  The finished tile
+// (tile_px RGB triples + hit bytes, zeros where no ray) is staged in shared memory and written with
+// coalesced stores to every destination: the local image and – when the frame is sharded over GPUs –
+// the same tile of every peer's image, straight over NVLink (peer pointers from gpnerf_peer_t).  The
+// last CTA to finish publishes the frame's sequence number in each peer's arrival flag
+// (fence.sys + st.release.sys); gpnerf_peer_wait is the matching acquire.  Every pixel of an owned tile
+// is written, so no destination needs a memset.
+constexpr int kMaxTilePx = 256;
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// one warp per ray
-__global__ void __launch_bounds__(256) composite_rays(const int32_t* __restrict__ valid,
-                                                      const float* __restrict__ alpha,
-                                                      const float* __restrict__ rgb,
-                                                      const int32_t* __restrict__ ray_pix,
-                                                      const int32_t* __restrict__ counters, int S,
-                                                      float t_min, float* __restrict__ rgb_map,
-                                                      float* __restrict__ pred_img,
-                                                      uint8_t* __restrict__ hit_mask) {
-  const int n_rays = __ldg(counters + GPNERF_CNT_RAYS);
-  const int n_pts = __ldg(counters + GPNERF_CNT_P1);
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int r = warp; r < n_rays; r += n_warps) {
-    int b0 = 0, b1 = 0;
-    if (lane == 0) b0 = lower_bound(valid, n_pts, r * S);
-    if (lane == 1) b1 = lower_bound(valid, n_pts, (r + 1) * S);
-    const int begin = __shfl_sync(0xffffffffu, b0, 0), end = __shfl_sync(0xffffffffu, b1, 1);
-    float T = 1.0f;            // transmittance carried between 32-sample chunks
-    float cr = 0.f, cg = 0.f, cb = 0.f;
-    for (int base = begin; base < end; base += 32) {
-      const int i = base + lane;
-      float a = 0.0f, pr = 0.f, pg = 0.f, pb = 0.f;
-      if (i < end) {
-        a = __ldg(alpha + i);
-        if (a > 1e-14f) {      // colour exists only for points that passed K4
-          pr = __ldg(rgb + (long long)i * 3);
-          pg = __ldg(rgb + (long long)i * 3 + 1);
-          pb = __ldg(rgb + (long long)i * 3 + 2);
+__global__ void __launch_bounds__(256) composite_tiles(const float* __restrict__ alpha,
+                                                       const float* __restrict__ rgb,
+                                                       const int32_t* __restrict__ ray_pix,
+                                                       const int32_t* __restrict__ tile_ray_begin,
+                                                       const int32_t* __restrict__ ray_pt_begin,
+                                                       const __grid_constant__ gpnerf_frame_t fparam, float t_min,
+                                                       float* __restrict__ rgb_map, float* __restrict__ pred_img,
+                                                       uint8_t* __restrict__ hit_mask,
+                                                       const gpnerf_peer_t* __restrict__ peer_dev) {
+  GPNERF_LOAD_FRAME(fparam)
+  __shared__ float tile_rgb[kMaxTilePx * 3];
+  __shared__ __align__(4) uint8_t tile_hit[kMaxTilePx];
+  __shared__ gpnerf_peer_t pr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (peer_dev != nullptr) {
+    for (int i = tid; i < (int)(sizeof(gpnerf_peer_t) / 4); i += blockDim.x)
+      reinterpret_cast<uint32_t*>(&pr)[i] = reinterpret_cast<const uint32_t*>(peer_dev)[i];
+    __syncthreads();
+  }
+  // destinations: without a peer block the plain local pointers; with one, everything listed there
+  // (entry 0 is this rank's own buffer of the current frame by convention)
+  const int n_dst = peer_dev ? pr.n_dst : 1;
+  const int tile_px = f.tile_px, n_px = f.H * f.W;
+  const int n_tiles = (n_px + tile_px - 1) / tile_px;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    if ((t + (int)(((long long)t * tile_px) / f.W)) % f.world != f.rank) continue;   // not this rank's tile
+    const int px0 = t * tile_px, npix = min(tile_px, n_px - px0);
+    for (int i = tid; i < npix * 3; i += blockDim.x) tile_rgb[i] = 0.0f;
+    for (int i = tid; i < (npix + 3) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tile_hit)[i] = 0u;
+    __syncthreads();
+    const int r0 = __ldg(tile_ray_begin + t), r1 = __ldg(tile_ray_begin + t + 1);
+    for (int r = r0 + warp; r < r1; r += (int)(blockDim.x >> 5)) {
+      const int begin = __ldg(ray_pt_begin + r), end = __ldg(ray_pt_begin + r + 1);
+      float T = 1.0f;            // transmittance carried between 32-sample chunks
+      float cr = 0.f, cg = 0.f, cb = 0.f;
+      for (int base = begin; base < end; base += 32) {
+        const int i = base + lane;
+        float a = 0.0f, pr_ = 0.f, pg = 0.f, pb = 0.f;
+        if (i < end) {
+          a = __ldg(alpha + i);
+          if (a > 1e-14f) {      // colour exists only for points that passed K4
+            pr_ = __ldg(rgb + (long long)i * 3);
+            pg = __ldg(rgb + (long long)i * 3 + 1);
+            pb = __ldg(rgb + (long long)i * 3 + 2);
+          }
         }
-      }
-      float fct = xadd(xsub(1.0f, a), 1e-10f);
-      float incl = fct;        // inclusive product scan
+        float fct = xadd(xsub(1.0f, a), 1e-10f);
+        float incl = fct;        // inclusive product scan
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        float t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl *= t;
+        for (int o = 1; o < 32; o <<= 1) {
+          float tt = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl *= tt;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float wgt = a * (T * excl);
+        cr += wgt * pr_;
+        cg += wgt * pg;
+        cb += wgt * pb;
+        T *= __shfl_sync(0xffffffffu, incl, 31);
+        if (T < t_min) break;    // early termination (off when t_min == 0)
       }
-      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-      if (lane == 0) excl = 1.0f;
-      const float wgt = a * (T * excl);
-      cr += wgt * pr;
-      cg += wgt * pg;
-      cb += wgt * pb;
-      T *= __shfl_sync(0xffffffffu, incl, 31);
-      if (T < t_min) break;    // early termination (off when t_min == 0)
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cr += __shfl_xor_sync(0xffffffffu, cr, o);
-      cg += __shfl_xor_sync(0xffffffffu, cg, o);
-      cb += __shfl_xor_sync(0xffffffffu, cb, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        cr += __shfl_xor_sync(0xffffffffu, cr, o);
+        cg += __shfl_xor_sync(0xffffffffu, cg, o);
+        cb += __shfl_xor_sync(0xffffffffu, cb, o);
+      }
+      if (lane == 0) {
+        rgb_map[(long long)r * 3 + 0] = cr;
+        rgb_map[(long long)r * 3 + 1] = cg;
+        rgb_map[(long long)r * 3 + 2] = cb;
+        const int p = __ldg(ray_pix + r) - px0;
+        tile_rgb[p * 3 + 0] = cr;
+        tile_rgb[p * 3 + 1] = cg;
+        tile_rgb[p * 3 + 2] = cb;
+        tile_hit[p] = 1;
+      }
     }
-    if (lane == 0) {
-      rgb_map[(long long)r * 3 + 0] = cr;
-      rgb_map[(long long)r * 3 + 1] = cg;
-      rgb_map[(long long)r * 3 + 2] = cb;
-      const int p = __ldg(ray_pix + r);
-      pred_img[(long long)p * 3 + 0] = cr;
-      pred_img[(long long)p * 3 + 1] = cg;
-      pred_img[(long long)p * 3 + 2] = cb;
-      hit_mask[p] = 1;
+    __syncthreads();
+    for (int k = 0; k < n_dst; ++k) {
+      float* img = peer_dev ? reinterpret_cast<float*>(pr.dst_img[k]) : pred_img;
+      uint8_t* hit = peer_dev ? reinterpret_cast<uint8_t*>(pr.dst_hit[k]) : hit_mask;
+      for (int i = tid; i < npix * 3; i += blockDim.x) img[(long long)px0 * 3 + i] = tile_rgb[i];
+      if ((npix & 3) == 0 && (px0 & 3) == 0) {
+        for (int i = tid; i < npix / 4; i += blockDim.x)
+          reinterpret_cast<uint32_t*>(hit + px0)[i] = reinterpret_cast<const uint32_t*>(tile_hit)[i];
+      } else {
+        for (int i = tid; i < npix; i += blockDim.x) hit[px0 + i] = tile_hit[i];
+      }
     }
+    __syncthreads();
+  }
+  if (peer_dev != nullptr && pr.n_flag > 0) {
+    __threadfence_system();      // this thread's peer stores before the CTA's ticket
+    __syncthreads();
+    if (tid == 0) {
+      int32_t* ticket = reinterpret_cast<int32_t*>(pr.ticket);
+      const int done = atomicAdd(ticket, 1);
+      if (done == (int)gridDim.x - 1) {
+        *ticket = 0;             // ready for the next launch (graph replay)
+        __threadfence_system();
+        for (int k = 0; k < pr.n_flag; ++k) st_release_sys(reinterpret_cast<int32_t*>(pr.dst_flag[k]), pr.seq);
+      }
+    }
+  }
+}
+
+// Matching acquire: thread k waits until flags[k] has reached the frame's sequence number (peers k
+// publish it from composite_tiles when all their tiles have landed here).  Bounded: traps after ~4 s.
+__global__ void peer_wait_kernel(const int32_t* __restrict__ flags, int n_flags, int self,
+                                 const gpnerf_peer_t* __restrict__ peer_dev) {
+  const int k = threadIdx.x;
+  if (k >= n_flags || k == self) return;
+  const int32_t seq = peer_dev->seq;
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(flags + k) - seq) < 0) {
+    __nanosleep(200);
+    if (clock64() - t0 > 8000000000ll) __trap();
   }
 }
 
@@ -319,24 +385,78 @@ int gpnerf_k4_compact_alpha(const float* sigma, int n_points_max, int32_t* count
                         counters + GPNERF_CNT_P2, st);
 }
 
-int gpnerf_k5_composite(const int32_t* valid, const float* alpha, const float* rgb,
-                        const int32_t* ray_pix, const gpnerf_frame_t* f, int n_rays_max,
-                        const int32_t* counters, float t_min, float* rgb_map, float* pred_img,
-                        uint8_t* hit_mask, void* stream) {
-  GPNERF_REQUIRE(valid && alpha && rgb && ray_pix && f && counters && rgb_map && pred_img && hit_mask && n_rays_max > 0);
-  cudaStream_t st = (cudaStream_t)stream;
-  size_t npx = (size_t)f->H * f->W;
-  cudaError_t e = cudaMemsetAsync(pred_img, 0, npx * 3 * sizeof(float), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(hit_mask, 0, npx, st);
+int gpnerf_k5_composite(const float* alpha, const float* rgb, const int32_t* ray_pix,
+                        const int32_t* tile_ray_begin, const int32_t* ray_pt_begin, const gpnerf_frame_t* f,
+                        float t_min, float* rgb_map, float* pred_img, uint8_t* hit_mask,
+                        const gpnerf_peer_t* peer_dev, void* stream) {
+  GPNERF_REQUIRE(alpha && rgb && ray_pix && tile_ray_begin && ray_pt_begin && f && rgb_map);
+  GPNERF_REQUIRE(peer_dev != nullptr || (pred_img && hit_mask));
+  GPNERF_REQUIRE(f->H > 0 && f->W > 0 && f->tile_px >= 1 && f->tile_px <= kMaxTilePx && f->world >= 1);
+  const long long n_px = (long long)f->H * f->W;
+  const long long n_tiles = (n_px + f->tile_px - 1) / f->tile_px;
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+  composite_tiles<<<grid, 256, 0, (cudaStream_t)stream>>>(alpha, rgb, ray_pix, tile_ray_begin, ray_pt_begin, *f,
+                                                          t_min, rgb_map, pred_img, hit_mask, peer_dev);
+  return check_launch("k5_composite");
+}
+
+int gpnerf_peer_wait(const int32_t* flags, int n_flags, int self, const gpnerf_peer_t* peer_dev, void* stream) {
+  GPNERF_REQUIRE(flags && peer_dev && n_flags >= 1 && n_flags <= GPNERF_MAX_PEERS);
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n_flags, self, peer_dev);
+  return check_launch("peer_wait");
+}
+
+// ---- peer (IPC) memory: one allocation per rank, opened by every other rank of the box -------------
+int gpnerf_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int gpnerf_peer_alloc(int64_t bytes, void** dev_ptr_host, void* handle_host) {
+  GPNERF_REQUIRE(bytes > 0 && dev_ptr_host && handle_host);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_host), p);
   if (e != cudaSuccess) {
-    set_error("memset pred_img", e);
+    set_error("peer_alloc", e);
+    if (p) cudaFree(p);
     return GPNERF_E_CUDA;
   }
-  long long blocks = ((long long)n_rays_max * 32 + 255) / 256;
-  int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : sm_count() * 8);
-  composite_rays<<<grid, 256, 0, st>>>(valid, alpha, rgb, ray_pix, counters, f->n_samples, t_min,
-                                       rgb_map, pred_img, hit_mask);
-  return check_launch("k5_composite");
+  *dev_ptr_host = p;
+  return GPNERF_OK;
+}
+
+int gpnerf_peer_open(const void* handle_host, void** dev_ptr_host) {
+  GPNERF_REQUIRE(handle_host && dev_ptr_host);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    set_error("peer_open (cudaIpcOpenMemHandle)", e);
+    return GPNERF_E_CUDA;
+  }
+  *dev_ptr_host = p;
+  return GPNERF_OK;
+}
+
+int gpnerf_peer_close(void* dev_ptr) {
+  GPNERF_REQUIRE(dev_ptr);
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  if (e != cudaSuccess) {
+    set_error("peer_close", e);
+    return GPNERF_E_CUDA;
+  }
+  return GPNERF_OK;
+}
+
+int gpnerf_peer_free(void* dev_ptr) {
+  GPNERF_REQUIRE(dev_ptr);
+  cudaError_t e = cudaFree(dev_ptr);
+  if (e != cudaSuccess) {
+    set_error("peer_free", e);
+    return GPNERF_E_CUDA;
+  }
+  return GPNERF_OK;
 }
 
 int gpnerf_k5_raw2outputs(const float* raw, const float* z_vals, const float* rgb_in, int n_rays,

@@ -30,9 +30,10 @@ HEAD_KEYS = {
 # bench.py's `gpu_launches`; keep in sync with csrc/.
 KERNELS_PER_CALL = {
     "k0_level_to_channels_last": 1, "k0_featmaps_to_channels_last": 1, "k0_images_to_rgbx": 1,
+    "k0_products_to_f16": 1,
     "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 5, "k2_occupancy_compact": 4,
     "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,
-    "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1,
+    "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1, "peer_wait": 1,
     "k23_gather_density_tc": 1, "k3_color_mlp_records": 1,
 }
 
@@ -145,8 +146,14 @@ class Engine:
         self.valid1 = buf(self.max_pts, i32)
         self.rgb = buf(self.max_pts * 3)
         self.rgb_map = buf(self.max_rays * 3)
-        self.pred_img = buf(npx * 3)
-        self.hit_mask = torch.empty(npx, dtype=torch.uint8, device=dev)
+        # K5 rewrites every pixel of this rank's tiles each frame (zeros where no ray); the tiles of other
+        # ranks are never touched, so they are cleared once here
+        self.pred_img = torch.zeros(npx * 3, dtype=f32, device=dev)
+        self.hit_mask = torch.zeros(npx, dtype=torch.uint8, device=dev)
+        # CSR offsets left behind by the two compactions: rays of every pixel tile, surviving points of every ray
+        self.tile_ray_begin = torch.zeros(math.ceil(npx / self.tile_px) + 1, dtype=i32, device=dev)
+        self.ray_pt_begin = torch.zeros(self.max_rays + 1, dtype=i32, device=dev)
+        self.exchange = None         # peer.PeerExchange when the image leaves through peer memory
         ws_bytes = self.lib.gpnerf_workspace_bytes(max(self.max_pts, npx))
         self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         # products of K0 (allocated on first upload)
@@ -234,17 +241,22 @@ class Engine:
             self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
         assert len(lv) == 4 and all(t.shape[1] == 32 and t.dtype == torch.float32 for t in lv)
         pad = int(self.bf16)
-        storage = 2 if self.bf16 else 0      # 0 fp32 lines, 2 fp16 lines (HFMA2 interpolation)
-        for t, (d, h, w), cl, cs in zip(lv, dims, self.levels_cl, self.chan_sums):
-            self._run("k0_level_to_channels_last", L.gpnerf_k0_level_to_channels_last, ptr(t), d, h, w,
-                      storage, pad, ptr(cl), ptr(cs), st)
         V, Cc, fh, fw = fm.shape
         assert V == self.V and Cc == 32
         n_fm = V * (fh + 2 * pad) * (fw + 2 * pad) * 32
         if self.featmaps_cl is None or self.featmaps_cl.numel() != n_fm:
             self.featmaps_cl = torch.zeros(n_fm, dtype=torch.float16 if self.bf16 else torch.float32, device=dev)
-        self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw,
-                  storage, pad, ptr(self.featmaps_cl), st)
+        if self.bf16:
+            # tensor-core path: the 4 levels and the maps → zero-bordered fp16 lines in one launch
+            dims_c = ((C.c_int32 * 3) * 4)(*[(C.c_int32 * 3)(*d) for d in dims])
+            self._run("k0_products_to_f16", L.gpnerf_k0_products_to_f16, ptr_array(lv), dims_c, ptr(fm), V, fh, fw,
+                      ptr_array(self.levels_cl), ptr_array(self.chan_sums), ptr(self.featmaps_cl), st)
+        else:
+            for t, (d, h, w), cl, cs in zip(lv, dims, self.levels_cl, self.chan_sums):
+                self._run("k0_level_to_channels_last", L.gpnerf_k0_level_to_channels_last, ptr(t), d, h, w,
+                          0, 0, ptr(cl), ptr(cs), st)
+            self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw,
+                      0, 0, ptr(self.featmaps_cl), st)
         _, _, ih, iw = im.shape
         n_im = V * (ih + 2 * pad) * (iw + 2 * pad) * 4
         if self.images_rgbx is None or self.images_rgbx.numel() != n_im:
@@ -268,6 +280,27 @@ class Engine:
         on the current stream).  Every render entry point calls it first."""
         C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
         self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
+        if self.exchange is not None:
+            self.exchange.next_frame()
+            self.exchange.upload()
+
+    def attach_exchange(self, exchange):
+        """Publish the rendered tiles through peer memory (peer.PeerExchange)
+        instead of (only) the local pred_img / hit_mask tensors."""
+        self.exchange = exchange
+        self._graph = None
+
+    def result_image(self, slot=0):
+        """[H*W, 3] image of the frame rendered last (a view: copy it before
+        rendering two more frames when an exchange double-buffers it)."""
+        if self.exchange is not None:
+            return self.exchange.image(slot)
+        return self.pred_img.view(-1, 3)
+
+    def result_hit_mask(self, slot=0):
+        if self.exchange is not None:
+            return self.exchange.hit_mask(slot)
+        return self.hit_mask
 
     # ------------------------------------------------------------ CUDA graph
     def set_static_inputs(self, levels, featmaps, src_imgs):
@@ -325,12 +358,16 @@ class Engine:
             l0 = self.launches
             with torch.cuda.graph(g):
                 self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
+                if self.exchange is not None:
+                    self.exchange.upload()
                 self.upload_products(lv, fm, im)
-                self.render_progressive(frame, upload=False)
+                self.render_progressive(frame, upload=False, in_capture=True)
             self._graph_launches = self.launches - l0
             self._graph, self._graph_key = g, key
             self.timing = timing
         C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
+        if self.exchange is not None:
+            self.exchange.next_frame()       # the replayed copy node picks the new sequence number / buffer half up
         self._graph.replay()
         self.launches += self._graph_launches
 
@@ -339,7 +376,7 @@ class Engine:
         self._run("k0_build_masks3d", self.lib.gpnerf_k0_build_masks3d, ptr_array(self.chan_sums),
                   C.byref(frame), ptr(self.masks3d), self._stream())
 
-    def render_progressive(self, frame, t_rand=None, upload=True):
+    def render_progressive(self, frame, t_rand=None, upload=True, in_capture=False):
         """demo_render.Renderer.render_rays downstream of the producers.
         Leaves results in self.{rgb_map,pred_img,hit_mask,counters,...}."""
         if self._weights is None:
@@ -352,14 +389,20 @@ class Engine:
                   ptr(self.can_bounds), ptr(self.pix_mask), st)
         self._run("k1_rays_bbox", L.gpnerf_k1_rays_bbox, ptr(self.pix_mask), ptr(self.can_bounds), fr,
                   ptr(self.ray_pix), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near), ptr(self.far),
-                  ptr(self.counters), ptr(self.workspace), st)
+                  ptr(self.counters), ptr(self.workspace), ptr(self.tile_ray_begin), st)
         self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays)
         self._run("k4_compact_alpha", L.gpnerf_k4_compact_alpha, ptr(self.sigma), self.max_pts,
                   ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
         self._color(ptr(self.valid1), self.max_pts, CNT_P2)
-        self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.valid), ptr(self.alpha), ptr(self.rgb),
-                  ptr(self.ray_pix), fr, self.max_rays, ptr(self.counters), C.c_float(self.t_min),
-                  ptr(self.rgb_map), ptr(self.pred_img), ptr(self.hit_mask), st)
+        ex = self.exchange
+        self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.alpha), ptr(self.rgb), ptr(self.ray_pix),
+                  ptr(self.tile_ray_begin), ptr(self.ray_pt_begin), fr, C.c_float(self.t_min), ptr(self.rgb_map),
+                  ptr(self.pred_img), ptr(self.hit_mask), None if ex is None else ptr(ex.peer_dev), st)
+        if ex is not None and ex.world > 1:
+            ev = self._tic("peer_wait")
+            ex.wait(st)
+            self._toc(ev)
+            self.launches += 1
 
     def _color(self, valid1_ptr, n_pts_max, slot):
         L, st = self.lib, self._stream()
@@ -377,7 +420,8 @@ class Engine:
         n_pts_max = n_rays_max * self.S
         self._run("k2_occupancy_compact", L.gpnerf_k2_occupancy_compact, ptr(masks3d), ptr(self.rays_o),
                   ptr(self.rays_d), ptr(self.near), ptr(self.far), ptr(self.t_vals), ptr(t_rand), fr, n_rays_max,
-                  ptr(self.valid), ptr(self.z_vals), ptr(self.counters), ptr(self.workspace), st)
+                  ptr(self.valid), ptr(self.z_vals), ptr(self.counters), ptr(self.workspace),
+                  ptr(self.ray_pt_begin), st)
         if self.bf16:
             self._run("k23_gather_density_tc", L.gpnerf_k23_gather_density_tc, ptr_array(self.levels_cl),
                       ptr(self.featmaps_cl), ptr(self.images_rgbx), ptr(self.valid), ptr(self.rays_o),

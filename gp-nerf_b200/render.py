@@ -71,7 +71,8 @@ class Projector:
 class Renderer(nn.Module):
     def __init__(self, encoder, nerfhead, is_train=True, neg_ray_train=False, neg_ray_val=False, n_rays=1024,
                  n_samples=64, voxel_size=(0.005, 0.005, 0.005), chunk=64, mesh_th=-1, progressive=False,
-                 precision=PREC_FP32, t_min=0.0, rank=0, world=1, tile_px=64, use_cuda_graph=True):
+                 precision=PREC_FP32, t_min=0.0, rank=0, world=1, tile_px=64, use_cuda_graph=True,
+                 shard="tiles", collective="peer"):
         super().__init__()
         self.encoder = encoder
         self.nerfhead = nerfhead
@@ -86,7 +87,15 @@ class Renderer(nn.Module):
         self.progressive = progressive
         self.precision = precision
         self.t_min = t_min
+        # Several GPUs of one box (progressive path).  shard = "tiles": one frame, its pixel tiles dealt over
+        # the ranks, every rank ends up with the full image; "frames": every rank renders its own batch
+        # (a sweep of novel views) and rank 0 additionally receives all images (slot r = rank r).
+        # collective = "peer": K5 writes the tiles into the peers' images over NVLink (peer.PeerExchange);
+        # "nccl": one all_gather of tile buffers (shard.gather_frame; also the gloo path of the CPU tests).
+        if shard not in ("tiles", "frames") or collective not in ("peer", "nccl"):
+            raise _lib.GpnerfError("shard must be 'tiles'|'frames', collective 'peer'|'nccl'")
         self.rank, self.world, self.tile_px = rank, world, tile_px
+        self.shard, self.collective = shard, collective
         self.use_cuda_graph = use_cuda_graph
         self._engine = None
 
@@ -95,11 +104,15 @@ class Renderer(nn.Module):
         e = self._engine
         key = (H, W, V, str(device), max_rays)
         if e is None or e._key != key:
-            e = Engine(H, W, self.n_samples, V, device=device, precision=self.precision, rank=self.rank,
-                       world=self.world, tile_px=self.tile_px, t_min=self.t_min, max_rays=max_rays,
-                       voxel_size=tuple(float(v) for v in self.voxel_size))
+            tiles = self.shard == "tiles"
+            e = Engine(H, W, self.n_samples, V, device=device, precision=self.precision,
+                       rank=self.rank if tiles else 0, world=self.world if tiles else 1, tile_px=self.tile_px,
+                       t_min=self.t_min, max_rays=max_rays, voxel_size=tuple(float(v) for v in self.voxel_size))
             e._key = key
             self._engine = e
+            if self.world > 1 and self.collective == "peer" and self.progressive:
+                from .peer import PeerExchange
+                e.attach_exchange(PeerExchange(H, W, device, self.rank, self.world, mode=self.shard))
         return e
 
     @staticmethod
@@ -190,7 +203,7 @@ class Renderer(nn.Module):
         if self.use_cuda_graph:
             # inputs land in static device buffers; the whole frame is one graph launch
             eng.copy_into_static_inputs(levels, featmaps, batch["src_imgs"],
-                                        sharded_upload=self.world > 1 and self._dist_ready())
+                                        sharded_upload=self.world > 1 and self.shard == "tiles" and self._dist_ready())
             if eng.level_dims is None:
                 eng.upload_products(*eng._static_inputs)      # first frame: learn the shapes
             frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
@@ -199,8 +212,9 @@ class Renderer(nn.Module):
             eng.upload_products(levels, featmaps, batch["src_imgs"])
             frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
             eng.render_progressive(frame)
-        img_d, hit_d = eng.pred_img.view(H * W, 3), eng.hit_mask
-        if self.world > 1:
+        img_d, hit_d = eng.result_image(), eng.result_hit_mask()
+        tiled = self.world > 1 and self.shard == "tiles"
+        if tiled and eng.exchange is None:
             # the frame's only collective: one all_gather of this rank's pixel tiles (RGB + hit flag)
             import torch.distributed as dist
             from . import shard
@@ -212,7 +226,7 @@ class Renderer(nn.Module):
         cnt = eng.read_counters()                     # the frame's single host sync
         pred_img = img_d.view(H, W, 3).cpu().numpy().astype(np.float64)
         mask_at_box = hit_d.cpu().numpy().astype(bool)
-        if self.world > 1:
+        if tiled:
             rgb_map = pred_img.reshape(-1, 3)[mask_at_box].astype(np.float32)   # ascending pixel order
         else:
             n = cnt["n_rays"]

@@ -225,6 +225,7 @@ def make_scene(kind="zju", H=512, W=512, V=3, C=32, seed=42, smooth_images=True,
         "levels": levels,
         "featmaps": featmaps.contiguous(),
         "frame_index": 0, "cam_ind": 0,
+        "_ring": (centre, up),
     }
     if with_rays or kind == "dense":
         o, d, near, far, at_box = dataset_rays(H, W, K_tgt, tgt_pose, can_bounds)
@@ -236,6 +237,15 @@ def make_scene(kind="zju", H=512, W=512, V=3, C=32, seed=42, smooth_images=True,
             "rgb": torch.zeros(1, int(at_box.sum()), 3),
         })
     return scene
+
+
+def retarget(scene, angle_deg):
+    """The same scene seen from another novel view on the camera ring (a sweep:
+    only target_pose changes; the volume, the source views and K stay)."""
+    centre, up = scene["_ring"]
+    out = dict(scene)
+    out["target_pose"] = torch.from_numpy(_ring_camera(centre, up, 3.0, float(angle_deg)))[None]
+    return out
 
 
 def make_head_weights(V=3, C=32, seed=42, random_bias=False):

@@ -214,7 +214,7 @@ class _RenderDenseFn(torch.autograd.Function):
         fr = C.byref(frame)
         eng._run("k2_occupancy_compact", L.gpnerf_k2_occupancy_compact, None, ptr(eng.rays_o), ptr(eng.rays_d),
                  ptr(eng.near), ptr(eng.far), ptr(eng.t_vals), ptr(tr), fr, R, ptr(eng.valid), ptr(eng.z_vals),
-                 ptr(eng.counters), ptr(eng.workspace), st)
+                 ptr(eng.counters), ptr(eng.workspace), None, st)
         eng._run("k2_gather_volume", L.gpnerf_k2_gather_volume, ptr_array(eng.levels_cl), 0, ptr(eng.valid),
                  ptr(eng.rays_o), ptr(eng.rays_d), ptr(eng.z_vals), None, fr, P, ptr(eng.counters),
                  ptr(eng.vol_feat), st)

@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define GPNERF_ABI_VERSION 1
+#define GPNERF_ABI_VERSION 2
+#define GPNERF_MAX_PEERS 8
 #define GPNERF_MAX_VIEWS 8
 #define GPNERF_N_LEVELS 4
 #define GPNERF_LEVEL_CH 32 /* head.sigma.outdims = [32]*4, configs/default.py:92 */
@@ -103,6 +104,25 @@ typedef struct gpnerf_head_weights {
   const void *tc_image;
 } gpnerf_head_weights_t;
 
+/* Where K5 publishes this rank's finished pixel tiles when a frame (or a batch
+ * of frames) is spread over the GPUs of one NVLink box: destination images in
+ * this rank's and its peers' exchange buffers (peer pointers obtained with
+ * gpnerf_peer_alloc / gpnerf_peer_open), and the arrival flags that replace a
+ * collective.  Lives in DEVICE memory (the host refreshes it per frame: `seq`
+ * and the double-buffer half the pointers select), so a captured CUDA graph
+ * replays with the current values.  The reference has no counterpart: its
+ * renders leave the GPU through `.cpu().numpy()` (demo_render.py:346-353). */
+typedef struct gpnerf_peer {
+  int32_t n_dst;                          /* images every owned tile is written to (entry 0 = own) */
+  int32_t n_flag;                         /* peers whose arrival flag is set when the frame is done */
+  int32_t seq;                            /* frame sequence number, monotonically increasing        */
+  int32_t reserved_;
+  uint64_t dst_img[GPNERF_MAX_PEERS];     /* float   [H*W*3]                                        */
+  uint64_t dst_hit[GPNERF_MAX_PEERS];     /* uint8_t [H*W]                                          */
+  uint64_t dst_flag[GPNERF_MAX_PEERS];    /* int32_t*: this rank's slot in each peer's flag array   */
+  uint64_t ticket;                        /* int32_t*: local CTA counter, zero between launches     */
+} gpnerf_peer_t;
+
 int gpnerf_abi_version(void);
 const char *gpnerf_last_error(void);
 /* number of SMs of the current device (grid sizing is a multiple of it) */
@@ -119,6 +139,13 @@ int gpnerf_sm_count(void);
  * bounds tests (the border is grid_sample's zeros padding). */
 int gpnerf_k0_level_to_channels_last(const float *ncdhw, int D, int H, int W, int storage, int pad,
                                      void *ndhwc, float *chan_sum, void *stream);
+/* The same for everything the tensor-core path gathers from, in ONE launch: the
+ * 4 levels (+ their channel sums) and the V encoder maps [V,32,fh,fw], all to
+ * fp16 (storage 2) inside the zero border (pad 1).  featmaps may be NULL. */
+int gpnerf_k0_products_to_f16(const float *const levels[GPNERF_N_LEVELS],
+                              const int32_t level_dims[GPNERF_N_LEVELS][3], const float *featmaps,
+                              int V, int fh, int fw, void *const levels_out[GPNERF_N_LEVELS],
+                              float *const chan_sums[GPNERF_N_LEVELS], void *featmaps_out, void *stream);
 /* masks3d on the level-1 grid = Σ_levels nearest-upsampled channel sums
  * (SparseConvNet.py:137-139). */
 int gpnerf_k0_build_masks3d(const float *const chan_sum[GPNERF_N_LEVELS],
@@ -145,7 +172,9 @@ int gpnerf_k1_voxel_pixel_mask(const float *masks3d, const gpnerf_frame_t *frame
 int gpnerf_k1_rays_bbox(const float *pix_mask, const float *can_bounds,
                         const gpnerf_frame_t *frame_host, int32_t *ray_pix, float *rays_o,
                         float *rays_d, float *near, float *far, int32_t *counters,
-                        void *workspace, void *stream);
+                        void *workspace, int32_t *tile_ray_begin, void *stream);
+/* tile_ray_begin (may be NULL): int32[ceil(H*W/tile_px) + 1], CSR offsets of the
+ * rays of every pixel tile (K5 walks its tiles with them). */
 
 /* ---- K2: occupancy test, gathers --------------------------------------- */
 /* demo_render.py:59-94, 270-283: sample S depths per ray (t_vals = linspace,
@@ -158,7 +187,10 @@ int gpnerf_k2_occupancy_compact(const float *masks3d, const float *rays_o, const
                                 const float *near, const float *far, const float *t_vals,
                                 const float *t_rand, const gpnerf_frame_t *frame_host,
                                 int n_rays_max, int32_t *valid, float *z_vals,
-                                int32_t *counters, void *workspace, void *stream);
+                                int32_t *counters, void *workspace, int32_t *ray_pt_begin,
+                                void *stream);
+/* ray_pt_begin (may be NULL): int32[n_rays_max + 1], CSR offsets of the
+ * surviving points of every ray (ray_pt_begin[n_rays] = counters[P1]). */
 /* Where the two gathers take their sample points from (`point_kind`):
  *   0  ray-parametrised: flat index valid[i] → (ray, sample), p = o + d·z;
  *      the live count is counters[P1] (n_points_max bounds the grid);
@@ -246,14 +278,34 @@ int gpnerf_k4_compact_alpha(const float *sigma, int n_points_max, int32_t *count
                             float *alpha, int32_t *valid1, void *workspace, void *stream);
 
 /* ---- K5: compositing ---------------------------------------------------- */
-/* demo_render.py:335-353: front-to-back compositing of the surviving samples
- * of each ray (CSR over `valid`), T = exclusive Π(1-α+1e-10), Σ w·rgb; writes
- * rgb_map float[R][3] and scatters into pred_img float[H*W][3] (pre-zeroed by
- * the call) and hit_mask uint8[H*W].  t_min > 0 stops a ray once T < t_min. */
-int gpnerf_k5_composite(const int32_t *valid, const float *alpha, const float *rgb,
-                        const int32_t *ray_pix, const gpnerf_frame_t *frame_host, int n_rays_max,
-                        const int32_t *counters, float t_min, float *rgb_map, float *pred_img,
-                        uint8_t *hit_mask, void *stream);
+/* demo_render.py:335-353 without the dense scatter: per ray, walk its surviving
+ * points (CSR offsets ray_pt_begin from K2), T = Π(1-α+1e-10) exclusive by a
+ * warp product scan, rgb_map = Σ α·T·rgb.  One CTA per pixel tile of this rank
+ * (tile_ray_begin from K1); the finished tile – zeros where no ray – goes with
+ * coalesced stores to pred_img float[H*W*3] / hit_mask uint8[H*W] (the
+ * reference's host-side `pred_img[mask_at_box] = rgb_map`), so neither needs
+ * clearing.  With `peer_dev` (DEVICE pointer to a gpnerf_peer_t) the tile is
+ * written to every image listed there instead – this rank's and its peers',
+ * over NVLink – and the frame's sequence number is published in the peers'
+ * arrival flags when the last tile has left; gpnerf_peer_wait is the matching
+ * wait.  t_min > 0 stops a ray once T < t_min (off at 0: exact). */
+int gpnerf_k5_composite(const float *alpha, const float *rgb, const int32_t *ray_pix,
+                        const int32_t *tile_ray_begin, const int32_t *ray_pt_begin,
+                        const gpnerf_frame_t *frame_host, float t_min, float *rgb_map,
+                        float *pred_img, uint8_t *hit_mask, const gpnerf_peer_t *peer_dev,
+                        void *stream);
+/* Blocks the stream until flags[k] >= peer_dev->seq for every k != self. */
+int gpnerf_peer_wait(const int32_t *flags, int n_flags, int self, const gpnerf_peer_t *peer_dev,
+                     void *stream);
+/* Peer (CUDA IPC) memory for the exchange buffers.  HOST-side calls: alloc =
+ * cudaMalloc + zero + cudaIpcGetMemHandle (handle_host receives
+ * gpnerf_peer_handle_bytes() bytes to send to the other ranks), open =
+ * cudaIpcOpenMemHandle on a handle received from a peer. */
+int gpnerf_peer_handle_bytes(void);
+int gpnerf_peer_alloc(int64_t bytes, void **dev_ptr_host, void *handle_host);
+int gpnerf_peer_open(const void *handle_host, void **dev_ptr_host);
+int gpnerf_peer_close(void *dev_ptr);
+int gpnerf_peer_free(void *dev_ptr);
 /* Renderer.raw2outputs (BaseRender.py:75-107,147): dense [R][S] path.
  * raw float[R][S][4] (rgb,σ); rgb_in float[R][S][V][3] or NULL.  Outputs
  * rgb_map[R][3], disp/acc/depth[R], weights[R][S], rgb_in_map[R][V][3]. */

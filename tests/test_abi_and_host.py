@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for n in names:
         assert hasattr(lib_built, n), f"{n} declared in gpnerf_abi.h but not exported"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert lib_built.gpnerf_abi_version() == 1
+    assert lib_built.gpnerf_abi_version() == 2
 
 
 def test_frame_struct_matches_header_size(lib_built):

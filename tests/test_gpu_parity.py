@@ -110,6 +110,40 @@ def test_sharded_render_equals_single_gpu():
     assert torch.equal(out, full)            # per-ray math does not depend on the sharding
 
 
+def test_csr_offsets_and_peer_exchange_single_rank():
+    """The CSR offsets the compactions leave for K5, and K5 publishing through a
+    PeerExchange (world = 1: its own IPC buffer, double-buffered by frame
+    parity) instead of the plain tensors: same image, bit for bit."""
+    from gpnerf_b200.peer import PeerExchange
+    scene = synth.make_scene("zju", H=128, W=128, V=3, seed=7)
+    w = synth.make_head_weights(V=3, seed=107)
+    S, tile = 32, 64
+    ref, _ = stages.run_engine_progressive(scene, w, S, tile_px=tile)
+    c = ref.read_counters()
+    n, p1 = c["n_rays"], c["P1"]
+    ray_pix = ref.ray_pix[:n].long()
+    trb = ref.tile_ray_begin.long().cpu()
+    n_tiles = (128 * 128 + tile - 1) // tile
+    want = torch.searchsorted(ray_pix.cpu(), torch.arange(n_tiles + 1) * tile)
+    assert torch.equal(trb, want)
+    rpb = ref.ray_pt_begin[: n + 1].long().cpu()
+    want = torch.searchsorted(ref.valid[:p1].long().cpu(), torch.arange(n + 1) * S)
+    assert torch.equal(rpb, want)
+    eng = Engine(128, 128, S, 3, device=DEV, tile_px=tile)
+    eng.set_weights(w)
+    ex = PeerExchange(128, 128, DEV, 0, 1, mode="tiles")
+    eng.attach_exchange(ex)
+    d = stages.to_dev(scene, DEV)
+    eng.upload_products(d["levels"], d["featmaps"], d["src_imgs"])
+    for _ in range(3):                       # both buffer halves get used
+        eng.render_progressive(eng.make_frame(scene))
+        torch.cuda.synchronize()
+        assert torch.equal(eng.result_image(), ref.pred_img.view(-1, 3))
+        assert torch.equal(eng.result_hit_mask(), ref.hit_mask)
+    assert ex.seq == 3
+    ex.close()
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)
