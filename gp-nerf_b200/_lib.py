@@ -41,9 +41,9 @@ MAX_PEERS = 8
 class Peer(C.Structure):
     """gpnerf_peer_t"""
     _fields_ = [
-        ("n_dst", C.c_int32), ("n_flag", C.c_int32), ("seq", C.c_int32), ("reserved_", C.c_int32),
-        ("dst_img", C.c_uint64 * MAX_PEERS), ("dst_hit", C.c_uint64 * MAX_PEERS),
-        ("dst_flag", C.c_uint64 * MAX_PEERS), ("ticket", C.c_uint64),
+        ("n_dst", C.c_int32), ("n_flag", C.c_int32),
+        ("dst_img", (C.c_uint64 * MAX_PEERS) * 2), ("dst_hit", (C.c_uint64 * MAX_PEERS) * 2),
+        ("dst_flag", C.c_uint64 * MAX_PEERS), ("ticket", C.c_uint64), ("seq", C.c_uint64),
     ]
 
 

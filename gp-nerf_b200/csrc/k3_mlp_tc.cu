@@ -256,7 +256,7 @@ struct ColSmem {
   static constexpr uint32_t ONES = F + V * op_bytes(128, 48);            // [128 x 16] constant (…, 1, 1 | 0×8): bias block
   static constexpr uint32_t BAR = ONES + op_bytes(128, 16);
   static constexpr uint32_t BYTES = BAR + 64;
-  static constexpr uint32_t TMEM_COLS = (V <= 2) ? 64 : 128;
+  static constexpr uint32_t TMEM_COLS = V == 1 ? 64 : (V == 2 ? 128 : 256);     // V blocks of 64 columns
 };
 
 // FROM_REC: rows come from the bf16 records of the fused kernel (rec_chunks(V)
@@ -310,6 +310,8 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
   }
   constexpr uint32_t F_STRIDE = op_bytes(128, 48);     // per-view feature operand
   constexpr uint32_t X_STRIDE = op_bytes(128, 32);     // per-view [128 x 32] operand
+  constexpr uint32_t HB_STRIDE = op_bytes(128, 64);    // per-view base_fc hidden tile
+  static_assert(V * HB_STRIDE <= S::ONES - S::G, "hidden tiles must fit the G|H|F pool");
   constexpr int RC = rec_chunks(V);
   uint32_t phase = 0;
   const int n = count_ptr ? __ldg(count_ptr) : n_const;
@@ -386,33 +388,49 @@ __global__ void __launch_bounds__(256, 2) color_mlp_tc(const float* __restrict__
       }
     }
     float x[V][16];                                   // this thread's half of base_fc's output, per view
+    // base_fc.0 on [mean|var|feat_v] for ALL views in one round: per view two accumulating GEMMs
+    // (K = 80 + 48) → 64, into V blocks of 64 TMEM columns (fewer issue→commit→wait→sync round trips
+    // per tile: the kernel is bound by their latency, not by the tensor pipe)
+    round_sync();
+    if (tid == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 64);
 #pragma unroll
-    for (int vw = 0; vw < V; ++vw) {
-      // base_fc.0 on [mean|var|feat_v]: two accumulating GEMMs (K = 80 + 48) → 64
-      round_sync();
-      if (tid == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, 64);
+      for (int vw = 0; vw < V; ++vw) {
         for (int k16 = 0; k16 < 5; ++k16)
-          umma_bf16(tmem, make_smem_desc(g_a + k16 * 2 * kLBO, kLBO, op_sbo(80)),
+          umma_bf16(tmem + vw * 64, make_smem_desc(g_a + k16 * 2 * kLBO, kLBO, op_sbo(80)),
                     make_smem_desc(wimg + I::Wb0a + k16 * 2 * kLBO, kLBO, op_sbo(80)), idesc, k16 > 0);
         for (int k16 = 0; k16 < 3; ++k16)
-          umma_bf16(tmem, make_smem_desc(f_a + vw * F_STRIDE + k16 * 2 * kLBO, kLBO, op_sbo(48)),
+          umma_bf16(tmem + vw * 64, make_smem_desc(f_a + vw * F_STRIDE + k16 * 2 * kLBO, kLBO, op_sbo(48)),
                     make_smem_desc(wimg + I::Wb0b + k16 * 2 * kLBO, kLBO, op_sbo(48)), idesc, 1u);
-        umma_commit(bar_m);
       }
-      wait_round(bar_m, phase);
-      epi32_to_tile(t_row, half * 32, Hb, op_sbo(64), row, 0);
-      // base_fc.2: 64 → 32, ELU ; keep x_v in registers
-      round_sync();
-      if (tid == 0) issue_gemm_bias(h_a, op_sbo(64), wimg + I::Wb1, 64, 32, ones, ONES_SBO, tmem, bar_m);
-      wait_round(bar_m, phase);
-      {
-        uint32_t r[16];
-        tmem_ld16(t_row + half * 16, r);
-        tmem_wait_ld();
+      umma_commit(bar_m);
+    }
+    wait_round(bar_m, phase);
+    // hidden tiles Hb_v [128 x 64] over the (now consumed) G | H | F pool
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[vw][k] = elu_scaled(__uint_as_float(r[k]));
+    for (int vw = 0; vw < V; ++vw) epi32_to_tile(t_row + vw * 64, half * 32, G + vw * HB_STRIDE, op_sbo(64), row, 0);
+    // base_fc.2 for all views: 64 → 32, ELU ; keep x_v in registers
+    round_sync();
+    if (tid == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 32);
+#pragma unroll
+      for (int vw = 0; vw < V; ++vw) {
+        for (int k16 = 0; k16 < 4; ++k16)
+          umma_bf16(tmem + vw * 32, make_smem_desc(g_a + vw * HB_STRIDE + k16 * 2 * kLBO, kLBO, op_sbo(64)),
+                    make_smem_desc(wimg + I::Wb1 + k16 * 2 * kLBO, kLBO, op_sbo(80)), idesc, k16 > 0);
+        umma_bf16(tmem + vw * 32, make_smem_desc(ones, kLBO, ONES_SBO),
+                  make_smem_desc(wimg + I::Wb1 + 4 * 2 * kLBO, kLBO, op_sbo(80)), idesc, 1u);
       }
+      umma_commit(bar_m);
+    }
+    wait_round(bar_m, phase);
+#pragma unroll
+    for (int vw = 0; vw < V; ++vw) {
+      uint32_t r[16];
+      tmem_ld16(t_row + vw * 32 + half * 16, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[vw][k] = elu_scaled(__uint_as_float(r[k]));
     }
     if constexpr (FROM_REC) {
       if (has_next) {     // pull the next tile's records into L2 (one 128-byte line per lane of the row quad)

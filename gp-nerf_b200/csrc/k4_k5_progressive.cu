@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(256) composite_tiles(const float* __restrict__
   // destinations: without a peer block the plain local pointers; with one, everything listed there
   // (entry 0 is this rank's own buffer of the current frame by convention)
   const int n_dst = peer_dev ? pr.n_dst : 1;
+  // frame number of this launch: stable while the kernel runs (only its last CTA advances the counter)
+  const int32_t seq = peer_dev ? *reinterpret_cast<const volatile int32_t*>(pr.seq) + 1 : 0;
+  const int hb = seq & 1;
   const int tile_px = f.tile_px, n_px = f.H * f.W;
   const int n_tiles = (n_px + tile_px - 1) / tile_px;
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -85,20 +88,35 @@ __global__ void __launch_bounds__(256) composite_tiles(const float* __restrict__
     for (int i = tid; i < (npix + 3) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tile_hit)[i] = 0u;
     __syncthreads();
     const int r0 = __ldg(tile_ray_begin + t), r1 = __ldg(tile_ray_begin + t + 1);
-    for (int r = r0 + warp; r < r1; r += (int)(blockDim.x >> 5)) {
-      const int begin = __ldg(ray_pt_begin + r), end = __ldg(ray_pt_begin + r + 1);
+    const int n_warps = (int)(blockDim.x >> 5);
+    // this warp's rays are r0 + warp + j·n_warps: lane j fetches the CSR offsets of ray j up front (one
+    // round trip for all of them; a tile has at most tile_px <= 256 rays, i.e. <= 32 per warp)
+    int my_begin = 0, my_end = 0;
+    {
+      const int rj = r0 + warp + lane * n_warps;
+      if (rj < r1) {
+        my_begin = __ldg(ray_pt_begin + rj);
+        my_end = __ldg(ray_pt_begin + rj + 1);
+      }
+    }
+    int j = 0;
+    for (int r = r0 + warp; r < r1; r += n_warps, ++j) {
+      const int begin = __shfl_sync(0xffffffffu, my_begin, j), end = __shfl_sync(0xffffffffu, my_end, j);
       float T = 1.0f;            // transmittance carried between 32-sample chunks
       float cr = 0.f, cg = 0.f, cb = 0.f;
       for (int base = begin; base < end; base += 32) {
         const int i = base + lane;
         float a = 0.0f, pr_ = 0.f, pg = 0.f, pb = 0.f;
         if (i < end) {
+          // colour exists only for points that passed K4 (a > 1e-14); the loads are issued together with
+          // α's and discarded otherwise (the rows of culled points hold stale finite-or-not bits)
           a = __ldg(alpha + i);
-          if (a > 1e-14f) {      // colour exists only for points that passed K4
-            pr_ = __ldg(rgb + (long long)i * 3);
-            pg = __ldg(rgb + (long long)i * 3 + 1);
-            pb = __ldg(rgb + (long long)i * 3 + 2);
-          }
+          const float q0 = __ldg(rgb + (long long)i * 3), q1 = __ldg(rgb + (long long)i * 3 + 1);
+          const float q2 = __ldg(rgb + (long long)i * 3 + 2);
+          const bool has = a > 1e-14f;
+          pr_ = has ? q0 : 0.f;
+          pg = has ? q1 : 0.f;
+          pb = has ? q2 : 0.f;
         }
         float fct = xadd(xsub(1.0f, a), 1e-10f);
         float incl = fct;        // inclusive product scan
@@ -135,8 +153,8 @@ __global__ void __launch_bounds__(256) composite_tiles(const float* __restrict__
     }
     __syncthreads();
     for (int k = 0; k < n_dst; ++k) {
-      float* img = peer_dev ? reinterpret_cast<float*>(pr.dst_img[k]) : pred_img;
-      uint8_t* hit = peer_dev ? reinterpret_cast<uint8_t*>(pr.dst_hit[k]) : hit_mask;
+      float* img = peer_dev ? reinterpret_cast<float*>(pr.dst_img[hb][k]) : pred_img;
+      uint8_t* hit = peer_dev ? reinterpret_cast<uint8_t*>(pr.dst_hit[hb][k]) : hit_mask;
       for (int i = tid; i < npix * 3; i += blockDim.x) img[(long long)px0 * 3 + i] = tile_rgb[i];
       if ((npix & 3) == 0 && (px0 & 3) == 0) {
         for (int i = tid; i < npix / 4; i += blockDim.x)
@@ -147,16 +165,17 @@ __global__ void __launch_bounds__(256) composite_tiles(const float* __restrict__
     }
     __syncthreads();
   }
-  if (peer_dev != nullptr && pr.n_flag > 0) {
+  if (peer_dev != nullptr) {
     __threadfence_system();      // this thread's peer stores before the CTA's ticket
     __syncthreads();
     if (tid == 0) {
       int32_t* ticket = reinterpret_cast<int32_t*>(pr.ticket);
       const int done = atomicAdd(ticket, 1);
-      if (done == (int)gridDim.x - 1) {
-        *ticket = 0;             // ready for the next launch (graph replay)
+      if (done == (int)gridDim.x - 1) {     // every CTA has read the counter and written its tiles
+        *ticket = 0;                        // ready for the next launch (graph replay)
+        *reinterpret_cast<volatile int32_t*>(pr.seq) = seq;
         __threadfence_system();
-        for (int k = 0; k < pr.n_flag; ++k) st_release_sys(reinterpret_cast<int32_t*>(pr.dst_flag[k]), pr.seq);
+        for (int k = 0; k < pr.n_flag; ++k) st_release_sys(reinterpret_cast<int32_t*>(pr.dst_flag[k]), seq);
       }
     }
   }
@@ -168,7 +187,7 @@ __global__ void peer_wait_kernel(const int32_t* __restrict__ flags, int n_flags,
                                  const gpnerf_peer_t* __restrict__ peer_dev) {
   const int k = threadIdx.x;
   if (k >= n_flags || k == self) return;
-  const int32_t seq = peer_dev->seq;
+  const int32_t seq = *reinterpret_cast<const volatile int32_t*>(peer_dev->seq);   // K5 ran before us
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_sys(flags + k) - seq) < 0) {
     __nanosleep(200);

@@ -170,9 +170,7 @@ class Engine:
         # captured CUDA graph can be replayed for a new pose) + its pinned staging buffer
         self.frame_pinned = torch.empty(C.sizeof(Frame), dtype=torch.uint8).pin_memory()
         self.frame_dev = torch.empty(C.sizeof(Frame), dtype=torch.uint8, device=dev)
-        self._graph = None
-        self._graph_key = None
-        self._graph_launches = 0
+        self._graphs = {}            # (shapes, with_k0) → (CUDAGraph, launches per replay)
         self._static_inputs = None
         self.timing = False          # when set, CUDA events bracket every stage (bench.py)
         self.stage_events = {}
@@ -208,7 +206,7 @@ class Engine:
         if keep[2 * (1 + 4 + 2 + 2)].shape[1] != 32 * self.V:
             raise _lib.GpnerfError("rgb_fc.0 expects 32·n_views input features")
         self._weights, self._weight_tensors = hw, keep
-        self._graph = None          # a captured graph holds the old weight pointers
+        self._graphs = {}           # a captured graph holds the old weight pointers
 
     def _run(self, name, fn, *args):
         ev = self._tic(name)
@@ -280,15 +278,12 @@ class Engine:
         on the current stream).  Every render entry point calls it first."""
         C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
         self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
-        if self.exchange is not None:
-            self.exchange.next_frame()
-            self.exchange.upload()
 
     def attach_exchange(self, exchange):
         """Publish the rendered tiles through peer memory (peer.PeerExchange)
         instead of (only) the local pred_img / hit_mask tensors."""
         self.exchange = exchange
-        self._graph = None
+        self._graphs = {}
 
     def result_image(self, slot=0):
         """[H*W, 3] image of the frame rendered last (a view: copy it before
@@ -312,7 +307,7 @@ class Engine:
         im = src_imgs.to(dev)
         im = (im[0] if im.dim() == 5 else im).contiguous()
         self._static_inputs = (lv, fm, im)
-        self._graph = None
+        self._graphs = {}
 
     def copy_into_static_inputs(self, levels, featmaps, src_imgs, sharded_upload=False):
         """Host (pinned) or device tensors → the static input buffers.  With
@@ -339,44 +334,59 @@ class Engine:
             for d, s in pairs:
                 d.copy_(s, non_blocking=True)
 
-    def run_progressive_graphed(self, frame):
-        """K0…K5 of one frame as ONE CUDA-graph launch.  The graph is captured
-        on first use (after an eager warm-up frame) and replayed afterwards;
-        per-frame values travel through the pinned frame buffer."""
-        if self._static_inputs is None:
+    def run_progressive_graphed(self, frame, with_k0=True, frame_src=None):
+        """One frame as ONE CUDA-graph launch.  The graph is captured on first
+        use (after an eager warm-up frame) and replayed afterwards.
+
+        with_k0=True   the graph is [frame constants ← pinned buffer, K0 from the
+                       static inputs, K1…K5]: call, then sync before changing
+                       the frame (the replay reads the pinned buffer when it runs).
+        with_k0=False  the caller has already launched upload_products(); the
+                       graph covers K1…K5 only and the frame constants are copied
+                       eagerly from `frame_src` (a pinned uint8 tensor the caller
+                       keeps untouched until the frame has run) – frames can then
+                       be queued ahead of the GPU (Renderer.render_stream)."""
+        if with_k0 and self._static_inputs is None:
             raise _lib.GpnerfError("set_static_inputs() first")
-        key = (tuple(self.level_dims or ()), getattr(self, "src_hw", None), getattr(self, "feat_hw", None))
-        if self._graph is None or self._graph_key != key:
+        key = (tuple(self.level_dims or ()), getattr(self, "src_hw", None), getattr(self, "feat_hw", None), with_k0)
+        graphs = self._graphs
+        if key not in graphs:
             timing, self.timing = self.timing, False
-            lv, fm, im = self._static_inputs
-            self.upload_products(lv, fm, im)                 # eager warm-up: allocations, func attributes
+            if with_k0:
+                lv, fm, im = self._static_inputs
+                self.upload_products(lv, fm, im)             # eager warm-up: allocations, func attributes
             self.render_progressive(frame)
             torch.cuda.synchronize(self.device)
-            key = (tuple(self.level_dims), self.src_hw, self.feat_hw)
+            key = (tuple(self.level_dims), self.src_hw, self.feat_hw, with_k0)
             C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
             g = torch.cuda.CUDAGraph()
             l0 = self.launches
             with torch.cuda.graph(g):
-                self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
-                if self.exchange is not None:
-                    self.exchange.upload()
-                self.upload_products(lv, fm, im)
-                self.render_progressive(frame, upload=False, in_capture=True)
-            self._graph_launches = self.launches - l0
-            self._graph, self._graph_key = g, key
+                if with_k0:
+                    self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
+                    self.upload_products(lv, fm, im)
+                self.render_progressive(frame, upload=False)
+            graphs[key] = (g, self.launches - l0)
             self.timing = timing
-        C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
+        g, n_launch = graphs[key]
+        if with_k0:
+            C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
+        else:
+            if frame_src is None:
+                raise _lib.GpnerfError("with_k0=False needs frame_src (pinned copy of the frame constants)")
+            C.memmove(frame_src.data_ptr(), C.addressof(frame), C.sizeof(Frame))
+            self.frame_dev.copy_(frame_src, non_blocking=True)
         if self.exchange is not None:
-            self.exchange.next_frame()       # the replayed copy node picks the new sequence number / buffer half up
-        self._graph.replay()
-        self.launches += self._graph_launches
+            self.exchange.next_frame()       # one more K5 launch queued (its frame counter lives on the device)
+        g.replay()
+        self.launches += n_launch
 
     # --------------------------------------------------------------- launches
     def build_occupancy(self, frame):
         self._run("k0_build_masks3d", self.lib.gpnerf_k0_build_masks3d, ptr_array(self.chan_sums),
                   C.byref(frame), ptr(self.masks3d), self._stream())
 
-    def render_progressive(self, frame, t_rand=None, upload=True, in_capture=False):
+    def render_progressive(self, frame, t_rand=None, upload=True):
         """demo_render.Renderer.render_rays downstream of the producers.
         Leaves results in self.{rgb_map,pred_img,hit_mask,counters,...}."""
         if self._weights is None:
@@ -398,6 +408,8 @@ class Engine:
         self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.alpha), ptr(self.rgb), ptr(self.ray_pix),
                   ptr(self.tile_ray_begin), ptr(self.ray_pt_begin), fr, C.c_float(self.t_min), ptr(self.rgb_map),
                   ptr(self.pred_img), ptr(self.hit_mask), None if ex is None else ptr(ex.peer_dev), st)
+        if ex is not None and not torch.cuda.is_current_stream_capturing():
+            ex.next_frame()
         if ex is not None and ex.world > 1:
             ev = self._tic("peer_wait")
             ex.wait(st)

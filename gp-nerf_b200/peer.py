@@ -13,6 +13,13 @@ Per rank one IPC allocation::
     [2 halves][n_slots][H*W]   uint8   hit masks
     [world]                    int32   arrival flags (flag[k] = last frame rank k finished)
     [1]                        int32   CTA ticket of the local K5 launch
+    [1]                        int32   frame counter (advanced by K5 on the device)
+
+The frame counter lives on the device: K5 renders frame ``*seq + 1`` into buffer
+half ``(seq + 1) & 1`` and stores the number back when its last CTA retires, so
+the host can queue frames ahead (CUDA-graph replays included) without touching
+any per-frame state; ``PeerExchange.seq`` only mirrors how many frames were
+queued, to know which half holds the newest image.
 
 Two ways of spreading work:
 
@@ -68,7 +75,8 @@ class PeerExchange:
         self.off_hit = [[base_hit + (h * self.n_slots + s) * hit_b for s in range(self.n_slots)] for h in range(2)]
         self.off_flags = base_hit + 2 * self.n_slots * hit_b
         self.off_ticket = self.off_flags + 4 * MAX_PEERS
-        self.bytes = self.off_ticket + 256
+        self.off_seq = self.off_ticket + 64
+        self.bytes = self.off_seq + 256
         # --- allocate, exchange the IPC handles, open the peers' buffers
         hb = self.lib.gpnerf_peer_handle_bytes()
         handle = C.create_string_buffer(hb)
@@ -91,46 +99,44 @@ class PeerExchange:
                 self.base[k] = p.value
                 self._opened.append(p.value)
             dist.barrier(group=group)
-        self.seq = 0
+        self.seq = 0                 # host mirror of the device-side frame counter
         self.flags_ptr = self.base[rank] + self.off_flags
-        # device-resident gpnerf_peer_t + pinned staging (refreshed per frame like the frame constants)
-        self.peer_pinned = torch.empty(C.sizeof(Peer), dtype=torch.uint8).pin_memory()
+        # device-resident gpnerf_peer_t, written once
+        p = self._struct()
+        staging = torch.empty(C.sizeof(Peer), dtype=torch.uint8).pin_memory()
+        C.memmove(staging.data_ptr(), C.addressof(p), C.sizeof(Peer))
         self.peer_dev = torch.empty(C.sizeof(Peer), dtype=torch.uint8, device=self.device)
+        self.peer_dev.copy_(staging)
+        torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------
-    def _struct_for(self, seq):
-        half = seq & 1
+    def _struct(self):
         p = Peer()
-        dst = []          # (rank, slot)
         if self.mode == "tiles":
             dst = [(self.rank, 0)] + [(k, 0) for k in range(self.world) if k != self.rank]
         else:
             dst = [(self.rank, 0)] + ([(0, self.rank)] if self.rank != 0 else [])
         p.n_dst = len(dst)
-        for i, (k, s) in enumerate(dst):
-            p.dst_img[i] = self.base[k] + self.off_img[half][s]
-            p.dst_hit[i] = self.base[k] + self.off_hit[half][s]
+        for half in range(2):
+            for i, (k, s) in enumerate(dst):
+                p.dst_img[half][i] = self.base[k] + self.off_img[half][s]
+                p.dst_hit[half][i] = self.base[k] + self.off_hit[half][s]
         others = [k for k in range(self.world) if k != self.rank]
         p.n_flag = len(others)
         for i, k in enumerate(others):
             p.dst_flag[i] = self.base[k] + self.off_flags + 4 * self.rank
-        p.seq = seq
         p.ticket = self.base[self.rank] + self.off_ticket
+        p.seq = self.base[self.rank] + self.off_seq
         return p
 
     def next_frame(self):
-        """Advance to the next frame: refresh the pinned copy of gpnerf_peer_t
-        (the caller – or the captured graph – copies it to the device)."""
+        """Book-keeping for one more queued K5 launch (the device advances its
+        own counter); returns the frame's sequence number."""
         self.seq += 1
-        p = self._struct_for(self.seq)
-        C.memmove(self.peer_pinned.data_ptr(), C.addressof(p), C.sizeof(Peer))
         return self.seq
 
-    def upload(self):
-        self.peer_dev.copy_(self.peer_pinned, non_blocking=True)
-
     def wait(self, stream_ptr):
-        """Enqueue the arrival wait of the current frame (no-op for one rank)."""
+        """Enqueue the arrival wait of the frame K5 just published (no-op for one rank)."""
         if self.world > 1:
             check(self.lib.gpnerf_peer_wait(C.c_void_p(self.flags_ptr), self.world, self.rank,
                                             C.c_void_p(self.peer_dev.data_ptr()), stream_ptr), "peer_wait")

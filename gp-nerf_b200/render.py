@@ -235,6 +235,100 @@ class Renderer(nn.Module):
         return {"rgb_map": rgb_map, "pred_img": pred_img, "mask_at_box": mask_at_box,
                 "time_slots": {"bc_render": rtime}, "etime": etime, "rtime": rtime, "counts": cnt}
 
+    @torch.no_grad()
+    def render_stream(self, batches, depth=3):
+        """Progressive renders of a sequence of batches (a sweep, a video), as a
+        generator yielding the same dicts as ``render`` in order.  The
+        host→device upload of batch i+1, i+2 (134 MB per 512² frame: the slowest
+        leg of an end-to-end frame) runs on a copy stream into one of `depth`
+        staging sets while batch i renders, and the image comes back through
+        pinned buffers, so a steady stream is bound by PCIe or by the kernels,
+        whichever is slower – not by their sum.  Upstream products must come with
+        the batch (``levels``, ``featmaps``) as in the benchmarks."""
+        import collections
+        import ctypes as C
+        from ._lib import Frame
+        if not self.progressive:
+            raise _lib.GpnerfError("render_stream is the progressive (inference) path")
+        if self.world > 1 and self.shard == "tiles":
+            for b in batches:             # a tile-sharded frame needs all ranks in lock step: no queueing ahead
+                yield self.render_progressive(b)
+            return
+        st = None
+        pending = collections.deque()
+
+        def finalize(item):
+            slot, H, W, t_start = item
+            st["done"][slot].synchronize()
+            cnt = dict(zip(("n_pix", "n_rays", "P1", "P2"), st["cnt"][slot][:4].tolist()))
+            pred_img = st["img"][slot].view(H, W, 3).numpy().astype(np.float64)
+            mask_at_box = st["hit"][slot].numpy().astype(bool)
+            rgb_map = pred_img.reshape(-1, 3)[mask_at_box].astype(np.float32)      # ascending pixel order
+            rtime = time.time() - t_start
+            return {"rgb_map": rgb_map, "pred_img": pred_img, "mask_at_box": mask_at_box,
+                    "time_slots": {"bc_render": rtime}, "etime": 0.0, "rtime": rtime, "counts": cnt}
+
+        for i, batch in enumerate(batches):
+            if "levels" not in batch or "featmaps" not in batch:
+                raise _lib.GpnerfError("render_stream needs batch['levels'] and batch['featmaps']")
+            src = batch["src_imgs"]
+            H, W = int(src.shape[-2]), int(src.shape[-1])
+            V = int(src.shape[1])
+            device = self._stream_device(batch)
+            eng = self.engine_for(H, W, V, device)
+            self._sync_weights(eng)
+            if st is None:
+                mk = lambda t: torch.empty(t.shape, dtype=torch.float32, device=device)     # noqa: E731
+                im0 = src[0] if src.dim() == 5 else src
+                st = {
+                    "copy": torch.cuda.Stream(device),
+                    "stage": [([mk(t) for t in batch["levels"]], mk(batch["featmaps"]), mk(im0)) for _ in range(depth)],
+                    "copied": [torch.cuda.Event() for _ in range(depth)],
+                    "free": [torch.cuda.Event() for _ in range(depth)],
+                    "done": [torch.cuda.Event() for _ in range(depth)],
+                    "frame": [torch.empty(C.sizeof(Frame), dtype=torch.uint8).pin_memory() for _ in range(depth)],
+                    "img": [torch.empty(H * W * 3, dtype=torch.float32).pin_memory() for _ in range(depth)],
+                    "hit": [torch.empty(H * W, dtype=torch.uint8).pin_memory() for _ in range(depth)],
+                    "cnt": [torch.empty(8, dtype=torch.int32).pin_memory() for _ in range(depth)],
+                }
+            if len(pending) == depth:
+                yield finalize(pending.popleft())
+            slot = i % depth
+            t_start = time.time()
+            main = torch.cuda.current_stream(device)
+            lv_d, fm_d, im_d = st["stage"][slot]
+            with torch.cuda.stream(st["copy"]):
+                if i >= depth:
+                    st["copy"].wait_event(st["free"][slot])        # K0 of the previous tenant has read the set
+                for d, s_ in zip(lv_d, batch["levels"]):
+                    d.copy_(s_, non_blocking=True)
+                fm_d.copy_(batch["featmaps"], non_blocking=True)
+                im_d.copy_(src[0] if src.dim() == 5 else src, non_blocking=True)
+                st["copied"][slot].record(st["copy"])
+            main.wait_event(st["copied"][slot])
+            eng.upload_products(lv_d, fm_d, im_d)                  # K0: staging set → gather layouts
+            st["free"][slot].record(main)
+            frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
+            if self.use_cuda_graph:
+                eng.run_progressive_graphed(frame, with_k0=False, frame_src=st["frame"][slot])
+            else:
+                C.memmove(st["frame"][slot].data_ptr(), C.addressof(frame), C.sizeof(Frame))
+                eng.frame_dev.copy_(st["frame"][slot], non_blocking=True)
+                eng.render_progressive(frame, upload=False)
+            st["img"][slot].copy_(eng.result_image().reshape(-1), non_blocking=True)
+            st["hit"][slot].copy_(eng.result_hit_mask(), non_blocking=True)
+            st["cnt"][slot].copy_(eng.counters, non_blocking=True)
+            st["done"][slot].record(main)
+            pending.append((slot, H, W, t_start))
+        while pending:
+            yield finalize(pending.popleft())
+
+    def _stream_device(self, batch):
+        src = batch["src_imgs"]
+        if src.is_cuda:
+            return src.device
+        return torch.device("cuda", torch.cuda.current_device())
+
     def render_dense(self, batch):
         """BaseRender.Renderer.render: rgb_map [1,R,3], disp/acc/depth [1,R,1],
         alpha (=weights) [1,R,S], z_vals [1,R,S], rgb_in_map [1,R,3V]."""

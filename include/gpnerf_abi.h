@@ -108,19 +108,20 @@ typedef struct gpnerf_head_weights {
  * of frames) is spread over the GPUs of one NVLink box: destination images in
  * this rank's and its peers' exchange buffers (peer pointers obtained with
  * gpnerf_peer_alloc / gpnerf_peer_open), and the arrival flags that replace a
- * collective.  Lives in DEVICE memory (the host refreshes it per frame: `seq`
- * and the double-buffer half the pointers select), so a captured CUDA graph
- * replays with the current values.  The reference has no counterpart: its
+ * collective.  Lives in DEVICE memory and is written once; the frame counter it
+ * points to advances on the device.  The reference has no counterpart: its
  * renders leave the GPU through `.cpu().numpy()` (demo_render.py:346-353). */
 typedef struct gpnerf_peer {
-  int32_t n_dst;                          /* images every owned tile is written to (entry 0 = own) */
-  int32_t n_flag;                         /* peers whose arrival flag is set when the frame is done */
-  int32_t seq;                            /* frame sequence number, monotonically increasing        */
-  int32_t reserved_;
-  uint64_t dst_img[GPNERF_MAX_PEERS];     /* float   [H*W*3]                                        */
-  uint64_t dst_hit[GPNERF_MAX_PEERS];     /* uint8_t [H*W]                                          */
-  uint64_t dst_flag[GPNERF_MAX_PEERS];    /* int32_t*: this rank's slot in each peer's flag array   */
-  uint64_t ticket;                        /* int32_t*: local CTA counter, zero between launches     */
+  int32_t n_dst;                             /* images every owned tile is written to (entry 0 = own) */
+  int32_t n_flag;                            /* peers whose arrival flag is set when the frame is done */
+  /* destinations, double-buffered: frame number `seq` uses half (seq & 1)                            */
+  uint64_t dst_img[2][GPNERF_MAX_PEERS];     /* float   [H*W*3]                                        */
+  uint64_t dst_hit[2][GPNERF_MAX_PEERS];     /* uint8_t [H*W]                                          */
+  uint64_t dst_flag[GPNERF_MAX_PEERS];       /* int32_t*: this rank's slot in each peer's flag array   */
+  uint64_t ticket;                           /* int32_t*: local CTA counter, zero between launches     */
+  uint64_t seq;                              /* int32_t*: local frame counter; K5 renders frame
+                                                *seq + 1 and its last CTA stores that number back – the
+                                                host never touches it, so frames can be queued ahead   */
 } gpnerf_peer_t;
 
 int gpnerf_abi_version(void);
@@ -294,7 +295,8 @@ int gpnerf_k5_composite(const float *alpha, const float *rgb, const int32_t *ray
                         const gpnerf_frame_t *frame_host, float t_min, float *rgb_map,
                         float *pred_img, uint8_t *hit_mask, const gpnerf_peer_t *peer_dev,
                         void *stream);
-/* Blocks the stream until flags[k] >= peer_dev->seq for every k != self. */
+/* Blocks the stream until flags[k] >= *peer_dev->seq (the frame K5 just
+ * published) for every k != self. */
 int gpnerf_peer_wait(const int32_t *flags, int n_flags, int self, const gpnerf_peer_t *peer_dev,
                      void *stream);
 /* Peer (CUDA IPC) memory for the exchange buffers.  HOST-side calls: alloc =

@@ -144,6 +144,50 @@ def test_csr_offsets_and_peer_exchange_single_rank():
     ex.close()
 
 
+def _renderer_for(weights, V, S, precision):
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Renderer
+    head = NeRFHead(code_dim=32, n_views=V, precision=precision)
+    sd = head.state_dict()
+    sd.update(weights)
+    head.load_state_dict(sd)
+    return Renderer(None, head.to(DEV), is_train=False, n_samples=S, progressive=True, precision=precision)
+
+
+def test_renderer_render_and_render_stream():
+    """The plugin-level calls: Renderer.render(batch) (demo_render.py:429-498
+    contract: numpy rgb_map / pred_img / mask_at_box) against the oracle, and
+    render_stream (uploads overlapped with the renders) against render."""
+    from gpnerf_b200._lib import PREC_FP32
+    S = 32
+    scene = synth.make_scene("zju", H=96, W=96, V=3, seed=23)
+    w = synth.make_head_weights(V=3, seed=123, random_bias=True)
+    o = orc.render_progressive(scene, w, S=S, keep=True)
+    r = _renderer_for(w, 3, S, PREC_FP32)
+    host = {k: v for k, v in scene.items() if torch.is_tensor(v)}
+    host["levels"] = [t.pin_memory() for t in scene["levels"]]
+    host["featmaps"] = scene["featmaps"].pin_memory()
+    b = dict(host)
+    b["src_imgs"] = scene["src_imgs"].to(DEV)
+    out = r.render(b)
+    assert out["pred_img"].dtype == np.float64 and out["pred_img"].shape == (96, 96, 3)
+    assert np.array_equal(out["mask_at_box"], o["mask_at_box"].numpy())
+    assert out["rgb_map"].shape == (o["n_rays"], 3)
+    assert float(np.abs(out["pred_img"] - o["pred_img"].numpy()).max()) < 1e-3
+    # a sweep of five frames, two alternating target views, everything from (pinned) host memory
+    host["src_imgs"] = scene["src_imgs"].pin_memory()
+    other = synth.retarget(scene, 160.0)
+    host2 = dict(host, target_pose=other["target_pose"])
+    want2 = r.render(dict(host2, src_imgs=scene["src_imgs"].to(DEV)))
+    outs = list(r.render_stream([host, host2, host, host2, host]))
+    assert len(outs) == 5
+    for i, got in enumerate(outs):
+        ref = want2 if i % 2 else out
+        assert np.array_equal(got["pred_img"], ref["pred_img"]) and np.array_equal(got["mask_at_box"], ref["mask_at_box"])
+        assert np.array_equal(got["rgb_map"], ref["rgb_map"]) and got["counts"] == ref["counts"]
+    assert not np.array_equal(out["pred_img"], want2["pred_img"])
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)
