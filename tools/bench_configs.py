@@ -101,12 +101,54 @@ def dense(tag, H, S, V, precision, seed=42):
                       "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30, "stages_ms": st}), flush=True)
 
 
+def train(tag, H, S, V, R, seed=42, steps=5):
+    """BASELINE configs[3]: one training step = dense render of R rays (every
+    sample through both heads, jitter on) + MSE on rgb_map + backward to the
+    head parameters, the encoder feature maps and the 4 volume levels –
+    forward and backward both by the library's kernels (gpnerf_b200.train)."""
+    from gpnerf_b200.train import render_dense_autograd
+    scene = synth.make_scene("zju", H=H, W=H, V=V, seed=seed, with_rays=True)
+    w0 = synth.make_head_weights(V=V, seed=seed, random_bias=True)
+    n_all = scene["ray_o"].shape[1]
+    sel = (torch.arange(R) * max(1, n_all // R)) % n_all
+    rays = tuple(scene[k][0][sel].to(DEV) for k in ("ray_o", "ray_d", "near", "far"))
+    eng = Engine(H, H, S, V, device=DEV, max_rays=R)
+    w_g = {k: v.clone().to(DEV).requires_grad_(True) for k, v in w0.items()}
+    lv_g = [t.clone().to(DEV).requires_grad_(True) for t in scene["levels"]]
+    fm_g = scene["featmaps"].clone().to(DEV).requires_grad_(True)
+    im = scene["src_imgs"].to(DEV)
+    eng.set_weights(w0)
+    eng.upload_products([t.detach() for t in lv_g], fm_g.detach(), im)
+    frame = eng.make_frame(scene)
+    target = torch.rand(R, 3, device=DEV)
+    gen = torch.Generator().manual_seed(1)
+
+    def step():
+        for t in list(w_g.values()) + lv_g + [fm_g]:
+            t.grad = None
+        t_rand = torch.rand(R, S, generator=gen)          # BaseRender.py:46: drawn on the CPU generator
+        out = render_dense_autograd(eng, frame, rays, lv_g, fm_g, im, w_g, t_rand=t_rand)
+        loss = ((out["rgb_map"] - target) ** 2).mean()
+        loss.backward()
+        return loss
+    ms = timed(step, steps=steps, warmup=2)
+    loss = float(step())
+    gn = float(sum(float(v.grad.pow(2).sum()) for v in w_g.values()) ** 0.5)
+    print(json.dumps({"config": tag, "H": H, "S": S, "V": V, "rays": R, "precision": "fp32",
+                      "ms_per_step": ms, "rays_per_s": R * 1e3 / ms, "points_per_s": R * S * 1e3 / ms,
+                      "loss": loss, "head_grad_norm": gn, "finite": bool(torch.isfinite(torch.tensor(gn))),
+                      "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 CONFIGS = {
     "zju512_fp32": lambda: progressive("zju512_fp32 (configs[1] geometry, fp32 parity heads)", 512, 64, 3, PREC_FP32,
                                        graph=False),
     "thu512": lambda: progressive("trainthu_valzju shape (configs[2]): same hot-path tensors, other seed", 512, 64, 3,
                                   PREC_BF16, seed=1234),
     "dense512": lambda: dense("dense 512x512 BaseRender path (worst case, no compaction)", 512, 64, 3, PREC_BF16),
+    "train4096": lambda: train("training step fwd+bwd, 4096 rays x 64 samples (configs[3] on one GPU)", 512, 64, 3, 4096),
+    "train512": lambda: train("training step fwd+bwd, 512 rays x 64 samples (configs[3]: one GPU's share of 8)", 512, 64,
+                              3, 512),
     "zju1024": lambda: progressive("1024x1024, S=128, V=4 (configs[4] single-GPU share)", 1024, 128, 4, PREC_BF16),
 }
 

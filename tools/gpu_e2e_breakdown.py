@@ -1,0 +1,36 @@
+"""Where a blocking Renderer.render(batch) call spends its wall time (1 GPU)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT]
+import torch
+import gpnerf_b200  # noqa
+from gpnerf_b200 import synth
+from gpnerf_b200._lib import PREC_BF16
+from gpnerf_b200.nerfhead import NeRFHead
+from gpnerf_b200.render import Renderer
+
+dev = torch.device("cuda", 0)
+scene = synth.make_scene("zju", H=512, W=512, V=3, seed=42)
+w = synth.make_head_weights(V=3, seed=42)
+head = NeRFHead(code_dim=32, n_views=3, precision=PREC_BF16)
+sd = head.state_dict(); sd.update(w); head.load_state_dict(sd)
+r = Renderer(None, head.to(dev), is_train=False, n_samples=64, progressive=True, precision=PREC_BF16)
+batch = {k: v for k, v in scene.items() if torch.is_tensor(v)}
+batch["levels"] = [t.pin_memory() for t in scene["levels"]]
+batch["featmaps"] = scene["featmaps"].pin_memory()
+batch["src_imgs"] = scene["src_imgs"].pin_memory()
+
+def step():
+    b = dict(batch); b["src_imgs"] = batch["src_imgs"].to(dev, non_blocking=True)
+    return r.render(b)
+for _ in range(3): step()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(20): step()
+torch.cuda.synchronize()
+print("blocking render ms/frame", (time.perf_counter() - t0) / 20 * 1e3)
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in range(20): step()
+torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
