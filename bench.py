@@ -405,18 +405,21 @@ def main():
             ach, peak, unit = amount / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
         else:
             ach, peak, unit = amount / dur_s / 1e12, pk["bf16_tflops"], "TFLOP/s"
-        traffic, traffic_src = None, None
+        traffic, traffic_src, ncu_units = None, None, None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tpath) and world == 1:
             tj = json.load(open(tpath))
             if top in tj:
-                traffic, traffic_src = tj[top], "ncu --set full, same workload (profiles/r01_ncu_summary.md)"
+                traffic, traffic_src = tj[top], "ncu --set full, same workload (profiles/r01_final_ncu_summary.md)"
+                ncu_units = tj.get("ncu", {}).get(top)
         roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic": what,
                     "algorithmic_bytes_or_flops": amount, "launch_ms": timed[top] * n_calls,
-                    "peak_source": pk["source"],
-                    "note": "achieved counts REQUESTED gather bytes; the volumes/maps are L2-resident, so it can "
-                            "exceed the HBM copy peak while DRAM traffic (`traffic`) stays far below it"
+                    "peak_source": pk["source"], "ncu": ncu_units,
+                    "note": "achieved counts REQUESTED gather bytes (SURVEY §8d per-point figure, 16-bit storage); the "
+                            "volumes/maps are L2-resident, so it can exceed the HBM copy peak while DRAM traffic "
+                            "(`traffic`) stays far below it.  What binds the kernel is the L1 data pipe (`ncu`): one "
+                            "128-byte wavefront per 64-byte corner fetch"
                     if bound == "hbm" else None}
     stages_out = {}
     for k, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
