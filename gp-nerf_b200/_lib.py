@@ -90,8 +90,9 @@ _SIGNATURES = {
     "gpnerf_k2_gather_volume_bwd": ([C.POINTER(_P), _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),
     "gpnerf_k2_project_gather_bwd": ([_P, _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),
     "gpnerf_k6_linear": ([_P, _I, _I, C.c_float, _P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I,
-                          C.c_longlong, _P], C.c_int),
-    "gpnerf_k6_grad_weights": ([_P, _I, _I, C.c_float, _P, _I, _I, _P, _I, _P, _I, _P, C.c_longlong, _P], C.c_int),
+                          C.c_longlong, _I, _P], C.c_int),
+    "gpnerf_k6_grad_weights": ([_P, _I, _I, C.c_float, _P, _I, _I, _P, _I, _P, _I, _P, C.c_longlong, _I, _P],
+                               C.c_int),
     "gpnerf_k6_assemble_raw": ([_P, _P, _P, _I, C.c_longlong, _P, _P], C.c_int),
     "gpnerf_k6_raw_grad_split": ([_P, _P, _P, _P, _I, C.c_longlong, _P, _P, _P], C.c_int),
     "gpnerf_k6_meanvar_bwd": ([_P, _P, _P, _I, C.c_longlong, _P, _P], C.c_int),

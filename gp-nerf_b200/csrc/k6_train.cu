@@ -272,13 +272,27 @@ static int grid_cap(long long blocks, int per_sm) {
 
 using namespace gpnerf;
 
+namespace gpnerf {   // k6_train_tc.cu
+int linear_tc_launch(const float* X, int ldx, int K, float in_scale, const float* in_aux, int ld_in_aux,
+                     const float* W, int ldw, int w_is_kn, int N, const float* bias, int epilogue, const float* aux,
+                     int ld_aux, float* Y, int ldy, int add_pre, int add_post, long long P, cudaStream_t st);
+int grad_weights_tc_launch(const float* X, int ldx, int K, float in_scale, const float* dY, int ldy, int N,
+                           const float* dy_aux, int ld_dy_aux, float* dW, int ldw, float* db, long long P,
+                           cudaStream_t st);
+}  // namespace gpnerf
+
 extern "C" {
 
 int gpnerf_k6_linear(const float* X, int ldx, int K, float in_scale, const float* in_aux, int ld_in_aux,
                      const float* W, int ldw, int w_is_kn, int N, const float* bias, int epilogue, const float* aux,
-                     int ld_aux, float* Y, int ldy, int add_pre, int add_post, long long P, void* stream) {
+                     int ld_aux, float* Y, int ldy, int add_pre, int add_post, long long P, int precision,
+                     void* stream) {
   GPNERF_REQUIRE(X && W && Y && K > 0 && K <= 160 && N > 0 && N <= 160 && P > 0 && ldx >= K && ldy >= N);
   GPNERF_REQUIRE(epilogue >= 0 && epilogue <= EPI_MUL_DELU && (epilogue != EPI_MUL_DELU || aux != nullptr));
+  GPNERF_REQUIRE(precision == 0 || precision == 1);
+  if (precision == 1)
+    return linear_tc_launch(X, ldx, K, in_scale, in_aux, ld_in_aux, W, ldw, w_is_kn, N, bias, epilogue, aux, ld_aux,
+                            Y, ldy, add_pre, add_post, P, (cudaStream_t)stream);
   LinArgs a{X, ldx, K, in_scale, in_aux, ld_in_aux, W, ldw, w_is_kn, N, bias, epilogue, aux, ld_aux, Y, ldy,
             add_pre, add_post, P};
   const int NP = (N + 3) & ~3;
@@ -305,8 +319,12 @@ int gpnerf_k6_linear(const float* X, int ldx, int K, float in_scale, const float
 
 int gpnerf_k6_grad_weights(const float* X, int ldx, int K, float in_scale, const float* dY, int ldy, int N,
                            const float* dy_aux, int ld_dy_aux, float* dW, int ldw, float* db, long long P,
-                           void* stream) {
+                           int precision, void* stream) {
   GPNERF_REQUIRE(X && dY && dW && K > 0 && K <= 144 && N > 0 && N <= 64 && P > 0 && ldw >= K);
+  GPNERF_REQUIRE(precision == 0 || precision == 1);
+  if (precision == 1)
+    return grad_weights_tc_launch(X, ldx, K, in_scale, dY, ldy, N, dy_aux, ld_dy_aux, dW, ldw, db, P,
+                                  (cudaStream_t)stream);
   GwArgs a{X, ldx, K, in_scale, dY, ldy, N, dy_aux, ld_dy_aux, dW, ldw, db, P};
   const size_t smem = (size_t)(GCH * (K + 1) + GCH * (N + 1)) * sizeof(float);
   static bool set = false;

@@ -39,10 +39,14 @@ def _p(t, off=0):
     return None if t is None else C.c_void_p(t.data_ptr() + 4 * off)
 
 
+PREC_TRAIN_FP32, PREC_TRAIN_TF32 = 0, 1     # GEMMs of the heads: CUDA-core fp32 (parity) | tcgen05 TF32
+
+
 class _Kernels:
-    def __init__(self, device):
+    def __init__(self, device, precision=PREC_TRAIN_FP32):
         self.lib = _lib.load()
         self.device = device
+        self.precision = int(precision)
 
     def st(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -52,13 +56,14 @@ class _Kernels:
                add_post=False):
         check(self.lib.gpnerf_k6_linear(_p(X, xoff), ldx, K, C.c_float(in_scale), _p(in_aux, in_aux_off), ld_in_aux,
                                         _p(W, woff), ldw, int(w_is_kn), N, _p(bias), epi, _p(aux, aux_off), ld_aux,
-                                        _p(Y, yoff), ldy, int(add_pre), int(add_post), P, self.st()), "k6_linear")
+                                        _p(Y, yoff), ldy, int(add_pre), int(add_post), P, self.precision, self.st()),
+              "k6_linear")
 
     def grad_w(self, X, ldx, K, dY, ldy, N, dW, ldw, db, P, *, xoff=0, dyoff=0, dwoff=0, in_scale=1.0, dy_aux=None,
                dy_aux_off=0, ld_dy_aux=0):
         check(self.lib.gpnerf_k6_grad_weights(_p(X, xoff), ldx, K, C.c_float(in_scale), _p(dY, dyoff), ldy, N,
                                               _p(dy_aux, dy_aux_off), ld_dy_aux, _p(dW, dwoff), ldw, _p(db), P,
-                                              self.st()), "k6_grad_weights")
+                                              self.precision, self.st()), "k6_grad_weights")
 
 
 def _heads_forward(k: _Kernels, w, vol, mv, rf, V, P):
@@ -191,7 +196,7 @@ class _RenderDenseFn(torch.autograd.Function):
         levels, featmaps, params = list(tensors[:n_levels]), tensors[n_levels], tensors[n_levels + 1:]
         assert len(params) == 2 * len(PARAM_KEYS)
         dev = eng.device
-        k = _Kernels(dev)
+        k = _Kernels(dev, getattr(eng, "train_precision", PREC_TRAIN_FP32))
         L, st = eng.lib, k.st()
         w = {key: (params[2 * i].detach().float().contiguous(), params[2 * i + 1].detach().float().contiguous())
              for i, key in enumerate(PARAM_KEYS)}
@@ -291,10 +296,13 @@ class _RenderDenseFn(torch.autograd.Function):
 
 
 def render_dense_autograd(eng: Engine, frame, rays, levels, featmaps, src_imgs, head_params, t_rand=None,
-                          neg_ray=False):
+                          neg_ray=False, precision=PREC_TRAIN_FP32):
     """Differentiable dense render.  `head_params`: dict name → tensor with the
     reference state_dict keys (prefix 'nerfhead.' optional).  Returns a dict
-    with the BaseRender output keys (BaseRender.py:148-156)."""
+    with the BaseRender output keys (BaseRender.py:148-156).  `precision`:
+    PREC_TRAIN_FP32 (CUDA-core fp32 GEMMs, the parity path) or PREC_TRAIN_TF32
+    (the heads' forward and backward GEMMs on tcgen05 in TF32)."""
+    eng.train_precision = int(precision)
     def get(name):
         for pre in ("", "nerfhead."):
             if pre + name in head_params:

@@ -346,16 +346,17 @@ int gpnerf_k2_project_gather_bwd(float *d_featmaps_nhwc, int point_kind, const i
  * B[k][n] = w_is_kn ? W[k*ldw+n] : W[n*ldw+k] (nn.Linear layout → forward; its
  * transpose → ∂L/∂X).  epilogue: 0 none, 1 ELU, 2 ReLU, 3 sigmoid, 4 multiply
  * by ELU'(aux[p][n]).  add_pre / add_post add the previous content of Y before
- * / after the epilogue. */
+ * / after the epilogue.  precision: 0 = fp32 FMA chains on CUDA cores (the
+ * parity path), 1 = tcgen05.mma.kind::tf32 with fp32 accumulators in TMEM. */
 int gpnerf_k6_linear(const float *X, int ldx, int K, float in_scale, const float *in_aux,
                      int ld_in_aux, const float *W, int ldw, int w_is_kn, int N, const float *bias,
                      int epilogue, const float *aux, int ld_aux, float *Y, int ldy, int add_pre,
-                     int add_post, long long P, void *stream);
+                     int add_post, long long P, int precision, void *stream);
 /* dW[n*ldw+k] += Σ_p dY'[p][n]·X[p][k]·in_scale ; db[n] += Σ_p dY'[p][n] (db may
  * be NULL); dY' = dY ⊙ ELU'(dy_aux) when dy_aux is given */
 int gpnerf_k6_grad_weights(const float *X, int ldx, int K, float in_scale, const float *dY, int ldy,
                            int N, const float *dy_aux, int ld_dy_aux, float *dW, int ldw, float *db,
-                           long long P, void *stream);
+                           long long P, int precision, void *stream);
 /* raw[p] = (rgb[p], σ[p]) with σ = s_relu[p], forced to 0 where Σ_v mask[p][v] < 1
  * (trainhead.py:136-137,162); and the matching split of ∂L/∂raw into the
  * pre-sigmoid / pre-ReLU gradients */

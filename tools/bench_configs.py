@@ -101,7 +101,7 @@ def dense(tag, H, S, V, precision, seed=42):
                       "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30, "stages_ms": st}), flush=True)
 
 
-def train(tag, H, S, V, R, seed=42, steps=5):
+def train(tag, H, S, V, R, seed=42, steps=5, precision=0):
     """BASELINE configs[3]: one training step = dense render of R rays (every
     sample through both heads, jitter on) + MSE on rgb_map + backward to the
     head parameters, the encoder feature maps and the 4 volume levels –
@@ -127,14 +127,14 @@ def train(tag, H, S, V, R, seed=42, steps=5):
         for t in list(w_g.values()) + lv_g + [fm_g]:
             t.grad = None
         t_rand = torch.rand(R, S, generator=gen)          # BaseRender.py:46: drawn on the CPU generator
-        out = render_dense_autograd(eng, frame, rays, lv_g, fm_g, im, w_g, t_rand=t_rand)
+        out = render_dense_autograd(eng, frame, rays, lv_g, fm_g, im, w_g, t_rand=t_rand, precision=precision)
         loss = ((out["rgb_map"] - target) ** 2).mean()
         loss.backward()
         return loss
     ms = timed(step, steps=steps, warmup=2)
     loss = float(step())
     gn = float(sum(float(v.grad.pow(2).sum()) for v in w_g.values()) ** 0.5)
-    print(json.dumps({"config": tag, "H": H, "S": S, "V": V, "rays": R, "precision": "fp32",
+    print(json.dumps({"config": tag, "H": H, "S": S, "V": V, "rays": R, "precision": "tf32 tcgen05 heads" if precision else "fp32",
                       "ms_per_step": ms, "rays_per_s": R * 1e3 / ms, "points_per_s": R * S * 1e3 / ms,
                       "loss": loss, "head_grad_norm": gn, "finite": bool(torch.isfinite(torch.tensor(gn))),
                       "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
@@ -149,6 +149,10 @@ CONFIGS = {
     "train4096": lambda: train("training step fwd+bwd, 4096 rays x 64 samples (configs[3] on one GPU)", 512, 64, 3, 4096),
     "train512": lambda: train("training step fwd+bwd, 512 rays x 64 samples (configs[3]: one GPU's share of 8)", 512, 64,
                               3, 512),
+    "train4096_tf32": lambda: train("training step fwd+bwd, 4096 rays x 64 samples, TF32 tcgen05 heads", 512, 64, 3, 4096,
+                                    precision=1),
+    "train512_tf32": lambda: train("training step fwd+bwd, 512 rays x 64 samples, TF32 tcgen05 heads", 512, 64, 3, 512,
+                                   precision=1),
     "zju1024": lambda: progressive("1024x1024, S=128, V=4 (configs[4] single-GPU share)", 1024, 128, 4, PREC_BF16),
 }
 
