@@ -74,6 +74,7 @@ _SIGNATURES = {
     "gpnerf_k0_images_to_rgbx": ([_P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
     "gpnerf_k1_voxel_pixel_mask": ([_P, C.POINTER(Frame), _P, _P, _P], C.c_int),
     "gpnerf_k1_rays_bbox": ([_P, _P, C.POINTER(Frame), _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k1_dataset_rays": ([_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k2_occupancy_compact": ([_P, _P, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P, _P, _P, _P],
                                     C.c_int),
     "gpnerf_k2_gather_volume": ([C.POINTER(_P), _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),

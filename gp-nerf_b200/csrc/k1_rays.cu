@@ -233,6 +233,117 @@ __global__ void __launch_bounds__(256) ray_finalize(const int32_t* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Row f3: the dataset path's rays on the GPU – what the reference's
+// CPU DataLoader workers compute per frame with numpy
+// (libs/datasets/data_utils.py:47-63 get_rays, :331-337 sample_ray test split,
+// :96-130 get_near_far).  Same dtype promotions: pixel → world in fp64, rays cast
+// to fp32, box test in fp64 on those fp32 rays (bounds ± 0.01 folded in by the
+// host, |d| < 1e-5 → 1e-5, eps 1e-6, exactly two hits, both depths signed by the
+// first hit's side).  numpy never contracts a*b+c: explicit _rn intrinsics below.
+// ---------------------------------------------------------------------------
+struct DsRayArgs {
+  double Kinv[9], Rinv[9], origin[3], bounds[6];   // bounds = (min xyz, max xyz) already widened by 0.01
+  int H, W;
+};
+struct DsRay {
+  float d[3], near, far;
+  bool at_box;
+};
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ DsRay dataset_ray(const DsRayArgs& a, int pix) {
+  const double x = (double)(float)(pix % a.W), y = (double)(float)(pix / a.W);
+  double pc[3], pw[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)      // np.dot(xy1, inv(K).T): dgemm accumulates k ascending with FMAs
+    pc[c] = fma(1.0, a.Kinv[c * 3 + 2], fma(y, a.Kinv[c * 3 + 1], dmul(x, a.Kinv[c * 3 + 0])));
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    pw[c] = dadd(fma(pc[2], a.Rinv[c * 3 + 2], fma(pc[1], a.Rinv[c * 3 + 1], dmul(pc[0], a.Rinv[c * 3 + 0]))), a.origin[c]);
+  DsRay r;
+  float o32[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    r.d[c] = (float)dsub(pw[c], a.origin[c]);
+    if (fabsf(r.d[c]) < 1e-5f) r.d[c] = 1e-5f;
+    o32[c] = (float)a.origin[c];
+  }
+  const double eps = 1e-6;
+  double hit[2][3];
+  int n_hit = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int c = k % 3;
+    const double t = dsub(a.bounds[k], (double)o32[c]) / (double)r.d[c];
+    double p[3];
+    bool in = true;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      p[q] = dadd(dmul(t, (double)r.d[q]), (double)o32[q]);
+      in = in && (p[q] >= dsub(a.bounds[q], eps)) && (p[q] <= dadd(a.bounds[3 + q], eps));
+    }
+    if (in) {
+      if (n_hit < 2) {
+        hit[n_hit][0] = p[0]; hit[n_hit][1] = p[1]; hit[n_hit][2] = p[2];
+      }
+      ++n_hit;
+    }
+  }
+  r.at_box = n_hit == 2;
+  r.near = r.far = 0.0f;
+  if (r.at_box) {
+    const float nrm32 = __fsqrt_rn(xadd(xadd(xmul(r.d[0], r.d[0]), xmul(r.d[1], r.d[1])), xmul(r.d[2], r.d[2])));
+    double dist[2], dot = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double vx = dsub(hit[h][0], (double)o32[0]), vy = dsub(hit[h][1], (double)o32[1]);
+      const double vz = dsub(hit[h][2], (double)o32[2]);
+      dist[h] = __dsqrt_rn(dadd(dadd(dmul(vx, vx), dmul(vy, vy)), dmul(vz, vz)));
+      if (h == 0) dot = dadd(dadd(dmul(vx, (double)r.d[0]), dmul(vy, (double)r.d[1])), dmul(vz, (double)r.d[2]));
+    }
+    const double sign = dot < 0.0 ? -1.0 : 1.0;
+    const double d0 = dmul(dist[0] / (double)nrm32, sign), d1 = dmul(dist[1] / (double)nrm32, sign);
+    r.near = (float)fmin(d0, d1);
+    r.far = (float)fmax(d0, d1);
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(256) dataset_ray_flags(const __grid_constant__ DsRayArgs a, uint32_t* __restrict__ words,
+                                                         uint8_t* __restrict__ mask_at_box) {
+  const int n = a.H * a.W, n_pad = (n + 31) & ~31;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pad; p += gridDim.x * blockDim.x) {
+    bool keep = false;
+    if (p < n) {
+      keep = dataset_ray(a, p).at_box;
+      mask_at_box[p] = keep ? 1 : 0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0) words[p >> 5] = b;
+  }
+}
+__global__ void __launch_bounds__(256) dataset_ray_finalize(const __grid_constant__ DsRayArgs a,
+                                                            const int32_t* __restrict__ ray_pix,
+                                                            const int32_t* __restrict__ n_rays,
+                                                            float* __restrict__ ray_o, float* __restrict__ ray_d,
+                                                            float* __restrict__ near, float* __restrict__ far) {
+  const int n = __ldg(n_rays);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const DsRay r = dataset_ray(a, __ldg(ray_pix + i));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ray_o[i * 3 + c] = (float)a.origin[c];
+      ray_d[i * 3 + c] = r.d[c];
+    }
+    near[i] = r.near;
+    far[i] = r.far;
+  }
+}
+
 }  // namespace gpnerf
 
 using namespace gpnerf;
@@ -290,6 +401,30 @@ int gpnerf_k1_rays_bbox(const float* pix_mask, const float* can_bounds, const gp
   if (rc != GPNERF_OK) return rc;
   ray_finalize<<<grid, 256, 0, st>>>(ray_pix, can_bounds, *f, counters, rays_d, near, far);
   return check_launch("k1_rays_bbox");
+}
+
+int gpnerf_k1_dataset_rays(const double* K_inv_host, const double* R_inv_host, const double* origin_host,
+                           const double* bounds_host, int H, int W, int32_t* ray_pix, float* ray_o, float* ray_d,
+                           float* near, float* far, uint8_t* mask_at_box, int32_t* n_rays, void* workspace,
+                           void* stream) {
+  GPNERF_REQUIRE(K_inv_host && R_inv_host && origin_host && bounds_host && ray_pix && ray_o && ray_d && near && far &&
+                 mask_at_box && n_rays && workspace);
+  GPNERF_REQUIRE(H > 0 && W > 0 && (long long)H * W < (1ll << 30));
+  DsRayArgs a;
+  for (int i = 0; i < 9; ++i) { a.Kinv[i] = K_inv_host[i]; a.Rinv[i] = R_inv_host[i]; }
+  for (int i = 0; i < 3; ++i) a.origin[i] = origin_host[i];
+  for (int i = 0; i < 6; ++i) a.bounds[i] = bounds_host[i];
+  a.H = H; a.W = W;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)H * W;
+  CompactWs ws = carve_workspace(workspace, n);
+  long long blocks = (n + 255) / 256;
+  int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : sm_count() * 8);
+  dataset_ray_flags<<<grid, 256, 0, st>>>(a, ws.words, mask_at_box);
+  int rc = compact_launch(ws, nullptr, 1, n, n, ray_pix, n_rays, st);
+  if (rc != GPNERF_OK) return rc;
+  dataset_ray_finalize<<<grid, 256, 0, st>>>(a, ray_pix, n_rays, ray_o, ray_d, near, far);
+  return check_launch("k1_dataset_rays");
 }
 
 }  // extern "C"

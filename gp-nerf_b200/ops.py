@@ -231,3 +231,40 @@ class _Raw2OutputsFn(torch.autograd.Function):
 def raw2outputs_autograd(raw, z_vals, rgb_in=None, neg=False):
     """Differentiable raw2outputs: (rgb_map, disp, acc, weights, depth[, rgb_in_map])."""
     return _Raw2OutputsFn.apply(raw, z_vals, rgb_in, neg)
+
+
+def dataset_rays(H, W, K, R, T, bounds, device):
+    """The reference's CPU loader rays on the GPU:
+    libs/datasets/data_utils.py get_rays (:47-63) + sample_ray's test split
+    (:331-337) + get_near_far (:96-130) for every pixel of an H×W view.
+
+    K [3,3], R [3,3], T [3] (or [3,1]) as the dataset holds them, `bounds` [2,3]
+    fp32 (world-frame box).  The three tiny host-side steps are the very numpy
+    calls the reference makes (two 3×3 inverses, one 3×3 · 3 product); everything
+    per pixel runs in the kernel.  Returns device tensors ray_o [R,3], ray_d
+    [R,3], near [R], far [R] (fp32, ascending pixel order) and mask_at_box [H*W]
+    bool – the batch entries ZjumocapDataset.__getitem__ builds from them."""
+    import numpy as np
+    lib = _lib.load()
+    dev = torch.device(device)
+    K, R = np.asarray(K), np.asarray(R)
+    T = np.asarray(T).reshape(3)
+    R_inv = np.linalg.inv(R)                         # data_utils.py:49
+    origin = (-R_inv @ T).ravel().astype(np.float64)  # :50-51
+    K_inv = np.linalg.inv(K).astype(np.float64)      # :57
+    b = (np.asarray(bounds) + np.array([-0.01, 0.01])[:, None]).astype(np.float64)   # :98
+    n = H * W
+    i32, f32 = torch.int32, torch.float32
+    ray_pix = torch.empty(n, dtype=i32, device=dev)
+    ray_o, ray_d = torch.empty(n * 3, dtype=f32, device=dev), torch.empty(n * 3, dtype=f32, device=dev)
+    near, far = torch.empty(n, dtype=f32, device=dev), torch.empty(n, dtype=f32, device=dev)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=i32, device=dev)
+    ws = torch.empty(int(lib.gpnerf_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    Ki, Ri, Oi, Bi = (np.ascontiguousarray(a, dtype=np.float64) for a in (K_inv, R_inv.astype(np.float64), origin, b))
+    check(lib.gpnerf_k1_dataset_rays(Ki.ctypes.data_as(C.c_void_p), Ri.ctypes.data_as(C.c_void_p),
+                                     Oi.ctypes.data_as(C.c_void_p), Bi.ctypes.data_as(C.c_void_p), H, W, ptr(ray_pix),
+                                     ptr(ray_o), ptr(ray_d), ptr(near), ptr(far), ptr(mask), ptr(cnt), ptr(ws),
+                                     _stream(dev)), "k1_dataset_rays")
+    r = int(cnt.item())
+    return (ray_o[: r * 3].view(r, 3), ray_d[: r * 3].view(r, 3), near[:r], far[:r], mask.bool())

@@ -177,6 +177,21 @@ int gpnerf_k1_rays_bbox(const float *pix_mask, const float *can_bounds,
 /* tile_ray_begin (may be NULL): int32[ceil(H*W/tile_px) + 1], CSR offsets of the
  * rays of every pixel tile (K5 walks its tiles with them). */
 
+/* The dataset path's rays: libs/datasets/data_utils.py:47-63
+ * get_rays + the test-split branch of sample_ray (:331-337) + get_near_far
+ * (:96-130) for every pixel of an H×W view, with numpy's dtype promotions (fp64
+ * pixel→world, fp32 rays, fp64 box test).  HOST inputs (computed by the caller
+ * with the same numpy calls the reference makes): K_inv = inv(K) and
+ * R_inv = inv(R) row-major 3×3, origin = -R_inv·T, bounds = (min xyz, max xyz)
+ * of the fp32 box widened by ∓0.01 in fp64.  Outputs (device): mask_at_box
+ * uint8[H*W]; for the n_rays[0] rays that hit the box exactly twice, in ascending
+ * pixel order: ray_pix, ray_o / ray_d [n][3], near / far [n].  Buffers sized H*W;
+ * workspace as for the other compactions. */
+int gpnerf_k1_dataset_rays(const double *K_inv_host, const double *R_inv_host,
+                           const double *origin_host, const double *bounds_host, int H, int W,
+                           int32_t *ray_pix, float *ray_o, float *ray_d, float *near, float *far,
+                           uint8_t *mask_at_box, int32_t *n_rays, void *workspace, void *stream);
+
 /* ---- K2: occupancy test, gathers --------------------------------------- */
 /* demo_render.py:59-94, 270-283: sample S depths per ray (t_vals = linspace,
  * optional jitter t_rand[R*S] or NULL), world→SMPL, trilinear tap of masks3d,

@@ -495,3 +495,50 @@ def psnr(a, b):
     """libs/evaluators/if_nerf.py:29-32 (10·log10(1/mse))."""
     mse = float(((a.double() - b.double()) ** 2).mean())
     return 10.0 * math.log10(1.0 / max(mse, 1e-20))
+
+
+# --------------------------------------------------------------------------
+# Row f3 (SURVEY §8f): the dataset path's rays – numpy, as the CPU loader computes them
+# --------------------------------------------------------------------------
+def dataset_rays(H, W, K, R, T, bounds):
+    """libs/datasets/data_utils.py:47-63 (get_rays) followed by the test-split
+    branch of sample_ray (:331-337) and get_near_far (:96-130), dtype promotions
+    included: the rays are formed in fp64 and cast to fp32, the box test then runs
+    in fp64 on those fp32 rays (bounds ± 0.01, |d| < 1e-5 → 1e-5, eps 1e-6, exactly
+    two hits, both depths signed by the FIRST hit's side).
+    Returns (ray_o [R,3] f32, ray_d [R,3] f32, near [R] f32, far [R] f32,
+    mask_at_box [H*W] bool) – numpy arrays."""
+    import numpy as np
+    K, R, T = np.asarray(K), np.asarray(R), np.asarray(T)
+    R_inv = np.linalg.inv(R)
+    T = -R_inv @ T.reshape(3)
+    rays_o = T.ravel()
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing="xy")
+    xy1 = np.stack([i, j, np.ones_like(i)], axis=2)
+    pixel_camera = np.dot(xy1, np.linalg.inv(K).T)
+    pixel_world = (pixel_camera @ R_inv.T) + T[np.newaxis, ...]
+    rays_d = pixel_world - rays_o[None, None]
+    ray_o = np.broadcast_to(rays_o, rays_d.shape).reshape(-1, 3).astype(np.float32)
+    ray_d = rays_d.reshape(-1, 3).astype(np.float32)
+    # get_near_far
+    b = np.asarray(bounds) + np.array([-0.01, 0.01])[:, None]
+    nominator = b[None] - ray_o[:, None]
+    ray_d = ray_d.copy()
+    ray_d[np.abs(ray_d) < 1e-5] = 1e-5
+    d_intersect = (nominator / ray_d[:, None]).reshape(-1, 6)
+    p_intersect = d_intersect[..., None] * ray_d[:, None] + ray_o[:, None]
+    min_x, min_y, min_z, max_x, max_y, max_z = b.ravel()
+    eps = 1e-6
+    inside = ((p_intersect[..., 0] >= (min_x - eps)) * (p_intersect[..., 0] <= (max_x + eps)) *
+              (p_intersect[..., 1] >= (min_y - eps)) * (p_intersect[..., 1] <= (max_y + eps)) *
+              (p_intersect[..., 2] >= (min_z - eps)) * (p_intersect[..., 2] <= (max_z + eps)))
+    mask_at_box = inside.sum(-1) == 2
+    p_int = p_intersect[mask_at_box][inside[mask_at_box]].reshape(-1, 2, 3)
+    ro, rd = ray_o[mask_at_box], ray_d[mask_at_box]
+    norm_ray = np.linalg.norm(rd, axis=1)
+    sign = np.array(((p_int[:, 0] - ro) * rd).sum(axis=1) < 0.0, dtype=np.int64) * -2 + 1
+    d0 = np.linalg.norm(p_int[:, 0] - ro, axis=1) / norm_ray * sign
+    d1 = np.linalg.norm(p_int[:, 1] - ro, axis=1) / norm_ray * sign
+    near = np.minimum(d0, d1).astype(np.float32)
+    far = np.maximum(d0, d1).astype(np.float32)
+    return ro, rd, near, far, mask_at_box

@@ -188,6 +188,33 @@ def test_renderer_render_and_render_stream():
     assert not np.array_equal(out["pred_img"], want2["pred_img"])
 
 
+@pytest.mark.parametrize("H,seed,angle", [(48, 3, 45.0), (64, 11, 200.0), (512, 42, 45.0), (250, 5, 310.0)])
+def test_dataset_rays_kernel_vs_oracle(H, seed, angle):
+    """Row f3: the CPU loader's rays (data_utils.get_rays / get_near_far) from the
+    kernel: mask_at_box and ray order bit-exact, rays and depths bit-exact fp32
+    (the first two cases are the committed golden vectors of the reference's own
+    functions, checked directly too)."""
+    sc = synth.retarget(synth.make_scene("zju", H=min(H, 96), W=min(H, 96), V=3, seed=seed), angle)
+    K = sc["target_K"][0].numpy().astype(np.float64)
+    if H > 96:      # same camera, finer image
+        K = K.copy()
+        K[:2] *= H / 96.0
+    pose = sc["target_pose"][0].numpy().astype(np.float64)
+    R, T = pose[:, :3].copy(), pose[:, 3].copy()
+    bounds = sc["can_bounds"][0].numpy()
+    if H <= 64:
+        z = np.load(os.path.join(GOLD, "dataset_rays.npz"))
+        tag = "a" if H == 48 else "b"
+        K, R, T, bounds = (z[f"{tag}.{k}"] for k in ("K", "R", "T", "bounds"))
+    o, d, near, far, mask = orc.dataset_rays(H, H, K, R, T, bounds)
+    go, gd, gn, gf, gm = ops.dataset_rays(H, H, K, R, T, bounds, DEV)
+    assert np.array_equal(gm.cpu().numpy(), mask) and mask.sum() > 100
+    for got, want, name in ((go, o, "ray_o"), (gd, d, "ray_d"), (gn, near, "near"), (gf, far, "far")):
+        assert np.array_equal(got.cpu().numpy(), want), name
+    if H <= 64:
+        assert np.array_equal(gd.cpu().numpy(), z[f"{tag}.ray_d"]) and np.array_equal(gn.cpu().numpy(), z[f"{tag}.near"])
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)

@@ -112,3 +112,15 @@ def test_empty_volume_gives_no_rays():
     w = synth.make_head_weights(V=3, seed=1)
     masks3d, mask_xyz = orc.build_masks3d(scene["levels"])
     assert mask_xyz.shape[0] == 0 and float(masks3d.max()) == 0.0
+
+
+def test_dataset_rays_restatement_vs_reference_numpy():
+    """Row f3: oracle.dataset_rays against the outputs of the reference's own
+    get_rays / get_near_far (oracle/gen_golden_rays.py), bit for bit."""
+    z = np.load(os.path.join(GOLD, "dataset_rays.npz"))
+    for tag in ("a", "b"):
+        H = int(z[f"{tag}.H"])
+        o, d, near, far, mask = orc.dataset_rays(H, H, z[f"{tag}.K"], z[f"{tag}.R"], z[f"{tag}.T"], z[f"{tag}.bounds"])
+        assert np.array_equal(mask, z[f"{tag}.mask_at_box"]) and mask.sum() > 100
+        for got, key in ((o, "ray_o"), (d, "ray_d"), (near, "near"), (far, "far")):
+            assert got.dtype == np.float32 and np.array_equal(got, z[f"{tag}.{key}"]), key
