@@ -10,8 +10,8 @@ mask + rays + box test (K1), occupancy compaction + gathers (K2), density head
 (K3), progressive compaction (K4), colour head (K3), compositing (K5).
 
 At N>1 (`--shard`):
-  frames (default)  one frame per GPU and step – a sweep of N novel views of the
-                    scene (rank r renders the ring camera at 45° + 360°·r/N);
+  frames (default)  one frame per GPU and step – N consecutive frames of an orbit
+                    sweep (rank r renders the ring camera at 45° + 2°·r);
                     every finished pixel tile is written by K5 straight into slot
                     r of rank 0's image buffer over NVLink (peer memory, no NCCL
                     on the data path).  Per-GPU work is fixed: weak scaling.
@@ -44,6 +44,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "rays/s"
+SWEEP_STEP_DEG = 2.0          # angular step between the frames of the N-view sweep (frames mode)
 S_SAMPLES = 64
 VIEWS = 3
 RES = 512
@@ -221,8 +222,8 @@ def main():
 
     scene = synth.make_scene("zju", H=RES, W=RES, V=VIEWS, seed=42)
     frames_mode = world > 1 and args.shard == "frames"
-    if frames_mode:          # rank r renders its own novel view of the sweep
-        scene = synth.retarget(scene, 45.0 + 360.0 * rank / world)
+    if frames_mode:          # rank r renders frame r of an orbit sweep: consecutive novel views, 2° apart
+        scene = synth.retarget(scene, 45.0 + SWEEP_STEP_DEG * rank)
     weights = synth.make_head_weights(V=VIEWS, seed=42)
     head = NeRFHead(code_dim=32, n_views=VIEWS, precision=prec)
     sd = head.state_dict()
@@ -325,6 +326,16 @@ def main():
         dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
     value = g_rays / (ms_per_step * 1e-3)
+    # per-rank share of the work (frames mode: the views differ, the slowest one paces every step)
+    per_rank = None
+    if world > 1:
+        own = sum(v for k, v in stage_ms.items() if k != "peer_wait")
+        mine = torch.tensor([counts["n_rays"], counts["P1"], counts["P2"], own, stage_ms.get("peer_wait", 0.0)],
+                            device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rays": int(t[0]), "P1": int(t[1]), "P2": int(t[2]), "stages_ms_sum": round(float(t[3]), 4),
+                     "peer_wait_ms": round(float(t[4]), 4)} for t in allr]
 
     # ---- e2e: Renderer.render(batch) with pinned host inputs, image read back
     e2e = None
@@ -447,19 +458,21 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak" if (frames_mode or world == 1) else "strong", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "frames_per_s": 1e3 / ms_per_step, "pixel_rays_per_s": n_px * 1e3 / ms_per_step,
+        "frames_per_s": (world if frames_mode else 1) * 1e3 / ms_per_step,
+        "pixel_rays_per_s": (world if frames_mode else 1) * n_px * 1e3 / ms_per_step,
         "config": {"workload": f"zju-like synthetic frame {RES}x{RES}, V={VIEWS}, S={S_SAMPLES} "
                                "(BASELINE configs[1], trainzju_valzju inference shape), progressive path",
                    "rays": g_rays, "points": g_rays * S_SAMPLES, "P1": g_p1, "P2": g_p2,
                    "l2": "256 MB flush between timed steps; inputs 135 MB > 126 MB L2",
                    "sharding": ("single GPU" if world == 1 else
-                                (f"one frame per GPU and step (sweep of {world} novel views), images gathered on rank 0"
+                                (f"one frame per GPU and step ({world} consecutive frames of an orbit sweep, {SWEEP_STEP_DEG}° apart), "
+                                 "images gathered on rank 0"
                                  if frames_mode else
                                  f"one frame, pixel tiles of {args.tile_px} dealt diagonally over {world} ranks") +
                                 ("; K5 writes the tiles into the peers' images over NVLink (CUDA-IPC peer memory, "
                                  "arrival flags; no NCCL on the data path)" if eng.exchange is not None else
                                  "; one NCCL all_gather per step")),
-                   "peer_check": peer_check,
+                   "peer_check": peer_check, "per_rank": per_rank,
                    "launch": "eager, one launch per kernel" if args.no_graph else
                              "one CUDA-graph replay per frame (frame constants through a pinned buffer)",
                    "stages_ms_from": "eager re-issue of the same steps with CUDA events around every stage",

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "gpnerf_abi_version": ([], C.c_int),
     "gpnerf_last_error": ([], C.c_char_p),
     "gpnerf_sm_count": ([], C.c_int),
+    "gpnerf_struct_bytes": ([_I], C.c_int),
     "gpnerf_workspace_bytes": ([C.c_int64], C.c_int64),
     "gpnerf_k0_level_to_channels_last": ([_P, _I, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "gpnerf_k0_products_to_f16": ([C.POINTER(_P), C.POINTER(C.c_int32 * 3), _P, _I, _I, _I, C.POINTER(_P),
@@ -136,6 +137,10 @@ def load():
         fn.restype = restype
     if lib.gpnerf_abi_version() != 2:
         raise GpnerfError("libgpnerf_b200.so ABI version mismatch")
+    for which, st in enumerate((Frame, HeadWeights, Peer)):
+        if lib.gpnerf_struct_bytes(which) != C.sizeof(st):
+            raise GpnerfError(f"{st.__name__}: ctypes layout ({C.sizeof(st)} B) differs from the library's "
+                              f"({lib.gpnerf_struct_bytes(which)} B)")
     _lib = lib
     return lib
 

@@ -192,6 +192,14 @@ extern "C" {
 int gpnerf_abi_version(void) { return GPNERF_ABI_VERSION; }
 const char* gpnerf_last_error(void) { return gpnerf::g_err; }
 int gpnerf_sm_count(void) { return gpnerf::sm_count(); }
+int gpnerf_struct_bytes(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(gpnerf_frame_t);
+    case 1: return (int)sizeof(gpnerf_head_weights_t);
+    case 2: return (int)sizeof(gpnerf_peer_t);
+    default: return GPNERF_E_ARG;
+  }
+}
 
 int64_t gpnerf_workspace_bytes(int64_t n_items) {
   if (n_items < 0) return GPNERF_E_ARG;

@@ -128,6 +128,10 @@ int gpnerf_abi_version(void);
 const char *gpnerf_last_error(void);
 /* number of SMs of the current device (grid sizing is a multiple of it) */
 int gpnerf_sm_count(void);
+/* sizeof of the ABI structs as this library was compiled (0 gpnerf_frame_t,
+ * 1 gpnerf_head_weights_t, 2 gpnerf_peer_t): a binding checks its own layout
+ * against these before the first call. */
+int gpnerf_struct_bytes(int which);
 
 /* ---- K0: layout of the upstream products ------------------------------- */
 /* One dense level NCDHW → NDHWC (one line per voxel; `storage`: 0 = 128 B fp32,

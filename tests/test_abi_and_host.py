@@ -35,6 +35,10 @@ def test_frame_struct_matches_header_size(lib_built):
     # 4-byte fields only: R9 Th3 bmin3 vox3 out_sh3 dims12 pose12 K9 Kinv9 H W nv KE128 4 + 2 + thr + 3
     assert C.sizeof(_lib.Frame) == 4 * (9 + 3 + 3 + 3 + 3 + 12 + 12 + 9 + 9 + 2 + 1 + 128 + 4 + 2 + 1 + 3 + 2 + 2)
     assert C.sizeof(_lib.HeadWeights) == 8 * (2 + 8 + 4 + 4 + 6 + 1)
+    # … and the library reports the sizes its own compiler gave the structs
+    for which, st in enumerate((_lib.Frame, _lib.HeadWeights, _lib.Peer)):
+        assert lib_built.gpnerf_struct_bytes(which) == C.sizeof(st)
+    assert lib_built.gpnerf_struct_bytes(99) < 0
 
 
 def test_argument_validation_without_gpu(lib_built):
