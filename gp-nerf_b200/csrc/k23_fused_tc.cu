@@ -40,6 +40,8 @@ struct FusedArgs {
   const uint8_t* image;          // packed weights
   float* sigma;
   uint4* rec;
+  float* alpha;              // optional: K4's α = 1 − exp(−σ) …
+  uint32_t* alpha_words;     // … and its survivor flags (one ballot word per 32 points), written here
 };
 
 struct FusedSmem {
@@ -388,7 +390,17 @@ __global__ void __launch_bounds__(256, 2) gather_density_tc(FusedArgs a, const _
 #pragma unroll
       for (int k = 0; k < 16; ++k) s = fmaf(elu_scaled(__uint_as_float(r16[k])), fl[DenImg::w3 + k], s);
       s = fmaxf(s, 0.0f);
-      if (row < n_valid) a.sigma[first + row] = (nvalid[row] < 1) ? 0.0f : s;
+      s = (nvalid[row] < 1) ? 0.0f : s;
+      if (row < n_valid) a.sigma[first + row] = s;
+      if (a.alpha != nullptr) {
+        // the progressive step's test (demo_render.py:312-317, as alpha_flags computes it), fused: the 4
+        // warps of this half hold the tile's 128 consecutive points = 4 flag words
+        const float al = xsub(1.0f, expf(-s));
+        const bool keep = row < n_valid && al > 1e-14f;
+        if (row < n_valid) a.alpha[first + row] = al;
+        const unsigned bits = __ballot_sync(0xffffffffu, keep);
+        if ((tid & 31) == 0) a.alpha_words[(first + row) >> 5] = bits;
+      }
     }
     // the next plan phase rewrites A1/nvalid: order it after every thread's
     // reads of this tile (TMEM reads are fenced by the next round_sync)
@@ -433,7 +445,7 @@ int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], 
                                  const float* images_rgbx, const int32_t* valid, const float* rays_o,
                                  const float* rays_d, const float* z_vals, const gpnerf_frame_t* f,
                                  const gpnerf_head_weights_t* w, int n_points_max, const int32_t* counters,
-                                 float* sigma, void* records, void* stream) {
+                                 float* sigma, void* records, float* alpha, void* k4_workspace, void* stream) {
   GPNERF_REQUIRE(levels_f16 && featmaps_f16 && images_rgbx && valid && rays_o && rays_d && z_vals && f && w &&
                  counters && sigma && records && n_points_max > 0);
   GPNERF_REQUIRE(w->tc_image != nullptr && f->n_samples > 0 && f->src_w > 1 && f->src_h > 1);
@@ -449,6 +461,9 @@ int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], 
   a.image = reinterpret_cast<const uint8_t*>(w->tc_image);
   a.sigma = sigma;
   a.rec = reinterpret_cast<uint4*>(records);
+  GPNERF_REQUIRE((alpha == nullptr) == (k4_workspace == nullptr));
+  a.alpha = alpha;
+  a.alpha_words = alpha ? carve_workspace(k4_workspace, n_points_max).words : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   switch (f->n_views) {
     case 1: return launch_fused<1>(a, f, n_points_max, st);

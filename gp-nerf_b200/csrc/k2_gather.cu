@@ -45,14 +45,18 @@ __global__ void __launch_bounds__(256) occupancy_flags(const float* __restrict__
         keep = true;
       } else {
         Tri t = trilinear_setup(world_to_grid(f, point_on_ray(o, d, z)), D, H, W);
-        float acc = 0.0f;
+        // all 8 taps are issued up front from clamped addresses (8 loads in flight instead of 8 dependent
+        // branches); an out-of-range corner contributes the exact +0 it is skipped with in the reference sum
+        float m[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          if ((t.inb >> c) & 1u) {
-            long long idx = ((long long)(t.z0 + (c >> 2)) * H + (t.y0 + ((c >> 1) & 1))) * W + (t.x0 + (c & 1));
-            acc = xadd(acc, xmul(__ldg(masks3d + idx), t.w[c]));
-          }
+          const int zc = min(max(t.z0 + (c >> 2), 0), D - 1), yc = min(max(t.y0 + ((c >> 1) & 1), 0), H - 1);
+          const int xc = min(max(t.x0 + (c & 1), 0), W - 1);
+          m[c] = __ldg(masks3d + ((zc * H + yc) * W + xc));
         }
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc = xadd(acc, ((t.inb >> c) & 1u) ? xmul(m[c], t.w[c]) : 0.0f);
         keep = acc > 0.0f;
       }
     }

@@ -3,12 +3,13 @@
 // reach the colour head.  4 B read + 4 B written per point, 4 B per survivor.
 //
 // K5 – front-to-back compositing.
-//   composite_rays   : demo_render.py:335-353.  `valid` is ascending in
-//     ray·S+sample, so the survivors of a ray are one contiguous run (CSR by
-//     binary search); a warp walks the run 32 samples at a time with a
-//     shuffle product-scan for the transmittance.  Samples that did not
+//   composite_tiles  : demo_render.py:335-353.  `valid` is ascending in
+//     ray·S+sample, so the survivors of a ray are one contiguous run (CSR
+//     offsets from the compactions); a warp walks the run 32 samples at a time
+//     with a shuffle product-scan for the transmittance.  Samples that did not
 //     survive have α = 0 and contribute the factor fl32(1+1e-10) = 1, so
-//     skipping them is exact.  Reads 16 B per surviving sample.
+//     skipping them is exact.  Reads 16 B per surviving sample; publishes whole
+//     pixel tiles, locally and into peer GPUs' images.
 //   raw2outputs      : BaseRender.py:75-107,147 dense [R][S] variant with the
 //     auxiliary maps the training loss consumes.
 #include <string.h>
@@ -394,12 +395,14 @@ extern "C" {
 
 int gpnerf_k4_compact_alpha(const float* sigma, int n_points_max, int32_t* counters, float* alpha,
                             int32_t* valid1, void* workspace, void* stream) {
-  GPNERF_REQUIRE(sigma && counters && alpha && valid1 && workspace && n_points_max > 0);
+  GPNERF_REQUIRE(counters && alpha && valid1 && workspace && n_points_max > 0);
   cudaStream_t st = (cudaStream_t)stream;
   CompactWs ws = carve_workspace(workspace, n_points_max);
-  long long blocks = ((long long)n_points_max + 255) / 256;
-  int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : sm_count() * 8);
-  alpha_flags<<<grid, 256, 0, st>>>(sigma, counters, alpha, ws.words);
+  if (sigma != nullptr) {     // else α and the flag words were written by gpnerf_k23_gather_density_tc
+    long long blocks = ((long long)n_points_max + 255) / 256;
+    int grid = (int)(blocks < (long long)sm_count() * 8 ? blocks : sm_count() * 8);
+    alpha_flags<<<grid, 256, 0, st>>>(sigma, counters, alpha, ws.words);
+  }
   return compact_launch(ws, counters + GPNERF_CNT_P1, 1, 0, n_points_max, valid1,
                         counters + GPNERF_CNT_P2, st);
 }

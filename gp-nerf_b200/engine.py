@@ -32,7 +32,7 @@ KERNELS_PER_CALL = {
     "k0_level_to_channels_last": 1, "k0_featmaps_to_channels_last": 1, "k0_images_to_rgbx": 1,
     "k0_products_to_f16": 1,
     "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 5, "k2_occupancy_compact": 4,
-    "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,
+    "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,   # 3 when fused
     "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1, "peer_wait": 1,
     "k23_gather_density_tc": 1, "k3_color_mlp_records": 1,
 }
@@ -400,8 +400,9 @@ class Engine:
         self._run("k1_rays_bbox", L.gpnerf_k1_rays_bbox, ptr(self.pix_mask), ptr(self.can_bounds), fr,
                   ptr(self.ray_pix), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near), ptr(self.far),
                   ptr(self.counters), ptr(self.workspace), ptr(self.tile_ray_begin), st)
-        self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays)
-        self._run("k4_compact_alpha", L.gpnerf_k4_compact_alpha, ptr(self.sigma), self.max_pts,
+        self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays, fuse_alpha=True)
+        # tensor-core path: α and the survivor flags were written by the fused kernel's epilogue
+        self._run("k4_compact_alpha", L.gpnerf_k4_compact_alpha, None if self.bf16 else ptr(self.sigma), self.max_pts,
                   ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
         self._color(ptr(self.valid1), self.max_pts, CNT_P2)
         ex = self.exchange
@@ -426,7 +427,7 @@ class Engine:
                       C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), slot, ptr(self.rgb),
                       self.precision, st)
 
-    def _heads(self, frame, masks3d, t_rand, n_rays_max):
+    def _heads(self, frame, masks3d, t_rand, n_rays_max, fuse_alpha=False):
         """occupancy (or identity) compaction → gathers → density head."""
         L, st, fr = self.lib, self._stream(), C.byref(frame)
         n_pts_max = n_rays_max * self.S
@@ -438,7 +439,8 @@ class Engine:
             self._run("k23_gather_density_tc", L.gpnerf_k23_gather_density_tc, ptr_array(self.levels_cl),
                       ptr(self.featmaps_cl), ptr(self.images_rgbx), ptr(self.valid), ptr(self.rays_o),
                       ptr(self.rays_d), ptr(self.z_vals), fr, C.byref(self._weights), n_pts_max,
-                      ptr(self.counters), ptr(self.sigma), ptr(self.rec), st)
+                      ptr(self.counters), ptr(self.sigma), ptr(self.rec),
+                      ptr(self.alpha) if fuse_alpha else None, ptr(self.workspace) if fuse_alpha else None, st)
             return
         self._run("k2_gather_volume", L.gpnerf_k2_gather_volume, ptr_array(self.levels_cl), 0, ptr(self.valid),
                   ptr(self.rays_o), ptr(self.rays_d), ptr(self.z_vals), None, fr, n_pts_max, ptr(self.counters),

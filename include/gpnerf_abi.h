@@ -284,7 +284,11 @@ int gpnerf_k23_gather_density_tc(const void *const levels_f16[GPNERF_N_LEVELS],
                                  const int32_t *valid, const float *rays_o, const float *rays_d,
                                  const float *z_vals, const gpnerf_frame_t *frame_host,
                                  const gpnerf_head_weights_t *weights_host, int n_points_max,
-                                 const int32_t *counters, float *sigma, void *records, void *stream);
+                                 const int32_t *counters, float *sigma, void *records, float *alpha,
+                                 void *k4_workspace, void *stream);
+/* With alpha / k4_workspace (both or neither) the kernel also writes K4's
+ * α = 1-exp(-σ) and its survivor flags straight into the compaction workspace:
+ * follow with gpnerf_k4_compact_alpha(sigma = NULL, …). */
 /* Colour trunk (trainhead.py:128-145) on the record rows listed in valid1. */
 int gpnerf_k3_color_mlp_records(const void *records, const int32_t *valid1,
                                 const gpnerf_head_weights_t *weights_host, int n_views,
@@ -294,6 +298,8 @@ int gpnerf_k3_color_mlp_records(const void *records, const int32_t *valid1,
 /* ---- K4: progressive step ---------------------------------------------- */
 /* demo_render.py:312-317: α = 1-exp(-σ); valid1 = ascending indices (into the
  * P1 arrays) with α > 1e-14; counters[P2]. */
+/* sigma == NULL: α and the flags come from gpnerf_k23_gather_density_tc (above);
+ * only the compaction runs. */
 int gpnerf_k4_compact_alpha(const float *sigma, int n_points_max, int32_t *counters,
                             float *alpha, int32_t *valid1, void *workspace, void *stream);
 
