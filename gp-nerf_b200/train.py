@@ -315,3 +315,40 @@ def render_dense_autograd(eng: Engine, frame, rays, levels, featmaps, src_imgs, 
     rgb_map, disp, acc, weights, depth, rin, z = outs
     return {"rgb_map": rgb_map, "disp_map": disp[:, None], "acc_map": acc[:, None], "depth_map": depth[:, None],
             "alpha": weights, "z_vals": z, "rgb_in_map": rin}
+
+
+class GradBucket:
+    """Data-parallel training over the GPUs of one box (BASELINE configs[3]: the
+    batch's rays are split over the ranks, every rank holds the full heads).
+
+    All head gradients live in ONE flat fp32 buffer (`param.grad` of every
+    parameter is a view into it, so autograd accumulates straight into the
+    bucket) and are averaged with a single all-reduce per step – 259,716 values
+    ≈ 1 MB for the reference's heads – NCCL over NVLink on GPUs,
+    gloo in the CPU tests.  The reference wraps the model in DDP but calls
+    `.module.render`, which bypasses DDP's reducer; this is the
+    reduction it meant to have."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, torch.float32
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=dt, device=dev)
+        self.group = group
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self):
+        """Average the bucket over the ranks (no-op without a process group)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(dist.get_world_size(self.group))
+        return self.flat

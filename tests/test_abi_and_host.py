@@ -146,3 +146,33 @@ def test_gather_frame_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from gpnerf_b200.train import GradBucket
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5)),
+              torch.nn.Parameter(torch.randn(2), requires_grad=False)]
+    b = GradBucket(params)
+    assert b.flat.numel() == 17 and params[2].grad is None
+    x = torch.full((3,), float(rank + 1))
+    loss = (params[0] @ x).sum() + (params[1] * (rank + 1)).sum()      # d/dW = x per row, d/db = rank + 1
+    loss.backward()                                                    # accumulates INTO the bucket views
+    assert params[0].grad.data_ptr() == b.flat.data_ptr()
+    b.all_reduce_mean()
+    mean = sum(range(1, world + 1)) / world
+    ok = bool(torch.allclose(params[0].grad, torch.full((4, 3), mean)) and torch.allclose(params[1].grad, torch.full((5,), mean)))
+    b.zero()
+    ok = ok and float(params[0].grad.abs().sum()) == 0.0
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write(str(int(ok)))
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_all_reduce_gloo_world2(tmp_path):
+    """Training config: one flat all-reduce of the head gradients."""
+    import torch.multiprocessing as mp
+    port = 29620 + os.getpid() % 200
+    mp.spawn(_bucket_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(os.path.join(tmp_path, f"ok{r}")).read() for r in range(2)] == ["1", "1"]
