@@ -53,6 +53,40 @@ def test_progressive_stages_vs_oracle(H, S, seed, bias):
     assert_progressive_report(rep)
 
 
+@pytest.mark.parametrize("S,tile_px,V,precision", [(24, 64, 3, 0), (40, 16, 2, 0), (33, 256, 1, 0), (40, 48, 3, 1),
+                                                   (7, 64, 3, 1)])
+def test_ragged_sample_counts_tile_sizes_and_view_counts(S, tile_px, V, precision):
+    """Shapes the reference's configs never use: sample counts that are not multiples of the 32-bit flag
+    words (the CSR offsets of the compactions then start mid-word), tile sizes that do not divide the
+    image width, 1 and 2 source views – fp32 stages against the oracle, tensor-core path against its
+    survivor lists and image."""
+    scene = synth.make_scene("zju", H=72, W=72, V=V, seed=41 + S)
+    w = synth.make_head_weights(V=V, seed=141, random_bias=True)
+    o = orc.render_progressive(scene, w, S=S, keep=True)
+    eng = Engine(72, 72, S, V, device=DEV, precision=precision, tile_px=tile_px)
+    eng.set_weights(w)
+    d = stages.to_dev(scene, DEV)
+    eng.upload_products(d["levels"], d["featmaps"], d["src_imgs"])
+    eng.render_progressive(eng.make_frame(scene))
+    torch.cuda.synchronize()
+    c = eng.read_counters()
+    n, p1 = c["n_rays"], c["P1"]
+    assert n == o["n_rays"] and p1 == o["P1"] and n > 50
+    assert torch.equal(eng.ray_pix[:n].cpu().long(), o["ray_pix"].long())
+    assert torch.equal(eng.valid[:p1].cpu().long(), o["valid"])
+    n_tiles = (72 * 72 + tile_px - 1) // tile_px
+    assert torch.equal(eng.tile_ray_begin.cpu().long(),
+                       torch.searchsorted(o["ray_pix"].long(), torch.arange(n_tiles + 1) * tile_px))
+    assert torch.equal(eng.ray_pt_begin[: n + 1].cpu().long(), torch.searchsorted(o["valid"], torch.arange(n + 1) * S))
+    assert torch.equal(eng.hit_mask.cpu().bool(), o["mask_at_box"])
+    img = eng.pred_img.cpu().view(72, 72, 3).double()
+    if precision == 0:
+        assert c["P2"] == o["P2"] and torch.equal(eng.valid1[: c["P2"]].cpu().long(), o["valid1"])
+        assert float((img - o["pred_img"]).abs().max()) < TOL
+    else:
+        assert float((img - o["pred_img"]).abs().max()) < 0.05 and orc.psnr(img, o["pred_img"]) > 40.0
+
+
 @pytest.mark.parametrize("tag", ["mini", "mini_s64"])
 def test_progressive_vs_reference_golden(tag):
     """Against the run of the real reference code stored in tests/golden."""
