@@ -28,4 +28,37 @@ for prec in (PREC_FP32, PREC_BF16):
     out = e2.render_dense(e2.make_frame(scene), *rays)
     torch.cuda.synchronize()
     print("dense", prec, float(out["rgb_map"].sum()))
+# peer exchange (one rank: its own IPC buffer), graph-free; TF32 training step; dataset rays
+from gpnerf_b200 import ops  # noqa: E402
+from gpnerf_b200.peer import PeerExchange  # noqa: E402
+from gpnerf_b200.train import render_dense_autograd  # noqa: E402
+import numpy as np  # noqa: E402
+e3 = Engine(64, 64, 16, 3, device="cuda:0", precision=PREC_BF16)
+e3.set_weights(w)
+ex = PeerExchange(64, 64, "cuda:0", 0, 1, mode="tiles")
+e3.attach_exchange(ex)
+e3.upload_products(d["levels"], d["featmaps"], d["src_imgs"])
+for _ in range(2):
+    e3.render_progressive(e3.make_frame(scene))
+torch.cuda.synchronize()
+print("exchange", float(e3.result_image().sum()))
+ex.close()
+R = 200
+rays = tuple(scene[k][0][:R].to("cuda:0") for k in ("ray_o", "ray_d", "near", "far"))
+for prec in (0, 1):
+    e4 = Engine(64, 64, 16, 3, device="cuda:0", max_rays=R)
+    wg = {k: v.clone().to("cuda:0").requires_grad_(True) for k, v in w.items()}
+    lv = [t.clone().requires_grad_(True) for t in d["levels"]]
+    fm = d["featmaps"].clone().requires_grad_(True)
+    e4.set_weights(w)
+    e4.upload_products([t.detach() for t in lv], fm.detach(), d["src_imgs"])
+    out = render_dense_autograd(e4, e4.make_frame(scene), rays, lv, fm, d["src_imgs"], wg, t_rand=torch.rand(R, 16),
+                                precision=prec)
+    out["rgb_map"].sum().backward()
+    torch.cuda.synchronize()
+    print("train", prec, float(fm.grad.abs().sum()))
+pose = scene["target_pose"][0].numpy().astype(np.float64)
+r = ops.dataset_rays(64, 64, scene["target_K"][0].numpy().astype(np.float64), pose[:, :3], pose[:, 3],
+                     scene["can_bounds"][0].numpy(), "cuda:0")
+print("dataset rays", r[0].shape)
 print("sanitize target done")
