@@ -269,6 +269,7 @@ def main():
         step_device()
     torch.cuda.synchronize(dev)
     counts = eng.read_counters()
+    ref_image = eng.result_image().cpu().clone()
     if world > 1:
         tot = torch.tensor([counts["n_rays"], counts["P1"], counts["P2"]], device=dev)
         dist.all_reduce(tot)
@@ -320,6 +321,41 @@ def main():
     torch.cuda.synchronize(dev)
     eng.timing = False
     stage_ms = eng.stage_times_ms()
+    # ---- the same frame with the levels handed over as the sparse-conv net holds them before .dense()
+    #      (active rows: features + voxel indices): K0's transposition of a >95 % empty
+    #      dense volume becomes a scatter.  Reported beside the headline, which keeps the reference's dense layout.
+    sparse_dev = None
+    if prec == PREC_BF16 and not args.no_graph:
+        import ctypes as C
+        from gpnerf_b200._lib import Frame
+        lv_s, dims_s = synth.sparsify_levels(scene["levels"])
+        d_lv_s = [(f.to(dev), i.to(dev)) for f, i in lv_s]
+        fpin = torch.empty(C.sizeof(Frame), dtype=torch.uint8).pin_memory()
+
+        def step_sparse():
+            eng.upload_products_sparse(d_lv_s, dims_s, d_feat, d_imgs)
+            eng.run_progressive_graphed(frame, with_k0=False, frame_src=fpin)
+        for _ in range(3):
+            flush.zero_()
+            step_sparse()
+        torch.cuda.synchronize(dev)
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        if world > 1:
+            dist.barrier()
+        for a, b in ev2:
+            flush.zero_()
+            a.record()
+            step_sparse()
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms_s = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+        same = torch.equal(eng.result_image().cpu(), ref_image) if world == 1 else None
+        sparse_dev = {"ms_per_step": float(ms_s), "value": g_rays / (float(ms_s) * 1e-3), "unit": "rays/s",
+                      "active_rows": [int(f.shape[0]) for f, _ in lv_s],
+                      "input_bytes": int(sum(f.numel() * 4 + i.numel() * 4 for f, i in lv_s)),
+                      "image_identical_to_dense_route": same}
     if world > 1:
         t = torch.tensor([dev_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -369,14 +405,25 @@ def main():
                 et = float(t.item())
             return et
         # (1) one blocking Renderer.render(batch) call per step (the reference's calling convention)
-        for _ in range(2):
+        for _ in range(6):
             e2e_step()
         et_sync = timed(lambda: [e2e_step() for _ in range(args.steps)])
+        if os.environ.get("GPNERF_PROFILE_BLOCKING"):
+            import cProfile
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(args.steps):
+                e2e_step()
+            torch.cuda.synchronize(dev)
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(18)
         # (2) the same frames through Renderer.render_stream: uploads of the next frames overlap the render of
         #     the current one (every frame's 134 MB still cross PCIe inside the timed region, every image
         #     is read back into host memory)
         stream_ok = not (world > 1 and args.shard == "tiles")
         et = et_sync
+        e2e_sparse = None
         if stream_ok:
             n_out = [0]
 
@@ -385,6 +432,23 @@ def main():
                     n_out[0] += int(out["mask_at_box"].sum() > 0)
             run_stream(4)
             et = timed(lambda: run_stream(args.steps))
+            if prec == PREC_BF16:
+                lv_s, dims_s = synth.sparsify_levels(scene["levels"])
+                sbatch = {k: v for k, v in batch.items() if k != "levels"}
+                sbatch["levels_sparse"] = [(f.pin_memory(), i.pin_memory()) for f, i in lv_s]
+                sbatch["level_dims"] = dims_s
+                h2d_s = (sum(f.numel() * 4 + i.numel() * 4 for f, i in lv_s) + batch["featmaps"].numel() * 4 +
+                         batch["src_imgs"].numel() * 4)
+
+                def run_stream_sparse(k):
+                    for out in renderer.render_stream(sbatch for _ in range(k)):
+                        n_out[0] += int(out["mask_at_box"].sum() > 0)
+                run_stream_sparse(4)
+                et_s = timed(lambda: run_stream_sparse(args.steps))
+                e2e_sparse = {"ms_per_step": 1e3 * et_s / args.steps, "value": g_rays * args.steps / et_s,
+                              "unit": "rays/s", "h2d_bytes_per_step": int(h2d_s),
+                              "what": "render_stream with the 4 levels as sparse rows (features + indices) instead of "
+                                      "dense NCDHW tensors"}
         e2e = {"value": g_rays * args.steps / et, "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(n_px * 3 * 4 + n_px + 32), "ms_per_step": 1e3 * et / args.steps,
                "frames_per_s": args.steps * (world if frames_mode else 1) / et,
@@ -393,7 +457,8 @@ def main():
                        "read back to the host") if stream_ok else
                       "gpnerf_b200.render.Renderer.render(batch) – levels/featmaps/src_imgs in pinned host memory",
                "blocking_call_ms_per_step": 1e3 * et_sync / args.steps,
-               "blocking_call_api": "gpnerf_b200.render.Renderer.render(batch), one blocking call per frame"}
+               "blocking_call_api": "gpnerf_b200.render.Renderer.render(batch), one blocking call per frame",
+               "sparse_levels": e2e_sparse}
 
     if world > 1:
         dist.barrier()
@@ -478,6 +543,7 @@ def main():
                    "stages_ms_from": "eager re-issue of the same steps with CUDA events around every stage",
                    "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "sparse_levels_device": sparse_dev,
         "stages_ms": stages_out, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

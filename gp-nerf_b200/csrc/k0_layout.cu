@@ -240,6 +240,71 @@ __global__ void __launch_bounds__(256) products_to_channels_last_f16(const __gri
   }
 }
 
+// ---------------------------------------------------------------------------
+// SURVEY §8f row 1, first step: the sparse-conv pyramid's outputs WITHOUT the
+// dense detour.  The reference materialises every level with
+// SparseConvTensor.dense() (SparseConvNet.py:110; an NCDHW fp32 tensor that is
+// >95 % zeros) only to sample it; here the active rows (features [N,32] fp32 +
+// voxel indices [N,idx_cols] int32, the last three columns = d,h,w) are scattered
+// straight into the zero-bordered channel-last fp16 volumes the fused kernel
+// gathers from, together with the per-voxel channel sums of masks3d.
+// 8 lanes per row: one float4 load and one 8-byte store per lane.
+// ---------------------------------------------------------------------------
+struct SparseJob {
+  const float* feat;
+  const int32_t* idx;
+  __half* dst;
+  float* chan_sum;
+  int n, D, H, W;
+  int row0;          // first global row of the job
+};
+struct SparseJobs {
+  SparseJob j[GPNERF_N_LEVELS];
+  int n_rows, idx_cols;
+};
+__global__ void __launch_bounds__(256) sparse_rows_to_f16(const __grid_constant__ SparseJobs jobs) {
+  const int lane = threadIdx.x & 31, q = lane & 7, sub = lane >> 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = warp * 4; r0 < jobs.n_rows; r0 += n_warps * 4) {
+    const int r = r0 + sub;
+    int ji = 0;
+#pragma unroll
+    for (int k = 1; k < GPNERF_N_LEVELS; ++k)
+      if (r >= jobs.j[k].row0) ji = k;
+    const SparseJob& J = jobs.j[ji];
+    const int lr = r - J.row0;
+    const bool ok = r < jobs.n_rows && lr < J.n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int d = 0, h = 0, w = 0;
+    if (ok) {
+      v = __ldg(reinterpret_cast<const float4*>(J.feat + (size_t)lr * 32) + q);
+      const int32_t* ip = J.idx + (size_t)lr * jobs.idx_cols + (jobs.idx_cols - 3);
+      d = __ldg(ip); h = __ldg(ip + 1); w = __ldg(ip + 2);
+    }
+    const bool inside = ok && d >= 0 && d < J.D && h >= 0 && h < J.H && w >= 0 && w < J.W;
+    // channel sum, c ascending with one rounding per add (the order torch.sum(dim=0) and K0 use)
+    float sum = 0.0f;
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+      const int src = (lane & 24) | qq;
+      const float a = __shfl_sync(0xffffffffu, v.x, src), b = __shfl_sync(0xffffffffu, v.y, src);
+      const float c = __shfl_sync(0xffffffffu, v.z, src), e = __shfl_sync(0xffffffffu, v.w, src);
+      sum = (qq == 0) ? a : xadd(sum, a);
+      sum = xadd(xadd(xadd(sum, b), c), e);
+    }
+    if (inside) {
+      const size_t vox = ((size_t)(d + 1) * (J.H + 2) + (h + 1)) * (J.W + 2) + (w + 1);
+      __half2 lo = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
+      __half2 hi = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(J.dst + vox * 32 + q * 4) = o;
+      if (q == 0) J.chan_sum[((size_t)d * J.H + h) * J.W + w] = sum;
+    }
+  }
+}
+
 struct MaskArgs {
   const float* cs[GPNERF_N_LEVELS];
   int dims[GPNERF_N_LEVELS][3];
@@ -367,6 +432,40 @@ int gpnerf_k0_products_to_f16(const float* const levels[GPNERF_N_LEVELS], const 
   const int grid = (int)(tile < (unsigned)cap ? tile : (unsigned)cap);
   products_to_channels_last_f16<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
   return check_launch("k0_products_to_f16");
+}
+
+int gpnerf_k0_sparse_to_f16(const float* const feats[GPNERF_N_LEVELS], const int32_t* const indices[GPNERF_N_LEVELS],
+                            const int32_t n_rows[GPNERF_N_LEVELS], int idx_cols,
+                            const int32_t level_dims[GPNERF_N_LEVELS][3], void* const levels_out[GPNERF_N_LEVELS],
+                            float* const chan_sums[GPNERF_N_LEVELS], void* stream) {
+  GPNERF_REQUIRE(feats && indices && n_rows && level_dims && levels_out && chan_sums && idx_cols >= 3 && idx_cols <= 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  SparseJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  int row = 0;
+  for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
+    const int D = level_dims[l][0], H = level_dims[l][1], W = level_dims[l][2];
+    GPNERF_REQUIRE(levels_out[l] && chan_sums[l] && n_rows[l] >= 0 && (n_rows[l] == 0 || (feats[l] && indices[l])));
+    GPNERF_REQUIRE(D > 0 && H > 0 && W > 0 && (long long)(D + 2) * (H + 2) * (W + 2) < (1ll << 31));
+    // yesterday's active sites go away with the whole volume: 64 B per voxel at HBM speed (≈10 µs for all levels)
+    cudaError_t e = cudaMemsetAsync(levels_out[l], 0, (size_t)(D + 2) * (H + 2) * (W + 2) * 64, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(chan_sums[l], 0, (size_t)D * H * W * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("memset sparse level", e);
+      return GPNERF_E_CUDA;
+    }
+    SparseJob& J = jobs.j[l];
+    J.feat = feats[l]; J.idx = indices[l]; J.dst = reinterpret_cast<__half*>(levels_out[l]); J.chan_sum = chan_sums[l];
+    J.n = n_rows[l]; J.D = D; J.H = H; J.W = W; J.row0 = row;
+    row += (n_rows[l] + 3) & ~3;          // a warp's 4 rows never straddle two levels
+  }
+  jobs.n_rows = row;
+  jobs.idx_cols = idx_cols;
+  if (row == 0) return GPNERF_OK;
+  const long long blocks = ((long long)row * 8 + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  sparse_rows_to_f16<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(jobs);
+  return check_launch("k0_sparse_to_f16");
 }
 
 int gpnerf_k0_build_masks3d(const float* const chan_sum[GPNERF_N_LEVELS],

@@ -30,7 +30,7 @@ HEAD_KEYS = {
 # bench.py's `gpu_launches`; keep in sync with csrc/.
 KERNELS_PER_CALL = {
     "k0_level_to_channels_last": 1, "k0_featmaps_to_channels_last": 1, "k0_images_to_rgbx": 1,
-    "k0_products_to_f16": 1,
+    "k0_products_to_f16": 1, "k0_sparse_to_f16": 1,
     "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 5, "k2_occupancy_compact": 4,
     "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,   # 3 when fused
     "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1, "peer_wait": 1,
@@ -264,13 +264,72 @@ class Engine:
         self.src_hw, self.feat_hw = (ih, iw), (fh, fw)
         self._keep_inputs = (lv, fm, im)     # keep alive until the stream drains
 
+    def upload_products_sparse(self, levels_sparse, level_dims, featmaps, src_imgs):
+        """The pyramid's levels as the sparse-conv network holds them before
+        `.dense()` (SparseConvNet.py:110): per level `(features [N,32] fp32,
+        indices [N,3|4] int32 with (d,h,w) last)`, `level_dims` 4 × (D,H,W).
+        Tensor-core path only: the active rows are scattered straight into the
+        bordered fp16 volumes (no dense fp32 tensor, no K0 transposition)."""
+        if not self.bf16:
+            raise _lib.GpnerfError("sparse level upload feeds the tensor-core path (precision = PREC_BF16)")
+        dev, st, L = self.device, self._stream(), self.lib
+        dims = [tuple(int(v) for v in d) for d in level_dims]
+        if len(levels_sparse) != 4 or len(dims) != 4:
+            raise _lib.GpnerfError("4 levels expected")
+        feats = [f.to(dev, non_blocking=True).to(torch.float32).contiguous() for f, _ in levels_sparse]
+        idxs = [i.to(dev, non_blocking=True).to(torch.int32).contiguous() for _, i in levels_sparse]
+        cols = int(idxs[0].shape[1])
+        assert all(f.shape[1] == 32 and i.shape[1] == cols and i.shape[0] == f.shape[0] for f, i in zip(feats, idxs))
+        fm = featmaps.to(dev, non_blocking=True).contiguous()
+        im = src_imgs.to(dev, non_blocking=True)
+        im = (im[0] if im.dim() == 5 else im).contiguous()
+        if self.level_dims != dims:
+            self.level_dims = dims
+            self.levels_cl = [torch.zeros((d + 2) * (h + 2) * (w + 2) * 32, dtype=torch.float16, device=dev)
+                              for d, h, w in dims]
+            self.chan_sums = [torch.empty(d * h * w, dtype=torch.float32, device=dev) for d, h, w in dims]
+            self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
+        dims_c = ((C.c_int32 * 3) * 4)(*[(C.c_int32 * 3)(*d) for d in dims])
+        n_rows = (C.c_int32 * 4)(*[int(f.shape[0]) for f in feats])
+        self._run("k0_sparse_to_f16", L.gpnerf_k0_sparse_to_f16, ptr_array(feats), ptr_array(idxs), n_rows, cols, dims_c,
+                  ptr_array(self.levels_cl), ptr_array(self.chan_sums), st)
+        V, Cc, fh, fw = fm.shape
+        assert V == self.V and Cc == 32
+        n_fm = V * (fh + 2) * (fw + 2) * 32
+        if self.featmaps_cl is None or self.featmaps_cl.numel() != n_fm:
+            self.featmaps_cl = torch.zeros(n_fm, dtype=torch.float16, device=dev)
+        self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw, 2, 1,
+                  ptr(self.featmaps_cl), st)
+        _, _, ih, iw = im.shape
+        n_im = V * (ih + 2) * (iw + 2) * 4
+        if self.images_rgbx is None or self.images_rgbx.numel() != n_im:
+            self.images_rgbx = torch.zeros(n_im, dtype=torch.float32, device=dev)
+        self._run("k0_images_to_rgbx", L.gpnerf_k0_images_to_rgbx, ptr(im), V, ih, iw, 1, 1, ptr(self.images_rgbx), st)
+        self.src_hw, self.feat_hw = (ih, iw), (fh, fw)
+        self._keep_inputs = (feats, idxs, fm, im)
+
     # ------------------------------------------------------------ frame setup
+    _STATIC_KEYS = ("Rh", "R", "Th", "bounds", "out_sh", "src_poses", "src_Ks")
+
     def make_frame(self, batch, neg_ray=False):
+        """gpnerf_frame_t of a batch.  In a sweep only the target camera changes from frame to frame: the
+        rest of the struct (SMPL pose, bounds, the K·E products of the source views) is packed once per
+        distinct VALUE of those inputs (their bytes are the cache key) and copied."""
+        vals = torch.cat([batch[k].detach().to("cpu", torch.float64).reshape(-1) for k in self._STATIC_KEYS if k in batch])
+        key = (vals.numpy().tobytes(), tuple(self.level_dims or ()), self.src_hw, self.feat_hw, bool(neg_ray))
+        cached = getattr(self, "_frame_cache", None)
+        if cached is not None and cached[0] == key:
+            f = Frame.from_buffer_copy(cached[1])
+            f.target_pose[:] = batch["target_pose"].detach().to("cpu", torch.float32).reshape(12).tolist()
+            f.target_K[:] = batch["target_K"].detach().to("cpu", torch.float32).reshape(9).tolist()
+            f.target_K_inv[:] = batch["target_K_inv"].detach().to("cpu", torch.float32).reshape(9).tolist()
+            return f
         f = frame_from_batch(batch, H=self.H, W=self.W, n_views=self.V, n_samples=self.S,
                              level_dims=self.level_dims, src_hw=self.src_hw, feat_hw=self.feat_hw,
                              voxel_size=self.voxel_size, mask_threshold=self.mask_threshold,
                              neg_ray=neg_ray, rank=self.rank, world=self.world, tile_px=self.tile_px)
         f.self_dev = self.frame_dev.data_ptr()
+        self._frame_cache = (key, bytes(f))
         return f
 
     def upload_frame(self, frame):

@@ -122,10 +122,9 @@ class Renderer(nn.Module):
 
     def _sync_weights(self, eng):
         """(Re)pack the head weights for the kernels when they changed."""
-        sd = self.nerfhead.hot_path_state()
-        ver = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        ver = tuple((p.data_ptr(), p._version) for p in self.nerfhead.parameters())
         if getattr(eng, "_weights_ver", None) != ver:
-            eng.set_weights(sd)
+            eng.set_weights(self.nerfhead.hot_path_state())
             eng._weights_ver = ver
 
     def _upstream(self, batch):
@@ -140,6 +139,8 @@ class Renderer(nn.Module):
             featmaps = self.encoder(src_imgs.squeeze(0))
         if "levels" in batch:
             return featmaps, batch["levels"]
+        if "levels_sparse" in batch:          # (features, indices) per level + batch['level_dims']: no dense volume at all
+            return featmaps, None
         sh = self.nerfhead.sigmahead
         if not hasattr(sh, "xyzc_net"):
             raise _lib.GpnerfError("no batch['levels'] and the sparse-conv producer (spconv) is unavailable")
@@ -200,7 +201,19 @@ class Renderer(nn.Module):
         V = batch["src_imgs"].shape[1]
         eng = self.engine_for(int(H), int(W), int(V), device)
         self._sync_weights(eng)
-        if self.use_cuda_graph:
+        if levels is None:
+            # sparse levels: scatter the active rows (no dense volume, no K0 transposition), then K1…K5
+            eng.upload_products_sparse(batch["levels_sparse"], batch["level_dims"], featmaps, batch["src_imgs"])
+            frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
+            if self.use_cuda_graph:
+                if getattr(self, "_frame_pinned", None) is None:
+                    import ctypes as C
+                    from ._lib import Frame
+                    self._frame_pinned = torch.empty(C.sizeof(Frame), dtype=torch.uint8).pin_memory()
+                eng.run_progressive_graphed(frame, with_k0=False, frame_src=self._frame_pinned)
+            else:
+                eng.render_progressive(frame)
+        elif self.use_cuda_graph:
             # inputs land in static device buffers; the whole frame is one graph launch
             eng.copy_into_static_inputs(levels, featmaps, batch["src_imgs"],
                                         sharded_upload=self.world > 1 and self.shard == "tiles" and self._dist_ready())
@@ -254,23 +267,32 @@ class Renderer(nn.Module):
             for b in batches:             # a tile-sharded frame needs all ranks in lock step: no queueing ahead
                 yield self.render_progressive(b)
             return
+        from concurrent.futures import ThreadPoolExecutor
         st = None
         pending = collections.deque()
+        # the host-side tail of a frame (wait for its event, fp32 → float64 image, boolean mask, the
+        # compact rgb_map) runs on two worker threads – numpy releases the GIL – while the main thread queues
+        # the next frames; results are still yielded in order
+        pool = ThreadPoolExecutor(max_workers=2)
 
-        def finalize(item):
-            slot, H, W, t_start = item
+        def host_tail(slot, H, W, t_start):
             st["done"][slot].synchronize()
             cnt = dict(zip(("n_pix", "n_rays", "P1", "P2"), st["cnt"][slot][:4].tolist()))
-            pred_img = st["img"][slot].view(H, W, 3).numpy().astype(np.float64)
+            img32 = st["img"][slot].numpy().reshape(-1, 3)
             mask_at_box = st["hit"][slot].numpy().astype(bool)
-            rgb_map = pred_img.reshape(-1, 3)[mask_at_box].astype(np.float32)      # ascending pixel order
+            rgb_map = img32[np.flatnonzero(mask_at_box)]                  # ascending pixel order, fp32
+            pred_img = img32.reshape(H, W, 3).astype(np.float64)
             rtime = time.time() - t_start
             return {"rgb_map": rgb_map, "pred_img": pred_img, "mask_at_box": mask_at_box,
                     "time_slots": {"bc_render": rtime}, "etime": 0.0, "rtime": rtime, "counts": cnt}
 
+        def finalize(item):
+            return item.result()
+
         for i, batch in enumerate(batches):
-            if "levels" not in batch or "featmaps" not in batch:
-                raise _lib.GpnerfError("render_stream needs batch['levels'] and batch['featmaps']")
+            sparse = "levels_sparse" in batch
+            if ("levels" not in batch and not sparse) or "featmaps" not in batch:
+                raise _lib.GpnerfError("render_stream needs batch['levels'] (or ['levels_sparse']) and batch['featmaps']")
             src = batch["src_imgs"]
             H, W = int(src.shape[-2]), int(src.shape[-1])
             V = int(src.shape[1])
@@ -282,7 +304,8 @@ class Renderer(nn.Module):
                 im0 = src[0] if src.dim() == 5 else src
                 st = {
                     "copy": torch.cuda.Stream(device),
-                    "stage": [([mk(t) for t in batch["levels"]], mk(batch["featmaps"]), mk(im0)) for _ in range(depth)],
+                    "stage": [([] if sparse else [mk(t) for t in batch["levels"]], mk(batch["featmaps"]), mk(im0))
+                              for _ in range(depth)],
                     "copied": [torch.cuda.Event() for _ in range(depth)],
                     "free": [torch.cuda.Event() for _ in range(depth)],
                     "done": [torch.cuda.Event() for _ in range(depth)],
@@ -292,7 +315,7 @@ class Renderer(nn.Module):
                     "cnt": [torch.empty(8, dtype=torch.int32).pin_memory() for _ in range(depth)],
                 }
             if len(pending) == depth:
-                yield finalize(pending.popleft())
+                yield finalize(pending.popleft())       # the slot's pinned buffers are free again after this
             slot = i % depth
             t_start = time.time()
             main = torch.cuda.current_stream(device)
@@ -300,13 +323,25 @@ class Renderer(nn.Module):
             with torch.cuda.stream(st["copy"]):
                 if i >= depth:
                     st["copy"].wait_event(st["free"][slot])        # K0 of the previous tenant has read the set
-                for d, s_ in zip(lv_d, batch["levels"]):
-                    d.copy_(s_, non_blocking=True)
+                if sparse:       # row counts change from frame to frame: fresh device tensors on the copy stream
+                    lv_s = [(f.to(device, non_blocking=True), i.to(device, non_blocking=True))
+                            for f, i in batch["levels_sparse"]]
+                else:
+                    if not lv_d:      # first dense batch of a stream that started with sparse ones
+                        lv_d.extend(torch.empty(t.shape, dtype=torch.float32, device=device) for t in batch["levels"])
+                    for d, s_ in zip(lv_d, batch["levels"]):
+                        d.copy_(s_, non_blocking=True)
                 fm_d.copy_(batch["featmaps"], non_blocking=True)
                 im_d.copy_(src[0] if src.dim() == 5 else src, non_blocking=True)
                 st["copied"][slot].record(st["copy"])
             main.wait_event(st["copied"][slot])
-            eng.upload_products(lv_d, fm_d, im_d)                  # K0: staging set → gather layouts
+            if sparse:
+                for f, i in lv_s:
+                    f.record_stream(main)
+                    i.record_stream(main)
+                eng.upload_products_sparse(lv_s, batch["level_dims"], fm_d, im_d)
+            else:
+                eng.upload_products(lv_d, fm_d, im_d)              # K0: staging set → gather layouts
             st["free"][slot].record(main)
             frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
             if self.use_cuda_graph:
@@ -319,9 +354,10 @@ class Renderer(nn.Module):
             st["hit"][slot].copy_(eng.result_hit_mask(), non_blocking=True)
             st["cnt"][slot].copy_(eng.counters, non_blocking=True)
             st["done"][slot].record(main)
-            pending.append((slot, H, W, t_start))
+            pending.append(pool.submit(host_tail, slot, H, W, t_start))
         while pending:
             yield finalize(pending.popleft())
+        pool.shutdown(wait=True)
 
     def _stream_device(self, batch):
         src = batch["src_imgs"]

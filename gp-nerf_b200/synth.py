@@ -239,6 +239,23 @@ def make_scene(kind="zju", H=512, W=512, V=3, C=32, seed=42, smooth_images=True,
     return scene
 
 
+def sparsify_levels(levels):
+    """The dense levels [1,32,D,H,W] as the sparse-conv network holds them before
+    `.dense()` (SparseConvNet.py:110): per level (features [N,32] fp32, indices
+    [N,4] int32 = (batch, d, h, w)) of the sites with any non-zero channel, in
+    row-major site order, plus the 4 (D,H,W)."""
+    out, dims = [], []
+    for t in levels:
+        vol = t[0]                                   # [32,D,H,W]
+        active = (vol != 0).any(0)
+        idx = active.nonzero()                       # [N,3] (d,h,w)
+        feat = vol[:, idx[:, 0], idx[:, 1], idx[:, 2]].t().contiguous()
+        idx4 = torch.cat([torch.zeros_like(idx[:, :1]), idx], 1).to(torch.int32).contiguous()
+        out.append((feat, idx4))
+        dims.append(tuple(int(v) for v in vol.shape[-3:]))
+    return out, dims
+
+
 def retarget(scene, angle_deg):
     """The same scene seen from another novel view on the camera ring (a sweep:
     only target_pose changes; the volume, the source views and K stay)."""

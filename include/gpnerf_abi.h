@@ -151,6 +151,17 @@ int gpnerf_k0_products_to_f16(const float *const levels[GPNERF_N_LEVELS],
                               const int32_t level_dims[GPNERF_N_LEVELS][3], const float *featmaps,
                               int V, int fh, int fw, void *const levels_out[GPNERF_N_LEVELS],
                               float *const chan_sums[GPNERF_N_LEVELS], void *featmaps_out, void *stream);
+/* SURVEY §8f row 1, first step – the pyramid's outputs without the dense detour:
+ * the active rows of every level (feats[l] float[n_rows[l]][32], indices[l]
+ * int32[n_rows[l]][idx_cols], last three columns = (d,h,w); what a
+ * SparseConvTensor holds before .dense(), SparseConvNet.py:110) scattered straight
+ * into the zero-bordered fp16 volumes + channel sums (both cleared first). */
+int gpnerf_k0_sparse_to_f16(const float *const feats[GPNERF_N_LEVELS],
+                            const int32_t *const indices[GPNERF_N_LEVELS],
+                            const int32_t n_rows[GPNERF_N_LEVELS], int idx_cols,
+                            const int32_t level_dims[GPNERF_N_LEVELS][3],
+                            void *const levels_out[GPNERF_N_LEVELS],
+                            float *const chan_sums[GPNERF_N_LEVELS], void *stream);
 /* masks3d on the level-1 grid = Σ_levels nearest-upsampled channel sums
  * (SparseConvNet.py:137-139). */
 int gpnerf_k0_build_masks3d(const float *const chan_sum[GPNERF_N_LEVELS],

@@ -249,6 +249,44 @@ def test_dataset_rays_kernel_vs_oracle(H, seed, angle):
         assert np.array_equal(gd.cpu().numpy(), z[f"{tag}.ray_d"]) and np.array_equal(gn.cpu().numpy(), z[f"{tag}.near"])
 
 
+def test_sparse_level_upload_equals_dense_upload():
+    """SURVEY §8f row 1, first step: the levels as (features, indices) rows – what
+    the sparse-conv net holds before .dense() – scattered straight into the fp16
+    volumes: same volumes, same channel sums, same image as the dense NCDHW route;
+    also through Renderer.render / render_stream."""
+    from gpnerf_b200._lib import PREC_BF16
+    scene = synth.make_scene("zju", H=96, W=96, V=3, seed=13)
+    w = synth.make_head_weights(V=3, seed=113, random_bias=True)
+    S = 32
+    lv_s, dims = synth.sparsify_levels(scene["levels"])
+    assert sum(f.shape[0] for f, _ in lv_s) < 0.2 * sum(t[0, 0].numel() for t in scene["levels"])
+    dense, _ = stages.run_engine_progressive(scene, w, S, precision=PREC_BF16)
+    eng = Engine(96, 96, S, 3, device=DEV, precision=PREC_BF16)
+    eng.set_weights(w)
+    for rep in range(2):      # the second upload must clear the first one's sites
+        use = lv_s if rep else [(f * 0 + 7.0, i) for f, i in lv_s]
+        eng.upload_products_sparse(use, dims, scene["featmaps"].to(DEV), scene["src_imgs"].to(DEV))
+    eng.render_progressive(eng.make_frame(scene))
+    torch.cuda.synchronize()
+    for a, b in zip(eng.levels_cl, dense.levels_cl):
+        assert torch.equal(a, b)
+    for a, b in zip(eng.chan_sums, dense.chan_sums):
+        assert torch.equal(a, b)
+    assert eng.read_counters() == dense.read_counters() and torch.equal(eng.pred_img, dense.pred_img)
+    # plugin level
+    r = _renderer_for(w, 3, S, PREC_BF16)
+    host = {k: v for k, v in scene.items() if torch.is_tensor(v)}
+    host["featmaps"] = scene["featmaps"].pin_memory()
+    host["src_imgs"] = scene["src_imgs"].pin_memory()
+    hs = dict(host, levels_sparse=[(f.pin_memory(), i.pin_memory()) for f, i in lv_s], level_dims=dims)
+    hd = dict(host, levels=[t.pin_memory() for t in scene["levels"]])
+    want = r.render(dict(hd, src_imgs=scene["src_imgs"].to(DEV)))
+    got = r.render(dict(hs, src_imgs=scene["src_imgs"].to(DEV)))
+    assert np.array_equal(got["pred_img"], want["pred_img"]) and got["counts"] == want["counts"]
+    outs = list(r.render_stream([hs, hd, hs, hs]))
+    assert all(np.array_equal(o["pred_img"], want["pred_img"]) for o in outs)
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)
