@@ -100,6 +100,7 @@ class PeerExchange:
                 self._opened.append(p.value)
             dist.barrier(group=group)
         self.seq = 0                 # host mirror of the device-side frame counter
+        self._views = {}
         self.flags_ptr = self.base[rank] + self.off_flags
         # device-resident gpnerf_peer_t, written once
         p = self._struct()
@@ -144,13 +145,22 @@ class PeerExchange:
     # ------------------------------------------------------------------ results of frame `seq`
     def image(self, slot=0, seq=None):
         half = (self.seq if seq is None else seq) & 1
-        return _view(self.base[self.rank] + self.off_img[half][slot], (self.n_px, 3), torch.float32, self.device)
+        key = ("img", half, slot)
+        if key not in self._views:      # views are built once: torch.as_tensor on a raw pointer is not free
+            self._views[key] = _view(self.base[self.rank] + self.off_img[half][slot], (self.n_px, 3), torch.float32,
+                                     self.device)
+        return self._views[key]
 
     def hit_mask(self, slot=0, seq=None):
         half = (self.seq if seq is None else seq) & 1
-        return _view(self.base[self.rank] + self.off_hit[half][slot], (self.n_px,), torch.uint8, self.device)
+        key = ("hit", half, slot)
+        if key not in self._views:
+            self._views[key] = _view(self.base[self.rank] + self.off_hit[half][slot], (self.n_px,), torch.uint8,
+                                     self.device)
+        return self._views[key]
 
     def close(self):
+        self._views = {}
         for p in self._opened:
             self.lib.gpnerf_peer_close(C.c_void_p(p))
         self._opened = []
