@@ -175,6 +175,24 @@ def color_mlp(rgb_feat, meanvar, weights: HeadWeights, precision=PREC_FP32):
     return rgb
 
 
+def alpha_of_sigma(sigma):
+    """α = 1 - exp(-σ) (demo_render.py:313, BaseRender.py:262) through K4's kernel."""
+    _need_cuda(sigma)
+    lib = _lib.load()
+    s = _c(sigma).reshape(-1)
+    n = s.numel()
+    dev = s.device
+    alpha = torch.empty(n, dtype=torch.float32, device=dev)
+    if n:
+        counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int32, device=dev)
+        counters[_lib.CNT_P1] = n
+        valid1 = torch.empty(n, dtype=torch.int32, device=dev)
+        ws = torch.empty(int(lib.gpnerf_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        check(lib.gpnerf_k4_compact_alpha(ptr(s), n, ptr(counters), ptr(alpha), ptr(valid1), ptr(ws), _stream(dev)),
+              "k4_compact_alpha")
+    return alpha
+
+
 def raw2outputs(raw, z_vals, rgb_in=None, neg=False):
     """Renderer.raw2outputs (+ rgb_in_map): raw [R,S,4], z_vals [R,S],
     rgb_in [R,S,V,3] → rgb_map, disp, acc, weights, depth, rgb_in_map."""

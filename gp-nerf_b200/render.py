@@ -184,6 +184,8 @@ class Renderer(nn.Module):
 
     # ------------------------------------------------------------------ render
     def render(self, batch):
+        if getattr(self.nerfhead, "use_rgbhead", True) is False:
+            return self.render_mesh(batch)
         return self.render_progressive(batch) if self.progressive else self.render_dense(batch)
 
     @torch.no_grad()
@@ -364,6 +366,57 @@ class Renderer(nn.Module):
         if src.is_cuda:
             return src.device
         return torch.device("cuda", torch.cuda.current_device())
+
+    @torch.no_grad()
+    def render_mesh(self, batch):
+        """The mesh branch (`cfg.head.rgb.use_rgbhead False`; BaseRender.py:255-272,
+        demo_render.py:249-268, 366-376): σ of the density head at the grid points
+        `batch['pts']` [1,X,Y,Z,3] selected by `batch['inside']` [1,X,Y,Z], α = 1 - exp(-σ)
+        scattered into the grid, zero-padded by 10 → ret['cube'] (float64 numpy, as
+        the reference builds it); ret['mesh'] when mcubes + trimesh are importable
+        (marching cubes stays their job, as in the reference).  Gathers and the head
+        run in the library's kernels at explicit points (no rays, no compaction)."""
+        device = batch["src_imgs"].device
+        featmaps, levels = self._upstream(batch)
+        if levels is None:
+            raise _lib.GpnerfError("render_mesh takes dense levels")
+        src = batch["src_imgs"]
+        H, W = int(src.shape[-2]), int(src.shape[-1])
+        V = int(src.shape[1])
+        from .engine import frame_from_batch
+        lv = [t.to(device) for t in levels]
+        fm = featmaps.to(device)
+        dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
+        frame = frame_from_batch(batch, H=H, W=W, n_views=V, n_samples=1, level_dims=dims, src_hw=(H, W),
+                                 feat_hw=tuple(int(v) for v in fm.shape[-2:]),
+                                 voxel_size=tuple(float(v) for v in self.voxel_size), neg_ray=self._neg_ray(batch))
+        hw, _keep = ops.pack_head_weights(self.nerfhead.hot_path_state(), device, V,
+                                          tensor_core_image=self.precision != PREC_FP32)
+        levels_cl = [ops.level_to_channels_last(t)[0] for t in lv]
+        fm_cl = ops.featmaps_to_channels_last(fm)
+        rgbx = ops.images_to_rgbx(src[0] if src.dim() == 5 else src, unnormalize=True)
+        inside = batch["inside"][0].bool()
+        pts = batch["pts"][0][inside].reshape(-1, 3).to(device=device, dtype=torch.float32).contiguous()
+        sigma = torch.empty(pts.shape[0], dtype=torch.float32, device=device)
+        step = 1 << 22                       # explicit points need fp32 rows: 800 B per point and chunk
+        for p0 in range(0, pts.shape[0], step):
+            p = pts[p0:p0 + step]
+            vol = ops.gather_volume(levels_cl, frame, p)
+            _rgb_feat, mask, meanvar = ops.project_gather_meanvar(rgbx, fm_cl, frame, p)
+            sigma[p0:p0 + step] = ops.density_mlp(vol, meanvar, mask, hw, self.precision)
+        alpha = ops.alpha_of_sigma(sigma)
+        cube = np.zeros(tuple(inside.shape))
+        cube[inside.cpu().numpy()] = alpha.cpu().numpy()
+        cube = np.pad(cube, 10, mode="constant")
+        ret = {"cube": cube}
+        try:
+            import mcubes
+            import trimesh
+            vertices, triangles = mcubes.marching_cubes(cube, self.mesh_th)
+            ret["mesh"] = trimesh.Trimesh(vertices, triangles)
+        except ImportError:
+            pass
+        return ret
 
     def render_dense(self, batch):
         """BaseRender.Renderer.render: rgb_map [1,R,3], disp/acc/depth [1,R,1],

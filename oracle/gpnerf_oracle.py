@@ -542,3 +542,29 @@ def dataset_rays(H, W, K, R, T, bounds):
     near = np.minimum(d0, d1).astype(np.float32)
     far = np.maximum(d0, d1).astype(np.float32)
     return ro, rd, near, far, mask_at_box
+
+
+@torch.no_grad()
+def mesh_cube(scene, w, pts_grid, inside, neg_ray=False, chunk=65536):
+    """Row f4: the mesh branch's occupancy cube, BaseRender.py:255-270
+    (demo_render.py:249-268): σ of the density head at the grid points selected by
+    `inside`, α = 1 - exp(-σ) scattered into the grid and zero-padded by 10 voxels
+    (marching cubes over it is mcubes' job in the reference).  pts_grid [X,Y,Z,3]
+    world points, inside [X,Y,Z] bool.  Returns the float64 numpy cube."""
+    import numpy as np
+    cams, imgs01, out_sh = _scene_common(scene)
+    R_, Th, bounds = scene["R"], scene["Th"], scene["bounds"]
+    pts = pts_grid[inside].reshape(-1, 3).float()
+    sig = []
+    for p0 in range(0, pts.shape[0], chunk):
+        p = pts[p0:p0 + chunk]
+        grid = grid_coords_of(pts_to_can_pts(p, R_, Th), bounds, out_sh)
+        rgb_feat, mask = projector_compute(p, imgs01, cams, scene["featmaps"], neg_ray)
+        sfeat = sigma_feat_of(gather_levels(scene["levels"], grid), w)
+        mean, var = mean_var(rgb_feat)
+        sig.append(density_mlp(sfeat, mean, var, mask, w))
+    sigma = torch.cat(sig) if sig else torch.zeros(0)
+    alpha = (1.0 - torch.exp(-sigma)).numpy()
+    cube = np.zeros(tuple(inside.shape))
+    cube[inside.numpy().astype(bool)] = alpha
+    return np.pad(cube, 10, mode="constant")

@@ -287,6 +287,27 @@ def test_sparse_level_upload_equals_dense_upload():
     assert all(np.array_equal(o["pred_img"], want["pred_img"]) for o in outs)
 
 
+def test_mesh_branch_cube_vs_oracle():
+    """Row f4: the mesh branch's α cube (use_rgbhead False; BaseRender.py:255-270)
+    at the grid points of the world-frame box, 2.5 cm apart."""
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=9)
+    w = synth.make_head_weights(V=3, seed=109, random_bias=True)
+    lo, hi = scene["can_bounds"][0, 0], scene["can_bounds"][0, 1]
+    axes = [torch.arange(float(lo[k]), float(hi[k]), 0.025) for k in range(3)]
+    pts = torch.stack(torch.meshgrid(*axes, indexing="ij"), -1)
+    inside = torch.ones(pts.shape[:3], dtype=torch.bool)
+    inside[::5] = False                                    # the reference masks points outside the body's hull
+    want = orc.mesh_cube(scene, w, pts, inside)
+    r = _renderer_for(w, 3, 16, PREC_FP32)
+    b = {k: v for k, v in scene.items() if torch.is_tensor(v)}
+    b.update(levels=scene["levels"], featmaps=scene["featmaps"], src_imgs=scene["src_imgs"].to(DEV),
+             pts=pts[None], inside=inside[None])
+    got = r.render_mesh(b)["cube"]
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert float(np.abs(got - want).max()) < TOL and float(want.max()) > 0.1
+    assert float(np.abs(got[:10]).max()) == 0.0           # the 10-voxel pad
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)
