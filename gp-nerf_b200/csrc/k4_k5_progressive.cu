@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(256) composite_tiles(const float* __restrict__
 }
 
 // Matching acquire: thread k waits until flags[k] has reached the frame's sequence number (peers k
-// publish it from composite_tiles when all their tiles have landed here).  Bounded: traps after ~4 s.
+// publish it from composite_tiles when all their tiles have landed here).  Bounded: traps after ~30 s
+// (a peer that is still capturing its graph or paging its image in must not take the job down).
 __global__ void peer_wait_kernel(const int32_t* __restrict__ flags, int n_flags, int self,
                                  const gpnerf_peer_t* __restrict__ peer_dev) {
   const int k = threadIdx.x;
@@ -192,7 +193,7 @@ __global__ void peer_wait_kernel(const int32_t* __restrict__ flags, int n_flags,
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_sys(flags + k) - seq) < 0) {
     __nanosleep(200);
-    if (clock64() - t0 > 8000000000ll) __trap();
+    if (clock64() - t0 > 60000000000ll) __trap();
   }
 }
 
