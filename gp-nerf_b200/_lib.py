@@ -70,8 +70,12 @@ _SIGNATURES = {
     "gpnerf_k0_level_to_channels_last": ([_P, _I, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "gpnerf_k0_products_to_f16": ([C.POINTER(_P), C.POINTER(C.c_int32 * 3), _P, _I, _I, _I, C.POINTER(_P),
                                    C.POINTER(_P), _P, _P], C.c_int),
-    "gpnerf_k0_sparse_to_f16": ([C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int32), _I, C.POINTER(C.c_int32 * 3),
-                                 C.POINTER(_P), C.POINTER(_P), _P], C.c_int),
+    "gpnerf_k0_sparse_to_f16": ([C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int32), C.POINTER(_P), _I,
+                                 C.POINTER(C.c_int32 * 3), C.POINTER(_P), C.POINTER(_P), _P], C.c_int),
+    "gpnerf_sc_index_input": ([_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_sc_gather_rows": ([_P, _I, _P, _P, _I, _P, _P], C.c_int),
+    "gpnerf_sc_strided_sites": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_sc_conv": ([_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P], C.c_int),
     "gpnerf_k0_build_masks3d": ([C.POINTER(_P), C.POINTER(Frame), _P, _P], C.c_int),
     "gpnerf_k0_featmaps_to_channels_last": ([_P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
     "gpnerf_k0_images_to_rgbx": ([_P, _I, _I, _I, _I, _I, _P, _P], C.c_int),

@@ -255,6 +255,7 @@ struct SparseJob {
   const int32_t* idx;
   __half* dst;
   float* chan_sum;
+  const int32_t* n_dev;   // optional: the live row count sits on the device (n is then the capacity)
   int n, D, H, W;
   int row0;          // first global row of the job
 };
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(256) sparse_rows_to_f16(const __grid_constant_
       if (r >= jobs.j[k].row0) ji = k;
     const SparseJob& J = jobs.j[ji];
     const int lr = r - J.row0;
-    const bool ok = r < jobs.n_rows && lr < J.n;
+    const bool ok = r < jobs.n_rows && lr < (J.n_dev ? min(J.n, __ldg(J.n_dev)) : J.n);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     int d = 0, h = 0, w = 0;
     if (ok) {
@@ -435,9 +436,10 @@ int gpnerf_k0_products_to_f16(const float* const levels[GPNERF_N_LEVELS], const 
 }
 
 int gpnerf_k0_sparse_to_f16(const float* const feats[GPNERF_N_LEVELS], const int32_t* const indices[GPNERF_N_LEVELS],
-                            const int32_t n_rows[GPNERF_N_LEVELS], int idx_cols,
-                            const int32_t level_dims[GPNERF_N_LEVELS][3], void* const levels_out[GPNERF_N_LEVELS],
-                            float* const chan_sums[GPNERF_N_LEVELS], void* stream) {
+                            const int32_t n_rows[GPNERF_N_LEVELS], const int32_t* const n_rows_dev[GPNERF_N_LEVELS],
+                            int idx_cols, const int32_t level_dims[GPNERF_N_LEVELS][3],
+                            void* const levels_out[GPNERF_N_LEVELS], float* const chan_sums[GPNERF_N_LEVELS],
+                            void* stream) {
   GPNERF_REQUIRE(feats && indices && n_rows && level_dims && levels_out && chan_sums && idx_cols >= 3 && idx_cols <= 4);
   cudaStream_t st = (cudaStream_t)stream;
   SparseJobs jobs;
@@ -456,6 +458,7 @@ int gpnerf_k0_sparse_to_f16(const float* const feats[GPNERF_N_LEVELS], const int
     }
     SparseJob& J = jobs.j[l];
     J.feat = feats[l]; J.idx = indices[l]; J.dst = reinterpret_cast<__half*>(levels_out[l]); J.chan_sum = chan_sums[l];
+    J.n_dev = n_rows_dev ? n_rows_dev[l] : nullptr;
     J.n = n_rows[l]; J.D = D; J.H = H; J.W = W; J.row0 = row;
     row += (n_rows[l] + 3) & ~3;          // a warp's 4 rows never straddle two levels
   }

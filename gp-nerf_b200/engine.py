@@ -264,7 +264,7 @@ class Engine:
         self.src_hw, self.feat_hw = (ih, iw), (fh, fw)
         self._keep_inputs = (lv, fm, im)     # keep alive until the stream drains
 
-    def upload_products_sparse(self, levels_sparse, level_dims, featmaps, src_imgs):
+    def upload_products_sparse(self, levels_sparse, level_dims, featmaps, src_imgs, n_rows_dev=None):
         """The pyramid's levels as the sparse-conv network holds them before
         `.dense()` (SparseConvNet.py:110): per level `(features [N,32] fp32,
         indices [N,3|4] int32 with (d,h,w) last)`, `level_dims` 4 × (D,H,W).
@@ -291,7 +291,10 @@ class Engine:
             self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
         dims_c = ((C.c_int32 * 3) * 4)(*[(C.c_int32 * 3)(*d) for d in dims])
         n_rows = (C.c_int32 * 4)(*[int(f.shape[0]) for f in feats])
-        self._run("k0_sparse_to_f16", L.gpnerf_k0_sparse_to_f16, ptr_array(feats), ptr_array(idxs), n_rows, cols, dims_c,
+        # n_rows_dev: 4 device int32 scalars with the live row counts (the arrays are then capacities:
+        # what sparseconv.SparseConvNet hands over without a host sync)
+        nrd = None if n_rows_dev is None else ptr_array([t.view(1) for t in n_rows_dev])
+        self._run("k0_sparse_to_f16", L.gpnerf_k0_sparse_to_f16, ptr_array(feats), ptr_array(idxs), n_rows, nrd, cols, dims_c,
                   ptr_array(self.levels_cl), ptr_array(self.chan_sums), st)
         V, Cc, fh, fw = fm.shape
         assert V == self.V and Cc == 32

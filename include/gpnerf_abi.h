@@ -155,10 +155,13 @@ int gpnerf_k0_products_to_f16(const float *const levels[GPNERF_N_LEVELS],
  * the active rows of every level (feats[l] float[n_rows[l]][32], indices[l]
  * int32[n_rows[l]][idx_cols], last three columns = (d,h,w); what a
  * SparseConvTensor holds before .dense(), SparseConvNet.py:110) scattered straight
- * into the zero-bordered fp16 volumes + channel sums (both cleared first). */
+ * into the zero-bordered fp16 volumes + channel sums (both cleared first).
+ * n_rows_dev (may be NULL): per level a DEVICE pointer to the live row count,
+ * n_rows[l] then being the capacity of the arrays (gpnerf_sc_* outputs). */
 int gpnerf_k0_sparse_to_f16(const float *const feats[GPNERF_N_LEVELS],
                             const int32_t *const indices[GPNERF_N_LEVELS],
-                            const int32_t n_rows[GPNERF_N_LEVELS], int idx_cols,
+                            const int32_t n_rows[GPNERF_N_LEVELS],
+                            const int32_t *const n_rows_dev[GPNERF_N_LEVELS], int idx_cols,
                             const int32_t level_dims[GPNERF_N_LEVELS][3],
                             void *const levels_out[GPNERF_N_LEVELS],
                             float *const chan_sums[GPNERF_N_LEVELS], void *stream);
@@ -305,6 +308,31 @@ int gpnerf_k3_color_mlp_records(const void *records, const int32_t *valid1,
                                 const gpnerf_head_weights_t *weights_host, int n_views,
                                 int n_points_max, const int32_t *counters, int counter_slot,
                                 float *rgb, void *stream);
+
+/* ---- K7: the sparse-conv geometry encoder -------------- */
+/* libs/nerfheads/networks/SparseConvNet.py:21-124 without spconv (1.2.1 @ abf0acf3, not in the reference tree,
+ * does not build for sm_100): SubMConv3d / SparseConv3d(3, 2, padding 1) as their published semantics – a dense
+ * cross-correlation restricted to the active output sites, weights [kd][kh][kw][in][out] – followed by the
+ * (folded, inference-form) BatchNorm1d scale/shift and ReLU.  Rows = active sites; counts stay on the device.
+ *  index_input : voxel coords [n][cols] (d,h,w last) → de-duplicated sites (the smallest row id owns a voxel):
+ *                owners int32[n] (input rows, ascending), coords_out int32[n][3], idx_vol int32[D*H*W]
+ *                (row id per site, 0x7f7f7f7f = none), n_out[0].
+ *  gather_rows : feat_out[j] = feat_in[rows[j]] for j < n_dev[0].
+ *  strided_sites: sites of the next level (stride 2) + its index volume; out_lin = scratch int32[n_out_max].
+ *  conv        : out_feat[o] = relu(scale ⊙ Σ_k W[k]ᵀ·in[nbr_k(o)] + shift), nbr_k(o) = o·stride − 1 + k.
+ * workspace: gpnerf_workspace_bytes(max(n, voxels of the level being compacted)). */
+int gpnerf_sc_index_input(const int32_t *coords, int cols, int n, int D, int H, int W, int32_t *idx_vol,
+                          int32_t *owners, int32_t *coords_out, int32_t *n_out, void *workspace,
+                          void *stream);
+int gpnerf_sc_gather_rows(const float *feat_in, int C, const int32_t *rows, const int32_t *n_dev,
+                          int n_max, float *feat_out, void *stream);
+int gpnerf_sc_strided_sites(const int32_t *in_coords, const int32_t *n_in_dev, int n_in_max, int Do,
+                            int Ho, int Wo, int32_t *out_lin, int32_t *out_coords,
+                            int32_t *out_idx_vol, int32_t *n_out_dev, void *workspace, void *stream);
+int gpnerf_sc_conv(const float *in_feat, int c_in, const int32_t *in_idx_vol, int Di, int Hi, int Wi,
+                   const int32_t *n_in_dev, const int32_t *out_coords, const int32_t *n_out_dev,
+                   int n_out_max, int stride, const float *weight, const float *scale,
+                   const float *shift, int c_out, float *out_feat, void *stream);
 
 /* ---- K4: progressive step ---------------------------------------------- */
 /* demo_render.py:312-317: α = 1-exp(-σ); valid1 = ascending indices (into the

@@ -568,3 +568,52 @@ def mesh_cube(scene, w, pts_grid, inside, neg_ray=False, chunk=65536):
     cube = np.zeros(tuple(inside.shape))
     cube[inside.numpy().astype(bool)] = alpha
     return np.pad(cube, 10, mode="constant")
+
+
+# --------------------------------------------------------------------------
+# Row f1: the sparse-conv pyramid as a dense emulation
+# --------------------------------------------------------------------------
+@torch.no_grad()
+def sparse_conv_net(state, features, coords, spatial_shape, n_layers=4, eps=1e-3):
+    """libs/nerfheads/networks/SparseConvNet.py:21-124 with every spconv layer
+    replaced by its dense equivalent (spconv 1.2.1's documented semantics, the
+    way its own unit tests check it against torch.nn.Conv3d):
+      SubMConv3d(3)       = conv3d(padding=1) evaluated on the input's active sites only
+      SparseConv3d(3,2,1) = conv3d(stride=2, padding=1), active where any input site is in reach
+    with weight[kd,kh,kw,in,out] ↔ conv3d weight[out,in,kd,kh,kw], followed by
+    BatchNorm1d (running statistics) and ReLU on the active sites.  PARITY UNPINNED
+    against spconv itself (absent from the reference tree and from this image).
+    `state`: the module's state_dict.  Duplicate voxels: the smallest row owns the site.
+    Returns the 4 dense levels [1, C, D_k, H_k, W_k] (what x.dense() gives)."""
+    D, H, W = [int(v) for v in spatial_shape]
+    C0 = features.shape[1]
+    dense = torch.zeros(1, C0, D, H, W)
+    active = torch.zeros(1, 1, D, H, W)
+    crd = coords[:, -3:].long()
+    for i in range(crd.shape[0] - 1, -1, -1):          # reverse order: the smallest row index wins
+        d, h, w = [int(v) for v in crd[i]]
+        if 0 <= d < D and 0 <= h < H and 0 <= w < W:
+            dense[0, :, d, h, w] = features[i]
+            active[0, 0, d, h, w] = 1.0
+
+    def layer(x, act, prefix, stride):
+        wt = state[prefix + ".weight"].permute(4, 3, 0, 1, 2).contiguous()
+        bn = prefix.rsplit(".", 1)[0] + "." + str(int(prefix.rsplit(".", 1)[1]) + 1)
+        y = F.conv3d(x, wt, stride=stride, padding=1)
+        if stride == 2:
+            act = (F.max_pool3d(act, 3, 2, 1) > 0).float()
+        inv = torch.rsqrt(state[bn + ".running_var"] + eps)
+        scale = state[bn + ".weight"] * inv
+        shift = state[bn + ".bias"] - state[bn + ".running_mean"] * scale
+        y = torch.relu(y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)) * act
+        return y, act
+    x, act = dense, active
+    x, act = layer(x, act, "net.0.0", 1)
+    x, act = layer(x, act, "net.0.3", 1)
+    levels = []
+    for i in range(n_layers):
+        x, act = layer(x, act, f"net.{2 * i + 1}.0", 2)
+        x, act = layer(x, act, f"net.{2 * i + 2}.0", 1)
+        x, act = layer(x, act, f"net.{2 * i + 2}.3", 1)
+        levels.append(x)
+    return levels

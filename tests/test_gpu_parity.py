@@ -308,6 +308,64 @@ def test_mesh_branch_cube_vs_oracle():
     assert float(np.abs(got[:10]).max()) == 0.0           # the 10-voxel pad
 
 
+@pytest.mark.parametrize("in_dim", [16, 32])
+def test_sparse_conv_net_vs_dense_emulation(in_dim):
+    """Row f1: the sparse-conv pyramid (SparseConvNet.py:21-124) from K7 against its dense conv3d
+    emulation (oracle.sparse_conv_net; spconv itself is absent: parity unpinned).  Random sites with
+    duplicates, random BatchNorm statistics; then the rows straight into the renderer."""
+    from gpnerf_b200._lib import PREC_BF16
+    from gpnerf_b200.sparseconv import SparseConvNet
+    torch.manual_seed(in_dim)
+    net = SparseConvNet(in_dim=in_dim).eval()
+    for k, v in net.state_dict().items():
+        if k.endswith("running_var"):
+            v.uniform_(0.5, 2.0)
+        elif k.endswith("running_mean"):
+            v.normal_(0.0, 0.3)
+        elif ".1.bias" in k or ".4.bias" in k:
+            v.normal_(0.0, 0.2)
+    scene = synth.make_scene("zju", H=96, W=96, V=3, seed=13)
+    coord = scene["coord"][0]                              # [6890,3] (d,h,w) with duplicate voxels
+    out_sh = [int(v) for v in scene["out_sh"][0]]
+    # a crop of the volume keeps the CPU conv3d emulation fast
+    lo = torch.tensor([16, 128, 64], dtype=coord.dtype)
+    keep = ((coord >= lo) & (coord < lo + torch.tensor([64, 96, 64], dtype=coord.dtype))).all(1)
+    coord, shape = (coord[keep] - lo).contiguous(), (64, 96, 64)
+    assert coord.shape[0] > 500 and len(torch.unique(coord, dim=0)) < coord.shape[0]
+    feats = torch.randn(coord.shape[0], in_dim)
+    want = orc.sparse_conv_net(net.state_dict(), feats, coord, shape)
+    net_d = net.to(DEV)
+    rows, dims, n_dev = net_d(feats.to(DEV), coord.to(DEV), shape)
+    torch.cuda.synchronize()
+    assert dims == [tuple(t.shape[-3:]) for t in want]
+    for (f, c), n, ref in zip(rows, n_dev, want):
+        n = int(n)
+        act = (ref[0].abs().sum(0) > 0)
+        f, c = f[:n].cpu(), c[:n].cpu().long()
+        got = torch.zeros_like(ref[0])
+        got[:, c[:, 0], c[:, 1], c[:, 2]] = f.t()
+        assert n >= int(act.sum())                          # every site with a non-zero feature is a row
+        assert float((got - ref[0]).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+        lin = (c[:, 0] * ref.shape[-2] + c[:, 1]) * ref.shape[-1] + c[:, 2]
+        assert bool((lin[1:] > lin[:-1]).all())             # unique sites, ascending
+    # the rows feed the renderer without a dense tensor in between
+    scene2 = synth.make_scene("zju", H=64, W=64, V=3, seed=13)
+    full = SparseConvNet(in_dim=in_dim).eval()
+    for k, v in full.state_dict().items():                  # keep the activations O(1) through the 14 layers
+        if k.endswith(".1.weight") or k.endswith(".4.weight"):
+            v.fill_(3.0)
+    full = full.to(DEV)
+    rows, dims, n_dev = full(torch.randn(6890, in_dim, device=DEV), scene2["coord"][0].to(DEV), out_sh)
+    eng = Engine(64, 64, 16, 3, device=DEV, precision=PREC_BF16)
+    eng.set_weights(synth.make_head_weights(V=3, seed=3))
+    eng.upload_products_sparse(rows, dims, scene2["featmaps"].to(DEV), scene2["src_imgs"].to(DEV), n_rows_dev=n_dev)
+    eng.render_progressive(eng.make_frame(scene2))
+    torch.cuda.synchronize()
+    c = eng.read_counters()
+    assert c["n_rays"] > 100 and c["P1"] > c["n_rays"] and bool(torch.isfinite(eng.pred_img).all())
+    assert dims == [tuple(d) for d in eng.level_dims] == [tuple(t.shape[-3:]) for t in scene2["levels"]]
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)
