@@ -7,9 +7,9 @@ as the reference, so `state_dict` keys line up:
 ``rgbhead.{base_fc.{0,2},vis_fc.{0,2},rgb_fc.{0,2,4},out_geometry_fc.{0,2,4,6}}``.
 The two upstream producers the sigma head owns in the reference –
 ``xyzc_attn`` (MultiHeadAttention) and ``xyzc_net`` (spconv SparseConvNet) – are
-outside the hot path; they are the reference's own modules when
-this file runs inside the reference tree, and absent otherwise (the geometry
-volume is then supplied by the caller, e.g. gpnerf_b200.synth).
+SURVEY.md §8f row 1 ("next"): mirrors on K8/K7 (attention.py, sparseconv.py)
+with the reference's parameter names, so the whole ``sigmahead.*`` state_dict
+loads; they run in inference form and hand the renderer sparse level rows.
 """
 from __future__ import annotations
 
@@ -18,6 +18,8 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import PREC_FP32
+from .attention import MultiHeadAttention
+from .sparseconv import SparseConvNet
 
 
 def weights_init(m):
@@ -28,18 +30,6 @@ def weights_init(m):
             nn.init.zeros_(m.bias.data)
 
 
-def _reference_upstream(code_dim, attn_n_heads, in_feat_ch, spconv_n_layers, spconv_out_dim):
-    """The reference's own producers, if importable (needs spconv)."""
-    try:
-        from libs.nerfheads.networks import MultiHeadAttention, SparseConvNet  # type: ignore
-        attn = MultiHeadAttention(attn_n_heads, code_dim, code_dim // attn_n_heads, code_dim // attn_n_heads,
-                                  kv_dim=in_feat_ch, sum=False)
-        net = SparseConvNet(n_layers=spconv_n_layers, in_dim=code_dim, out_dim=spconv_out_dim)
-        return attn, net
-    except Exception:
-        return None, None
-
-
 class NeRFSigmaHead(nn.Module):
     """trainhead.py:27-76"""
 
@@ -47,12 +37,22 @@ class NeRFSigmaHead(nn.Module):
                  spconv_out_dim=(32, 32, 32, 32), precision=PREC_FP32):
         super().__init__()
         self.c = nn.Embedding(n_smpl, code_dim)
-        attn, net = _reference_upstream(code_dim, attn_n_heads, in_feat_ch, spconv_n_layers, list(spconv_out_dim))
-        if attn is not None:
-            self.xyzc_attn, self.xyzc_net = attn, net
+        self.xyzc_attn = MultiHeadAttention(attn_n_heads, code_dim, code_dim // attn_n_heads, code_dim // attn_n_heads,
+                                            kv_dim=in_feat_ch, sum=False)
+        self.xyzc_net = SparseConvNet(n_layers=spconv_n_layers, in_dim=code_dim, out_dim=list(spconv_out_dim))
         self.out_geometry_fc = nn.Sequential(nn.Linear(sum(spconv_out_dim), 64), nn.ELU(inplace=True))
         self.out_geometry_fc.apply(weights_init)
         self.precision = precision
+
+    @torch.no_grad()
+    def encode_geometry(self, smpl_feat_sampled, coord, out_sh):
+        """trainhead.py:44-54 up to the SparseConvTensor, then SparseConvNet.py:104-110 without ``.dense()``:
+        smpl_feat_sampled [1|B, n_smpl, V, C] (Projector.compute_smpl), coord [n_smpl, 3|4] voxel indices,
+        out_sh (D, H, W) → (levels_sparse, level_dims, n_rows_dev) for Engine.upload_products_sparse."""
+        code = self.c.weight.detach()                         # = self.c(arange(n_smpl)), trainhead.py:48
+        feats = smpl_feat_sampled.flatten(0, 1)
+        fused = self.xyzc_attn(code.unsqueeze(1), feats, feats)[0].squeeze(1)
+        return self.xyzc_net(fused, coord, out_sh)
 
     def volume_features(self, sp_input, grid_coords):
         """The gather half of SparseConvNet.forward (SparseConvNet.py:111-122)

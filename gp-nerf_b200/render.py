@@ -65,7 +65,7 @@ class Projector:
         dummy = torch.zeros(f.n_views * f.src_h * f.src_w * 4, device=featmaps.device)
         fm = ops.featmaps_to_channels_last(featmaps)
         rgb_feat, _, _ = ops.project_gather_meanvar(dummy, fm, f, smpl_xyz.reshape(-1, 3))
-        return rgb_feat[..., 3:].reshape(*smpl_xyz.shape[:2], f.n_views, 32)
+        return rgb_feat.view(*smpl_xyz.shape[:2], f.n_views, 35)[..., 3:]      # a view: K8 takes the strides
 
 
 class Renderer(nn.Module):
@@ -141,24 +141,19 @@ class Renderer(nn.Module):
             return featmaps, batch["levels"]
         if "levels_sparse" in batch:          # (features, indices) per level + batch['level_dims']: no dense volume at all
             return featmaps, None
+        # the reference's producers (demo_render.py:103-157, trainhead.py:44-54) on K2/K8/K7: project the SMPL
+        # vertices, attend, run the sparse-conv pyramid; its rows go to the renderer without a dense volume
         sh = self.nerfhead.sigmahead
-        if not hasattr(sh, "xyzc_net"):
-            raise _lib.GpnerfError("no batch['levels'] and the sparse-conv producer (spconv) is unavailable")
-        import spconv  # noqa: F401  (reference dependency, only on this upstream branch)
         device = featmaps.device
-        xyz = batch["feature"][..., :3]
-        R, Th = batch["Rh"].float(), batch["Th"].float()
+        xyz = batch["feature"][..., :3].to(device).float()
+        R, Th = batch["Rh"].to(device).float(), batch["Th"].to(device).float()
         smpl_xyz = torch.bmm(xyz, R.transpose(1, 2)) + Th
         cams = self._pack_cameras(batch, src_imgs.shape[-2:], device)
-        code = sh.c(torch.arange(0, sh.c.num_embeddings, device=device))
-        feats = Projector(device).compute_smpl(smpl_xyz, cams, featmaps).flatten(0, 1)
-        fused = sh.xyzc_attn(code.unsqueeze(1), feats, feats)[0].squeeze(1)
-        coord = batch["coord"].view(-1, 3)
-        coord = torch.cat([torch.zeros_like(coord[:, :1]), coord], 1)
-        out_sh = batch["out_sh"].max(0)[0].tolist()
-        xyzc = spconv.SparseConvTensor(fused, coord, out_sh, 1)
-        levels = sh.xyzc_net(xyzc)          # grid_coords=None → the dense levels
-        return featmaps, levels
+        feats = Projector(device).compute_smpl(smpl_xyz, cams, featmaps)
+        out_sh = [int(v) for v in torch.as_tensor(batch["out_sh"]).reshape(-1, 3).max(0)[0].tolist()]
+        rows, dims, n_dev = sh.encode_geometry(feats, batch["coord"].reshape(-1, batch["coord"].shape[-1]).to(device), out_sh)
+        batch["levels_sparse"], batch["level_dims"], batch["levels_sparse_rows"] = rows, dims, n_dev
+        return featmaps, None
 
     @staticmethod
     def _pack_cameras(batch, img_size, device):
@@ -205,7 +200,8 @@ class Renderer(nn.Module):
         self._sync_weights(eng)
         if levels is None:
             # sparse levels: scatter the active rows (no dense volume, no K0 transposition), then K1…K5
-            eng.upload_products_sparse(batch["levels_sparse"], batch["level_dims"], featmaps, batch["src_imgs"])
+            eng.upload_products_sparse(batch["levels_sparse"], batch["level_dims"], featmaps, batch["src_imgs"],
+                                       n_rows_dev=batch.get("levels_sparse_rows"))
             frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
             if self.use_cuda_graph:
                 if getattr(self, "_frame_pinned", None) is None:

@@ -334,6 +334,17 @@ int gpnerf_sc_conv(const float *in_feat, int c_in, const int32_t *in_idx_vol, in
                    int n_out_max, int stride, const float *weight, const float *scale,
                    const float *shift, int c_out, float *out_feat, void *stream);
 
+/* ---- K8: SMPL-code attention (trainhead.py:48-51; MultiHeadAttention.py:40-98, sum=False) ---- */
+/* out[i] = W_fc · concat_h( softmax_v( (W_q·code[i])_h/√d_k · (W_k·feat[i,v])_h ) · (W_v·feat[i,v])_h ).
+ * code [n][d_model]; feat[i,v] = feats + i*vertex_stride + v*view_stride (floats, kv_dim of them – lets the
+ * caller pass the [n][V][35] rows of gpnerf_k2_project_gather_meanvar with an offset of 3); weights in
+ * torch.nn.Linear layout [out][in]; out [n][d_model].  (d_model, kv_dim, n_head·d_k) ∈ {(16,32,16),(32,32,32)},
+ * n_views ≤ 8, n_head ≤ 8. */
+int gpnerf_attn_smpl_code(const float *code, const float *feats, long long view_stride,
+                          long long vertex_stride, int n, int n_views, const float *w_q,
+                          const float *w_k, const float *w_v, const float *w_fc, int d_model,
+                          int kv_dim, int n_head, int d_k, float *out, void *stream);
+
 /* ---- K4: progressive step ---------------------------------------------- */
 /* demo_render.py:312-317: α = 1-exp(-σ); valid1 = ascending indices (into the
  * P1 arrays) with α > 1e-14; counters[P2]. */

@@ -617,3 +617,26 @@ def sparse_conv_net(state, features, coords, spatial_shape, n_layers=4, eps=1e-3
         x, act = layer(x, act, f"net.{2 * i + 2}.3", 1)
         levels.append(x)
     return levels
+
+
+def smpl_code_attention(state, code, feats, n_head=4, prefix=""):
+    """libs/nerfheads/networks/MultiHeadAttention.py:62-98 as trainhead.py:50 calls it (sum=False, mask=None):
+    code [n, d_model] (one query per SMPL vertex), feats [n, V, kv_dim] (keys = values) → [n, d_model].
+    Pinned against the reference module itself: tests/golden/attention.npz (oracle/gen_golden_attn.py)."""
+    wq, wk, wv, wfc = (state[prefix + k].double() for k in ("w_qs.weight", "w_ks.weight", "w_vs.weight", "fc.weight"))
+    n, V, _ = feats.shape
+    d_k = wq.shape[0] // n_head
+    q = (code.double() @ wq.t()).view(n, 1, n_head, d_k).transpose(1, 2)            # [n, h, 1, dk]
+    k = (feats.double() @ wk.t()).view(n, V, n_head, d_k).transpose(1, 2)           # [n, h, V, dk]
+    v = (feats.double() @ wv.t()).view(n, V, n_head, d_k).transpose(1, 2)
+    attn = torch.softmax((q / d_k ** 0.5) @ k.transpose(2, 3), dim=-1)              # [n, h, 1, V]
+    o = (attn @ v).transpose(1, 2).reshape(n, n_head * d_k)
+    return (o @ wfc.t()).float()
+
+
+def smpl_features(smpl_xyz, cams, featmaps, neg_ray=False):
+    """Projector.compute_smpl (demo_render.py:612-632): smpl_xyz [n,3], cams [1,V,34], featmaps [V,C,h,w] →
+    [n, V, C]: the pixel-aligned features of the SMPL vertices (bilinear, zeros outside, no mask)."""
+    dummy = torch.zeros(featmaps.shape[0], 3, int(cams[0, 0, 0]), int(cams[0, 0, 1]))
+    rgb_feat, _mask = projector_compute(smpl_xyz, dummy, cams, featmaps, neg_ray)
+    return rgb_feat[..., 3:].contiguous()

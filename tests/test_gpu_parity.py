@@ -366,6 +366,72 @@ def test_sparse_conv_net_vs_dense_emulation(in_dim):
     assert dims == [tuple(d) for d in eng.level_dims] == [tuple(t.shape[-3:]) for t in scene2["levels"]]
 
 
+def test_smpl_code_attention_vs_reference_golden():
+    """Row f1 (K8): the attention kernel behind the MultiHeadAttention mirror against the reference
+    module's own outputs (tests/golden/attention.npz), through load_state_dict with the reference's keys;
+    also with the strided [n,V,35] feature rows compute_smpl hands over."""
+    from gpnerf_b200.attention import MultiHeadAttention
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "attention.npz"))
+    for tag in ("a", "b", "c"):
+        state = {k.split(".state.")[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{tag}.state.")}
+        code, feats = torch.from_numpy(z[f"{tag}.code"]), torch.from_numpy(z[f"{tag}.feats"])
+        dm, nh = code.shape[1], int(z[f"{tag}.n_head"])
+        m = MultiHeadAttention(nh, dm, dm // nh, dm // nh, kv_dim=feats.shape[2], sum=False)
+        m.load_state_dict(state, strict=True)
+        m = m.to(DEV)
+        want = torch.from_numpy(z[f"{tag}.out"])
+        f = feats.to(DEV)
+        got = m(code.to(DEV).unsqueeze(1), f, f)[0].squeeze(1).cpu()
+        assert float((got - want).abs().max()) < 1e-5, tag
+        wide = torch.randn(f.shape[0], f.shape[1], 35, device=DEV)
+        wide[..., 3:] = f
+        got2 = m(code.to(DEV).unsqueeze(1), wide[..., 3:], wide[..., 3:])[0].squeeze(1).cpu()
+        assert torch.equal(got, got2)
+
+
+def test_renderer_native_upstream_chain():
+    """Row f1 end to end: Renderer.render on a batch without 'levels' runs project → K8 attention → K7
+    pyramid → sparse upload → K1…K5 on the device; the same image as rendering the dense levels built on
+    the CPU from the oracle's attention + dense conv3d emulation with the same parameters."""
+    from gpnerf_b200._lib import PREC_BF16
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Renderer
+    torch.manual_seed(5)
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=13)
+    head = NeRFHead(n_views=3, precision=PREC_BF16).eval()
+    w = synth.make_head_weights(V=3, seed=3)
+    sd = head.state_dict()
+    for k, v in w.items():
+        sd[k].copy_(v)
+    for k, v in sd.items():                                 # keep the activations O(1) through the 14 layers
+        if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+            v.fill_(3.0)
+    sd["sigmahead.c.weight"].normal_(0.0, 1.0)
+    head.load_state_dict(sd)
+    # CPU chain with the same parameters (oracle)
+    sg = {k[len("sigmahead."):]: v.clone() for k, v in head.state_dict().items() if k.startswith("sigmahead.")}
+    xyz = scene["feature"][..., :3].float()
+    smpl_xyz = torch.bmm(xyz, scene["Rh"].float().transpose(1, 2)) + scene["Th"].float()
+    cams = orc.pack_cameras(scene["src_poses"][0], scene["src_Ks"][0], 64, 64)
+    want_feats = orc.smpl_features(smpl_xyz[0], cams, scene["featmaps"])
+    fused = orc.smpl_code_attention({k[len("xyzc_attn."):]: v for k, v in sg.items() if k.startswith("xyzc_attn.")},
+                                    sg["c.weight"], want_feats)
+    out_sh = [int(v) for v in scene["out_sh"][0]]
+    levels = orc.sparse_conv_net({k[len("xyzc_net."):]: v for k, v in sg.items() if k.startswith("xyzc_net.")},
+                                 fused, scene["coord"][0], out_sh)
+    ref_scene = dict(scene)
+    ref_scene["levels"] = levels
+    eng, _ = stages.run_engine_progressive(ref_scene, w, 16, precision=PREC_BF16)
+    want_img = eng.pred_img.view(64, 64, 3).cpu().numpy()
+    # device chain through the plugin API
+    r = Renderer(None, head.to(DEV), is_train=False, n_samples=16, progressive=True, precision=PREC_BF16)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in scene.items() if k != "levels"}
+    out = r.render(batch)
+    assert out["counts"]["n_rays"] > 100 and out["counts"]["P1"] > out["counts"]["n_rays"]
+    assert out["counts"]["n_rays"] == eng.read_counters()["n_rays"]
+    assert float(np.abs(out["pred_img"] - want_img).max()) < 0.02
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)

@@ -124,3 +124,16 @@ def test_dataset_rays_restatement_vs_reference_numpy():
         assert np.array_equal(mask, z[f"{tag}.mask_at_box"]) and mask.sum() > 100
         for got, key in ((o, "ray_o"), (d, "ray_d"), (near, "near"), (far, "far")):
             assert got.dtype == np.float32 and np.array_equal(got, z[f"{tag}.{key}"]), key
+
+
+def test_attention_restatement_vs_reference_module():
+    """Row f1 (K8): oracle.smpl_code_attention against outputs of the reference's own MultiHeadAttention
+    module (oracle/gen_golden_attn.py).  fp32 module vs fp64 restatement: 1e-5."""
+    z = np.load(os.path.join(GOLD, "attention.npz"))
+    for tag in ("a", "b", "c"):
+        state = {k.split(".state.")[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{tag}.state.")}
+        got = orc.smpl_code_attention(state, torch.from_numpy(z[f"{tag}.code"]), torch.from_numpy(z[f"{tag}.feats"]),
+                                      n_head=int(z[f"{tag}.n_head"]))
+        want = torch.from_numpy(z[f"{tag}.out"])
+        assert got.shape == want.shape and float(want.abs().max()) > 0.1
+        assert float((got - want).abs().max()) < 1e-5
