@@ -75,7 +75,8 @@ _SIGNATURES = {
     "gpnerf_sc_index_input": ([_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_sc_gather_rows": ([_P, _I, _P, _P, _I, _P, _P], C.c_int),
     "gpnerf_sc_strided_sites": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
-    "gpnerf_sc_conv": ([_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P], C.c_int),
+    "gpnerf_sc_neighbours": ([_P, _P, _I, _I, _P, _I, _I, _I, _P, _P, _P], C.c_int),
+    "gpnerf_sc_conv": ([_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P], C.c_int),
     "gpnerf_attn_smpl_code": ([_P, _P, C.c_longlong, C.c_longlong, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
                               C.c_int),
     "gpnerf_k0_build_masks3d": ([C.POINTER(_P), C.POINTER(Frame), _P, _P], C.c_int),

@@ -62,6 +62,8 @@ class SparseConvNet(nn.Module):
             prev = out_dim[i]
         self.net.append(_block([(prev, prev), (prev, prev)], 1))              # double_conv, 'subm<n>'
         self._folded = None
+        self._plans = {}
+        self.use_cuda_graph = True
 
     # ------------------------------------------------------------------
     def _layers(self):
@@ -73,33 +75,36 @@ class SparseConvNet(nn.Module):
         return out
 
     def _fold(self, device):
+        """BatchNorm (running statistics) as per-channel scale/shift; weights as fp32 [27·in, out].  The device
+        tensors are allocated once and refreshed in place, so a captured graph keeps reading the right memory."""
         ver = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
-        if self._folded is None or self._folded[0] != ver:
-            packed = []
-            for _bi, conv, bn in self._layers():
-                inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
-                scale = (bn.weight.detach().float() * inv).contiguous().to(device)
-                shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * bn.weight.detach().float() * inv)
-                packed.append((conv.weight.detach().float().contiguous().to(device), scale,
-                               shift.contiguous().to(device)))
-            self._folded = (ver, packed)
-        return self._folded[1]
+        if self._folded is not None and self._folded[0] == ver and self._folded[1] == device:
+            return self._folded[2]
+        fresh = []
+        for _bi, conv, bn in self._layers():
+            g, inv = bn.weight.detach().float(), torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+            fresh.append((conv.weight.detach().float().contiguous(), g * inv,
+                          bn.bias.detach().float() - bn.running_mean.detach().float() * g * inv))
+        if self._folded is not None and self._folded[1] == device:
+            packed = self._folded[2]
+            for old, new in zip(packed, fresh):
+                for o, n in zip(old, new):
+                    o.copy_(n)
+        else:
+            packed = [tuple(t.to(device).contiguous().clone() for t in trip) for trip in fresh]
+            self._plans = {}
+        self._folded = (ver, device, packed)
+        return packed
 
-    @torch.no_grad()
-    def forward(self, features, coords, spatial_shape):
-        """features [N, in_dim] fp32, coords [N, 3|4] int (…, d, h, w), spatial_shape (D, H, W) →
-        (levels_sparse, level_dims, n_rows_dev): per level (features [cap, 32], coords [cap, 3]) with
-        `cap` = capacity and the live row counts in four device int32 scalars (no host sync)."""
-        if self.training:
-            raise _lib.GpnerfError("SparseConvNet runs in inference form (BatchNorm running statistics): call .eval()")
+    # ------------------------------------------------------------------
+    def _plan(self, n0, cols, spatial_shape, c_in, dev):
+        """Buffers of one (vertex count, grid) geometry; every row count stays on the device, so the launch
+        sequence is the same for every frame and is captured into a CUDA graph on its second use."""
+        key = (n0, cols, tuple(spatial_shape), str(dev))
+        pl = self._plans.get(key)
+        if pl is not None:
+            return pl
         lib = _lib.load()
-        dev = features.device
-        if dev.type != "cuda":
-            raise _lib.GpnerfError("gpnerf_b200 runs on CUDA devices only (no CPU fallback)")
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        feats = features.detach().float().contiguous()
-        crd = coords.detach().to(device=dev, dtype=torch.int32).contiguous()
-        n0, cols = int(crd.shape[0]), int(crd.shape[1])
         dims = [tuple(int(v) for v in spatial_shape)]
         for _ in range(self.n_layers):
             dims.append(tuple((v - 1) // 2 + 1 for v in dims[-1]))       # SparseConv3d(3, 2, padding=1)
@@ -108,39 +113,86 @@ class SparseConvNet(nn.Module):
         for k in range(1, 5):
             caps.append(min(8 * caps[-1], vox[k]))
         i32 = dict(dtype=torch.int32, device=dev)
-        ws = torch.empty(int(lib.gpnerf_workspace_bytes(max(vox[1], n0))), dtype=torch.uint8, device=dev)
-        idx_vol = [torch.empty(v, **i32) for v in vox]
-        counts = torch.zeros(5, **i32)
-        coords_l = [torch.empty(c * 3, **i32) for c in caps]
-        owners = torch.empty(n0, **i32)
-        check(lib.gpnerf_sc_index_input(ptr(crd), cols, n0, *dims[0], ptr(idx_vol[0]), ptr(owners), ptr(coords_l[0]),
-                                        ptr(counts[0:1]), ptr(ws), st), "sc_index_input")
-        c_in = feats.shape[1]
-        x = torch.empty(n0 * c_in, dtype=torch.float32, device=dev)
-        check(lib.gpnerf_sc_gather_rows(ptr(feats), c_in, ptr(owners), ptr(counts[0:1]), n0, ptr(x), st), "sc_gather_rows")
-        packed = self._fold(dev)
-        level, li = 0, 0
+        pl = {
+            "dims": dims, "caps": caps,
+            "feat_in": torch.empty(n0, c_in, dtype=torch.float32, device=dev),
+            "coord_in": torch.empty(n0, cols, **i32),
+            "ws": torch.empty(int(lib.gpnerf_workspace_bytes(max(vox[1], n0))), dtype=torch.uint8, device=dev),
+            "idx_vol": [torch.empty(v, **i32) for v in vox],
+            "counts": torch.zeros(5, **i32),
+            "coords": [torch.empty(c * 3, **i32) for c in caps],
+            "owners": torch.empty(n0, **i32),
+            "lin": torch.empty(max(caps[1:]), **i32),
+            "nbr": [torch.empty(27 * max(caps), **i32) for _ in range(2)],      # [0]: SubM table, [1]: strided
+            "x0": torch.empty(n0 * c_in, dtype=torch.float32, device=dev),
+            "y": [], "graph": None, "uses": 0,
+        }
+        level = 0
+        for _bi, conv, _bn in self._layers():
+            level += conv.stride == 2
+            pl["y"].append(torch.empty(caps[level] * conv.c_out, dtype=torch.float32, device=dev))
+        self._plans[key] = pl
+        return pl
+
+    def _launch(self, pl, packed, st):
+        lib = _lib.load()
+        dims, caps, counts, coords_l, idx_vol = pl["dims"], pl["caps"], pl["counts"], pl["coords"], pl["idx_vol"]
+        n0, cols = pl["coord_in"].shape
+        check(lib.gpnerf_sc_index_input(ptr(pl["coord_in"]), cols, n0, *dims[0], ptr(idx_vol[0]), ptr(pl["owners"]),
+                                        ptr(coords_l[0]), ptr(counts[0:1]), ptr(pl["ws"]), st), "sc_index_input")
+        c_in = pl["feat_in"].shape[1]
+        check(lib.gpnerf_sc_gather_rows(ptr(pl["feat_in"]), c_in, ptr(pl["owners"]), ptr(counts[0:1]), n0, ptr(pl["x0"]), st),
+              "sc_gather_rows")
+        x, level, subm_level = pl["x0"], 0, -1
         outs = []
-        lin = torch.empty(max(caps[1:]), **i32)
-        for bi, conv, _bn in self._layers():
+        for li, (bi, conv, _bn) in enumerate(self._layers()):
             w, scale, shift = packed[li]
-            li += 1
             if conv.stride == 2:
                 check(lib.gpnerf_sc_strided_sites(ptr(coords_l[level]), ptr(counts[level:level + 1]), caps[level],
-                                                  *dims[level + 1], ptr(lin), ptr(coords_l[level + 1]),
-                                                  ptr(idx_vol[level + 1]), ptr(counts[level + 1:level + 2]), ptr(ws), st),
-                      "sc_strided_sites")
-                out_level = level + 1
+                                                  *dims[level + 1], ptr(pl["lin"]), ptr(coords_l[level + 1]),
+                                                  ptr(idx_vol[level + 1]), ptr(counts[level + 1:level + 2]), ptr(pl["ws"]),
+                                                  st), "sc_strided_sites")
+                out_level, nbr = level + 1, pl["nbr"][1]
+                build = True
             else:
-                out_level = level
-            y = torch.empty(caps[out_level] * conv.c_out, dtype=torch.float32, device=dev)
-            check(lib.gpnerf_sc_conv(ptr(x), conv.c_in, ptr(idx_vol[level]), *dims[level], ptr(counts[level:level + 1]),
-                                     ptr(coords_l[out_level]), ptr(counts[out_level:out_level + 1]), caps[out_level],
-                                     conv.stride, ptr(w), ptr(scale), ptr(shift), conv.c_out, ptr(y), st), "sc_conv")
+                out_level, nbr = level, pl["nbr"][0]
+                build, subm_level = subm_level != level, level
+            if build:
+                check(lib.gpnerf_sc_neighbours(ptr(coords_l[out_level]), ptr(counts[out_level:out_level + 1]),
+                                               caps[out_level], conv.stride, ptr(idx_vol[level]), *dims[level],
+                                               ptr(counts[level:level + 1]), ptr(nbr), st), "sc_neighbours")
+            y = pl["y"][li]
+            check(lib.gpnerf_sc_conv(ptr(x), conv.c_in, ptr(nbr), ptr(counts[out_level:out_level + 1]), caps[out_level],
+                                     ptr(w), ptr(scale), ptr(shift), conv.c_out, ptr(y), st), "sc_conv")
             x, level = y, out_level
             # a level's features are final after the double_conv that follows its stride_conv (blocks 2, 4, 6, 8)
             if bi >= 2 and bi % 2 == 0 and conv is self.net[bi][3]:
                 outs.append((x.view(caps[level], conv.c_out), coords_l[level].view(caps[level], 3)))
-        n_rows_dev = [counts[k:k + 1] for k in range(1, 5)]
-        self._keep = (idx_vol, ws, lin, owners, counts)
-        return outs, dims[1:], n_rows_dev
+        return outs
+
+    @torch.no_grad()
+    def forward(self, features, coords, spatial_shape):
+        """features [N, in_dim] fp32, coords [N, 3|4] int (…, d, h, w), spatial_shape (D, H, W) →
+        (levels_sparse, level_dims, n_rows_dev): per level (features [cap, 32], coords [cap, 3]) with
+        `cap` = capacity and the live row counts in four device int32 scalars (no host sync).  The results
+        live in buffers of the module (one set per input geometry) and are overwritten by the next call."""
+        if self.training:
+            raise _lib.GpnerfError("SparseConvNet runs in inference form (BatchNorm running statistics): call .eval()")
+        dev = features.device
+        if dev.type != "cuda":
+            raise _lib.GpnerfError("gpnerf_b200 runs on CUDA devices only (no CPU fallback)")
+        packed = self._fold(dev)
+        pl = self._plan(int(coords.shape[0]), int(coords.shape[1]), spatial_shape, int(features.shape[1]), dev)
+        pl["feat_in"].copy_(features.detach(), non_blocking=True)
+        pl["coord_in"].copy_(coords.detach(), non_blocking=True)
+        pl["uses"] += 1
+        if self.use_cuda_graph and pl["graph"] is None and pl["uses"] >= 2 and not torch.cuda.is_current_stream_capturing():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                pl["outs"] = self._launch(pl, packed, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            pl["graph"] = g
+        if pl["graph"] is not None:
+            pl["graph"].replay()
+        else:
+            pl["outs"] = self._launch(pl, packed, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        return pl["outs"], pl["dims"][1:], [pl["counts"][k:k + 1] for k in range(1, 5)]

@@ -319,7 +319,9 @@ int gpnerf_k3_color_mlp_records(const void *records, const int32_t *valid1,
  *                (row id per site, 0x7f7f7f7f = none), n_out[0].
  *  gather_rows : feat_out[j] = feat_in[rows[j]] for j < n_dev[0].
  *  strided_sites: sites of the next level (stride 2) + its index volume; out_lin = scratch int32[n_out_max].
- *  conv        : out_feat[o] = relu(scale ⊙ Σ_k W[k]ᵀ·in[nbr_k(o)] + shift), nbr_k(o) = o·stride − 1 + k.
+ *  neighbours  : nbr[k*n_out_max + o] = input row at o·stride − 1 + k (k = (kd*3+kh)*3+kw), −1 if none; int32[27*n_out_max].
+ *                One table per (output site list, stride, input level); shared by the convolutions on it.
+ *  conv        : out_feat[o] = relu(scale ⊙ Σ_k W[k]ᵀ·in[nbr[k][o]] + shift).
  * workspace: gpnerf_workspace_bytes(max(n, voxels of the level being compacted)). */
 int gpnerf_sc_index_input(const int32_t *coords, int cols, int n, int D, int H, int W, int32_t *idx_vol,
                           int32_t *owners, int32_t *coords_out, int32_t *n_out, void *workspace,
@@ -329,10 +331,12 @@ int gpnerf_sc_gather_rows(const float *feat_in, int C, const int32_t *rows, cons
 int gpnerf_sc_strided_sites(const int32_t *in_coords, const int32_t *n_in_dev, int n_in_max, int Do,
                             int Ho, int Wo, int32_t *out_lin, int32_t *out_coords,
                             int32_t *out_idx_vol, int32_t *n_out_dev, void *workspace, void *stream);
-int gpnerf_sc_conv(const float *in_feat, int c_in, const int32_t *in_idx_vol, int Di, int Hi, int Wi,
-                   const int32_t *n_in_dev, const int32_t *out_coords, const int32_t *n_out_dev,
-                   int n_out_max, int stride, const float *weight, const float *scale,
-                   const float *shift, int c_out, float *out_feat, void *stream);
+int gpnerf_sc_neighbours(const int32_t *out_coords, const int32_t *n_out_dev, int n_out_max, int stride,
+                         const int32_t *in_idx_vol, int Di, int Hi, int Wi, const int32_t *n_in_dev,
+                         int32_t *nbr, void *stream);
+int gpnerf_sc_conv(const float *in_feat, int c_in, const int32_t *nbr, const int32_t *n_out_dev,
+                   int n_out_max, const float *weight, const float *scale, const float *shift,
+                   int c_out, float *out_feat, void *stream);
 
 /* ---- K8: SMPL-code attention (trainhead.py:48-51; MultiHeadAttention.py:40-98, sum=False) ---- */
 /* out[i] = W_fc · concat_h( softmax_v( (W_q·code[i])_h/√d_k · (W_k·feat[i,v])_h ) · (W_v·feat[i,v])_h ).

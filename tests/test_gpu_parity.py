@@ -348,6 +348,14 @@ def test_sparse_conv_net_vs_dense_emulation(in_dim):
         assert float((got - ref[0]).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
         lin = (c[:, 0] * ref.shape[-2] + c[:, 1]) * ref.shape[-1] + c[:, 2]
         assert bool((lin[1:] > lin[:-1]).all())             # unique sites, ascending
+    # second and third call: the captured launch sequence (CUDA graph) gives the same rows
+    first = [(f.clone(), c.clone(), int(n)) for (f, c), n in zip(rows, n_dev)]
+    for _ in range(2):
+        rows, dims, n_dev = net_d(feats.to(DEV), coord.to(DEV), shape)
+    torch.cuda.synchronize()
+    assert next(iter(net_d._plans.values()))["graph"] is not None
+    for (f0, c0, n0), (f, c), n in zip(first, rows, n_dev):
+        assert int(n) == n0 and torch.equal(f[:n0], f0[:n0]) and torch.equal(c[:n0], c0[:n0])
     # the rows feed the renderer without a dense tensor in between
     scene2 = synth.make_scene("zju", H=64, W=64, V=3, seed=13)
     full = SparseConvNet(in_dim=in_dim).eval()

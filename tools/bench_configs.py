@@ -140,7 +140,54 @@ def train(tag, H, S, V, R, seed=42, steps=5, precision=0):
                       "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
 
 
+def upstream(tag, H, S, V, seed=42):
+    """Row f1: a frame from the encoder's feature maps – project the SMPL vertices, K8 attention, K7 sparse-conv
+    pyramid, sparse rows into the fp16 volumes, then K1…K5 – all on the device (no dense fp32 volume)."""
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Projector, Renderer
+    scene = synth.make_scene("zju", H=H, W=H, V=V, seed=seed)
+    head = NeRFHead(n_views=V, precision=PREC_BF16).eval()
+    sd = head.state_dict()
+    for k, v in synth.make_head_weights(V=V, seed=seed).items():
+        sd[k].copy_(v)
+    for k, v in sd.items():
+        if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+            v.fill_(3.0)
+    head.load_state_dict(sd)
+    head = head.to(DEV)
+    r = Renderer(None, head, is_train=False, n_samples=S, progressive=True, precision=PREC_BF16)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in scene.items() if k != "levels"}
+    out = r.render(dict(batch))
+    sh = head.sigmahead
+    xyz = batch["feature"][..., :3].float()
+    smpl_xyz = torch.bmm(xyz, batch["Rh"].float().transpose(1, 2)) + batch["Th"].float()
+    cams = r._pack_cameras(batch, batch["src_imgs"].shape[-2:], DEV)
+    out_sh = [int(v) for v in batch["out_sh"][0]]
+    coord = batch["coord"][0]
+    proj = Projector(DEV)
+    st = {}
+    feats = proj.compute_smpl(smpl_xyz, cams, batch["featmaps"])
+    st["project+gather SMPL (K2)"] = timed(lambda: proj.compute_smpl(smpl_xyz, cams, batch["featmaps"]))
+    code = sh.c.weight.detach().unsqueeze(1)
+    f2 = feats.flatten(0, 1)
+    st["attention (K8)"] = timed(lambda: sh.xyzc_attn(code, f2, f2))
+    fused = sh.xyzc_attn(code, f2, f2)[0].squeeze(1)
+    st["sparse-conv pyramid (K7, 14 layers)"] = timed(lambda: sh.xyzc_net(fused, coord, out_sh))
+    rows, dims, n_dev = sh.xyzc_net(fused, coord, out_sh)
+    eng = r.engine_for(H, H, V, torch.device(DEV))
+    st["rows -> fp16 volumes (K0 sparse)"] = timed(lambda: eng.upload_products_sparse(
+        rows, dims, batch["featmaps"], batch["src_imgs"], n_rows_dev=n_dev))
+    ms_all = timed(lambda: r.render(dict(batch)))
+    live = [int(n) for n in n_dev]
+    print(json.dumps({"config": tag, "H": H, "S": S, "V": V, "precision": "bf16 heads, fp32 sparse conv",
+                      "ms_per_frame_render_call": ms_all, "rays": out["counts"]["n_rays"], "level_rows": live,
+                      "stages_ms": {k: round(v, 4) for k, v in st.items()},
+                      "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 CONFIGS = {
+    "upstream512": lambda: upstream("frame from feature maps: SMPL attention + sparse-conv pyramid + render (row f1)", 512,
+                                    64, 3),
     "zju512_fp32": lambda: progressive("zju512_fp32 (configs[1] geometry, fp32 parity heads)", 512, 64, 3, PREC_FP32,
                                        graph=False),
     "thu512": lambda: progressive("trainthu_valzju shape (configs[2]): same hot-path tensors, other seed", 512, 64, 3,
