@@ -285,3 +285,21 @@ def make_head_weights(V=3, C=32, seed=42, random_bias=False):
         w[name + ".weight"] = torch.randn((o, i), generator=gen) * math.sqrt(2.0 / i)
         w[name + ".bias"] = (torch.randn((o,), generator=gen) * 0.1) if random_bias else torch.zeros(o)
     return w
+
+
+def fill_encoder_params(module, seed=42):
+    """Seeded parameters for an image-encoder module (reference ResUNet or its mirror): walks the state_dict
+    in order, so two modules end up with identical values only if their keys and shapes agree.  Convolutions
+    He-normal, norm scales 1 + 0.1·N(0,1), every bias 0.1·N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = module.state_dict()
+    for name, v in sd.items():
+        r = torch.randn(v.shape, generator=g)
+        if v.dim() == 4:
+            v.copy_(r * (2.0 / (v.shape[1] * v.shape[2] * v.shape[3])) ** 0.5)
+        elif name.endswith("weight"):
+            v.copy_(1.0 + 0.1 * r)
+        else:
+            v.copy_(0.1 * r)
+    module.load_state_dict(sd)
+    return module

@@ -349,6 +349,23 @@ int gpnerf_attn_smpl_code(const float *code, const float *feats, long long view_
                           const float *w_k, const float *w_v, const float *w_fc, int d_model,
                           int kv_dim, int n_head, int d_k, float *out, void *stream);
 
+/* ---- K9: the image encoder's layers between its convolutions (UNet.py:32-51,120-130,204-216) ---- */
+/* Tensors are channels-last, dtype 0 = fp32, 1 = bf16, 2 = fp16.
+ * Output geometry (y, H, W, y_pad, y_ctot, y_coff): y is [N][H+2*y_pad][W+2*y_pad][y_ctot]; the call writes
+ * channels [y_coff, y_coff+C); y_pad = 1 also fills the one-pixel border with the reflection of the interior
+ * (= F.pad(mode="reflect") for the next 3x3 convolution).
+ * instance_norm_act: x dense [N][H][W][C]; residual NULL or [N][H+2*res_pad][W+2*res_pad][C];
+ *   y = act((x - mean_nc) * rsqrt(var_nc + eps) * gamma_c + beta_c [+ residual]), biased variance over H*W,
+ *   act 0 none | 1 ReLU | 2 ELU; sums: scratch double[N*C*2]; y may alias x when y_pad = 0 and y_ctot = C.
+ * resample_pad: src [N][Hs+2*src_pad][Ws+2*src_pad][C]; mode 0 copy (H = Hs, W = Ws), mode 1 bilinear
+ *   (align_corners = True) to H x W.
+ * C, y_ctot, y_coff multiples of 4 (fp32) / 8 (16-bit); for instance_norm_act C/4 resp. C/8 divides 256. */
+int gpnerf_k9_instance_norm_act(const void *x, const void *residual, int res_pad, int dtype, int N, int H,
+                                int W, int C, const float *gamma, const float *beta, float eps, int act,
+                                double *sums, void *y, int y_pad, int y_ctot, int y_coff, void *stream);
+int gpnerf_k9_resample_pad(const void *src, int dtype, int N, int Hs, int Ws, int src_pad, int C, int mode,
+                           void *y, int H, int W, int y_pad, int y_ctot, int y_coff, void *stream);
+
 /* ---- K4: progressive step ---------------------------------------------- */
 /* demo_render.py:312-317: α = 1-exp(-σ); valid1 = ascending indices (into the
  * P1 arrays) with α > 1e-14; counters[P2]. */

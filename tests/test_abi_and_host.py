@@ -176,3 +176,17 @@ def test_grad_bucket_all_reduce_gloo_world2(tmp_path):
     port = 29620 + os.getpid() % 200
     mp.spawn(_bucket_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(os.path.join(tmp_path, f"ok{r}")).read() for r in range(2)] == ["1", "1"]
+
+
+def test_encoder_mirror_has_the_reference_state_dict():
+    """Row f2: the ResUNet mirror exposes exactly the reference module's parameter names and shapes
+    (recorded from the reference's own ResUNet by oracle/gen_golden_encoder.py), in the same order."""
+    import json
+    import numpy as np
+    from gpnerf_b200.encoder import ResUNet
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder.npz"))
+    want = [(k, tuple(s)) for k, s in json.loads(str(z["keys"]))]
+    got = [(k, tuple(v.shape)) for k, v in ResUNet().state_dict().items()]
+    assert got == want and len(got) > 100
+    with pytest.raises(Exception):
+        ResUNet()(torch.zeros(1, 3, 64, 64))           # no CPU fallback

@@ -440,6 +440,32 @@ def test_renderer_native_upstream_chain():
     assert float(np.abs(out["pred_img"] - want_img).max()) < 0.02
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+def test_image_encoder_vs_reference_golden(precision):
+    """Row f2: the ResUNet mirror (cuDNN convolutions + K9 instance-norm/activation kernels, CUDA graph on the
+    third call) against the reference module's own CPU fp32 output for the same seeded parameters
+    (tests/golden/encoder.npz).  fp32: 1e-3 abs; rms error below 1 % (fp16, the default) / 10 % (bf16) of the
+    output's rms – 36 convolutions deep, random weights."""
+    from gpnerf_b200.encoder import ResUNet
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder.npz"))
+    enc = synth.fill_encoder_params(ResUNet(precision=precision), seed=42).eval().to(DEV)
+    for tag in ("a", "b"):
+        V, H, W, seed = (int(v) for v in z[f"{tag}.shape"])
+        x = torch.rand(V, 3, H, W, generator=torch.Generator().manual_seed(seed)) * 2 - 1
+        assert abs(float(x.double().sum()) - float(z[f"{tag}.x_sum"])) < 1e-6
+        want = torch.from_numpy(z[f"{tag}.out"])
+        for call in range(4):                       # eager, eager, capture + replay, replay
+            got = enc(x.to(DEV)).cpu()
+            assert got.shape == want.shape
+            err = (got - want).abs()
+            if precision == "fp32":
+                assert float(err.max()) < 1e-3, (tag, call, float(err.max()))
+            else:
+                rel = float(err.pow(2).mean().sqrt()) / float(want.pow(2).mean().sqrt())
+                assert rel < (0.01 if precision == "fp16" else 0.10), (tag, call, rel)
+        assert enc._graphs[(tuple(x.shape), x.dtype)]["graph"] is not None
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)

@@ -185,7 +185,66 @@ def upstream(tag, H, S, V, seed=42):
                       "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
 
 
+def encoder(tag, H, V, precision):
+    """Row f2: the image encoder on V source views of H×H (120.6 GFLOP at V=3, 512²)."""
+    from gpnerf_b200.encoder import ResUNet
+    enc = synth.fill_encoder_params(ResUNet(precision=precision), seed=42).eval().to(DEV)
+    x = (torch.rand(V, 3, H, H, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+    for _ in range(3):
+        y = enc(x)
+    ms = timed(lambda: enc(x))
+    enc.use_cuda_graph = False
+    ms_eager = timed(lambda: enc(x))
+    # the reference's own module structure in plain torch (channels-last, same dtype, same parameters)
+    import torch.nn as nn
+    import torch.nn.functional as F
+    w = {k: v for k, v in enc._params(x.device).items()}
+    dt = next(v for v in w.values() if v.dim() == 4).dtype
+
+    def cv(t, wt, b, stride):
+        k = wt.shape[-1]
+        if k > 1:
+            t = F.pad(t, ((k - 1) // 2,) * 4, mode="reflect")
+        return F.conv2d(t, wt, b, stride)
+
+    def inorm(t, pre):
+        return F.instance_norm(t, weight=w[pre + ".weight"].to(dt), bias=w[pre + ".bias"].to(dt), eps=1e-5)
+
+    def torch_forward():
+        t = x.to(dt).contiguous(memory_format=torch.channels_last)
+        t = F.relu(inorm(cv(t, w["conv1.weight"], None, 2), "bn1"))
+        feats = []
+        for name in ("layer1", "layer2", "layer3"):
+            for i, blk in enumerate(getattr(enc, name)):
+                pre = f"{name}.{i}"
+                y = F.relu(inorm(cv(t, w[pre + ".conv1.weight"], None, blk.stride), pre + ".bn1"))
+                y = inorm(cv(y, w[pre + ".conv2.weight"], None, 1), pre + ".bn2")
+                if blk.downsample is not None:
+                    t = inorm(cv(t, w[pre + ".downsample.0.weight"], None, blk.stride), pre + ".downsample.1")
+                t = F.relu(y + t)
+            feats.append(t)
+        x1, x2, x3 = feats
+        up = lambda z: F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=True)      # noqa: E731
+        cbe = lambda z, pre: F.elu(inorm(cv(z, w[pre + ".conv.weight"], w[pre + ".conv.bias"], 1), pre + ".bn"))  # noqa: E731
+        t = cbe(up(x3), "upconv3.conv")
+        t = cbe(torch.cat([t, x2], 1), "iconv3")
+        t = cbe(up(t), "upconv2.conv")
+        t = cbe(torch.cat([t, x1], 1), "iconv2")
+        return F.conv2d(t, w["out_conv.weight"], w["out_conv.bias"]).float()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        y_t = torch_forward()
+        ms_torch = timed(torch_forward)
+    dev = float((y_t - y).abs().max())
+    print(json.dumps({"config": tag, "H": H, "V": V, "precision": precision, "ms_graph": ms, "ms_eager": ms_eager,
+                      "ms_eager_plain_torch_ops": ms_torch, "max_abs_diff_vs_plain_torch": dev, "GFLOP": 120.6 * V / 3 * (H / 512) ** 2,
+                      "TFLOP_per_s": 120.6 * V / 3 * (H / 512) ** 2 / ms, "out": list(y.shape),
+                      "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 CONFIGS = {
+    "encoder512": lambda: encoder("image encoder, 3 views 512x512, fp16 cuDNN + K9 norms (row f2)", 512, 3, "fp16"),
+    "encoder512_bf16": lambda: encoder("image encoder, 3 views 512x512, bf16", 512, 3, "bf16"),
+    "encoder512_fp32": lambda: encoder("image encoder, 3 views 512x512, fp32 parity mode", 512, 3, "fp32"),
     "upstream512": lambda: upstream("frame from feature maps: SMPL attention + sparse-conv pyramid + render (row f1)", 512,
                                     64, 3),
     "zju512_fp32": lambda: progressive("zju512_fp32 (configs[1] geometry, fp32 parity heads)", 512, 64, 3, PREC_FP32,
