@@ -3,8 +3,9 @@
 // statistics; UNet.py:32,36,120,162) and then ReLU (UNet.py:42,51), "+ identity, ReLU" (UNet.py:50-51) or ELU
 // (UNet.py:123).  In torch that is 2–4 elementwise passes per layer; here two:
 //
-//   in_stats : Σx, Σx² per (image, channel) over H·W – fp32 partials per thread, fp64 atomics
-//   in_apply : y = act((x − mean)·rstd·γ + β [+ residual]),  act ∈ {none, ReLU, ELU}; may run in place; can
+//   in_stats : Σx, Σx² per (image, channel) over H·W – fp32 partials per thread, fp64 atomics; the last block
+//              of an image folds mean, variance, γ, β into one (scale, shift) pair per channel
+//   in_apply : y = act(scale·x + shift [+ residual]),  act ∈ {none, ReLU, ELU}; may run in place; can
 //              write into a reflect-bordered buffer / a channel slice of a concatenation buffer (PadGeom)
 //   resample_pad : skip-connection copy or bilinear ×2 upsampling into such a buffer
 //
@@ -80,7 +81,9 @@ struct Vec<__half> {                      // 8 channels per 16-byte access
 // grid (chunks, N); a thread owns one channel group (VN channels) and strides over the pixels of its chunk.
 template <typename T>
 __global__ void __launch_bounds__(256) in_stats(const T* __restrict__ x, int HW, int C, int px_per_block,
-                                                double* __restrict__ sums /* [N][C][2] */) {
+                                                double* __restrict__ sums /* [N][C][2] */, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float eps, double inv_hw,
+                                                float2* __restrict__ ab, unsigned* __restrict__ tickets) {
   constexpr int VN = Vec<T>::N;
   const int groups = C / VN;                            // ≤ 256 / … checked by the caller: 256 % groups == 0
   const int g = threadIdx.x % groups, lane_px = threadIdx.x / groups, px_step = blockDim.x / groups;
@@ -113,6 +116,21 @@ __global__ void __launch_bounds__(256) in_stats(const T* __restrict__ x, int HW,
     for (int r = 0; r < px_step; ++r) acc += (double)red[r * groups + gg][j];
     atomicAdd(sums + ((size_t)n * C + gg * VN) * 2 + j, acc);
   }
+  // the last block of an image turns the sums into y = a·x + b per channel (fp64 once per channel, not per thread)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(tickets + n, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double m = __ldcg(sums + ((size_t)n * C + c) * 2) * inv_hw;
+    const double var = fmax(fma(__ldcg(sums + ((size_t)n * C + c) * 2 + 1), inv_hw, -m * m), 0.0);   // biased, as instance_norm
+    const float a = __ldg(gamma + c) * rsqrtf((float)var + eps);
+    ab[(size_t)n * C + c] = make_float2(a, __ldg(beta + c) - (float)m * a);
+  }
+  if (threadIdx.x == 0) tickets[n] = 0;
 }
 
 // Where a kernel writes: a channels-last tensor [N][H+2p][W+2p][Ctot] of which this producer owns the channels
@@ -143,15 +161,21 @@ __device__ __forceinline__ void store_reflect(T* __restrict__ y, const PadGeom& 
 
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) in_apply(const T* __restrict__ x, const T* __restrict__ residual, int res_pad,
-                                                const double* __restrict__ sums, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta, int C, float eps, PadGeom out,
-                                                T* __restrict__ y) {
+                                                const float2* __restrict__ ab, int C, PadGeom out, T* __restrict__ y) {
   constexpr int VN = Vec<T>::N;
   const int groups = C / VN, HW = out.H * out.W;
-  const size_t per_img = (size_t)HW * groups;
   const int n = blockIdx.y;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(t % groups), px = (int)(t / groups);
+  // a thread keeps its channel group (groups divides the block size)
+  const int g = threadIdx.x % groups;
+  float a[VN], b[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    const float2 t = __ldg(ab + (size_t)n * C + g * VN + i);
+    a[i] = t.x;
+    b[i] = t.y;
+  }
+  const int px_step = gridDim.x * (blockDim.x / groups);
+  for (int px = blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups; px < HW; px += px_step) {
     const int h = px / out.W, w = px - h * out.W;
     float v[VN], r[VN];
     Vec<T>::load(x + ((size_t)n * HW + px) * C + g * VN, v);
@@ -160,11 +184,7 @@ __global__ void __launch_bounds__(256) in_apply(const T* __restrict__ x, const T
                        g * VN, r);
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
-      const int c = g * VN + i;
-      const double m = sums[((size_t)n * C + c) * 2] / HW;
-      const double var = fmax(sums[((size_t)n * C + c) * 2 + 1] / HW - m * m, 0.0);       // biased, as instance_norm
-      const float a = __ldg(gamma + c) * rsqrtf((float)var + eps);
-      float o = fmaf(v[i] - (float)m, a, __ldg(beta + c));
+      float o = fmaf(v[i], a[i], b[i]);
       if (residual) o += r[i];
       if (ACT == 1) o = fmaxf(o, 0.0f);
       if (ACT == 2) o = o > 0.0f ? o : expm1f(o);
@@ -174,6 +194,7 @@ __global__ void __launch_bounds__(256) in_apply(const T* __restrict__ x, const T
   }
 }
 
+// mode 2: every second pixel (the input of a 1×1 stride-2 convolution, UNet.py:187-190);
 // mode 0: copy (skip connection into its channel slice of the concatenation buffer, UNet.py:204-216 with equal
 // sizes); mode 1: bilinear ×2, align_corners=True (UNet.py:128; torch's upsample_bilinear2d arithmetic in fp32).
 // src: channels-last [N][Hs+2ps][Ws+2ps][C]; dst geometry as above (H, W = output size).
@@ -194,6 +215,8 @@ __global__ void __launch_bounds__(256) resample_pad(const T* __restrict__ src, i
     float v[VN];
     if (MODE == 0) {
       Vec<T>::load(base + ((size_t)(h + src_pad) * Wsp + w + src_pad) * C + g * VN, v);
+    } else if (MODE == 2) {
+      Vec<T>::load(base + ((size_t)(2 * h + src_pad) * Wsp + 2 * w + src_pad) * C + g * VN, v);
     } else {
       const float h1r = rh * h, w1r = rw * w;
       const int h1 = (int)h1r, w1 = (int)w1r;
@@ -228,9 +251,12 @@ static int launch_norm(const void* x, const void* residual, int res_pad, int N, 
     set_error("instance_norm: channel counts must be multiples of the vector width, C/width dividing 256", cudaSuccess);
     return GPNERF_E_UNSUPPORTED;
   }
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double), st);
+  // scratch: double sums[N*C*2] | float2 ab[N*C] | unsigned tickets[N] (tickets return to 0 by themselves)
+  float2* ab = reinterpret_cast<float2*>(sums + (size_t)N * C * 2);
+  unsigned* tickets = reinterpret_cast<unsigned*>(ab + (size_t)N * C);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double) + (size_t)N * C * sizeof(float2) + N * sizeof(unsigned), st);
   if (e != cudaSuccess) {
-    set_error("memset instance-norm sums", e);
+    set_error("memset instance-norm scratch", e);
     return GPNERF_E_CUDA;
   }
   // enough blocks to fill the machine, at least 8 pixels per thread row to amortise the atomics
@@ -239,14 +265,14 @@ static int launch_norm(const void* x, const void* residual, int res_pad, int N, 
   int px_per_block = (HW + chunks - 1) / chunks;
   if (px_per_block < px_step * 8) px_per_block = px_step * 8;
   chunks = (HW + px_per_block - 1) / px_per_block;
-  in_stats<T><<<dim3(chunks, N), 256, 0, st>>>((const T*)x, HW, C, px_per_block, sums);
+  in_stats<T><<<dim3(chunks, N), 256, 0, st>>>((const T*)x, HW, C, px_per_block, sums, gamma, beta, eps, 1.0 / HW, ab, tickets);
   const dim3 grid = apply_grid(N, (size_t)HW * groups);
   const T* xx = (const T*)x;
   const T* rr = (const T*)residual;
   switch (act) {
-    case 0: in_apply<T, 0><<<grid, 256, 0, st>>>(xx, rr, res_pad, sums, gamma, beta, C, eps, out, (T*)y); break;
-    case 1: in_apply<T, 1><<<grid, 256, 0, st>>>(xx, rr, res_pad, sums, gamma, beta, C, eps, out, (T*)y); break;
-    default: in_apply<T, 2><<<grid, 256, 0, st>>>(xx, rr, res_pad, sums, gamma, beta, C, eps, out, (T*)y); break;
+    case 0: in_apply<T, 0><<<grid, 256, 0, st>>>(xx, rr, res_pad, ab, C, out, (T*)y); break;
+    case 1: in_apply<T, 1><<<grid, 256, 0, st>>>(xx, rr, res_pad, ab, C, out, (T*)y); break;
+    default: in_apply<T, 2><<<grid, 256, 0, st>>>(xx, rr, res_pad, ab, C, out, (T*)y); break;
   }
   return check_launch("instance_norm_act");
 }
@@ -262,6 +288,8 @@ static int launch_resample(const void* src, int N, int Hs, int Ws, int src_pad, 
   const dim3 grid = apply_grid(N, (size_t)out.H * out.W * (C / VN));
   if (mode == 0)
     resample_pad<T, 0><<<grid, 256, 0, st>>>((const T*)src, Hs, Ws, src_pad, C, out, (T*)y);
+  else if (mode == 2)
+    resample_pad<T, 2><<<grid, 256, 0, st>>>((const T*)src, Hs, Ws, src_pad, C, out, (T*)y);
   else
     resample_pad<T, 1><<<grid, 256, 0, st>>>((const T*)src, Hs, Ws, src_pad, C, out, (T*)y);
   return check_launch("resample_pad");
@@ -288,9 +316,10 @@ int gpnerf_k9_instance_norm_act(const void* x, const void* residual, int res_pad
 
 int gpnerf_k9_resample_pad(const void* src, int dtype, int N, int Hs, int Ws, int src_pad, int C, int mode, void* y,
                            int H, int W, int y_pad, int y_ctot, int y_coff, void* stream) {
-  GPNERF_REQUIRE(src && y && N > 0 && Hs > 0 && Ws > 0 && C > 0 && H > 0 && W > 0 && (mode == 0 || mode == 1));
+  GPNERF_REQUIRE(src && y && N > 0 && Hs > 0 && Ws > 0 && C > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 2);
   GPNERF_REQUIRE(dtype >= 0 && dtype <= 2 && (y_pad == 0 || (y_pad == 1 && H >= 2 && W >= 2)) && (src_pad == 0 || src_pad == 1));
-  GPNERF_REQUIRE(y_ctot >= y_coff + C && y_coff >= 0 && (mode == 1 || (H == Hs && W == Ws)));
+  GPNERF_REQUIRE(y_ctot >= y_coff + C && y_coff >= 0 && (mode != 0 || (H == Hs && W == Ws)) &&
+                 (mode != 2 || (H == (Hs + 1) / 2 && W == (Ws + 1) / 2)));
   cudaStream_t st = (cudaStream_t)stream;
   const PadGeom out{H, W, y_pad, y_ctot, y_coff};
   if (dtype == 0) return launch_resample<float>(src, N, Hs, Ws, src_pad, C, mode, out, y, st);

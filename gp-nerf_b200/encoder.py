@@ -142,7 +142,7 @@ class ResUNet(nn.Module):
         n, c, h, wd = x.shape
         if out is None:
             out = self._buf(n, h, wd, c, out_pad, x.device)
-        sums = torch.empty(n * c * 2, dtype=torch.float64, device=x.device)
+        sums = torch.empty(n * c * 3 + (n + 1) // 2, dtype=torch.float64, device=x.device)     # N·C·24 + N·4 bytes
         dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())       # noqa: E731
         check(lib.gpnerf_k9_instance_norm_act(dp(x), dp(residual), res_pad, _DTYPES[self.precision][1], n, h, wd, c,
                                               ptr(w[prefix + ".weight"]), ptr(w[prefix + ".bias"]), 1e-5, act,
@@ -153,7 +153,7 @@ class ResUNet(nn.Module):
     def _resample(self, src, src_pad, mode, out=None, out_pad=1, coff=0):
         lib = _lib.load()
         n, hs, ws, c = src.shape[0], src.shape[1] - 2 * src_pad, src.shape[2] - 2 * src_pad, src.shape[3]
-        h, wd = (hs, ws) if mode == 0 else (2 * hs, 2 * ws)
+        h, wd = {0: (hs, ws), 1: (2 * hs, 2 * ws), 2: ((hs + 1) // 2, (ws + 1) // 2)}[mode]
         if out is None:
             out = self._buf(n, h, wd, c, out_pad, src.device)
         check(lib.gpnerf_k9_resample_pad(C.c_void_p(src.data_ptr()), _DTYPES[self.precision][1], n, hs, ws, src_pad, c, mode,
@@ -172,7 +172,9 @@ class ResUNet(nn.Module):
                            out_pad=1)
         y = self._conv_p(y, w[prefix + ".conv2.weight"], None, 1)
         if blk.downsample is not None:
-            idt = F.conv2d(a[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2), w[prefix + ".downsample.0.weight"], None, blk.stride)
+            # 1×1 stride-2 convolution = a GEMM over every second pixel
+            sub = self._resample(a, 1, 2, out_pad=0) if blk.stride == 2 else a[:, 1:-1, 1:-1, :].contiguous()
+            idt = F.conv2d(sub.permute(0, 3, 1, 2), w[prefix + ".downsample.0.weight"])
             idt = self._norm_act(idt, w, prefix + ".downsample.1", ACT_NONE)
             return self._norm_act(y, w, prefix + ".bn2", ACT_RELU, residual=idt, res_pad=0, out_pad=1)
         return self._norm_act(y, w, prefix + ".bn2", ACT_RELU, residual=a, res_pad=1, out_pad=1)
@@ -193,7 +195,7 @@ class ResUNet(nn.Module):
             """upconv (×2 bilinear → conv → IN → ELU) into the first channels of the concatenation buffer, the
             skip tensor into the rest (UNet.py:122-131, 204-216, 223-229)."""
             u = self._resample(src, src_pad, 1)
-            y = self._conv_p(u, w[prefix + ".conv.conv.weight"], w[prefix + ".conv.conv.bias"], 1)
+            y = self._conv_p(u, w[prefix + ".conv.conv.weight"], None, 1)      # bias: cancelled by the norm
             c_up, c_skip = y.shape[1], skip.shape[3]
             hs, ws = skip.shape[1] - 2, skip.shape[2] - 2
             if (hs, ws) == tuple(y.shape[2:]):
@@ -210,9 +212,11 @@ class ResUNet(nn.Module):
             return F.pad(cat, (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1).contiguous()
 
         cat3 = up_cat(x3, 1, x2, "upconv3")
-        i3 = self._norm_act(self._conv_p(cat3, w["iconv3.conv.weight"], w["iconv3.conv.bias"], 1), w, "iconv3.bn", ACT_ELU)
+        # a per-channel bias in front of an InstanceNorm drops out of (x − mean): the four conv biases of the
+        # decoder are loaded (state_dict) but never added
+        i3 = self._norm_act(self._conv_p(cat3, w["iconv3.conv.weight"], None, 1), w, "iconv3.bn", ACT_ELU)
         cat2 = up_cat(i3, 0, x1, "upconv2")
-        i2 = self._norm_act(self._conv_p(cat2, w["iconv2.conv.weight"], w["iconv2.conv.bias"], 1), w, "iconv2.bn", ACT_ELU)
+        i2 = self._norm_act(self._conv_p(cat2, w["iconv2.conv.weight"], None, 1), w, "iconv2.bn", ACT_ELU)
         y = F.conv2d(i2.permute(0, 3, 1, 2), w["out_conv.weight"], w["out_conv.bias"])
         return y.float().contiguous()                           # [V, out_ch, H/4, W/4] fp32 NCHW, as the reference
 

@@ -438,13 +438,14 @@ class Renderer(nn.Module):
 
 def build_render(cfg, progressive=False):
     """BaseRender.py:367-403 / demo_render.py:635-671.  `cfg.encoder.file` and
-    `cfg.head.file` keep their plugin meaning; a head file that cannot be
-    imported falls back to this package's NeRFHead mirror."""
+    `cfg.head.file` keep their plugin meaning; files that cannot be imported
+    fall back to this package's ResUNet / NeRFHead mirrors."""
     from importlib import import_module as impm
     try:
         encoder = getattr(impm(cfg.encoder.file), "build_encoder")(cfg)
     except Exception:
-        encoder = None            # feature maps must then come with the batch
+        from .encoder import build_encoder            # the ResUNet mirror (row f2)
+        encoder = build_encoder(cfg)
     try:
         nerfhead = getattr(impm(cfg.head.file), "build_head")(cfg)
         if not hasattr(nerfhead, "hot_path_state"):

@@ -466,6 +466,35 @@ def test_image_encoder_vs_reference_golden(precision):
         assert enc._graphs[(tuple(x.shape), x.dtype)]["graph"] is not None
 
 
+def test_renderer_from_images_only():
+    """Rows f1 + f2 together: a batch with neither 'featmaps' nor 'levels' – Renderer.render runs the image
+    encoder, the SMPL attention, the sparse-conv pyramid and K1…K5; identical to handing it the encoder's
+    feature maps explicitly."""
+    from gpnerf_b200._lib import PREC_BF16
+    from gpnerf_b200.encoder import ResUNet
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Renderer
+    torch.manual_seed(7)
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=13)
+    head = NeRFHead(n_views=3, precision=PREC_BF16).eval()
+    sd = head.state_dict()
+    for k, v in synth.make_head_weights(V=3, seed=3).items():
+        sd[k].copy_(v)
+    for k, v in sd.items():
+        if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+            v.fill_(3.0)
+    head.load_state_dict(sd)
+    enc = synth.fill_encoder_params(ResUNet(), seed=42).eval().to(DEV)
+    r = Renderer(enc, head.to(DEV), is_train=False, n_samples=16, progressive=True, precision=PREC_BF16)
+    base = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in scene.items() if k not in ("levels", "featmaps")}
+    a = r.render(dict(base))
+    fm = enc(base["src_imgs"][0]).clone()
+    assert fm.shape == (3, 32, 16, 16)
+    b = r.render(dict(base, featmaps=fm))
+    assert a["counts"]["n_rays"] > 100 and a["counts"] == b["counts"]
+    assert np.array_equal(a["pred_img"], b["pred_img"]) and float(a["pred_img"].max()) > 0.0
+
+
 def test_early_termination_within_tolerance():
     scene = synth.make_scene("zju", H=128, W=128, V=3, seed=13)
     w = synth.make_head_weights(V=3, seed=113)

@@ -241,7 +241,50 @@ def encoder(tag, H, V, precision):
                       "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
 
 
+def from_images(tag, H, S, V, seed=42):
+    """Rows f1 + f2 + the path: images → encoder → SMPL attention → sparse-conv pyramid → K1…K5, device time of
+    the whole chain per frame (inputs resident; Renderer.render's own host work and D2H excluded)."""
+    from gpnerf_b200.encoder import ResUNet
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Projector, Renderer
+    torch.manual_seed(seed)
+    scene = synth.make_scene("zju", H=H, W=H, V=V, seed=seed)
+    head = NeRFHead(n_views=V, precision=PREC_BF16).eval()
+    sd = head.state_dict()
+    for k, v in synth.make_head_weights(V=V, seed=seed).items():
+        sd[k].copy_(v)
+    for k, v in sd.items():
+        if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+            v.fill_(3.0)
+    head.load_state_dict(sd)
+    head = head.to(DEV)
+    enc = synth.fill_encoder_params(ResUNet(), seed=seed).eval().to(DEV)
+    r = Renderer(enc, head, is_train=False, n_samples=S, progressive=True, precision=PREC_BF16)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in scene.items() if k not in ("levels", "featmaps")}
+    out = r.render(dict(batch))
+    eng = r.engine_for(H, H, V, torch.device(DEV))
+    import ctypes as C
+    from gpnerf_b200._lib import Frame
+    pinned = torch.empty(C.sizeof(Frame), dtype=torch.uint8).pin_memory()
+
+    def device_chain():
+        b = dict(batch)
+        fm, _ = r._upstream(b)
+        eng.upload_products_sparse(b["levels_sparse"], b["level_dims"], fm, b["src_imgs"], n_rows_dev=b["levels_sparse_rows"])
+        eng.run_progressive_graphed(eng.make_frame(b), with_k0=False, frame_src=pinned)
+    for _ in range(3):
+        device_chain()
+    ms = timed(device_chain)
+    ms_call = timed(lambda: r.render(dict(batch)))
+    print(json.dumps({"config": tag, "H": H, "S": S, "V": V, "precision": "fp16 encoder, fp32 sparse conv, bf16 heads",
+                      "ms_per_frame_device_chain": ms, "frames_per_s": 1e3 / ms, "ms_per_render_call": ms_call,
+                      "rays": out["counts"]["n_rays"], "rays_per_s": out["counts"]["n_rays"] * 1e3 / ms,
+                      "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+
+
 CONFIGS = {
+    "from_images512": lambda: from_images("frame from source images: encoder + attention + pyramid + render (f2+f1+a)", 512,
+                                          64, 3),
     "encoder512": lambda: encoder("image encoder, 3 views 512x512, fp16 cuDNN + K9 norms (row f2)", 512, 3, "fp16"),
     "encoder512_bf16": lambda: encoder("image encoder, 3 views 512x512, bf16", 512, 3, "bf16"),
     "encoder512_fp32": lambda: encoder("image encoder, 3 views 512x512, fp32 parity mode", 512, 3, "fp32"),
