@@ -97,16 +97,25 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples that arrived during [t0, t1] widened by one sampling period on each side (the GPU is under
+        the same load there: warm-up steps before, per-stage timing steps after).  Waits until nvidia-smi has
+        exited: its tear-down holds driver locks and must not overlap the end-to-end timing that follows."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 - 0.12 <= ts <= t1 + 0.12):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -264,10 +273,28 @@ def main():
             return shard.gather_frame(eng.pred_img.view(n_px, 3), RES, args.tile_px)
         return eng.result_image()
 
+    # nvidia-smi starts here so that its start-up (driver locks) falls into the warm-up, not the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step_device()
     torch.cuda.synchronize(dev)
+    # keep stepping (untimed, all ranks together) until the first clock sample has arrived, so that samples
+    # bracket the timed region with the GPU under the same load
+    t_wait = time.perf_counter()
+    while True:
+        go = torch.tensor([int(rank == 0 and sampler.proc is not None and not sampler.lines and
+                               time.perf_counter() - t_wait < 3.0)], device=dev)
+        if world > 1:
+            dist.broadcast(go, 0)
+        if not int(go.item()):
+            break
+        for _ in range(5):
+            flush.zero_()
+            step_device()
+        torch.cuda.synchronize(dev)
     counts = eng.read_counters()
     ref_image = eng.result_image().cpu().clone()
     if world > 1:
@@ -290,14 +317,11 @@ def main():
             peer_check = "ok" if ok else "MISMATCH"
 
     # ---- timed region: exactly K steps, device-timed, L2 flushed between steps
-    sampler = ClockSampler(local_rank)
     launches0 = eng.launches
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     for a, b in evs:
         flush.zero_()
@@ -308,7 +332,7 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall0 + wall) if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = (eng.launches - launches0) // args.steps
     # per-stage device times: CUDA events cannot sit inside a graph replay, so the same steps are
@@ -430,8 +454,20 @@ def main():
             def run_stream(k):
                 for out in renderer.render_stream(batch for _ in range(k)):
                     n_out[0] += int(out["mask_at_box"].sum() > 0)
-            run_stream(4)
+            run_stream(8)
             et = timed(lambda: run_stream(args.steps))
+            if os.environ.get("GPNERF_PROFILE_BLOCKING"):
+                import cProfile
+                import pstats
+                t0p, arr = time.perf_counter(), []
+                for out in renderer.render_stream(batch for _ in range(args.steps)):
+                    arr.append(round((time.perf_counter() - t0p) * 1e3, 1))
+                print("stream arrivals ms", arr, file=sys.stderr)
+                pr = cProfile.Profile()
+                pr.enable()
+                run_stream(args.steps)
+                pr.disable()
+                pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(16)
             if prec == PREC_BF16:
                 lv_s, dims_s = synth.sparsify_levels(scene["levels"])
                 sbatch = {k: v for k, v in batch.items() if k != "levels"}
@@ -443,7 +479,7 @@ def main():
                 def run_stream_sparse(k):
                     for out in renderer.render_stream(sbatch for _ in range(k)):
                         n_out[0] += int(out["mask_at_box"].sum() > 0)
-                run_stream_sparse(4)
+                run_stream_sparse(8)
                 et_s = timed(lambda: run_stream_sparse(args.steps))
                 e2e_sparse = {"ms_per_step": 1e3 * et_s / args.steps, "value": g_rays * args.steps / et_s,
                               "unit": "rays/s", "h2d_bytes_per_step": int(h2d_s),

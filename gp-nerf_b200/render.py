@@ -122,7 +122,12 @@ class Renderer(nn.Module):
 
     def _sync_weights(self, eng):
         """(Re)pack the head weights for the kernels when they changed."""
-        ver = tuple((p.data_ptr(), p._version) for p in self.nerfhead.parameters())
+        plist = getattr(self, "_hot_params", None)
+        if plist is None:          # the parameters the kernels read; walking the module tree every frame costs 0.4 ms
+            plist = self._hot_params = [p for k, p in self.nerfhead.named_parameters()
+                                        if k.startswith("rgbhead.") or k.startswith("sigmahead.out_geometry_fc")] \
+                or list(self.nerfhead.parameters())
+        ver = tuple((p.data_ptr(), p._version) for p in plist)
         if getattr(eng, "_weights_ver", None) != ver:
             eng.set_weights(self.nerfhead.hot_path_state())
             eng._weights_ver = ver
@@ -304,6 +309,7 @@ class Renderer(nn.Module):
                     "copy": torch.cuda.Stream(device),
                     "stage": [([] if sparse else [mk(t) for t in batch["levels"]], mk(batch["featmaps"]), mk(im0))
                               for _ in range(depth)],
+                    "sparse": [[] for _ in range(depth)],
                     "copied": [torch.cuda.Event() for _ in range(depth)],
                     "free": [torch.cuda.Event() for _ in range(depth)],
                     "done": [torch.cuda.Event() for _ in range(depth)],
@@ -321,9 +327,26 @@ class Renderer(nn.Module):
             with torch.cuda.stream(st["copy"]):
                 if i >= depth:
                     st["copy"].wait_event(st["free"][slot])        # K0 of the previous tenant has read the set
-                if sparse:       # row counts change from frame to frame: fresh device tensors on the copy stream
-                    lv_s = [(f.to(device, non_blocking=True), i.to(device, non_blocking=True))
-                            for f, i in batch["levels_sparse"]]
+                if sparse:
+                    # row counts change from frame to frame: per-slot staging buffers with spare capacity (fresh
+                    # tensors allocated on the copy stream would make the caching allocator fall back to
+                    # cudaMalloc – a device-wide synchronisation – whenever the host runs ahead of the GPU)
+                    bufs = st["sparse"][slot]
+                    lv_s = []
+                    for l, (f, ix) in enumerate(batch["levels_sparse"]):
+                        n = int(f.shape[0])
+                        if l >= len(bufs) or bufs[l][0].shape[0] < n or bufs[l][1].shape[1] != ix.shape[1]:
+                            cap = n + n // 4 + 1024
+                            pair = (torch.empty(cap, f.shape[1], dtype=torch.float32, device=device),
+                                    torch.empty(cap, ix.shape[1], dtype=torch.int32, device=device))
+                            if l < len(bufs):
+                                bufs[l] = pair
+                            else:
+                                bufs.append(pair)
+                        fb, ib = bufs[l][0][:n], bufs[l][1][:n]
+                        fb.copy_(f, non_blocking=True)
+                        ib.copy_(ix, non_blocking=True)
+                        lv_s.append((fb, ib))
                 else:
                     if not lv_d:      # first dense batch of a stream that started with sparse ones
                         lv_d.extend(torch.empty(t.shape, dtype=torch.float32, device=device) for t in batch["levels"])
@@ -334,9 +357,6 @@ class Renderer(nn.Module):
                 st["copied"][slot].record(st["copy"])
             main.wait_event(st["copied"][slot])
             if sparse:
-                for f, i in lv_s:
-                    f.record_stream(main)
-                    i.record_stream(main)
                 eng.upload_products_sparse(lv_s, batch["level_dims"], fm_d, im_d)
             else:
                 eng.upload_products(lv_d, fm_d, im_d)              # K0: staging set → gather layouts

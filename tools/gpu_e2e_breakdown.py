@@ -34,3 +34,19 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(20): step()
 torch.cuda.synchronize(); pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+
+# ---- render_stream: per-frame arrival times, then a profile of the main thread
+sb = dict(batch)
+for _ in r.render_stream(sb for _ in range(4)):
+    pass
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+stamps = []
+for out in r.render_stream(sb for _ in range(20)):
+    stamps.append((time.perf_counter() - t0) * 1e3)
+print("render_stream ms/frame", stamps[-1] / 20, "arrivals", [round(s, 1) for s in stamps])
+pr = cProfile.Profile(); pr.enable()
+for out in r.render_stream(sb for _ in range(20)):
+    pass
+pr.disable()
+pstats.Stats(pr).sort_stats("tottime").print_stats(14)
