@@ -136,6 +136,11 @@ class Renderer(nn.Module):
         """featmaps and dense levels: from the batch, or from the reference's
         producer modules (demo_render.py:103-157, 442)."""
         src_imgs = batch["src_imgs"]
+        produce = "levels" not in batch and "levels_sparse" not in batch
+        if produce:
+            # host-side constants first: reading them back after the encoder has been queued would wait for it
+            cams = self._pack_cameras(batch, src_imgs.shape[-2:], "cpu")
+            out_sh = [int(v) for v in torch.as_tensor(batch["out_sh"]).reshape(-1, 3).max(0)[0].tolist()]
         if "featmaps" in batch:
             featmaps = batch["featmaps"]
         else:
@@ -153,9 +158,7 @@ class Renderer(nn.Module):
         xyz = batch["feature"][..., :3].to(device).float()
         R, Th = batch["Rh"].to(device).float(), batch["Th"].to(device).float()
         smpl_xyz = torch.bmm(xyz, R.transpose(1, 2)) + Th
-        cams = self._pack_cameras(batch, src_imgs.shape[-2:], device)
         feats = Projector(device).compute_smpl(smpl_xyz, cams, featmaps)
-        out_sh = [int(v) for v in torch.as_tensor(batch["out_sh"]).reshape(-1, 3).max(0)[0].tolist()]
         rows, dims, n_dev = sh.encode_geometry(feats, batch["coord"].reshape(-1, batch["coord"].shape[-1]).to(device), out_sh)
         batch["levels_sparse"], batch["level_dims"], batch["levels_sparse_rows"] = rows, dims, n_dev
         return featmaps, None
@@ -193,12 +196,12 @@ class Renderer(nn.Module):
         """demo_render.Renderer.render: returns numpy rgb_map [R,3], pred_img
         [H,W,3] (float64), mask_at_box [H*W] bool, time_slots, etime, rtime."""
         device = batch["src_imgs"].device
-        torch.cuda.synchronize(device)
-        t0 = time.time()
+        # etime / rtime (demo_render.py:98-101, 442-447) from stream events instead of two device-wide
+        # synchronisations: the host keeps queueing while the producers run
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(torch.cuda.current_stream(device))
         featmaps, levels = self._upstream(batch)
-        torch.cuda.synchronize(device)
-        etime = time.time() - t0
-        t0 = time.time()
+        ev[1].record(torch.cuda.current_stream(device))
         H, W = batch["src_imgs"].shape[-2:]
         V = batch["src_imgs"].shape[1]
         eng = self.engine_for(int(H), int(W), int(V), device)
@@ -228,6 +231,7 @@ class Renderer(nn.Module):
             eng.upload_products(levels, featmaps, batch["src_imgs"])
             frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
             eng.render_progressive(frame)
+        ev[2].record(torch.cuda.current_stream(device))
         img_d, hit_d = eng.result_image(), eng.result_hit_mask()
         tiled = self.world > 1 and self.shard == "tiles"
         if tiled and eng.exchange is None:
@@ -247,7 +251,7 @@ class Renderer(nn.Module):
         else:
             n = cnt["n_rays"]
             rgb_map = eng.rgb_map[: n * 3].view(n, 3).cpu().numpy()
-        rtime = time.time() - t0
+        etime, rtime = ev[0].elapsed_time(ev[1]) * 1e-3, ev[1].elapsed_time(ev[2]) * 1e-3
         return {"rgb_map": rgb_map, "pred_img": pred_img, "mask_at_box": mask_at_box,
                 "time_slots": {"bc_render": rtime}, "etime": etime, "rtime": rtime, "counts": cnt}
 

@@ -62,6 +62,7 @@ class SparseConvNet(nn.Module):
             prev = out_dim[i]
         self.net.append(_block([(prev, prev), (prev, prev)], 1))              # double_conv, 'subm<n>'
         self._folded = None
+        self._plist = None
         self._plans = {}
         self.use_cuda_graph = True
 
@@ -77,7 +78,9 @@ class SparseConvNet(nn.Module):
     def _fold(self, device):
         """BatchNorm (running statistics) as per-channel scale/shift; weights as fp32 [27·in, out].  The device
         tensors are allocated once and refreshed in place, so a captured graph keeps reading the right memory."""
-        ver = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        if self._plist is None or self._plist[0].device != device:
+            self._plist = list(self.parameters()) + list(self.buffers())
+        ver = tuple((p.data_ptr(), p._version) for p in self._plist)
         if self._folded is not None and self._folded[0] == ver and self._folded[1] == device:
             return self._folded[2]
         fresh = []
