@@ -527,7 +527,7 @@ def main():
                 for _ in range(args.steps):
                     images_step()
                 pr.disable()
-                pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
+                pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(25)
             rays_i = int(out_i["counts"]["n_rays"])
             e2e_images = {"ms_per_step": 1e3 * et_i / args.steps, "value": rays_i * args.steps / et_i, "unit": "rays/s",
                           "rays": rays_i, "h2d_bytes_per_step": int(h2d_i),

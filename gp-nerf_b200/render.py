@@ -68,6 +68,10 @@ class Projector:
         return rgb_feat.view(*smpl_xyz.shape[:2], f.n_views, 35)[..., 3:]      # a view: K8 takes the strides
 
 
+# small per-frame constants that end up in gpnerf_frame_t (engine.frame_from_batch) or in host-side set-up
+_HOST_KEYS = ("Rh", "R", "Th", "bounds", "out_sh", "src_poses", "src_Ks", "target_pose", "target_K", "target_K_inv")
+
+
 class Renderer(nn.Module):
     def __init__(self, encoder, nerfhead, is_train=True, neg_ray_train=False, neg_ray_val=False, n_rays=1024,
                  n_samples=64, voxel_size=(0.005, 0.005, 0.005), chunk=64, mesh_th=-1, progressive=False,
@@ -199,6 +203,10 @@ class Renderer(nn.Module):
         # etime / rtime (demo_render.py:98-101, 442-447) from stream events instead of two device-wide
         # synchronisations: the host keeps queueing while the producers run
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        # the frame constants are read back now, while the stream is idle: read after the producers have been
+        # queued, each of these tiny copies would wait for the encoder and the pyramid
+        hostc = {k: batch[k].detach().cpu() for k in _HOST_KEYS if k in batch and torch.is_tensor(batch[k]) and batch[k].is_cuda}
+        batch = {**batch, **hostc}               # (a copy: the caller's dict is never modified)
         ev[0].record(torch.cuda.current_stream(device))
         featmaps, levels = self._upstream(batch)
         ev[1].record(torch.cuda.current_stream(device))
