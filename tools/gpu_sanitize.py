@@ -62,3 +62,25 @@ r = ops.dataset_rays(64, 64, scene["target_K"][0].numpy().astype(np.float64), po
                      scene["can_bounds"][0].numpy(), "cuda:0")
 print("dataset rays", r[0].shape)
 print("sanitize target done")
+# rows f1 + f2: encoder (K9), SMPL attention (K8), sparse-conv pyramid (K7), eager and as captured graphs
+from gpnerf_b200.encoder import ResUNet  # noqa: E402
+from gpnerf_b200.nerfhead import NeRFHead  # noqa: E402
+from gpnerf_b200.render import Renderer  # noqa: E402
+head = NeRFHead(n_views=3, precision=PREC_BF16).eval()
+sd = head.state_dict()
+for k, v in w.items():
+    sd[k].copy_(v)
+for k, v in sd.items():
+    if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+        v.fill_(3.0)
+head.load_state_dict(sd)
+for prec_e in ("fp16", "fp32"):
+    enc = synth.fill_encoder_params(ResUNet(precision=prec_e), seed=1).eval().to("cuda:0")
+    rr = Renderer(enc, head.to("cuda:0"), is_train=False, n_samples=16, progressive=True, precision=PREC_BF16)
+    base = {k: (v.to("cuda:0") if torch.is_tensor(v) else v) for k, v in scene.items() if k not in ("levels", "featmaps")}
+    for _ in range(3):
+        out = rr.render(dict(base))
+    print("from images", prec_e, out["counts"], float(out["pred_img"].sum()))
+odd = torch.rand(2, 3, 72, 56, device="cuda:0") * 2 - 1          # skip tensors that need zero padding
+print("encoder odd size", tuple(enc(odd).shape))
+print("sanitize target done (f1/f2)")
