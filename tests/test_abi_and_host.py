@@ -190,3 +190,38 @@ def test_encoder_mirror_has_the_reference_state_dict():
     assert got == want and len(got) > 100
     with pytest.raises(Exception):
         ResUNet()(torch.zeros(1, 3, 64, 64))           # no CPU fallback
+
+
+def test_head_mirror_has_the_reference_state_dict():
+    """NeRFHead (sigma head incl. the K7/K8 producer mirrors, rgb head) exposes exactly the parameter and buffer
+    names, shapes and order of the reference's trainhead.NeRFHead (oracle/gen_golden_keys.py), for both code_dim
+    settings of the configs: reference checkpoints load with strict=True."""
+    import json
+    from gpnerf_b200.nerfhead import NeRFHead
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "head_state_keys.json")))
+    for code_dim in (16, 32):
+        got = [(k, list(v.shape)) for k, v in NeRFHead(code_dim=code_dim).state_dict().items()]
+        assert got == [(k, s) for k, s in want[str(code_dim)]] and len(got) == 115
+
+
+def test_build_render_plugin_entry_points():
+    """build_render(cfg) / build_head(cfg) / build_encoder(cfg) with a config shaped like the reference's yacs tree
+    (configs/default.py): module tree, constructor wiring and the inference/training switches."""
+    from types import SimpleNamespace as NS
+    from gpnerf_b200.encoder import ResUNet
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Renderer, build_render
+    cfg = NS(encoder=NS(file="no_such_encoder_file", name="resnet34", out_ch=32),
+             head=NS(file="no_such_head_file", sigma=NS(code_dim=16, n_heads=4, n_layers=4, n_smpl=6890, outdims=[32, 32, 32, 32]),
+                     rgb=NS(use_rgbhead=True)),
+             dataset=NS(train=NS(name="zju_mocap_train", chunk=400), test=NS(name="thuman_test", chunk=2000),
+                        voxel_size=[0.005, 0.005, 0.005]),
+             train=NS(n_rays=1024, n_samples=64), test=NS(mesh_th=50.0), src_view_num=3)
+    r = build_render(cfg, progressive=True)
+    assert isinstance(r, Renderer) and isinstance(r.encoder, ResUNet) and isinstance(r.nerfhead, NeRFHead)
+    assert r.progressive and not r.is_train and r.neg_ray_val and not r.neg_ray_train and r.n_samples == 64
+    keys = list(r.state_dict())
+    assert "encoder.conv1.weight" in keys and "nerfhead.sigmahead.xyzc_net.net.0.0.weight" in keys
+    assert "nerfhead.rgbhead.rgb_fc.4.bias" in keys and "nerfhead.sigmahead.c.weight" in keys
+    with pytest.raises(Exception):
+        r.render({"src_imgs": torch.zeros(1, 3, 3, 64, 64)})          # CPU tensors: no fallback
