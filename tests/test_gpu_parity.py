@@ -466,7 +466,8 @@ def test_image_encoder_vs_reference_golden(precision):
         assert enc._graphs[(tuple(x.shape), x.dtype)]["graph"] is not None
 
 
-def test_renderer_from_images_only():
+@pytest.mark.parametrize("V,H", [(3, 64), (4, 96)])
+def test_renderer_from_images_only(V, H):
     """Rows f1 + f2 together: a batch with neither 'featmaps' nor 'levels' – Renderer.render runs the image
     encoder, the SMPL attention, the sparse-conv pyramid and K1…K5; identical to handing it the encoder's
     feature maps explicitly."""
@@ -475,10 +476,10 @@ def test_renderer_from_images_only():
     from gpnerf_b200.nerfhead import NeRFHead
     from gpnerf_b200.render import Renderer
     torch.manual_seed(7)
-    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=13)
-    head = NeRFHead(n_views=3, precision=PREC_BF16).eval()
+    scene = synth.make_scene("zju", H=H, W=H, V=V, seed=13)
+    head = NeRFHead(n_views=V, precision=PREC_BF16).eval()
     sd = head.state_dict()
-    for k, v in synth.make_head_weights(V=3, seed=3).items():
+    for k, v in synth.make_head_weights(V=V, seed=3).items():
         sd[k].copy_(v)
     for k, v in sd.items():
         if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
@@ -489,7 +490,7 @@ def test_renderer_from_images_only():
     base = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in scene.items() if k not in ("levels", "featmaps")}
     a = r.render(dict(base))
     fm = enc(base["src_imgs"][0]).clone()
-    assert fm.shape == (3, 32, 16, 16)
+    assert fm.shape == (V, 32, H // 4, H // 4)
     b = r.render(dict(base, featmaps=fm))
     assert a["counts"]["n_rays"] > 100 and a["counts"] == b["counts"]
     assert np.array_equal(a["pred_img"], b["pred_img"]) and float(a["pred_img"].max()) > 0.0
