@@ -26,7 +26,7 @@ namespace cg = cooperative_groups;
 
 namespace gpnerf {
 
-constexpr int32_t kNoRow = 0x7f7f7f7f;      // what cudaMemset(0x7f) leaves behind
+constexpr int32_t kNoRow = 0x7f7f7f7f;      // what cudaMemset(0x7f) leaves behind (rows >= n_in read as "none")
 
 struct Dims3 {
   int D, H, W;

@@ -30,6 +30,20 @@ from . import _lib
 from ._lib import check, ptr
 
 
+def _pack_tf32x3(w):
+    """spconv weight [3,3,3,in,out] → per tap the two UMMA B-operand images of W[k]ᵀ ([out × in], K-major,
+    8 × 16-byte core matrices) that csrc/k7_sparseconv_tc.cu multiplies with: the part that is exact in TF32 (13
+    low mantissa bits cleared) and the remainder.  float32 [27, 2, out·in]."""
+    c_in, c_out = w.shape[3], w.shape[4]
+    b = w.reshape(27, c_in, c_out).transpose(1, 2).contiguous()                   # [27, out, in]
+    hi = (b.view(torch.int32) & -8192).view(torch.float32)                         # 0xffffe000
+    lo = b - hi
+
+    def image(m):                                                                  # (n, c) → (n/8, c/4, n%8, c%4)
+        return m.reshape(27, c_out // 8, 8, c_in // 4, 4).permute(0, 1, 3, 2, 4).reshape(27, c_out * c_in)
+    return torch.stack([image(hi), image(lo)], 1).contiguous()
+
+
 class _ConvWeight(nn.Module):
     """Parameter holder with spconv's layout: weight [3, 3, 3, in, out], no bias."""
 
@@ -65,6 +79,7 @@ class SparseConvNet(nn.Module):
         self._plist = None
         self._plans = {}
         self.use_cuda_graph = True
+        self.precision = "tf32x3"        # tcgen05 TF32 with a 3-term split (fp32-grade); "fp32": CUDA-core FFMA
 
     # ------------------------------------------------------------------
     def _layers(self):
@@ -86,8 +101,9 @@ class SparseConvNet(nn.Module):
         fresh = []
         for _bi, conv, bn in self._layers():
             g, inv = bn.weight.detach().float(), torch.rsqrt(bn.running_var.detach().float() + bn.eps)
-            fresh.append((conv.weight.detach().float().contiguous(), g * inv,
-                          bn.bias.detach().float() - bn.running_mean.detach().float() * g * inv))
+            w = conv.weight.detach().float().contiguous()
+            fresh.append((w, g * inv, bn.bias.detach().float() - bn.running_mean.detach().float() * g * inv,
+                          _pack_tf32x3(w)))
         if self._folded is not None and self._folded[1] == device:
             packed = self._folded[2]
             for old, new in zip(packed, fresh):
@@ -149,7 +165,7 @@ class SparseConvNet(nn.Module):
         x, level, subm_level = pl["x0"], 0, -1
         outs = []
         for li, (bi, conv, _bn) in enumerate(self._layers()):
-            w, scale, shift = packed[li]
+            w, scale, shift, w_tc = packed[li]
             if conv.stride == 2:
                 check(lib.gpnerf_sc_strided_sites(ptr(coords_l[level]), ptr(counts[level:level + 1]), caps[level],
                                                   *dims[level + 1], ptr(pl["lin"]), ptr(coords_l[level + 1]),
@@ -165,8 +181,13 @@ class SparseConvNet(nn.Module):
                                                caps[out_level], conv.stride, ptr(idx_vol[level]), *dims[level],
                                                ptr(counts[level:level + 1]), ptr(nbr), st), "sc_neighbours")
             y = pl["y"][li]
-            check(lib.gpnerf_sc_conv(ptr(x), conv.c_in, ptr(nbr), ptr(counts[out_level:out_level + 1]), caps[out_level],
-                                     ptr(w), ptr(scale), ptr(shift), conv.c_out, ptr(y), st), "sc_conv")
+            if self.precision == "tf32x3":
+                check(lib.gpnerf_sc_conv_tc(ptr(x), conv.c_in, ptr(nbr), ptr(counts[out_level:out_level + 1]),
+                                            caps[out_level], ptr(w_tc), ptr(scale), ptr(shift), conv.c_out, ptr(y), st),
+                      "sc_conv_tc")
+            else:
+                check(lib.gpnerf_sc_conv(ptr(x), conv.c_in, ptr(nbr), ptr(counts[out_level:out_level + 1]), caps[out_level],
+                                         ptr(w), ptr(scale), ptr(shift), conv.c_out, ptr(y), st), "sc_conv")
             x, level = y, out_level
             # a level's features are final after the double_conv that follows its stride_conv (blocks 2, 4, 6, 8)
             if bi >= 2 and bi % 2 == 0 and conv is self.net[bi][3]:

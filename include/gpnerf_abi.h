@@ -338,6 +338,14 @@ int gpnerf_sc_conv(const float *in_feat, int c_in, const int32_t *nbr, const int
                    int n_out_max, const float *weight, const float *scale, const float *shift,
                    int c_out, float *out_feat, void *stream);
 
+/* The same convolution on tensor cores (tcgen05.mma.kind::tf32, three-term hi/lo split: fp32-grade accuracy).
+ * w_packed: per tap k two UMMA B-operand images of W[k]^T ([c_out x c_in], K-major, 8x16-byte core matrices):
+ * the TF32-exact part (13 low mantissa bits cleared) and the remainder; float[27][2][c_out*c_in] –
+ * element (n, c) of an image at ((n/8)*(c_in/4)*32 + (c/4)*32 + (n%8)*4 + c%4). */
+int gpnerf_sc_conv_tc(const float *in_feat, int c_in, const int32_t *nbr, const int32_t *n_out_dev,
+                      int n_out_max, const float *w_packed, const float *scale, const float *shift,
+                      int c_out, float *out_feat, void *stream);
+
 /* ---- K8: SMPL-code attention (trainhead.py:48-51; MultiHeadAttention.py:40-98, sum=False) ---- */
 /* out[i] = W_fc · concat_h( softmax_v( (W_q·code[i])_h/√d_k · (W_k·feat[i,v])_h ) · (W_v·feat[i,v])_h ).
  * code [n][d_model]; feat[i,v] = feats + i*vertex_stride + v*view_stride (floats, kv_dim of them – lets the

@@ -308,8 +308,8 @@ def test_mesh_branch_cube_vs_oracle():
     assert float(np.abs(got[:10]).max()) == 0.0           # the 10-voxel pad
 
 
-@pytest.mark.parametrize("in_dim", [16, 32])
-def test_sparse_conv_net_vs_dense_emulation(in_dim):
+@pytest.mark.parametrize("in_dim,precision", [(16, "tf32x3"), (32, "tf32x3"), (16, "fp32"), (32, "fp32")])
+def test_sparse_conv_net_vs_dense_emulation(in_dim, precision):
     """Row f1: the sparse-conv pyramid (SparseConvNet.py:21-124) from K7 against its dense conv3d
     emulation (oracle.sparse_conv_net; spconv itself is absent: parity unpinned).  Random sites with
     duplicates, random BatchNorm statistics; then the rows straight into the renderer."""
@@ -317,6 +317,7 @@ def test_sparse_conv_net_vs_dense_emulation(in_dim):
     from gpnerf_b200.sparseconv import SparseConvNet
     torch.manual_seed(in_dim)
     net = SparseConvNet(in_dim=in_dim).eval()
+    net.precision = precision          # tcgen05 TF32 with the 3-term split (default) | plain fp32 FFMA
     for k, v in net.state_dict().items():
         if k.endswith("running_var"):
             v.uniform_(0.5, 2.0)
