@@ -77,7 +77,8 @@ _SIGNATURES = {
     "gpnerf_sc_strided_sites": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_sc_neighbours": ([_P, _P, _I, _I, _P, _I, _I, _I, _P, _P, _P], C.c_int),
     "gpnerf_sc_conv": ([_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P], C.c_int),
-    "gpnerf_sc_conv_tc": ([_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P], C.c_int),
+    "gpnerf_sc_conv_tc": ([_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P], C.c_int),
+    "gpnerf_sc_gather_rows_split": ([_P, _I, _P, _P, _I, _P, _P], C.c_int),
     "gpnerf_attn_smpl_code": ([_P, _P, C.c_longlong, C.c_longlong, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
                               C.c_int),
     "gpnerf_k9_instance_norm_act": ([_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, C.c_float, _I, _P, _P, _I, _I, _I, _P],

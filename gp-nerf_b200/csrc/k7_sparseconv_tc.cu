@@ -11,23 +11,22 @@
 // B operands once on the host side (sparseconv.SparseConvNet._fold); the gathered rows are split on their way
 // from registers to shared memory.
 //
-// One CTA = 256 threads = a tile of 128 output sites; a cluster of 3 CTAs splits the 27 taps (9 each: kd = rank)
-// and reduces the three partial tiles over DSMEM in a fixed order, as the fp32 kernel does.  Per active tap:
-// the 128 neighbour rows (16-byte loads issued one tap ahead, zero rows where there is no neighbour) and the
-// tap's two weight images go to one of two shared-memory stages; thread 0 issues 3·CIN/8 MMAs
-// (M=128, N=COUT, K=8) and commits to the stage's mbarrier, which gates the stage's reuse.  Taps no site of
-// the tile has are skipped.
+// Between the layers the features travel already split: a row is [x_hi (C) | x_lo (C)], written by the producing
+// layer's epilogue, so the gather is a plain 16-byte asynchronous copy (cp.async, zero-fill where a site has no
+// neighbour) straight into the two A operands – no register staging, two taps in flight beyond the current one.
+//
+// One CTA = 256 threads = a tile of 128 output sites, all 27 taps (those no site of the tile has are skipped).
+// Per active tap the 128 neighbour rows and the tap's two weight images land in one of four shared-memory
+// stages; thread 0 issues 3·CIN/8 MMAs (M=128, N=COUT, K=8) and commits to the stage's mbarrier, which gates the
+// stage's refill.  Epilogue: TMEM → scale/shift → ReLU → split → rows of the next layer (+ plain fp32 rows for
+// the renderer where the layer closes a pyramid level).
 //
 // Operand layout (32-bit elements, K-major, no swizzle; core matrix = 8 rows × 16 bytes):
 //     byte(r, k) = (r/8)·SBO + (k/4)·128 + (r%8)·16 + (k%4)·4,   SBO = (CIN/4)·128.
 // Lane mapping of the staging: lane%8 = row within its group of 8, lane/8 = 16-byte chunk, so a quarter-warp
 // writes 128 contiguous bytes (no bank conflicts) and reads 8 rows × one chunk from global memory.
-#include <cooperative_groups.h>
-
 #include "tc_common.cuh"
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace gpnerf {
 using namespace tc;
@@ -35,7 +34,7 @@ using namespace tc;
 namespace {
 
 constexpr uint32_t kFmtTF32x = 2;
-constexpr int kTile = 128, kThreads = 256, kSplit = 3, kTaps = 27 / kSplit, kStages = 2;
+constexpr int kTile = 128, kThreads = 256, kNTaps = 27, kStages = 4, kAhead = kStages - 2;   // taps in flight beyond the current one
 
 __device__ __forceinline__ void umma_tf32x(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -46,35 +45,41 @@ __device__ __forceinline__ void umma_tf32x(uint32_t tmem_d, uint64_t adesc, uint
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_addr, const void* gmem, bool valid) {
+  const int n = valid ? 16 : 0;                        // src-size 0: 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 template <int CIN, int COUT>
 struct ScTc {
-  static constexpr int CH = CIN / 4;                              // 16-byte chunks per row
+  static constexpr int CH = CIN / 4;                              // 16-byte chunks per operand row
   static constexpr uint32_t SBO = (uint32_t)CH * kLBO;            // bytes between 8-row groups (A and B alike)
   static constexpr uint32_t A_BYTES = kTile / 8 * SBO;            // one [128 × CIN] fp32 operand
   static constexpr uint32_t B_BYTES = COUT / 8 * SBO;             // one [COUT × CIN] fp32 operand
   static constexpr uint32_t STAGE = 2 * A_BYTES + 2 * B_BYTES;    // A_hi | A_lo | B_hi | B_lo
-  static constexpr int A_ITEMS = kTile * CH / kThreads;           // float4 per thread and tap (4 | 2)
+  static constexpr int A_ITEMS = 2 * kTile * CH / kThreads;       // 16-byte copies per thread and tap (8 | 4)
   static constexpr int B_F4 = 2 * (int)B_BYTES / 16;              // float4 in a tap's packed weight image
-  static constexpr size_t SMEM = (size_t)kStages * STAGE + kTaps * kTile * 4 + 256;
+  static constexpr size_t SMEM = (size_t)kStages * STAGE + kNTaps * kTile * 4 + 512;
 };
 
+// in_split / out_split: rows of 2·C floats, [TF32-exact part | remainder] (written by the producing layer's
+// epilogue, so the gather is a plain asynchronous copy into the two A operands)
 template <int CIN, int COUT>
-__global__ void __cluster_dims__(kSplit, 1, 1) __launch_bounds__(kThreads, 2)
-    sc_conv_tc(const float* __restrict__ in_feat, const int32_t* __restrict__ nbr, int n_out_max,
+__global__ void __launch_bounds__(kThreads, 1)
+    sc_conv_tc(const float* __restrict__ in_split, const int32_t* __restrict__ nbr, int n_out_max,
                const int32_t* __restrict__ n_out_dev, const float* __restrict__ w_packed,
-               const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out_feat) {
+               const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out_split,
+               float* __restrict__ out_full) {
   using L = ScTc<CIN, COUT>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* stages = smem;
-  int* ids = reinterpret_cast<int*>(smem + kStages * L::STAGE);                      // [kTaps][kTile]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ids + kTaps * kTile);                 // [kStages] stage free, [kStages] = all done
+  int* ids = reinterpret_cast<int*>(smem + kStages * L::STAGE);                      // [27][kTile]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ids + kNTaps * kTile);                // [kStages] stage free, [kStages] = tile done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
-  int* tap_any = reinterpret_cast<int*>(tmem_slot + 1);                              // [kTaps]
-  int* taps = tap_any + kTaps;                                                       // [kTaps]
-  int* n_taps_s = taps + kTaps;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
+  int* tap_any = reinterpret_cast<int*>(tmem_slot + 1);                              // [27]
+  int* taps = tap_any + kNTaps;                                                      // [27]
+  int* n_taps_s = taps + kNTaps;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s <= kStages; ++s) mbar_init(bars + s, 1);
@@ -88,101 +93,99 @@ __global__ void __cluster_dims__(kSplit, 1, 1) __launch_bounds__(kThreads, 2)
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t idesc = make_idesc(128, COUT, kFmtTF32x);
+  const uint32_t stages_u32 = smem_u32(stages);
+  const uint64_t d_ah = make_smem_desc(stages_u32, kLBO, L::SBO), d_al = make_smem_desc(stages_u32 + L::A_BYTES, kLBO, L::SBO);
+  const uint64_t d_bh = make_smem_desc(stages_u32 + 2 * L::A_BYTES, kLBO, L::SBO);
+  const uint64_t d_bl = make_smem_desc(stages_u32 + 2 * L::A_BYTES + L::B_BYTES, kLBO, L::SBO);
   const int n_out = __ldg(n_out_dev);
   const int n_tiles = (n_out + kTile - 1) / kTile;
-  uint32_t stage_uses[kStages] = {0, 0};       // how often each stage has been committed so far (all threads agree)
+  uint32_t commits = 0;                          // MMAs committed so far by this CTA (stage = commit index % kStages)
   uint32_t done_phase = 0;
-  float* park = reinterpret_cast<float*>(stages);                                    // [kTile][COUT] partial sums
 
-  // staging coordinates of this thread: item i covers row rg*8 + lane%8, chunk c
-  int st_row[L::A_ITEMS];
-  uint32_t st_off[L::A_ITEMS];
+  // this thread's copies of a tap: item i → (part hi|lo, row, chunk); a quarter-warp fills 128 contiguous bytes
+  int it_row[L::A_ITEMS];
+  uint32_t it_dst[L::A_ITEMS], it_src[L::A_ITEMS];
 #pragma unroll
   for (int i = 0; i < L::A_ITEMS; ++i) {
-    const int blk = (i * kThreads + tid) >> 5;                   // 32-item block
-    const int rg = L::CH == 8 ? blk >> 1 : blk, c = (L::CH == 8 ? (blk & 1) * 4 : 0) + (lane >> 3);
-    st_row[i] = rg * 8 + (lane & 7);
-    st_off[i] = (uint32_t)rg * L::SBO + (uint32_t)c * kLBO + (uint32_t)(lane & 7) * 16;
-    st_row[i] |= c << 16;                                         // chunk in the high half
+    const int blk = (i * kThreads + tid) >> 5;                         // 32-copy block: 8 rows × 4 chunks
+    constexpr int BLK_PER_PART = kTile / 8 * (L::CH / 4);
+    const int part = blk / BLK_PER_PART, b2 = blk - part * BLK_PER_PART;
+    const int rg = b2 / (L::CH / 4), c = (b2 % (L::CH / 4)) * 4 + (lane >> 3);
+    it_row[i] = rg * 8 + (lane & 7);
+    it_dst[i] = (uint32_t)part * L::A_BYTES + (uint32_t)rg * L::SBO + (uint32_t)c * kLBO + (uint32_t)(lane & 7) * 16;
+    it_src[i] = (uint32_t)(part * CIN + c * 4);                        // float offset inside the 2·CIN row
   }
 
-  for (int tile = blockIdx.x / kSplit; tile < n_tiles; tile += gridDim.x / kSplit) {
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int o0 = tile * kTile;
-    if (tid < kTaps) tap_any[tid] = 0;
+    if (tid < kNTaps) tap_any[tid] = 0;
     __syncthreads();
-    for (int t = tid; t < kTaps * kTile; t += kThreads) {
+    for (int t = tid; t < kNTaps * kTile; t += kThreads) {
       const int kk = t / kTile, r = t - kk * kTile;
-      const int row = o0 + r < n_out ? __ldg(nbr + (size_t)(crank * kTaps + kk) * n_out_max + o0 + r) : -1;
+      const int row = o0 + r < n_out ? __ldg(nbr + (size_t)kk * n_out_max + o0 + r) : -1;
       ids[t] = row;
       if (row >= 0) tap_any[kk] = 1;                   // benign race: every writer stores 1
     }
     __syncthreads();
     if (tid == 0) {
       int n = 0;
-      for (int kk = 0; kk < kTaps; ++kk)
+      for (int kk = 0; kk < kNTaps; ++kk)
         if (tap_any[kk]) taps[n++] = kk;
       *n_taps_s = n;
     }
     __syncthreads();
     const int n_taps = *n_taps_s;
 
-    float4 xa[L::A_ITEMS];
-    auto load_tap = [&](int j) {                       // global → registers (rows of tap taps[j])
-      const int kk = taps[j];
+    auto issue = [&](int j, uint32_t stage) {          // tap taps[j] → shared-memory stage (asynchronous copies)
+      if (j < n_taps) {
+        const int kk = taps[j];
+        const uint32_t sb = stages_u32 + stage * L::STAGE;
 #pragma unroll
-      for (int i = 0; i < L::A_ITEMS; ++i) {
-        const int row = ids[kk * kTile + (st_row[i] & 0xffff)];
-        xa[i] = row >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)row * CIN) + (st_row[i] >> 16))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    if (n_taps > 0) load_tap(0);
-    for (int j = 0; j < n_taps; ++j) {
-      const int s = j % kStages;
-      uint8_t* sb = stages + (size_t)s * L::STAGE;
-      if (stage_uses[s] > 0) mbar_wait(bars + s, (stage_uses[s] - 1) & 1u);        // MMAs that read the stage are done
-      tc_fence_after();
-      // registers → A_hi | A_lo
-#pragma unroll
-      for (int i = 0; i < L::A_ITEMS; ++i) {
-        const float v[4] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w};
-        float hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          hi[q] = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
-          lo[q] = v[q] - hi[q];
+        for (int i = 0; i < L::A_ITEMS; ++i) {
+          const int row = ids[kk * kTile + it_row[i]];
+          cp_async16_zfill(sb + it_dst[i], in_split + (size_t)(row >= 0 ? row : 0) * (2 * CIN) + it_src[i], row >= 0);
         }
-        *reinterpret_cast<float4*>(sb + st_off[i]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(sb + L::A_BYTES + st_off[i]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        const float4* wsrc = reinterpret_cast<const float4*>(w_packed) + (size_t)kk * L::B_F4;
+        for (int t = tid; t < L::B_F4; t += kThreads) cp_async16_zfill(sb + 2 * L::A_BYTES + (uint32_t)t * 16, wsrc + t, true);
       }
-      // the tap's weight images (already in operand layout): B_hi | B_lo
-      {
-        const float4* wsrc = reinterpret_cast<const float4*>(w_packed) + (size_t)(crank * kTaps + taps[j]) * L::B_F4;
-        float4* wdst = reinterpret_cast<float4*>(sb + 2 * L::A_BYTES);
-        for (int t = tid; t < L::B_F4; t += kThreads) wdst[t] = __ldg(wsrc + t);
+      asm volatile("cp.async.commit_group;" ::: "memory");          // one group per call, empty past the last tap
+    };
+    // stage of tap j = (commits_at_tile_start + j) % kStages
+    const uint32_t c0 = commits;
+    // A stage is refilled two taps after it was multiplied (kStages = kAhead + 2): the wait below is for a commit
+    // that is one whole iteration old, so the MMA → mbarrier → wake-up latency stays off the tap chain.  Stages
+    // touched before the first wait held taps of the previous tile, all older than its tile-done barrier.
+    for (int j = 0; j < kAhead; ++j) issue(j, (c0 + j) % kStages);
+    for (int j = 0; j < n_taps; ++j) {
+      const uint32_t s = (c0 + j) % kStages;
+      if (j >= 2) {
+        const uint32_t g = c0 + j - 2;                               // global index of the commit to wait for
+        mbar_wait(bars + g % kStages, (g / kStages) & 1u);
+        tc_fence_after();
       }
-      if (j + 1 < n_taps) load_tap(j + 1);             // in flight across the barrier and the MMA issue
+      issue(j + kAhead, (c0 + j + kAhead) % kStages);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
       if (tid == 0) {
-        const uint32_t a_hi = smem_u32(sb), a_lo = a_hi + L::A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * L::A_BYTES, b_lo = b_hi + L::B_BYTES;
+        // descriptors differ from the stage-0, k=0 ones only in the address field (bits 0-13, 16-byte units): the
+        // issuing thread is on the critical path between two barriers, so it adds instead of rebuilding them
+        const uint64_t so = (uint64_t)((s * L::STAGE) >> 4);
 #pragma unroll
         for (int k8 = 0; k8 < CIN / 8; ++k8) {
-          const uint32_t ko = (uint32_t)k8 * 2 * kLBO;
-          const uint64_t ah = make_smem_desc(a_hi + ko, kLBO, L::SBO), al = make_smem_desc(a_lo + ko, kLBO, L::SBO);
-          const uint64_t bh = make_smem_desc(b_hi + ko, kLBO, L::SBO), bl = make_smem_desc(b_lo + ko, kLBO, L::SBO);
-          umma_tf32x(tmem, ah, bh, idesc, (j > 0 || k8 > 0) ? 1u : 0u);
-          umma_tf32x(tmem, al, bh, idesc, 1u);
-          umma_tf32x(tmem, ah, bl, idesc, 1u);
+          const uint64_t o = so + (uint64_t)((k8 * 2 * kLBO) >> 4);
+          umma_tf32x(tmem, d_ah + o, d_bh + o, idesc, (j > 0 || k8 > 0) ? 1u : 0u);
+          umma_tf32x(tmem, d_al + o, d_bh + o, idesc, 1u);
+          umma_tf32x(tmem, d_ah + o, d_bl + o, idesc, 1u);
         }
         umma_commit(bars + s);
         if (j == n_taps - 1) umma_commit(bars + kStages);          // everything of this tile
       }
-      stage_uses[s] += 1;
     }
+    commits += (uint32_t)n_taps;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // ---- epilogue: thread (row, half) owns 16 columns of its row
     const int row = tid & 127, half = tid >> 7;
     const bool has_cols = half * 16 < COUT;
@@ -201,34 +204,26 @@ __global__ void __cluster_dims__(kSplit, 1, 1) __launch_bounds__(kThreads, 2)
         for (int c = 0; c < 16; ++c) acc[c] = __uint_as_float(r[c]);
       }
     }
-    tc_fence_before();
-    __syncthreads();                                   // all MMAs done, all TMEM reads done: stages are free
-    if (crank != 0 && has_cols) {
+    const int o = o0 + row;
+    if (has_cols && o < n_out) {
 #pragma unroll
-      for (int c = 0; c < 16; c += 4)
-        *reinterpret_cast<float4*>(park + row * COUT + half * 16 + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-    }
-    cluster.sync();                                    // partial sums of CTAs 1, 2 are visible
-    if (crank == 0 && has_cols) {
-      const int o = o0 + row;
-      if (o < n_out) {
-        const float* p1 = cluster.map_shared_rank(park, 1) + row * COUT + half * 16;
-        const float* p2 = cluster.map_shared_rank(park, 2) + row * COUT + half * 16;
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-          const float4 b1 = *reinterpret_cast<const float4*>(p1 + c), b2 = *reinterpret_cast<const float4*>(p2 + c);
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + half * 16 + c));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + half * 16 + c));
-          float4 y;
-          y.x = fmaxf(fmaf((acc[c] + b1.x) + b2.x, sc.x, sh.x), 0.0f);
-          y.y = fmaxf(fmaf((acc[c + 1] + b1.y) + b2.y, sc.y, sh.y), 0.0f);
-          y.z = fmaxf(fmaf((acc[c + 2] + b1.z) + b2.z, sc.z, sh.z), 0.0f);
-          y.w = fmaxf(fmaf((acc[c + 3] + b1.w) + b2.w, sc.w, sh.w), 0.0f);
-          *reinterpret_cast<float4*>(out_feat + (size_t)o * COUT + half * 16 + c) = y;
-        }
+      for (int c = 0; c < 16; c += 4) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + half * 16 + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + half * 16 + c));
+        float4 y;
+        y.x = fmaxf(fmaf(acc[c], sc.x, sh.x), 0.0f);
+        y.y = fmaxf(fmaf(acc[c + 1], sc.y, sh.y), 0.0f);
+        y.z = fmaxf(fmaf(acc[c + 2], sc.z, sh.z), 0.0f);
+        y.w = fmaxf(fmaf(acc[c + 3], sc.w, sh.w), 0.0f);
+        const float4 hi = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
+        float* dst = out_split + (size_t)o * (2 * COUT) + half * 16 + c;
+        *reinterpret_cast<float4*>(dst) = hi;
+        *reinterpret_cast<float4*>(dst + COUT) = make_float4(y.x - hi.x, y.y - hi.y, y.z - hi.z, y.w - hi.w);
+        if (out_full) *reinterpret_cast<float4*>(out_full + (size_t)o * COUT + half * 16 + c) = y;
       }
     }
-    cluster.sync();                                    // parked sums were read: the stages may be refilled
+    tc_fence_before();
+    __syncthreads();                                   // TMEM reads done before the next tile's first MMA
     tc_fence_after();
   }
   tc_fence_before();
@@ -236,9 +231,21 @@ __global__ void __cluster_dims__(kSplit, 1, 1) __launch_bounds__(kThreads, 2)
   if (warp == 0) tmem_dealloc(tmem, 32);
 }
 
+// x0 rows of the first layer: feat_out[j] = split(feat_in[rows[j]])
+__global__ void __launch_bounds__(256) sc_gather_rows_split(const float* __restrict__ in, int C, const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ n_dev, float* __restrict__ out) {
+  const long long n = (long long)__ldg(n_dev) * C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t / C), c = (int)(t - (long long)j * C);
+    const float v = __ldg(in + (size_t)__ldg(rows + j) * C + c), hi = tf32_hi(v);
+    out[(size_t)j * 2 * C + c] = hi;
+    out[(size_t)j * 2 * C + C + c] = v - hi;
+  }
+}
+
 template <int CIN, int COUT>
-int launch(const float* in_feat, const int32_t* nbr, const int32_t* n_out_dev, int n_out_max, const float* w_packed,
-           const float* scale, const float* shift, float* out_feat, cudaStream_t st) {
+int launch(const float* in_split, const int32_t* nbr, const int32_t* n_out_dev, int n_out_max, const float* w_packed,
+           const float* scale, const float* shift, float* out_split, float* out_full, cudaStream_t st) {
   using L = ScTc<CIN, COUT>;
   static bool set = false;
   if (!set) {
@@ -253,8 +260,8 @@ int launch(const float* in_feat, const int32_t* nbr, const int32_t* n_out_dev, i
   const long long cap = (long long)sm_count() * 2;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  sc_conv_tc<CIN, COUT><<<(int)tiles * kSplit, kThreads, L::SMEM, st>>>(in_feat, nbr, n_out_max, n_out_dev, w_packed,
-                                                                        scale, shift, out_feat);
+  sc_conv_tc<CIN, COUT><<<(int)tiles, kThreads, L::SMEM, st>>>(in_split, nbr, n_out_max, n_out_dev, w_packed, scale, shift,
+                                                               out_split, out_full);
   return check_launch("sc_conv_tc");
 }
 
@@ -265,17 +272,27 @@ using namespace gpnerf;
 
 extern "C" {
 
-int gpnerf_sc_conv_tc(const float* in_feat, int c_in, const int32_t* nbr, const int32_t* n_out_dev, int n_out_max,
-                      const float* w_packed, const float* scale, const float* shift, int c_out, float* out_feat,
-                      void* stream) {
-  GPNERF_REQUIRE(in_feat && nbr && n_out_dev && w_packed && scale && shift && out_feat && n_out_max > 0);
+int gpnerf_sc_conv_tc(const float* in_split, int c_in, const int32_t* nbr, const int32_t* n_out_dev, int n_out_max,
+                      const float* w_packed, const float* scale, const float* shift, int c_out, float* out_split,
+                      float* out_full, void* stream) {
+  GPNERF_REQUIRE(in_split && nbr && n_out_dev && w_packed && scale && shift && out_split && n_out_max > 0);
   cudaStream_t st = (cudaStream_t)stream;
-#define GPNERF_SC(CI, CO) \
-  if (c_in == CI && c_out == CO) return launch<CI, CO>(in_feat, nbr, n_out_dev, n_out_max, w_packed, scale, shift, out_feat, st);
+#define GPNERF_SC(CI, CO)        \
+  if (c_in == CI && c_out == CO) \
+    return launch<CI, CO>(in_split, nbr, n_out_dev, n_out_max, w_packed, scale, shift, out_split, out_full, st);
   GPNERF_SC(16, 16) GPNERF_SC(16, 32) GPNERF_SC(32, 32) GPNERF_SC(32, 16)
 #undef GPNERF_SC
   set_error("sc_conv_tc supports channel widths 16 and 32", cudaSuccess);
   return GPNERF_E_UNSUPPORTED;
+}
+
+int gpnerf_sc_gather_rows_split(const float* feat_in, int C, const int32_t* rows, const int32_t* n_dev, int n_max,
+                                float* feat_out, void* stream) {
+  GPNERF_REQUIRE(feat_in && rows && n_dev && feat_out && C > 0 && n_max > 0);
+  long long b = ((long long)n_max * C + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  sc_gather_rows_split<<<(int)(b < cap ? b : cap), 256, 0, (cudaStream_t)stream>>>(feat_in, C, rows, n_dev, feat_out);
+  return check_launch("sc_gather_rows_split");
 }
 
 }  // extern "C"

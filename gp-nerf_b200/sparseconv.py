@@ -79,7 +79,10 @@ class SparseConvNet(nn.Module):
         self._plist = None
         self._plans = {}
         self.use_cuda_graph = True
-        self.precision = "tf32x3"        # tcgen05 TF32 with a 3-term split (fp32-grade); "fp32": CUDA-core FFMA
+        # "fp32": CUDA-core FFMA kernel (cluster tap split) – the default, and the faster one: the pyramid's tiles are
+        # latency-bound, not math-bound.  "tf32x3": tcgen05 kind::tf32 with a 3-term split (fp32-grade accuracy),
+        # kept as the tensor-core variant (profiles/r01_final_ncu_summary.md §8: 0.58 ms vs 0.47 ms per pyramid)
+        self.precision = "fp32"
 
     # ------------------------------------------------------------------
     def _layers(self):
@@ -119,7 +122,8 @@ class SparseConvNet(nn.Module):
     def _plan(self, n0, cols, spatial_shape, c_in, dev):
         """Buffers of one (vertex count, grid) geometry; every row count stays on the device, so the launch
         sequence is the same for every frame and is captured into a CUDA graph on its second use."""
-        key = (n0, cols, tuple(spatial_shape), str(dev))
+        tc = self.precision == "tf32x3"          # rows travel as [hi | lo] between the layers: twice the width
+        key = (n0, cols, tuple(spatial_shape), str(dev), tc)
         pl = self._plans.get(key)
         if pl is not None:
             return pl
@@ -143,15 +147,21 @@ class SparseConvNet(nn.Module):
             "owners": torch.empty(n0, **i32),
             "lin": torch.empty(max(caps[1:]), **i32),
             "nbr": [torch.empty(27 * max(caps), **i32) for _ in range(2)],      # [0]: SubM table, [1]: strided
-            "x0": torch.empty(n0 * c_in, dtype=torch.float32, device=dev),
-            "y": [], "graph": None, "uses": 0,
+            "x0": torch.empty(n0 * c_in * (2 if tc else 1), dtype=torch.float32, device=dev),
+            "y": [], "y_full": {}, "graph": None, "uses": 0,
         }
         level = 0
-        for _bi, conv, _bn in self._layers():
+        for li, (bi, conv, _bn) in enumerate(self._layers()):
             level += conv.stride == 2
-            pl["y"].append(torch.empty(caps[level] * conv.c_out, dtype=torch.float32, device=dev))
+            pl["y"].append(torch.empty(caps[level] * conv.c_out * (2 if tc else 1), dtype=torch.float32, device=dev))
+            if tc and self._closes_level(bi, conv):
+                pl["y_full"][li] = torch.empty(caps[level] * conv.c_out, dtype=torch.float32, device=dev)
         self._plans[key] = pl
         return pl
+
+    def _closes_level(self, bi, conv):
+        """A level's features are final after the double_conv that follows its stride_conv (blocks 2, 4, 6, 8)."""
+        return bi >= 2 and bi % 2 == 0 and conv is self.net[bi][3]
 
     def _launch(self, pl, packed, st):
         lib = _lib.load()
@@ -160,8 +170,9 @@ class SparseConvNet(nn.Module):
         check(lib.gpnerf_sc_index_input(ptr(pl["coord_in"]), cols, n0, *dims[0], ptr(idx_vol[0]), ptr(pl["owners"]),
                                         ptr(coords_l[0]), ptr(counts[0:1]), ptr(pl["ws"]), st), "sc_index_input")
         c_in = pl["feat_in"].shape[1]
-        check(lib.gpnerf_sc_gather_rows(ptr(pl["feat_in"]), c_in, ptr(pl["owners"]), ptr(counts[0:1]), n0, ptr(pl["x0"]), st),
-              "sc_gather_rows")
+        tc = self.precision == "tf32x3"
+        gather = lib.gpnerf_sc_gather_rows_split if tc else lib.gpnerf_sc_gather_rows
+        check(gather(ptr(pl["feat_in"]), c_in, ptr(pl["owners"]), ptr(counts[0:1]), n0, ptr(pl["x0"]), st), "sc_gather_rows")
         x, level, subm_level = pl["x0"], 0, -1
         outs = []
         for li, (bi, conv, _bn) in enumerate(self._layers()):
@@ -181,17 +192,18 @@ class SparseConvNet(nn.Module):
                                                caps[out_level], conv.stride, ptr(idx_vol[level]), *dims[level],
                                                ptr(counts[level:level + 1]), ptr(nbr), st), "sc_neighbours")
             y = pl["y"][li]
-            if self.precision == "tf32x3":
+            y_full = pl["y_full"].get(li)
+            if tc:
                 check(lib.gpnerf_sc_conv_tc(ptr(x), conv.c_in, ptr(nbr), ptr(counts[out_level:out_level + 1]),
-                                            caps[out_level], ptr(w_tc), ptr(scale), ptr(shift), conv.c_out, ptr(y), st),
-                      "sc_conv_tc")
+                                            caps[out_level], ptr(w_tc), ptr(scale), ptr(shift), conv.c_out, ptr(y),
+                                            ptr(y_full), st), "sc_conv_tc")
             else:
                 check(lib.gpnerf_sc_conv(ptr(x), conv.c_in, ptr(nbr), ptr(counts[out_level:out_level + 1]), caps[out_level],
                                          ptr(w), ptr(scale), ptr(shift), conv.c_out, ptr(y), st), "sc_conv")
             x, level = y, out_level
-            # a level's features are final after the double_conv that follows its stride_conv (blocks 2, 4, 6, 8)
-            if bi >= 2 and bi % 2 == 0 and conv is self.net[bi][3]:
-                outs.append((x.view(caps[level], conv.c_out), coords_l[level].view(caps[level], 3)))
+            if self._closes_level(bi, conv):
+                rows = y_full if tc else x
+                outs.append((rows.view(caps[level], conv.c_out), coords_l[level].view(caps[level], 3)))
         return outs
 
     @torch.no_grad()

@@ -339,12 +339,16 @@ int gpnerf_sc_conv(const float *in_feat, int c_in, const int32_t *nbr, const int
                    int c_out, float *out_feat, void *stream);
 
 /* The same convolution on tensor cores (tcgen05.mma.kind::tf32, three-term hi/lo split: fp32-grade accuracy).
- * w_packed: per tap k two UMMA B-operand images of W[k]^T ([c_out x c_in], K-major, 8x16-byte core matrices):
- * the TF32-exact part (13 low mantissa bits cleared) and the remainder; float[27][2][c_out*c_in] –
- * element (n, c) of an image at ((n/8)*(c_in/4)*32 + (c/4)*32 + (n%8)*4 + c%4). */
-int gpnerf_sc_conv_tc(const float *in_feat, int c_in, const int32_t *nbr, const int32_t *n_out_dev,
+ * Features travel split between the layers: a row is [hi (c) | lo (c)] floats, hi = the value with its 13 low
+ * mantissa bits cleared (TF32-exact), lo = the remainder.  gather_rows_split makes the first layer's rows;
+ * conv_tc writes out_split [n][2*c_out] and, if out_full != NULL, plain fp32 rows [n][c_out] as well.
+ * w_packed: per tap k two UMMA B-operand images of W[k]^T ([c_out x c_in], K-major, 8x16-byte core matrices),
+ * hi then lo; float[27][2][c_out*c_in] – element (n, c) at ((n/8)*(c_in/4)*32 + (c/4)*32 + (n%8)*4 + c%4). */
+int gpnerf_sc_gather_rows_split(const float *feat_in, int C, const int32_t *rows, const int32_t *n_dev,
+                                int n_max, float *feat_out, void *stream);
+int gpnerf_sc_conv_tc(const float *in_split, int c_in, const int32_t *nbr, const int32_t *n_out_dev,
                       int n_out_max, const float *w_packed, const float *scale, const float *shift,
-                      int c_out, float *out_feat, void *stream);
+                      int c_out, float *out_split, float *out_full, void *stream);
 
 /* ---- K8: SMPL-code attention (trainhead.py:48-51; MultiHeadAttention.py:40-98, sum=False) ---- */
 /* out[i] = W_fc · concat_h( softmax_v( (W_q·code[i])_h/√d_k · (W_k·feat[i,v])_h ) · (W_v·feat[i,v])_h ).
