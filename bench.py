@@ -553,11 +553,19 @@ def main():
                 pr.disable()
                 pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(25)
             rays_i = int(out_i["counts"]["n_rays"])
+
+            def images_stream(k):
+                for out in r2.render_stream(ibatch for _ in range(k)):
+                    n_out[0] += int(out["mask_at_box"].sum() > 0)
+            images_stream(8)
+            et_is = timed(lambda: images_stream(args.steps), "from_images_stream")
             e2e_images = {"ms_per_step": 1e3 * et_i / args.steps, "value": rays_i * args.steps / et_i, "unit": "rays/s",
                           "rays": rays_i, "h2d_bytes_per_step": int(h2d_i),
+                          "stream_ms_per_step": 1e3 * et_is / args.steps, "stream_value": rays_i * args.steps / et_is,
                           "what": "Renderer.render(batch) with only src_imgs + the SMPL fit in the batch (host tensors): "
                                   "image encoder, SMPL-code attention, sparse-conv pyramid and K1..K5 all inside the "
-                                  "call; random-init producers, so the ray count differs from the synthetic-volume frame"}
+                                  "call; random-init producers, so the ray count differs from the synthetic-volume frame; "
+                                  "stream_* = the same batches through Renderer.render_stream"}
         e2e = {"value": g_rays * args.steps / et, "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(n_px * 3 * 4 + n_px + 32), "ms_per_step": 1e3 * et / args.steps,
                "frames_per_s": args.steps * (world if frames_mode else 1) / et,

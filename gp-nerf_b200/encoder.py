@@ -243,7 +243,7 @@ class ResUNet(nn.Module):
             g["x"].copy_(x, non_blocking=True)
             if g["graph"] is None:
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     g["y"] = self._run(g["x"], w)
                 g["graph"] = graph
             g["graph"].replay()

@@ -423,7 +423,7 @@ class Engine:
             C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
             g = torch.cuda.CUDAGraph()
             l0 = self.launches
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 if with_k0:
                     self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
                     self.upload_products(lv, fm, im)

@@ -271,8 +271,9 @@ class Renderer(nn.Module):
         leg of an end-to-end frame) runs on a copy stream into one of `depth`
         staging sets while batch i renders, and the image comes back through
         pinned buffers, so a steady stream is bound by PCIe or by the kernels,
-        whichever is slower – not by their sum.  Upstream products must come with
-        the batch (``levels``, ``featmaps``) as in the benchmarks."""
+        whichever is slower – not by their sum.  Upstream products come with the
+        batch (``levels`` | ``levels_sparse``, ``featmaps``) or, when missing, are
+        produced on the device by the encoder and the sigma head's K8/K7 mirrors."""
         import collections
         import ctypes as C
         from ._lib import Frame
@@ -306,8 +307,10 @@ class Renderer(nn.Module):
 
         for i, batch in enumerate(batches):
             sparse = "levels_sparse" in batch
-            if ("levels" not in batch and not sparse) or "featmaps" not in batch:
-                raise _lib.GpnerfError("render_stream needs batch['levels'] (or ['levels_sparse']) and batch['featmaps']")
+            produce = "levels" not in batch and not sparse      # pyramid (and encoder) run here, on the device
+            need_fm = "featmaps" not in batch
+            if need_fm and self.encoder is None:
+                raise _lib.GpnerfError("render_stream: no batch['featmaps'] and no encoder")
             src = batch["src_imgs"]
             H, W = int(src.shape[-2]), int(src.shape[-1])
             V = int(src.shape[1])
@@ -319,8 +322,8 @@ class Renderer(nn.Module):
                 im0 = src[0] if src.dim() == 5 else src
                 st = {
                     "copy": torch.cuda.Stream(device),
-                    "stage": [([] if sparse else [mk(t) for t in batch["levels"]], mk(batch["featmaps"]), mk(im0))
-                              for _ in range(depth)],
+                    "stage": [([] if (sparse or produce) else [mk(t) for t in batch["levels"]],
+                               None if need_fm else mk(batch["featmaps"]), mk(im0)) for _ in range(depth)],
                     "sparse": [[] for _ in range(depth)],
                     "copied": [torch.cuda.Event() for _ in range(depth)],
                     "free": [torch.cuda.Event() for _ in range(depth)],
@@ -359,16 +362,34 @@ class Renderer(nn.Module):
                         fb.copy_(f, non_blocking=True)
                         ib.copy_(ix, non_blocking=True)
                         lv_s.append((fb, ib))
-                else:
+                elif not produce:
                     if not lv_d:      # first dense batch of a stream that started with sparse ones
                         lv_d.extend(torch.empty(t.shape, dtype=torch.float32, device=device) for t in batch["levels"])
                     for d, s_ in zip(lv_d, batch["levels"]):
                         d.copy_(s_, non_blocking=True)
-                fm_d.copy_(batch["featmaps"], non_blocking=True)
+                if not need_fm:
+                    if fm_d is None:
+                        fm_d = torch.empty(batch["featmaps"].shape, dtype=torch.float32, device=device)
+                        st["stage"][slot] = (lv_d, fm_d, im_d)
+                    fm_d.copy_(batch["featmaps"], non_blocking=True)
                 im_d.copy_(src[0] if src.dim() == 5 else src, non_blocking=True)
                 st["copied"][slot].record(st["copy"])
             main.wait_event(st["copied"][slot])
-            if sparse:
+            if need_fm or produce:
+                # the producers (f2, f1) on the main stream, fed from the staging set; their results live in
+                # module-owned buffers that the sparse upload below consumes before the next frame overwrites them
+                b2 = {**batch, "src_imgs": im_d.unsqueeze(0)}
+                if not need_fm:
+                    b2["featmaps"] = fm_d
+                fm_d, _lv = self._upstream(b2)
+                if produce:
+                    eng.upload_products_sparse(b2["levels_sparse"], b2["level_dims"], fm_d, im_d,
+                                               n_rows_dev=b2["levels_sparse_rows"])
+                elif sparse:
+                    eng.upload_products_sparse(lv_s, batch["level_dims"], fm_d, im_d)
+                else:
+                    eng.upload_products(lv_d, fm_d, im_d)
+            elif sparse:
                 eng.upload_products_sparse(lv_s, batch["level_dims"], fm_d, im_d)
             else:
                 eng.upload_products(lv_d, fm_d, im_d)              # K0: staging set → gather layouts

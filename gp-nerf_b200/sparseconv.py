@@ -224,7 +224,7 @@ class SparseConvNet(nn.Module):
         pl["uses"] += 1
         if self.use_cuda_graph and pl["graph"] is None and pl["uses"] >= 2 and not torch.cuda.is_current_stream_capturing():
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 pl["outs"] = self._launch(pl, packed, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             pl["graph"] = g
         if pl["graph"] is not None:

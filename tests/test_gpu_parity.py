@@ -495,6 +495,17 @@ def test_renderer_from_images_only(V, H):
     b = r.render(dict(base, featmaps=fm))
     assert a["counts"]["n_rays"] > 100 and a["counts"] == b["counts"]
     assert np.array_equal(a["pred_img"], b["pred_img"]) and float(a["pred_img"].max()) > 0.0
+    # the same through render_stream from host batches: a sweep of target views, producers run per frame on the
+    # device while the next frames upload; every frame equals its blocking render
+    host = {k: v for k, v in scene.items() if k not in ("levels", "featmaps")}
+    views = [synth.retarget(host, 45.0 + 7.0 * i) for i in range(5)]
+    want = [r.render({k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in vb.items()}) for vb in views]
+    got = list(r.render_stream(iter(views)))
+    assert len(got) == 5
+    for g_, w_ in zip(got, want):
+        assert g_["counts"] == w_["counts"] and np.array_equal(g_["pred_img"], w_["pred_img"])
+        assert np.array_equal(g_["mask_at_box"], w_["mask_at_box"])
+    assert not np.array_equal(got[0]["pred_img"], got[4]["pred_img"])
 
 
 def test_early_termination_within_tolerance():
