@@ -559,6 +559,12 @@ def main():
                     n_out[0] += int(out["mask_at_box"].sum() > 0)
             images_stream(8)
             et_is = timed(lambda: images_stream(args.steps), "from_images_stream")
+            if os.environ.get("GPNERF_PROFILE_BLOCKING"):
+                pr = cProfile.Profile()
+                pr.enable()
+                images_stream(args.steps)
+                pr.disable()
+                pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(22)
             e2e_images = {"ms_per_step": 1e3 * et_i / args.steps, "value": rays_i * args.steps / et_i, "unit": "rays/s",
                           "rays": rays_i, "h2d_bytes_per_step": int(h2d_i),
                           "stream_ms_per_step": 1e3 * et_is / args.steps, "stream_value": rays_i * args.steps / et_is,

@@ -324,7 +324,7 @@ class Renderer(nn.Module):
                     "copy": torch.cuda.Stream(device),
                     "stage": [([] if (sparse or produce) else [mk(t) for t in batch["levels"]],
                                None if need_fm else mk(batch["featmaps"]), mk(im0)) for _ in range(depth)],
-                    "sparse": [[] for _ in range(depth)],
+                    "sparse": [[] for _ in range(depth)], "small": {},
                     "copied": [torch.cuda.Event() for _ in range(depth)],
                     "free": [torch.cuda.Event() for _ in range(depth)],
                     "done": [torch.cuda.Event() for _ in range(depth)],
@@ -339,6 +339,8 @@ class Renderer(nn.Module):
             t_start = time.time()
             main = torch.cuda.current_stream(device)
             lv_d, fm_d, im_d = st["stage"][slot]
+            if i >= depth:
+                st["copied"][slot].synchronize()                   # the slot's pinned staging has been read (long ago)
             with torch.cuda.stream(st["copy"]):
                 if i >= depth:
                     st["copy"].wait_event(st["free"][slot])        # K0 of the previous tenant has read the set
@@ -373,12 +375,28 @@ class Renderer(nn.Module):
                         st["stage"][slot] = (lv_d, fm_d, im_d)
                     fm_d.copy_(batch["featmaps"], non_blocking=True)
                 im_d.copy_(src[0] if src.dim() == 5 else src, non_blocking=True)
+                small = {}
+                if produce:
+                    # the SMPL fit goes through pinned staging too: a pageable host→device copy on the main stream
+                    # would first wait for everything queued there, i.e. for the previous frame
+                    for k in ("feature", "coord", "Rh", "Th"):
+                        t = batch[k]
+                        if t.is_cuda:
+                            continue
+                        key = (slot, k)
+                        if key not in st["small"] or st["small"][key][0].shape != t.shape or st["small"][key][0].dtype != t.dtype:
+                            st["small"][key] = (torch.empty(t.shape, dtype=t.dtype).pin_memory(),
+                                                torch.empty(t.shape, dtype=t.dtype, device=device))
+                        pin, dbuf = st["small"][key]
+                        pin.copy_(t)
+                        dbuf.copy_(pin, non_blocking=True)
+                        small[k] = dbuf
                 st["copied"][slot].record(st["copy"])
             main.wait_event(st["copied"][slot])
             if need_fm or produce:
                 # the producers (f2, f1) on the main stream, fed from the staging set; their results live in
                 # module-owned buffers that the sparse upload below consumes before the next frame overwrites them
-                b2 = {**batch, "src_imgs": im_d.unsqueeze(0)}
+                b2 = {**batch, **small, "src_imgs": im_d.unsqueeze(0)}
                 if not need_fm:
                     b2["featmaps"] = fm_d
                 fm_d, _lv = self._upstream(b2)
