@@ -81,7 +81,7 @@ _SIGNATURES = {
     "gpnerf_sc_gather_rows_split": ([_P, _I, _P, _P, _I, _P, _P], C.c_int),
     "gpnerf_attn_smpl_code": ([_P, _P, C.c_longlong, C.c_longlong, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
                               C.c_int),
-    "gpnerf_k9_instance_norm_act": ([_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, C.c_float, _I, _P, _P, _I, _I, _I, _P],
+    "gpnerf_k9_instance_norm_act": ([_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, C.c_float, _I, _P, _I, _P, _I, _I, _I, _P],
                                     C.c_int),
     "gpnerf_k9_resample_pad": ([_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "gpnerf_k0_build_masks3d": ([C.POINTER(_P), C.POINTER(Frame), _P, _P], C.c_int),

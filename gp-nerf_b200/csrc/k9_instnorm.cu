@@ -3,7 +3,8 @@
 // statistics; UNet.py:32,36,120,162) and then ReLU (UNet.py:42,51), "+ identity, ReLU" (UNet.py:50-51) or ELU
 // (UNet.py:123).  In torch that is 2–4 elementwise passes per layer; here two:
 //
-//   in_stats : Σx, Σx² per (image, channel) over H·W – fp32 partials per thread, fp64 atomics; the last block
+//   in_stats : Σx, Σx² per (image, channel) over H·W – fp32 partials per thread, fp64 atomics into a scratch that
+//              is zero on entry and zeroed again by its reader (no memset node per norm); the last block
 //              of an image folds mean, variance, γ, β into one (scale, shift) pair per channel
 //   in_apply : y = act(scale·x + shift [+ residual]),  act ∈ {none, ReLU, ELU}; may run in place; can
 //              write into a reflect-bordered buffer / a channel slice of a concatenation buffer (PadGeom)
@@ -129,6 +130,8 @@ __global__ void __launch_bounds__(256) in_stats(const T* __restrict__ x, int HW,
     const double var = fmax(fma(__ldcg(sums + ((size_t)n * C + c) * 2 + 1), inv_hw, -m * m), 0.0);   // biased, as instance_norm
     const float a = __ldg(gamma + c) * rsqrtf((float)var + eps);
     ab[(size_t)n * C + c] = make_float2(a, __ldg(beta + c) - (float)m * a);
+    sums[((size_t)n * C + c) * 2] = 0.0;               // self-cleaning scratch: the next norm finds zeros again
+    sums[((size_t)n * C + c) * 2 + 1] = 0.0;
   }
   if (threadIdx.x == 0) tickets[n] = 0;
 }
@@ -244,21 +247,19 @@ static dim3 apply_grid(int N, size_t per_img) {
 
 template <typename T>
 static int launch_norm(const void* x, const void* residual, int res_pad, int N, int C, const float* gamma,
-                       const float* beta, float eps, int act, double* sums, PadGeom out, void* y, cudaStream_t st) {
+                       const float* beta, float eps, int act, void* scratch, int scratch_nc, PadGeom out, void* y,
+                       cudaStream_t st) {
   constexpr int VN = Vec<T>::N;
   const int groups = C / VN, HW = out.H * out.W;
   if (C % VN || groups > 256 || 256 % groups || out.Ctot % VN || out.coff % VN) {
     set_error("instance_norm: channel counts must be multiples of the vector width, C/width dividing 256", cudaSuccess);
     return GPNERF_E_UNSUPPORTED;
   }
-  // scratch: double sums[N*C*2] | float2 ab[N*C] | unsigned tickets[N] (tickets return to 0 by themselves)
-  float2* ab = reinterpret_cast<float2*>(sums + (size_t)N * C * 2);
-  unsigned* tickets = reinterpret_cast<unsigned*>(ab + (size_t)N * C);
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double) + (size_t)N * C * sizeof(float2) + N * sizeof(unsigned), st);
-  if (e != cudaSuccess) {
-    set_error("memset instance-norm scratch", e);
-    return GPNERF_E_CUDA;
-  }
+  // scratch (zeroed once by the caller, self-cleaning afterwards – no memset node per norm):
+  //   unsigned tickets[64] | double sums[scratch_nc * 2] | float2 ab[scratch_nc]
+  unsigned* tickets = reinterpret_cast<unsigned*>(scratch);
+  double* sums = reinterpret_cast<double*>(tickets + 64);
+  float2* ab = reinterpret_cast<float2*>(sums + (size_t)scratch_nc * 2);
   // enough blocks to fill the machine, at least 8 pixels per thread row to amortise the atomics
   const int px_step = 256 / groups;
   int chunks = (sm_count() * 4 + N - 1) / N;
@@ -302,16 +303,17 @@ using namespace gpnerf;
 extern "C" {
 
 int gpnerf_k9_instance_norm_act(const void* x, const void* residual, int res_pad, int dtype, int N, int H, int W, int C,
-                                const float* gamma, const float* beta, float eps, int act, double* sums, void* y,
-                                int y_pad, int y_ctot, int y_coff, void* stream) {
-  GPNERF_REQUIRE(x && gamma && beta && sums && y && N > 0 && H > 0 && W > 0 && C > 0 && act >= 0 && act <= 2);
+                                const float* gamma, const float* beta, float eps, int act, void* scratch, int scratch_nc,
+                                void* y, int y_pad, int y_ctot, int y_coff, void* stream) {
+  GPNERF_REQUIRE(x && gamma && beta && scratch && y && N > 0 && N <= 64 && H > 0 && W > 0 && C > 0 && act >= 0 && act <= 2);
+  GPNERF_REQUIRE((long long)N * C <= scratch_nc);
   GPNERF_REQUIRE(dtype >= 0 && dtype <= 2 && (y_pad == 0 || (y_pad == 1 && H >= 2 && W >= 2)) && (res_pad == 0 || res_pad == 1));
   GPNERF_REQUIRE(y_ctot >= y_coff + C && y_coff >= 0);
   cudaStream_t st = (cudaStream_t)stream;
   const PadGeom out{H, W, y_pad, y_ctot, y_coff};
-  if (dtype == 0) return launch_norm<float>(x, residual, res_pad, N, C, gamma, beta, eps, act, sums, out, y, st);
-  if (dtype == 1) return launch_norm<__nv_bfloat16>(x, residual, res_pad, N, C, gamma, beta, eps, act, sums, out, y, st);
-  return launch_norm<__half>(x, residual, res_pad, N, C, gamma, beta, eps, act, sums, out, y, st);
+  if (dtype == 0) return launch_norm<float>(x, residual, res_pad, N, C, gamma, beta, eps, act, scratch, scratch_nc, out, y, st);
+  if (dtype == 1) return launch_norm<__nv_bfloat16>(x, residual, res_pad, N, C, gamma, beta, eps, act, scratch, scratch_nc, out, y, st);
+  return launch_norm<__half>(x, residual, res_pad, N, C, gamma, beta, eps, act, scratch, scratch_nc, out, y, st);
 }
 
 int gpnerf_k9_resample_pad(const void* src, int dtype, int N, int Hs, int Ws, int src_pad, int C, int mode, void* y,

@@ -89,6 +89,7 @@ class ResUNet(nn.Module):
         self.out_conv = nn.Conv2d(out_ch, out_ch, 1, 1)
         self._packed = None
         self._plist = None
+        self._scratch = {}           # per device: zeroed once, self-cleaning (csrc/k9_instnorm.cu)
         self._graphs = {}
 
     def _make_layer(self, planes, blocks, stride):
@@ -145,11 +146,15 @@ class ResUNet(nn.Module):
         n, c, h, wd = x.shape
         if out is None:
             out = self._buf(n, h, wd, c, out_pad, x.device)
-        sums = torch.empty(n * c * 3 + (n + 1) // 2, dtype=torch.float64, device=x.device)     # N·C·24 + N·4 bytes
+        nc_cap = n * 256                                   # widest layer of the trunk
+        sc = self._scratch.get(x.device)
+        if sc is None or sc[1] < max(nc_cap, n * c):
+            nc_cap = max(nc_cap, n * c)
+            sc = self._scratch[x.device] = (torch.zeros(32 + nc_cap * 3, dtype=torch.float64, device=x.device), nc_cap)
         dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())       # noqa: E731
         check(lib.gpnerf_k9_instance_norm_act(dp(x), dp(residual), res_pad, _DTYPES[self.precision][1], n, h, wd, c,
                                               ptr(w[prefix + ".weight"]), ptr(w[prefix + ".bias"]), 1e-5, act,
-                                              ptr(sums), dp(out), out_pad, out.shape[3], coff, self._st(x.device)),
+                                              ptr(sc[0]), sc[1], dp(out), out_pad, out.shape[3], coff, self._st(x.device)),
               "instance_norm_act")
         return out
 

@@ -368,13 +368,16 @@ int gpnerf_attn_smpl_code(const float *code, const float *feats, long long view_
  * (= F.pad(mode="reflect") for the next 3x3 convolution).
  * instance_norm_act: x dense [N][H][W][C]; residual NULL or [N][H+2*res_pad][W+2*res_pad][C];
  *   y = act((x - mean_nc) * rsqrt(var_nc + eps) * gamma_c + beta_c [+ residual]), biased variance over H*W,
- *   act 0 none | 1 ReLU | 2 ELU; sums: scratch of N*C*24 + N*4 bytes (8-byte aligned); y may alias x when y_pad = 0 and y_ctot = C.
+ *   act 0 none | 1 ReLU | 2 ELU; scratch: 256 + scratch_nc*24 bytes (8-byte aligned, scratch_nc >= N*C, N <= 64),
+ *   zeroed ONCE by the caller – the kernels leave its accumulators zeroed again, so consecutive norms on one
+ *   stream share it without a memset in between; y may alias x when y_pad = 0 and y_ctot = C.
  * resample_pad: src [N][Hs+2*src_pad][Ws+2*src_pad][C]; mode 0 copy (H = Hs, W = Ws), mode 1 bilinear
  *   (align_corners = True) to H x W, mode 2 every second pixel (H = ceil(Hs/2), W = ceil(Ws/2)).
  * C, y_ctot, y_coff multiples of 4 (fp32) / 8 (16-bit); for instance_norm_act C/4 resp. C/8 divides 256. */
 int gpnerf_k9_instance_norm_act(const void *x, const void *residual, int res_pad, int dtype, int N, int H,
                                 int W, int C, const float *gamma, const float *beta, float eps, int act,
-                                double *sums, void *y, int y_pad, int y_ctot, int y_coff, void *stream);
+                                void *scratch, int scratch_nc, void *y, int y_pad, int y_ctot, int y_coff,
+                                void *stream);
 int gpnerf_k9_resample_pad(const void *src, int dtype, int N, int Hs, int Ws, int src_pad, int C, int mode,
                            void *y, int H, int W, int y_pad, int y_ctot, int y_coff, void *stream);
 
