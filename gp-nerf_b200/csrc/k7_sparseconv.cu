@@ -26,7 +26,8 @@ namespace cg = cooperative_groups;
 
 namespace gpnerf {
 
-constexpr int32_t kNoRow = 0x7f7f7f7f;      // what cudaMemset(0x7f) leaves behind (rows >= n_in read as "none")
+// index volumes are filled by cudaMemset(0x7f): an untouched voxel reads 0x7f7f7f7f, which is >= any row count and
+// therefore "no site" for sc_neighbours
 
 struct Dims3 {
   int D, H, W;
