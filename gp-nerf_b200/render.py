@@ -489,6 +489,7 @@ class Renderer(nn.Module):
         """BaseRender.Renderer.render: rgb_map [1,R,3], disp/acc/depth [1,R,1],
         alpha (=weights) [1,R,S], z_vals [1,R,S], rgb_in_map [1,R,3V]."""
         device = batch["src_imgs"].device
+        batch = dict(batch)                     # _upstream may add the produced rows: never to the caller's dict
         featmaps, levels = self._upstream(batch)
         H, W = batch["src_imgs"].shape[-2:]
         V = batch["src_imgs"].shape[1]
@@ -496,7 +497,11 @@ class Renderer(nn.Module):
         R = int(rays_o.shape[1])
         eng = self.engine_for(int(H), int(W), int(V), device, max_rays=R)
         self._sync_weights(eng)
-        eng.upload_products(levels, featmaps, batch["src_imgs"])
+        if levels is None:                      # sparse rows (from the batch or from the sigma head's own producers)
+            eng.upload_products_sparse(batch["levels_sparse"], batch["level_dims"], featmaps, batch["src_imgs"],
+                                       n_rows_dev=batch.get("levels_sparse_rows"))
+        else:
+            eng.upload_products(levels, featmaps, batch["src_imgs"])
         neg = self._neg_ray(batch)
         frame = eng.make_frame(batch, neg_ray=neg)
         t_rand = None

@@ -495,6 +495,16 @@ def test_renderer_from_images_only(V, H):
     b = r.render(dict(base, featmaps=fm))
     assert a["counts"]["n_rays"] > 100 and a["counts"] == b["counts"]
     assert np.array_equal(a["pred_img"], b["pred_img"]) and float(a["pred_img"].max()) > 0.0
+    # the dense (validation) path takes the same route when the batch has no levels
+    rays = {k: scene[k][:, :300].to(DEV) for k in ("ray_o", "ray_d", "near", "far")} if "ray_o" in scene else None
+    if rays is None:
+        sc_r = synth.make_scene("zju", H=H, W=H, V=V, seed=13, with_rays=True)
+        rays = {k: sc_r[k][:, :300].to(DEV) for k in ("ray_o", "ray_d", "near", "far")}
+    rd = Renderer(enc, head, is_train=False, n_samples=16, progressive=False, precision=PREC_BF16)
+    d1 = rd.render({**base, **rays})
+    d2 = rd.render({**base, **rays, "featmaps": fm})
+    assert d1["rgb_map"].shape == (1, 300, 3) and bool(torch.isfinite(d1["rgb_map"]).all())
+    assert torch.equal(d1["rgb_map"], d2["rgb_map"]) and float(d1["acc_map"].max()) > 0.0
     # the same through render_stream from host batches: a sweep of target views, producers run per frame on the
     # device while the next frames upload; every frame equals its blocking render
     host = {k: v for k, v in scene.items() if k not in ("levels", "featmaps")}
