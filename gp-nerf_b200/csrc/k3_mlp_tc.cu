@@ -16,6 +16,8 @@
 // This file: weight packing, the stand-alone density head (operator API) and
 // the colour head (operator API from fp32 rows, engine path from the bf16
 // records the fused gather+density kernel of k23_fused_tc.cu leaves behind).
+#include <stdlib.h>
+
 #include "tc_heads.cuh"
 
 namespace gpnerf {
@@ -577,7 +579,8 @@ static int launch_color_tc(const float* rgb_feat, const float* meanvar, const vo
     attr_set = true;
   }
   int tiles = (n_points_max + 127) / 128;
-  int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+  static const int per_sm = getenv("GPNERF_COLOR_CTAS_PER_SM") ? atoi(getenv("GPNERF_COLOR_CTAS_PER_SM")) : 2;   // experiment knob
+  int grid = tiles < per_sm * sm_count() ? tiles : per_sm * sm_count();
   color_mlp_tc<V, FROM_REC><<<grid, 256, ColSmem<V>::BYTES, st>>>(rgb_feat, meanvar,
                                                                   reinterpret_cast<const uint4*>(rec), valid1,
                                                                   image + kColImgOffset, count_ptr, n_points_max,
