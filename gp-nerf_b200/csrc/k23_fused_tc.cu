@@ -26,6 +26,7 @@
 // kernel does not reproduce the reference's rounding sequence – the integer
 // results (which points exist) were fixed upstream by the exact K1/K2 kernels.
 // 256 threads, 2 CTAs/SM: one CTA's gather overlaps the other's MMA/epilogue.
+#include <stdlib.h>
 #include "tc_heads.cuh"
 
 namespace gpnerf {
@@ -432,7 +433,8 @@ static int launch_fused(const FusedArgs& a, const gpnerf_frame_t* f, int n_point
     attr_set = true;
   }
   int tiles = (n_points_max + 127) / 128;
-  int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+  static const int per_sm = getenv("GPNERF_FUSED_CTAS_PER_SM") ? atoi(getenv("GPNERF_FUSED_CTAS_PER_SM")) : 2;   // experiment knob
+  int grid = tiles < per_sm * sm_count() ? tiles : per_sm * sm_count();
   gather_density_tc<V><<<grid, 256, FusedSmem::BYTES, st>>>(a, *f);
   return check_launch("k23_gather_density_tc");
 }
