@@ -146,13 +146,16 @@ class SparseConvNet(nn.Module):
             "coords": [torch.empty(c * 3, **i32) for c in caps],
             "owners": torch.empty(n0, **i32),
             "lin": torch.empty(max(caps[1:]), **i32),
-            "nbr": [torch.empty(27 * max(caps), **i32) for _ in range(2)],      # [0]: SubM table, [1]: strided
+            "nbr": {}, "side": torch.cuda.Stream(dev),
             "x0": torch.empty(n0 * c_in * (2 if tc else 1), dtype=torch.float32, device=dev),
             "y": [], "y_full": {}, "graph": None, "uses": 0,
         }
-        level = 0
+        level, have_subm = 0, False
         for li, (bi, conv, _bn) in enumerate(self._layers()):
             level += conv.stride == 2
+            if conv.stride == 2 or not have_subm:             # one neighbour table per (site list, stride)
+                pl["nbr"][li] = torch.empty(27 * caps[level], **i32)
+            have_subm = conv.stride == 1
             pl["y"].append(torch.empty(caps[level] * conv.c_out * (2 if tc else 1), dtype=torch.float32, device=dev))
             if tc and self._closes_level(bi, conv):
                 pl["y_full"][li] = torch.empty(caps[level] * conv.c_out, dtype=torch.float32, device=dev)
@@ -163,34 +166,57 @@ class SparseConvNet(nn.Module):
         """A level's features are final after the double_conv that follows its stride_conv (blocks 2, 4, 6, 8)."""
         return bi >= 2 and bi % 2 == 0 and conv is self.net[bi][3]
 
-    def _launch(self, pl, packed, st):
+    def _launch(self, pl, packed, main):
+        """One pyramid.  The site lists, index volumes and neighbour tables depend on the voxel coordinates only, so
+        they run on a side stream ahead of the convolutions (which chain through the features on `main`): in the
+        captured graph the two chains are parallel branches, joined table by table."""
         lib = _lib.load()
         dims, caps, counts, coords_l, idx_vol = pl["dims"], pl["caps"], pl["counts"], pl["coords"], pl["idx_vol"]
+        side = pl["side"]
+        st = C.c_void_p(main.cuda_stream)
+        st_s = C.c_void_p(side.cuda_stream)
         n0, cols = pl["coord_in"].shape
         check(lib.gpnerf_sc_index_input(ptr(pl["coord_in"]), cols, n0, *dims[0], ptr(idx_vol[0]), ptr(pl["owners"]),
                                         ptr(coords_l[0]), ptr(counts[0:1]), ptr(pl["ws"]), st), "sc_index_input")
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
         c_in = pl["feat_in"].shape[1]
         tc = self.precision == "tf32x3"
         gather = lib.gpnerf_sc_gather_rows_split if tc else lib.gpnerf_sc_gather_rows
         check(gather(ptr(pl["feat_in"]), c_in, ptr(pl["owners"]), ptr(counts[0:1]), n0, ptr(pl["x0"]), st), "sc_gather_rows")
-        x, level, subm_level = pl["x0"], 0, -1
-        outs = []
+        # ---- geometry (side stream): per layer its neighbour table and the event that marks it ready
+        tables, level, subm = {}, 0, None
         for li, (bi, conv, _bn) in enumerate(self._layers()):
-            w, scale, shift, w_tc = packed[li]
             if conv.stride == 2:
                 check(lib.gpnerf_sc_strided_sites(ptr(coords_l[level]), ptr(counts[level:level + 1]), caps[level],
                                                   *dims[level + 1], ptr(pl["lin"]), ptr(coords_l[level + 1]),
                                                   ptr(idx_vol[level + 1]), ptr(counts[level + 1:level + 2]), ptr(pl["ws"]),
-                                                  st), "sc_strided_sites")
-                out_level, nbr = level + 1, pl["nbr"][1]
-                build = True
+                                                  st_s), "sc_strided_sites")
+                in_level, out_level, subm = level, level + 1, None
             else:
-                out_level, nbr = level, pl["nbr"][0]
-                build, subm_level = subm_level != level, level
-            if build:
+                in_level = out_level = level
+            if conv.stride == 2 or subm is None:
+                nbr = pl["nbr"][li]
                 check(lib.gpnerf_sc_neighbours(ptr(coords_l[out_level]), ptr(counts[out_level:out_level + 1]),
-                                               caps[out_level], conv.stride, ptr(idx_vol[level]), *dims[level],
-                                               ptr(counts[level:level + 1]), ptr(nbr), st), "sc_neighbours")
+                                               caps[out_level], conv.stride, ptr(idx_vol[in_level]), *dims[in_level],
+                                               ptr(counts[in_level:in_level + 1]), ptr(nbr), st_s), "sc_neighbours")
+                ready = torch.cuda.Event()
+                ready.record(side)
+                entry = (nbr, ready, out_level)
+                if conv.stride == 1:
+                    subm = entry
+            else:
+                entry = (subm[0], None, out_level)              # second convolution of a double_conv: same table
+            tables[li] = entry
+            level = out_level
+        # ---- convolutions (main stream)
+        x, outs = pl["x0"], []
+        for li, (bi, conv, _bn) in enumerate(self._layers()):
+            w, scale, shift, w_tc = packed[li]
+            nbr, ready, out_level = tables[li]
+            if ready is not None:
+                main.wait_event(ready)
             y = pl["y"][li]
             y_full = pl["y_full"].get(li)
             if tc:
@@ -200,10 +226,10 @@ class SparseConvNet(nn.Module):
             else:
                 check(lib.gpnerf_sc_conv(ptr(x), conv.c_in, ptr(nbr), ptr(counts[out_level:out_level + 1]), caps[out_level],
                                          ptr(w), ptr(scale), ptr(shift), conv.c_out, ptr(y), st), "sc_conv")
-            x, level = y, out_level
+            x = y
             if self._closes_level(bi, conv):
                 rows = y_full if tc else x
-                outs.append((rows.view(caps[level], conv.c_out), coords_l[level].view(caps[level], 3)))
+                outs.append((rows.view(caps[out_level], conv.c_out), coords_l[out_level].view(caps[out_level], 3)))
         return outs
 
     @torch.no_grad()
@@ -225,10 +251,10 @@ class SparseConvNet(nn.Module):
         if self.use_cuda_graph and pl["graph"] is None and pl["uses"] >= 2 and not torch.cuda.is_current_stream_capturing():
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                pl["outs"] = self._launch(pl, packed, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                pl["outs"] = self._launch(pl, packed, torch.cuda.current_stream(dev))
             pl["graph"] = g
         if pl["graph"] is not None:
             pl["graph"].replay()
         else:
-            pl["outs"] = self._launch(pl, packed, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            pl["outs"] = self._launch(pl, packed, torch.cuda.current_stream(dev))
         return pl["outs"], pl["dims"][1:], [pl["counts"][k:k + 1] for k in range(1, 5)]
