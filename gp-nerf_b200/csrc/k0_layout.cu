@@ -167,38 +167,60 @@ __global__ void __launch_bounds__(256) products_to_channels_last_f16(const __gri
   constexpr int TP = 256;
   __shared__ __align__(16) float tile[32 * TP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (unsigned t = blockIdx.x; t < jobs.n_tiles; t += gridDim.x) {
+  auto job_of = [&](unsigned t) {
     int ji = 0;
 #pragma unroll
     for (int k = 1; k < kMaxJobs; ++k)
       if (k < jobs.n_jobs && t >= jobs.j[k].tile0) ji = k;
-    const LayoutJob& J = jobs.j[ji];
+    return ji;
+  };
+  // a tile's 32 channels × 256 positions as 8 float4 per thread (channel warp + 8i, positions hf·128 + 4·lane …)
+  auto load_tile = [&](unsigned t, float4 (&x)[8]) {
+    const LayoutJob& J = jobs.j[job_of(t)];
     const unsigned lt = t - J.tile0;
     const unsigned b = lt / J.tiles_per_batch;
     const unsigned v0 = (lt - b * J.tiles_per_batch) * TP;
     const float* src = J.src + (size_t)b * 32 * J.n;
     const bool vec_ok = (J.n % 4 == 0);
-    // ---- load phase
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = warp + 8 * i;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const unsigned v = v0 + hf * 128 + 4 * lane;
+        const float* g = src + (size_t)c * J.n + v;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec_ok && v + 3 < J.n) {
+          q = __ldg(reinterpret_cast<const float4*>(g));
+        } else {
+          if (v < J.n) q.x = __ldg(g);
+          if (v + 1 < J.n) q.y = __ldg(g + 1);
+          if (v + 2 < J.n) q.z = __ldg(g + 2);
+          if (v + 3 < J.n) q.w = __ldg(g + 3);
+        }
+        x[i * 2 + hf] = q;
+      }
+    }
+  };
+  float4 x[8];
+  if (blockIdx.x < jobs.n_tiles) load_tile(blockIdx.x, x);
+  for (unsigned t = blockIdx.x; t < jobs.n_tiles; t += gridDim.x) {
+    const LayoutJob& J = jobs.j[job_of(t)];
+    const unsigned lt = t - J.tile0;
+    const unsigned b = lt / J.tiles_per_batch;
+    const unsigned v0 = (lt - b * J.tiles_per_batch) * TP;
+    // ---- registers → shared memory (swizzled), then the next tile's loads go out: they are in flight while this
+    //      tile is summed and stored (the kernel is bound by DRAM latency × bytes in flight, not by bandwidth)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = warp + 8 * i;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const unsigned p = hf * 128 + 4 * lane;
-        const unsigned v = v0 + p;
-        const float* g = src + (size_t)c * J.n + v;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vec_ok && v + 3 < J.n) {
-          x = __ldg(reinterpret_cast<const float4*>(g));
-        } else {
-          if (v < J.n) x.x = __ldg(g);
-          if (v + 1 < J.n) x.y = __ldg(g + 1);
-          if (v + 2 < J.n) x.z = __ldg(g + 2);
-          if (v + 3 < J.n) x.w = __ldg(g + 3);
-        }
-        *reinterpret_cast<float4*>(&tile[c * TP + (p ^ ((c >> 3) << 3))]) = x;
+        *reinterpret_cast<float4*>(&tile[c * TP + (p ^ ((c >> 3) << 3))]) = x[i * 2 + hf];
       }
     }
+    if (t + gridDim.x < jobs.n_tiles) load_tile(t + gridDim.x, x);
     __syncthreads();
     // ---- channel sums (exact: c ascending, one rounding per add)
     if (J.chan_sum != nullptr && v0 + tid < J.n) {
