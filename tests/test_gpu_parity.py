@@ -375,6 +375,28 @@ def test_sparse_conv_net_vs_dense_emulation(in_dim, precision):
     assert dims == [tuple(d) for d in eng.level_dims] == [tuple(t.shape[-3:]) for t in scene2["levels"]]
 
 
+def test_sparse_conv_net_without_any_site():
+    """Edge case of row f1: every coordinate outside the grid – no site on any level, no crash, an empty frame."""
+    from gpnerf_b200._lib import PREC_BF16
+    from gpnerf_b200.sparseconv import SparseConvNet
+    net = SparseConvNet(in_dim=16).eval().to(DEV)
+    coord = torch.full((500, 3), -5, dtype=torch.int32, device=DEV)
+    for _ in range(3):                                       # eager, capture + replay, replay
+        rows, dims, n_dev = net(torch.randn(500, 16, device=DEV), coord, (32, 48, 32))
+    torch.cuda.synchronize()
+    assert [int(n) for n in n_dev] == [0, 0, 0, 0] and len(rows) == 4
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=13)
+    rows, dims, n_dev = net(torch.randn(6890, 16, device=DEV), torch.full((6890, 3), -1, dtype=torch.int32, device=DEV),
+                            [int(v) for v in scene["out_sh"][0]])
+    eng = Engine(64, 64, 16, 3, device=DEV, precision=PREC_BF16)
+    eng.set_weights(synth.make_head_weights(V=3, seed=3))
+    eng.upload_products_sparse(rows, dims, scene["featmaps"].to(DEV), scene["src_imgs"].to(DEV), n_rows_dev=n_dev)
+    eng.render_progressive(eng.make_frame(scene))
+    torch.cuda.synchronize()
+    c = eng.read_counters()
+    assert c["n_rays"] == 0 and c["P1"] == 0 and float(eng.pred_img.abs().max()) == 0.0
+
+
 def test_smpl_code_attention_vs_reference_golden():
     """Row f1 (K8): the attention kernel behind the MultiHeadAttention mirror against the reference
     module's own outputs (tests/golden/attention.npz), through load_state_dict with the reference's keys;
