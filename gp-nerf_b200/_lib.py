@@ -72,6 +72,8 @@ _SIGNATURES = {
                                    C.POINTER(_P), _P, _P], C.c_int),
     "gpnerf_k0_sparse_to_f16": ([C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int32), C.POINTER(_P), _I,
                                  C.POINTER(C.c_int32 * 3), C.POINTER(_P), C.POINTER(_P), _P], C.c_int),
+    "gpnerf_k0_sparse_to_f32": ([C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int32), C.POINTER(_P), _I,
+                                 C.POINTER(C.c_int32 * 3), C.POINTER(_P), C.POINTER(_P), _P], C.c_int),
     "gpnerf_sc_index_input": ([_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_sc_gather_rows": ([_P, _I, _P, _P, _I, _P, _P], C.c_int),
     "gpnerf_sc_strided_sites": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),

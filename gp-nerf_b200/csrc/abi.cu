@@ -175,6 +175,7 @@ int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t 
     row_begin = nullptr;
     row_len = 1;
   }
+  if (n_src != nullptr) n_const = n_items_max;      // a device-side count is clamped to the buffers' capacity
   int64_t n_words = div_up(n_items_max, 32);
   int64_t n_tiles = div_up(n_words, kTileWords);
   int grid = (int)(n_tiles < (int64_t)sm_count() * 8 ? (n_tiles > 0 ? n_tiles : 1) : sm_count() * 8);

@@ -173,8 +173,12 @@ int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t 
                    int64_t n_items_max, int32_t* out_idx, int32_t* out_count, cudaStream_t st,
                    int row_len = 0, int32_t* row_begin = nullptr);
 
+// Live item count of a pass: a device-side counter times `mult`, clamped to the capacity `n_const` the buffers
+// were sized for (n_const > 0), or the constant itself.
 __device__ __forceinline__ long long live_count(const int32_t* n_src, int mult, long long n_const) {
-  return n_src ? (long long)__ldg(n_src) * mult : n_const;
+  if (n_src == nullptr) return n_const;
+  const long long n = (long long)__ldg(n_src) * mult;
+  return (n_const > 0 && n > n_const) ? n_const : n;
 }
 
 }  // namespace gpnerf

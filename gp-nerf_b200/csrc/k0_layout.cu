@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) products_to_channels_last_f16(const __gri
 struct SparseJob {
   const float* feat;
   const int32_t* idx;
-  __half* dst;
+  void* dst;
   float* chan_sum;
   const int32_t* n_dev;   // optional: the live row count sits on the device (n is then the capacity)
   int n, D, H, W;
@@ -285,7 +285,9 @@ struct SparseJobs {
   SparseJob j[GPNERF_N_LEVELS];
   int n_rows, idx_cols;
 };
-__global__ void __launch_bounds__(256) sparse_rows_to_f16(const __grid_constant__ SparseJobs jobs) {
+// F32 = true: the same scatter into the fp32 channel-last volumes (no border) of the exact-arithmetic path.
+template <bool F32>
+__global__ void __launch_bounds__(256) sparse_rows_scatter(const __grid_constant__ SparseJobs jobs) {
   const int lane = threadIdx.x & 31, q = lane & 7, sub = lane >> 3;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int r0 = warp * 4; r0 < jobs.n_rows; r0 += n_warps * 4) {
@@ -315,14 +317,18 @@ __global__ void __launch_bounds__(256) sparse_rows_to_f16(const __grid_constant_
       sum = (qq == 0) ? a : xadd(sum, a);
       sum = xadd(xadd(xadd(sum, b), c), e);
     }
-    if (inside) {
+    if (inside && F32) {
+      const size_t vox = ((size_t)d * J.H + h) * J.W + w;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(J.dst) + vox * 32 + q * 4) = v;
+      if (q == 0) J.chan_sum[vox] = sum;
+    } else if (inside) {
       const size_t vox = ((size_t)(d + 1) * (J.H + 2) + (h + 1)) * (J.W + 2) + (w + 1);
       __half2 lo = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
       __half2 hi = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&lo);
       o.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(J.dst + vox * 32 + q * 4) = o;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(J.dst) + vox * 32 + q * 4) = o;
       if (q == 0) J.chan_sum[((size_t)d * J.H + h) * J.W + w] = sum;
     }
   }
@@ -457,11 +463,13 @@ int gpnerf_k0_products_to_f16(const float* const levels[GPNERF_N_LEVELS], const 
   return check_launch("k0_products_to_f16");
 }
 
-int gpnerf_k0_sparse_to_f16(const float* const feats[GPNERF_N_LEVELS], const int32_t* const indices[GPNERF_N_LEVELS],
+static int sparse_scatter_launch(bool f32, const float* const feats[GPNERF_N_LEVELS], const int32_t* const indices[GPNERF_N_LEVELS],
                             const int32_t n_rows[GPNERF_N_LEVELS], const int32_t* const n_rows_dev[GPNERF_N_LEVELS],
                             int idx_cols, const int32_t level_dims[GPNERF_N_LEVELS][3],
                             void* const levels_out[GPNERF_N_LEVELS], float* const chan_sums[GPNERF_N_LEVELS],
                             void* stream) {
+  const int pad = f32 ? 0 : 1;
+  const size_t voxel_bytes = f32 ? 128 : 64;
   GPNERF_REQUIRE(feats && indices && n_rows && level_dims && levels_out && chan_sums && idx_cols >= 3 && idx_cols <= 4);
   cudaStream_t st = (cudaStream_t)stream;
   SparseJobs jobs;
@@ -470,16 +478,16 @@ int gpnerf_k0_sparse_to_f16(const float* const feats[GPNERF_N_LEVELS], const int
   for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
     const int D = level_dims[l][0], H = level_dims[l][1], W = level_dims[l][2];
     GPNERF_REQUIRE(levels_out[l] && chan_sums[l] && n_rows[l] >= 0 && (n_rows[l] == 0 || (feats[l] && indices[l])));
-    GPNERF_REQUIRE(D > 0 && H > 0 && W > 0 && (long long)(D + 2) * (H + 2) * (W + 2) < (1ll << 31));
+    GPNERF_REQUIRE(D > 0 && H > 0 && W > 0 && (long long)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad) < (1ll << 31));
     // yesterday's active sites go away with the whole volume: 64 B per voxel at HBM speed (≈10 µs for all levels)
-    cudaError_t e = cudaMemsetAsync(levels_out[l], 0, (size_t)(D + 2) * (H + 2) * (W + 2) * 64, st);
+    cudaError_t e = cudaMemsetAsync(levels_out[l], 0, (size_t)(D + 2 * pad) * (H + 2 * pad) * (W + 2 * pad) * voxel_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(chan_sums[l], 0, (size_t)D * H * W * sizeof(float), st);
     if (e != cudaSuccess) {
       set_error("memset sparse level", e);
       return GPNERF_E_CUDA;
     }
     SparseJob& J = jobs.j[l];
-    J.feat = feats[l]; J.idx = indices[l]; J.dst = reinterpret_cast<__half*>(levels_out[l]); J.chan_sum = chan_sums[l];
+    J.feat = feats[l]; J.idx = indices[l]; J.dst = levels_out[l]; J.chan_sum = chan_sums[l];
     J.n_dev = n_rows_dev ? n_rows_dev[l] : nullptr;
     J.n = n_rows[l]; J.D = D; J.H = H; J.W = W; J.row0 = row;
     row += (n_rows[l] + 3) & ~3;          // a warp's 4 rows never straddle two levels
@@ -489,9 +497,31 @@ int gpnerf_k0_sparse_to_f16(const float* const feats[GPNERF_N_LEVELS], const int
   if (row == 0) return GPNERF_OK;
   const long long blocks = ((long long)row * 8 + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
-  sparse_rows_to_f16<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(jobs);
-  return check_launch("k0_sparse_to_f16");
+  if (f32)
+    sparse_rows_scatter<true><<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(jobs);
+  else
+    sparse_rows_scatter<false><<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(jobs);
+  return check_launch("k0_sparse_scatter");
 }
+
+int gpnerf_k0_sparse_to_f16(const float* const feats[GPNERF_N_LEVELS], const int32_t* const indices[GPNERF_N_LEVELS],
+                            const int32_t n_rows[GPNERF_N_LEVELS], const int32_t* const n_rows_dev[GPNERF_N_LEVELS],
+                            int idx_cols, const int32_t level_dims[GPNERF_N_LEVELS][3],
+                            void* const levels_out[GPNERF_N_LEVELS], float* const chan_sums[GPNERF_N_LEVELS],
+                            void* stream) {
+  return sparse_scatter_launch(false, feats, indices, n_rows, n_rows_dev, idx_cols, level_dims, levels_out, chan_sums,
+                               stream);
+}
+
+int gpnerf_k0_sparse_to_f32(const float* const feats[GPNERF_N_LEVELS], const int32_t* const indices[GPNERF_N_LEVELS],
+                            const int32_t n_rows[GPNERF_N_LEVELS], const int32_t* const n_rows_dev[GPNERF_N_LEVELS],
+                            int idx_cols, const int32_t level_dims[GPNERF_N_LEVELS][3],
+                            void* const levels_out[GPNERF_N_LEVELS], float* const chan_sums[GPNERF_N_LEVELS],
+                            void* stream) {
+  return sparse_scatter_launch(true, feats, indices, n_rows, n_rows_dev, idx_cols, level_dims, levels_out, chan_sums,
+                               stream);
+}
+
 
 int gpnerf_k0_build_masks3d(const float* const chan_sum[GPNERF_N_LEVELS],
                             const gpnerf_frame_t* f, float* masks3d, void* stream) {

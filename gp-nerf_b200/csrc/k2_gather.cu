@@ -26,10 +26,10 @@ __global__ void __launch_bounds__(256) occupancy_flags(const float* __restrict__
                                                        const __grid_constant__ gpnerf_frame_t fparam,
                                                        const int32_t* __restrict__ counters,
                                                        uint32_t* __restrict__ words,
-                                                       float* __restrict__ z_vals) {
+                                                       float* __restrict__ z_vals, int n_rays_max) {
   GPNERF_LOAD_FRAME(fparam)
   const int S = f.n_samples;
-  const long long n = (long long)__ldg(counters + GPNERF_CNT_RAYS) * S;
+  const long long n = (long long)min(__ldg(counters + GPNERF_CNT_RAYS), n_rays_max) * S;   // never past the buffers
   const long long n_pad = (n + 31) & ~31ll;
   const float o[3] = {__ldg(rays_o), __ldg(rays_o + 1), __ldg(rays_o + 2)};
   const int D = f.level_dims[0][0], H = f.level_dims[0][1], W = f.level_dims[0][2];
@@ -386,7 +386,7 @@ int gpnerf_k2_occupancy_compact(const float* masks3d, const float* rays_o, const
   long long blocks = (n_max + 255) / 256;
   int grid = (int)(blocks < (long long)persistent_grid(8) ? blocks : persistent_grid(8));
   occupancy_flags<<<grid, 256, 0, st>>>(masks3d, rays_o, rays_d, near, far, t_vals, t_rand, *f,
-                                        counters, ws.words, z_vals);
+                                        counters, ws.words, z_vals, n_rays_max);
   return compact_launch(ws, counters + GPNERF_CNT_RAYS, f->n_samples, 0, n_max, valid,
                         counters + GPNERF_CNT_P1, st, f->n_samples, ray_pt_begin);
 }

@@ -91,7 +91,7 @@ class Engine:
 
     def __init__(self, H, W, n_samples, n_views, device="cuda:0", precision=PREC_FP32,
                  rank=0, world=1, tile_px=64, max_rays=None, t_min=0.0, voxel_size=(0.005,) * 3,
-                 mask_threshold=0.1):
+                 mask_threshold=0.1, fused_gather=True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -104,8 +104,10 @@ class Engine:
         self.mask_threshold = float(mask_threshold)
         npx = self.H * self.W
         if max_rays is None:
-            n_tiles = math.ceil(npx / self.tile_px)
-            max_rays = min(npx, math.ceil(n_tiles / self.world) * self.tile_px)
+            # capacity = the most pixels any rank can own under the diagonal tile deal (it is not perfectly
+            # balanced: 512², tile 64, world 3 gives one rank 1,536 of the 4,096 tiles), not ceil(tiles / world)
+            from .shard import max_tiles_per_rank
+            max_rays = min(npx, max_tiles_per_rank(npx, self.W, self.tile_px, self.world) * self.tile_px)
         self.max_rays = int(max_rays)
         self.max_pts = self.max_rays * self.S
         if self.max_pts >= 2 ** 31:
@@ -127,7 +129,10 @@ class Engine:
         self.t_vals = torch.linspace(0.0, 1.0, steps=self.S, device="cpu").to(dev)  # BaseRender.py:37
         self.valid = buf(self.max_pts, i32)
         self.z_vals = buf(self.max_pts)
-        self.bf16 = self.precision == PREC_BF16
+        # fused_gather=False with PREC_BF16: fp32 gathers (reference rounding) feeding the tcgen05 heads – the
+        # error-budget configuration (tests/test_gpu_parity.py: which share of the bf16 path's image error comes
+        # from the 16-bit storage + HFMA2 interpolation of the fused kernel, which from the bf16 MLPs)
+        self.bf16 = self.precision == PREC_BF16 and bool(fused_gather)
         if self.bf16:
             # tensor-core path: gathered features stay on chip; one bf16 record per point for the colour head
             if not 1 <= self.V <= 4:
@@ -268,10 +273,9 @@ class Engine:
         """The pyramid's levels as the sparse-conv network holds them before
         `.dense()` (SparseConvNet.py:110): per level `(features [N,32] fp32,
         indices [N,3|4] int32 with (d,h,w) last)`, `level_dims` 4 × (D,H,W).
-        Tensor-core path only: the active rows are scattered straight into the
-        bordered fp16 volumes (no dense fp32 tensor, no K0 transposition)."""
-        if not self.bf16:
-            raise _lib.GpnerfError("sparse level upload feeds the tensor-core path (precision = PREC_BF16)")
+        The active rows are scattered straight into the gather layouts – the
+        bordered fp16 volumes of the tensor-core path or the fp32 channel-last
+        volumes of the exact path (no dense NCDHW tensor, no K0 transposition)."""
         dev, st, L = self.device, self._stream(), self.lib
         dims = [tuple(int(v) for v in d) for d in level_dims]
         if len(levels_sparse) != 4 or len(dims) != 4:
@@ -283,10 +287,14 @@ class Engine:
         fm = featmaps.to(dev, non_blocking=True).contiguous()
         im = src_imgs.to(dev, non_blocking=True)
         im = (im[0] if im.dim() == 5 else im).contiguous()
+        pad = int(self.bf16)
         if self.level_dims != dims:
             self.level_dims = dims
-            self.levels_cl = [torch.zeros((d + 2) * (h + 2) * (w + 2) * 32, dtype=torch.float16, device=dev)
-                              for d, h, w in dims]
+            if self.bf16:
+                self.levels_cl = [torch.zeros((d + 2) * (h + 2) * (w + 2) * 32, dtype=torch.float16, device=dev)
+                                  for d, h, w in dims]
+            else:
+                self.levels_cl = [torch.zeros(d * h * w * 32, dtype=torch.float32, device=dev) for d, h, w in dims]
             self.chan_sums = [torch.empty(d * h * w, dtype=torch.float32, device=dev) for d, h, w in dims]
             self.masks3d = torch.empty(dims[0][0] * dims[0][1] * dims[0][2], dtype=torch.float32, device=dev)
         dims_c = ((C.c_int32 * 3) * 4)(*[(C.c_int32 * 3)(*d) for d in dims])
@@ -294,20 +302,25 @@ class Engine:
         # n_rows_dev: 4 device int32 scalars with the live row counts (the arrays are then capacities:
         # what sparseconv.SparseConvNet hands over without a host sync)
         nrd = None if n_rows_dev is None else ptr_array([t.view(1) for t in n_rows_dev])
-        self._run("k0_sparse_to_f16", L.gpnerf_k0_sparse_to_f16, ptr_array(feats), ptr_array(idxs), n_rows, nrd, cols, dims_c,
-                  ptr_array(self.levels_cl), ptr_array(self.chan_sums), st)
+        if self.bf16:
+            self._run("k0_sparse_to_f16", L.gpnerf_k0_sparse_to_f16, ptr_array(feats), ptr_array(idxs), n_rows, nrd, cols,
+                      dims_c, ptr_array(self.levels_cl), ptr_array(self.chan_sums), st)
+        else:
+            self._run("k0_sparse_to_f16", L.gpnerf_k0_sparse_to_f32, ptr_array(feats), ptr_array(idxs), n_rows, nrd, cols,
+                      dims_c, ptr_array(self.levels_cl), ptr_array(self.chan_sums), st)
         V, Cc, fh, fw = fm.shape
         assert V == self.V and Cc == 32
-        n_fm = V * (fh + 2) * (fw + 2) * 32
-        if self.featmaps_cl is None or self.featmaps_cl.numel() != n_fm:
-            self.featmaps_cl = torch.zeros(n_fm, dtype=torch.float16, device=dev)
-        self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw, 2, 1,
-                  ptr(self.featmaps_cl), st)
+        n_fm = V * (fh + 2 * pad) * (fw + 2 * pad) * 32
+        fm_dtype = torch.float16 if self.bf16 else torch.float32
+        if self.featmaps_cl is None or self.featmaps_cl.numel() != n_fm or self.featmaps_cl.dtype != fm_dtype:
+            self.featmaps_cl = torch.zeros(n_fm, dtype=fm_dtype, device=dev)
+        self._run("k0_featmaps_to_channels_last", L.gpnerf_k0_featmaps_to_channels_last, ptr(fm), V, fh, fw,
+                  2 if self.bf16 else 0, pad, ptr(self.featmaps_cl), st)
         _, _, ih, iw = im.shape
-        n_im = V * (ih + 2) * (iw + 2) * 4
+        n_im = V * (ih + 2 * pad) * (iw + 2 * pad) * 4
         if self.images_rgbx is None or self.images_rgbx.numel() != n_im:
             self.images_rgbx = torch.zeros(n_im, dtype=torch.float32, device=dev)
-        self._run("k0_images_to_rgbx", L.gpnerf_k0_images_to_rgbx, ptr(im), V, ih, iw, 1, 1, ptr(self.images_rgbx), st)
+        self._run("k0_images_to_rgbx", L.gpnerf_k0_images_to_rgbx, ptr(im), V, ih, iw, 1, pad, ptr(self.images_rgbx), st)
         self.src_hw, self.feat_hw = (ih, iw), (fh, fw)
         self._keep_inputs = (feats, idxs, fm, im)
 

@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from ._lib import PREC_FP32
+from ._lib import PREC_BF16, PREC_FP32
 from .engine import Engine
 
 
@@ -485,9 +485,77 @@ class Renderer(nn.Module):
             pass
         return ret
 
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def render_dense_train(self, batch):
+        """BaseRender.Renderer.render under autograd (what BaseTrainer._forward calls, BaseTrainer.py:99-131): the
+        same outputs as `render_dense`, connected to the module's parameters.  The hot path (sampling, gathers,
+        both heads, raw2outputs; BaseRender.py:110-157) runs forward and backward in the K6 kernels
+        (train.render_dense_autograd) with this module's head parameters as differentiable leaves; the upstream
+        producers run in their training form (trainmode.py: batch-statistics BatchNorm, torch autograd ops on the
+        same parameters), so gradients reach the encoder, the SMPL codes, the attention and the pyramid too."""
+        from . import train, trainmode
+        device = batch["src_imgs"].device
+        src_imgs = batch["src_imgs"]
+        H, W = (int(v) for v in src_imgs.shape[-2:])
+        V = int(src_imgs.shape[1])
+        if "featmaps" in batch:
+            featmaps = batch["featmaps"].to(device)
+        elif hasattr(self.encoder, "_run"):                       # this package's mirror: its training form
+            featmaps = trainmode.encoder_forward(self.encoder, src_imgs.squeeze(0))
+        else:                                                     # the reference's own torch module
+            featmaps = self.encoder(src_imgs.squeeze(0))
+        if "levels" in batch:
+            levels = [t.to(device) for t in batch["levels"]]
+        else:
+            sh = self.nerfhead.sigmahead
+            cams = self._pack_cameras(batch, src_imgs.shape[-2:], device)
+            out_sh = [int(v) for v in torch.as_tensor(batch["out_sh"]).reshape(-1, 3).max(0)[0].tolist()]
+            xyz = batch["feature"][..., :3].to(device).float()
+            Rm, Th = batch["Rh"].to(device).float(), batch["Th"].to(device).float()
+            smpl_xyz = torch.bmm(xyz, Rm.transpose(1, 2)) + Th
+            feats = trainmode.smpl_features(smpl_xyz, cams, featmaps, self._neg_ray(batch)).flatten(0, 1)
+            code = sh.c(torch.arange(sh.c.num_embeddings, device=device))                   # trainhead.py:48
+            fused = trainmode.attention_forward(sh.xyzc_attn, code.unsqueeze(1), feats).squeeze(1)
+            coord = batch["coord"].reshape(-1, batch["coord"].shape[-1]).to(device)
+            rows, dims = trainmode.pyramid_forward(sh.xyzc_net, fused, coord, out_sh)
+            levels = [trainmode.rows_to_dense(r, c, d) for (r, c), d in zip(rows, dims)]
+        rays_o, rays_d = batch["ray_o"], batch["ray_d"]
+        R = int(rays_o.shape[1])
+        eng = getattr(self, "_train_engine", None)
+        key = (H, W, V, str(device), R)
+        if eng is None or eng._key != key:
+            eng = Engine(H, W, self.n_samples, V, device=device, precision=PREC_FP32, max_rays=R, t_min=self.t_min,
+                         voxel_size=tuple(float(v) for v in self.voxel_size))
+            eng._key = key
+            self._train_engine = eng
+        eng.level_dims = [tuple(int(v) for v in t.shape[-3:]) for t in levels]
+        eng.src_hw, eng.feat_hw = (H, W), tuple(int(v) for v in featmaps.shape[-2:])
+        neg = self._neg_ray(batch)
+        frame = eng.make_frame({k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in batch.items()
+                                if k in _HOST_KEYS}, neg_ray=neg)
+        eng.level_dims = None                                    # upload_products (inside the Function) allocates
+        t_rand = torch.rand((1, R, self.n_samples)) if self.is_train else None            # BaseRender.py:40-47
+        params = {k: p for k, p in self.nerfhead.named_parameters()
+                  if k.startswith("rgbhead.") or k.startswith("sigmahead.out_geometry_fc")}
+        rays = tuple(batch[k][0].to(device) for k in ("ray_o", "ray_d", "near", "far"))
+        out = train.render_dense_autograd(eng, frame, rays, levels, featmaps, src_imgs.to(device), params, t_rand=t_rand,
+                                          neg_ray=neg, precision=getattr(self, "train_precision", train.PREC_TRAIN_TF32))
+        keys = ("rgb_map", "disp_map", "acc_map", "depth_map", "alpha", "z_vals", "rgb_in_map")
+        return {k: out[k].view(1, R, -1) for k in keys}
+
     def render_dense(self, batch):
         """BaseRender.Renderer.render: rgb_map [1,R,3], disp/acc/depth [1,R,1],
-        alpha (=weights) [1,R,S], z_vals [1,R,S], rgb_in_map [1,R,3V]."""
+        alpha (=weights) [1,R,S], z_vals [1,R,S], rgb_in_map [1,R,3V].  With gradients
+        enabled and trainable parameters the differentiable route is taken
+        (`render_dense_train`); otherwise the forward-only inference kernels."""
+        if self._wants_grad():
+            return self.render_dense_train(batch)
+        with torch.no_grad():
+            return self._render_dense_infer(batch)
+
+    def _render_dense_infer(self, batch):
         device = batch["src_imgs"].device
         batch = dict(batch)                     # _upstream may add the produced rows: never to the caller's dict
         featmaps, levels = self._upstream(batch)
@@ -534,7 +602,14 @@ def build_render(cfg, progressive=False):
     is_train = nerfhead.training or (encoder is not None and encoder.training)
     chunk = cfg.dataset.train.chunk if is_train else cfg.dataset.test.chunk
     mesh_th = 1.0 / cfg.test.mesh_th if cfg.head.rgb.use_rgbhead is False else -1
+    # arithmetic of the inference kernels: `cfg.head.precision` ("fp32" | "bf16", or 0 | 1) when the config names
+    # one, else the tensor-core path (bf16 MLPs, north_star).  Training (gradients enabled) always runs the K6 path.
+    prec = getattr(cfg.head, "precision", None)
+    if prec is None:
+        prec = PREC_BF16
+    elif isinstance(prec, str):
+        prec = {"fp32": PREC_FP32, "bf16": PREC_BF16}[prec.lower()]
     return Renderer(encoder=encoder, nerfhead=nerfhead, is_train=False if progressive else is_train,
                     neg_ray_train=neg_ray_train, neg_ray_val=neg_ray_val, n_rays=cfg.train.n_rays,
                     n_samples=cfg.train.n_samples, voxel_size=cfg.dataset.voxel_size, chunk=chunk,
-                    mesh_th=mesh_th, progressive=progressive)
+                    mesh_th=mesh_th, progressive=progressive, precision=int(prec))

@@ -28,6 +28,16 @@ def owner_of_tile(t, tile_px: int, width: int, world: int):
     return (t + (t * tile_px) // width) % world
 
 
+def max_tiles_per_rank(n_px: int, width: int, tile_px: int, world: int) -> int:
+    """Largest number of tiles any rank owns under the diagonal deal (host-side, pure Python ints)."""
+    if world <= 1:
+        return n_tiles(n_px, tile_px)
+    counts = [0] * world
+    for t in range(n_tiles(n_px, tile_px)):
+        counts[owner_of_tile(t, tile_px, width, world)] += 1
+    return max(counts)
+
+
 def owner_of_pixel(p, tile_px: int, width: int, world: int):
     return owner_of_tile(p // tile_px, tile_px, width, world)
 

@@ -256,6 +256,18 @@ def sparsify_levels(levels):
     return out, dims
 
 
+def flip_cameras(scene):
+    """The same scene in the camera convention the reference's `neg_ray` switch exists for (THuman,
+    BaseRender.py:165-168, 319-323; demo_render.py:236-237): every camera looks down its -z axis, i.e. visible
+    points have negative depth and sit at negative ray parameters.  Built by negating the third row of every
+    pose [R|t] (x_cam' = diag(1,1,-1) x_cam); intrinsics unchanged."""
+    out = dict(scene)
+    flip = torch.tensor([1.0, 1.0, -1.0]).view(3, 1)
+    out["src_poses"] = scene["src_poses"] * flip
+    out["target_pose"] = scene["target_pose"] * flip
+    return out
+
+
 def retarget(scene, angle_deg):
     """The same scene seen from another novel view on the camera ring (a sweep:
     only target_pose changes; the volume, the source views and K stay)."""

@@ -165,6 +165,16 @@ int gpnerf_k0_sparse_to_f16(const float *const feats[GPNERF_N_LEVELS],
                             const int32_t level_dims[GPNERF_N_LEVELS][3],
                             void *const levels_out[GPNERF_N_LEVELS],
                             float *const chan_sums[GPNERF_N_LEVELS], void *stream);
+/* The same scatter into the fp32 channel-last volumes of the exact-arithmetic path
+ * (float[D][H][W][32], no border): lets `render.file B200Render` run in fp32 from the
+ * pyramid's rows (what a dataset batch leads to) without a dense NCDHW tensor. */
+int gpnerf_k0_sparse_to_f32(const float *const feats[GPNERF_N_LEVELS],
+                            const int32_t *const indices[GPNERF_N_LEVELS],
+                            const int32_t n_rows[GPNERF_N_LEVELS],
+                            const int32_t *const n_rows_dev[GPNERF_N_LEVELS], int idx_cols,
+                            const int32_t level_dims[GPNERF_N_LEVELS][3],
+                            void *const levels_out[GPNERF_N_LEVELS],
+                            float *const chan_sums[GPNERF_N_LEVELS], void *stream);
 /* masks3d on the level-1 grid = Σ_levels nearest-upsampled channel sums
  * (SparseConvNet.py:137-139). */
 int gpnerf_k0_build_masks3d(const float *const chan_sum[GPNERF_N_LEVELS],

@@ -497,6 +497,17 @@ def psnr(a, b):
     return 10.0 * math.log10(1.0 / max(mse, 1e-20))
 
 
+def psnr_masked(a, b, mask_at_box):
+    """PSNR the way the reference's evaluator forms it for a rendered frame
+    (libs/evaluators/if_nerf.py:49-57: `rgb_pred = output['pred_img'][mask_at_box]`,
+    then mse over those pixels only): the ≈87 % background pixels, which are
+    exactly 0 in every render, do not dilute the error."""
+    m = torch.as_tensor(mask_at_box).reshape(-1).bool()
+    a2, b2 = a.reshape(-1, 3)[m].double(), b.reshape(-1, 3)[m].double()
+    mse = float(((a2 - b2) ** 2).mean()) if a2.numel() else 0.0
+    return 10.0 * math.log10(1.0 / max(mse, 1e-20))
+
+
 # --------------------------------------------------------------------------
 # Row f3 (SURVEY §8f): the dataset path's rays – numpy, as the CPU loader computes them
 # --------------------------------------------------------------------------

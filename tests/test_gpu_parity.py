@@ -17,6 +17,11 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
 TOL = 1e-3      # north_star: RGB/alpha within 1e-3 absolute in fp32
+# tensor-core (bf16) path, image figures over the mask_at_box pixels only (libs/evaluators/if_nerf.py:49-57):
+# worst pixel and PSNR against the fp32 oracle; the north_star bar itself (PSNR delta < 0.05 dB) is asserted
+# beside them in assert_bf16_frame
+BF16_MAX_ABS = 0.05
+BF16_PSNR_MASK_MIN = 52.0      # measured 56.6–58.4 dB on the four cases of tools/gpu_error_budget.py (profiles/r02_error_budget.json)
 
 
 def gold(name):
@@ -84,7 +89,8 @@ def test_ragged_sample_counts_tile_sizes_and_view_counts(S, tile_px, V, precisio
         assert c["P2"] == o["P2"] and torch.equal(eng.valid1[: c["P2"]].cpu().long(), o["valid1"])
         assert float((img - o["pred_img"]).abs().max()) < TOL
     else:
-        assert float((img - o["pred_img"]).abs().max()) < 0.05 and orc.psnr(img, o["pred_img"]) > 40.0
+        st = stages.masked_image_stats(img, o["pred_img"], o["mask_at_box"])
+        assert st["max_abs"] < BF16_MAX_ABS and st["psnr_mask"] > BF16_PSNR_MASK_MIN, st
 
 
 @pytest.mark.parametrize("tag", ["mini", "mini_s64"])
@@ -660,10 +666,8 @@ def test_dense_render_vs_oracle(jitter):
 
 
 # ------------------------------------------------- full size (BASELINE config)
-def test_full_size_512_vs_oracle_and_properties():
-    scene = synth.make_scene("zju", H=512, W=512, V=3, seed=42)
-    w = synth.make_head_weights(V=3, seed=42)
-    o = orc.render_progressive(scene, w, S=64, chunk=131072, keep=True)
+def test_full_size_512_vs_oracle_and_properties(full_size_oracle):
+    scene, w, o = full_size_oracle
     rep, eng, _ = stages.compare_progressive(scene, w, 64, oracle_out=o)
     assert_progressive_report(rep)
     c = eng.read_counters()
@@ -675,13 +679,28 @@ def test_full_size_512_vs_oracle_and_properties():
 
 
 # ------------------------------------------------ bf16 tensor-core (tcgen05) heads
-def _psnr_delta_vs_pseudo_gt(img_test, img_ref):
-    """north_star: PSNR delta < 0.05 dB with bf16 MLPs.  Random-init weights have
-    no ground truth, so one is synthesised: the fp32 render plus noise that puts
-    the fp32 render at ~30 dB; the bf16 render must score within 0.05 dB of it."""
-    g = torch.Generator().manual_seed(0)
-    gt = img_ref + torch.randn(img_ref.shape, generator=g, dtype=img_ref.dtype) * 10 ** (-30 / 20)
-    return abs(orc.psnr(img_test, gt) - orc.psnr(img_ref, gt))
+def assert_bf16_frame(eng, o, H, S):
+    """The bars of the tensor-core path against the oracle (north_star: sample indices, masks and compaction
+    order bit-exact – they do not depend on the head precision; PSNR delta < 0.05 dB with bf16 MLPs).  Every
+    image figure is taken over the mask_at_box pixels only, as the reference's evaluator does
+    (libs/evaluators/if_nerf.py:49-57)."""
+    c = eng.read_counters()
+    assert c["n_rays"] == o["n_rays"] and c["P1"] == o["P1"]
+    assert torch.equal(eng.ray_pix[: c["n_rays"]].cpu().long(), o["ray_pix"].long())
+    assert torch.equal(eng.valid[: c["P1"]].cpu().long(), o["valid"])
+    assert torch.equal(eng.hit_mask.cpu().bool(), o["mask_at_box"])
+    # the density-sign survivor set may differ only where σ is within bf16 noise of 0
+    diff = np.setxor1d(eng.valid1[: c["P2"]].cpu().numpy(), o["valid1"].numpy())
+    assert len(diff) <= 0.02 * max(1, o["P2"])
+    if len(diff):
+        assert float(o["sigma"][torch.from_numpy(diff).long()].abs().max()) < 0.05
+    img = eng.pred_img.cpu().view(H, -1, 3).double()
+    st = stages.masked_image_stats(img, o["pred_img"], o["mask_at_box"])
+    st["psnr_delta"] = stages.psnr_delta_vs_pseudo_gt(img, o["pred_img"], o["mask_at_box"])
+    assert st["max_abs"] < BF16_MAX_ABS, st
+    assert st["psnr_mask"] > BF16_PSNR_MASK_MIN, st
+    assert st["psnr_delta"] < 0.05, st
+    return st
 
 
 def test_tc_heads_vs_oracle_ops(fn):
@@ -705,19 +724,74 @@ def test_progressive_bf16_psnr(H, S, seed):
     w = synth.make_head_weights(V=3, seed=seed + 100, random_bias=True)
     o = orc.render_progressive(scene, w, S=S, keep=True)
     eng, _ = stages.run_engine_progressive(scene, w, S, precision=PREC_BF16)
-    c = eng.read_counters()
-    # geometry-driven integer results do not depend on the head precision
-    assert c["n_rays"] == o["n_rays"] and c["P1"] == o["P1"]
-    assert torch.equal(eng.valid[: c["P1"]].cpu().long(), o["valid"])
-    # the density-sign survivor set may differ only where σ is within bf16 noise of 0
-    diff = np.setxor1d(eng.valid1[: c["P2"]].cpu().numpy(), o["valid1"].numpy())
-    assert len(diff) <= 0.02 * max(1, o["P2"])
-    if len(diff):
-        assert float(o["sigma"][torch.from_numpy(diff).long()].abs().max()) < 0.05
-    img = eng.pred_img.cpu().view(H, H, 3).double()
-    assert float((img - o["pred_img"]).abs().max()) < 0.05
-    assert _psnr_delta_vs_pseudo_gt(img, o["pred_img"]) < 0.05
-    assert orc.psnr(img, o["pred_img"]) > 45.0
+    assert_bf16_frame(eng, o, H, S)
+
+
+@pytest.fixture(scope="module")
+def full_size_oracle():
+    """BASELINE configs[1] (the benchmarked frame): 512², V=3, S=64, scene and weight seed 42 – rendered once by
+    the CPU oracle for the fp32 and the bf16 full-size tests."""
+    scene = synth.make_scene("zju", H=512, W=512, V=3, seed=42)
+    w = synth.make_head_weights(V=3, seed=42)
+    return scene, w, orc.render_progressive(scene, w, S=64, chunk=131072, keep=True)
+
+
+def test_full_size_512_bf16_vs_oracle(full_size_oracle):
+    """The path bench.py times (bf16 storage + tcgen05 heads, fused gather) against the oracle AT the
+    benchmarked configuration."""
+    from gpnerf_b200._lib import PREC_BF16
+    scene, w, o = full_size_oracle
+    eng, _ = stages.run_engine_progressive(scene, w, 64, precision=PREC_BF16)
+    st = assert_bf16_frame(eng, o, 512, 64)
+    print("bf16 @ configs[1] vs oracle (mask_at_box pixels):", st)
+
+
+def test_bf16_error_budget_gather_vs_heads():
+    """Which share of the tensor-core path's error is the 16-bit storage + HFMA2 interpolation of the fused
+    gather, which the bf16 MLPs: the same frame with fp32 gathers feeding the same tcgen05 heads
+    (`fused_gather=False`).  The fused gather may not cost more than the heads do."""
+    from gpnerf_b200._lib import PREC_BF16
+    scene = synth.make_scene("zju", H=192, W=192, V=3, seed=29)
+    w = synth.make_head_weights(V=3, seed=129, random_bias=True)
+    o = orc.render_progressive(scene, w, S=64, keep=True)
+    rms = {}
+    for fused in (False, True):
+        eng, _ = stages.run_engine_progressive(scene, w, 64, precision=PREC_BF16, fused_gather=fused)
+        img = eng.pred_img.cpu().view(192, 192, 3).double()
+        rms[fused] = stages.masked_image_stats(img, o["pred_img"], o["mask_at_box"])["rms"]
+    print("masked rms image error: fp32 gather + bf16 heads", rms[False], "; fused 16-bit gather + bf16 heads", rms[True])
+    assert rms[True] < 2.0 * rms[False] + 1e-4, rms
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_neg_ray_whole_path(precision):
+    """`neg_ray=True` end to end (THuman's camera convention, BASELINE configs[2]; BaseRender.py:165-168,
+    319-323, demo_render.py:236-237): cameras looking down -z, the second box depth negated before min/max,
+    the in-front test reversed in the projector."""
+    scene = synth.flip_cameras(synth.make_scene("zju", H=160, W=160, V=3, seed=31))
+    w = synth.make_head_weights(V=3, seed=131, random_bias=True)
+    o = orc.render_progressive(scene, w, S=64, keep=True, neg_ray=True)
+    assert o["n_rays"] > 1000 and o["P1"] > 3000 and o["P2"] > 300 and bool((o["near"] < 0).all())
+    if precision == 0:
+        rep, _, _ = stages.compare_progressive(scene, w, 64, oracle_out=o, neg_ray=True)
+        assert_progressive_report(rep)
+    else:
+        eng, _ = stages.run_engine_progressive(scene, w, 64, precision=precision, neg_ray=True)
+        assert_bf16_frame(eng, o, 160, 64)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_four_views_128_samples(precision):
+    """BASELINE configs[4]'s shape (V=4, S=128) at a size the oracle finishes in seconds."""
+    scene = synth.make_scene("zju", H=128, W=128, V=4, seed=7)
+    w = synth.make_head_weights(V=4, seed=107, random_bias=True)
+    o = orc.render_progressive(scene, w, S=128, keep=True)
+    if precision == 0:
+        rep, _, _ = stages.compare_progressive(scene, w, 128, oracle_out=o)
+        assert_progressive_report(rep)
+    else:
+        eng, _ = stages.run_engine_progressive(scene, w, 128, precision=precision)
+        assert_bf16_frame(eng, o, 128, 128)
 
 
 def test_dense_render_bf16_vs_oracle():
