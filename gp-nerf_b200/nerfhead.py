@@ -137,10 +137,19 @@ class NeRFHead(nn.Module):
         return torch.cat([rgb_out, sigma_out], dim=-1), rgb_in
 
 
+def _precision_of(cfg):
+    """`cfg.head.precision`: "fp32" | "bf16" or 0 | 1 (absent in the reference's config tree: fp32 for the
+    module-level calls, which mirror the reference's fp32 arithmetic)."""
+    p = getattr(cfg.head, "precision", PREC_FP32)
+    if isinstance(p, str):
+        return {"fp32": 0, "bf16": 1}[p.lower()]
+    return int(p)
+
+
 def build_head(cfg):
     """trainhead.py:166-177"""
     return NeRFHead(in_feat_ch=cfg.encoder.out_ch, use_rgbhead=cfg.head.rgb.use_rgbhead,
                     n_smpl=cfg.head.sigma.n_smpl, code_dim=cfg.head.sigma.code_dim,
                     attn_n_heads=cfg.head.sigma.n_heads, spconv_n_layers=cfg.head.sigma.n_layers,
                     spconv_out_dim=cfg.head.sigma.outdims, n_views=getattr(cfg, "src_view_num", 3),
-                    precision=int(getattr(cfg.head, "precision", PREC_FP32)))
+                    precision=_precision_of(cfg))

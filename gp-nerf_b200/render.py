@@ -530,12 +530,14 @@ class Renderer(nn.Module):
                          voxel_size=tuple(float(v) for v in self.voxel_size))
             eng._key = key
             self._train_engine = eng
-        eng.level_dims = [tuple(int(v) for v in t.shape[-3:]) for t in levels]
-        eng.src_hw, eng.feat_hw = (H, W), tuple(int(v) for v in featmaps.shape[-2:])
+        from .engine import frame_from_batch
         neg = self._neg_ray(batch)
-        frame = eng.make_frame({k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in batch.items()
-                                if k in _HOST_KEYS}, neg_ray=neg)
-        eng.level_dims = None                                    # upload_products (inside the Function) allocates
+        host = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in batch.items() if k in _HOST_KEYS}
+        frame = frame_from_batch(host, H=H, W=W, n_views=V, n_samples=self.n_samples,
+                                 level_dims=[tuple(int(v) for v in t.shape[-3:]) for t in levels], src_hw=(H, W),
+                                 feat_hw=tuple(int(v) for v in featmaps.shape[-2:]),
+                                 voxel_size=tuple(float(v) for v in self.voxel_size), neg_ray=neg)
+        frame.self_dev = eng.frame_dev.data_ptr()
         t_rand = torch.rand((1, R, self.n_samples)) if self.is_train else None            # BaseRender.py:40-47
         params = {k: p for k, p in self.nerfhead.named_parameters()
                   if k.startswith("rgbhead.") or k.startswith("sigmahead.out_geometry_fc")}

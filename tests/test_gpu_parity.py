@@ -983,3 +983,143 @@ def test_training_step_forward_backward_vs_torch_autograd(jitter, precision):
         close(lv_g[i].grad.cpu(), lv_c[i].grad, f"level{i}")
     bad = [f"{n}: {e:.2e}" for n, e, ok in report if not ok]
     assert not bad, f"gradient error / scale above {grad_rel}: {bad}; all: {[(n, round(e, 5)) for n, e, _ in report]}"
+
+
+# ------------------------------------------------ the plugin under the reference trainer's sequence
+def _fake_cfg(train_name="zju_mocap_train", test_name="zju_mocap_test", precision=None, code_dim=16):
+    from types import SimpleNamespace as NS
+    head = NS(file="no_such_head_file", sigma=NS(code_dim=code_dim, n_heads=4, n_layers=4, n_smpl=6890, outdims=[32, 32, 32, 32]),
+              rgb=NS(use_rgbhead=True))
+    if precision is not None:
+        head.precision = precision
+    return NS(encoder=NS(file="no_such_encoder_file", name="resnet34", out_ch=32), head=head,
+              dataset=NS(train=NS(name=train_name, chunk=400), test=NS(name=test_name, chunk=2000),
+                         voxel_size=[0.005, 0.005, 0.005]),
+              train=NS(n_rays=1024, n_samples=16), test=NS(mesh_th=50.0), src_view_num=3)
+
+
+def test_build_render_default_paths_render_a_dataset_batch():
+    """`build_render(cfg)` with the reference's stock config tree (no precision key) and a batch
+    as the dataset produces it (no `levels`, no `featmaps`): the progressive and the dense inference renders both
+    run – encoder, SMPL attention, pyramid, sparse upload, K1…K5 – in the default (tensor-core) arithmetic and in
+    `cfg.head.precision = "fp32"`, which takes the fp32 sparse upload."""
+    from gpnerf_b200.render import build_render
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=13, with_rays=True)
+    base = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in scene.items() if k not in ("levels", "featmaps")}
+    imgs = {}
+    for prec in (None, "fp32"):
+        torch.manual_seed(3)
+        r = build_render(_fake_cfg(precision=prec), progressive=True).to(DEV).eval()
+        for k, v in r.nerfhead.state_dict().items():        # random-init BatchNorm scales let the pyramid die out
+            if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+                v.fill_(3.0)
+        out = r.render(dict(base))
+        assert out["counts"]["n_rays"] > 100 and out["counts"]["P1"] > 0 and float(out["pred_img"].max()) > 0.0
+        imgs[prec] = out
+        rd = build_render(_fake_cfg(precision=prec), progressive=False).to(DEV).eval()
+        rd.load_state_dict(r.state_dict())
+        rays = {k: base[k][:, :256] for k in ("ray_o", "ray_d", "near", "far")}
+        with torch.no_grad():
+            d = rd.render({**base, **rays})
+        assert d["rgb_map"].shape == (1, 256, 3) and bool(torch.isfinite(d["rgb_map"]).all())
+    assert imgs[None]["counts"]["n_rays"] == imgs["fp32"]["counts"]["n_rays"]
+    assert np.array_equal(imgs[None]["mask_at_box"], imgs["fp32"]["mask_at_box"])
+    st = stages.masked_image_stats(torch.from_numpy(imgs[None]["pred_img"]), torch.from_numpy(imgs["fp32"]["pred_img"]),
+                                   imgs["fp32"]["mask_at_box"])
+    assert st["max_abs"] < BF16_MAX_ABS, st
+
+
+def test_plugin_trains_under_the_reference_trainer_sequence():
+    """`render.file B200Render` under tools/train.py: the exact sequence of BaseTrainer.train/_forward
+    (BaseTrainer.py:99-131) – render(batch) → criterion (BaseNeRFCriterion.py:30-50: MSE over mask_at_box rays) →
+    zero_grad → backward → AdamW step – on a dataset-shaped batch (no `levels`, no `featmaps`), training mode.
+    Every parameter group of the module must receive a gradient: heads (hot path, K6 kernels), encoder, SMPL
+    codes, attention, sparse-conv pyramid (producers in training form); the head gradients must agree with
+    torch autograd through the CPU oracle fed the same upstream products; the step must lower the loss."""
+    from gpnerf_b200 import train, trainmode
+    from gpnerf_b200.render import build_render
+    torch.manual_seed(5)
+    scene = synth.make_scene("zju", H=64, W=64, V=3, seed=19, with_rays=True)
+    R = 512
+    sel = torch.arange(R) * (scene["ray_o"].shape[1] // R)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in scene.items() if k not in ("levels", "featmaps")}
+    for k in ("ray_o", "ray_d", "near", "far", "rgb"):
+        batch[k] = batch[k][:, sel.to(DEV)]
+    gen = torch.Generator().manual_seed(1)
+    batch["rgb"] = torch.rand(1, R, 3, generator=gen).to(DEV)
+    batch["mask_at_box"] = torch.ones(1, R, dtype=torch.bool, device=DEV)
+    r = build_render(_fake_cfg(), progressive=False).to(DEV)
+    r.train()
+    r.train_precision = train.PREC_TRAIN_FP32                # parity run: fp32 GEMMs (TF32 is the default)
+    assert r.is_train
+    for k, v in r.nerfhead.state_dict().items():
+        if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+            v.fill_(3.0)
+    opt = torch.optim.AdamW(r.parameters(), lr=1e-3)
+
+    def criterion(ret, data):                                 # BaseNeRFCriterion.py:36-50, rgb term
+        mask = data["mask_at_box"]
+        return torch.mean((ret["rgb_map"][mask] - data["rgb"][mask]) ** 2)
+
+    torch.manual_seed(11)                                     # the jitter (BaseRender.py:40-47) is drawn on the CPU generator
+    ret = r.render(batch)
+    assert ret["rgb_map"].requires_grad and ret["rgb_map"].shape == (1, R, 3)
+    loss0 = criterion(ret, batch)
+    opt.zero_grad()
+    loss0.backward(retain_graph=True)
+    missing = [k for k, p in r.named_parameters() if p.grad is None or not bool(torch.isfinite(p.grad).all())]
+    # conv biases in front of an InstanceNorm and `layer_norm` (sum=False) never reach the output: the reference's
+    # own graph leaves them without a gradient as well
+    missing = [k for k in missing if "layer_norm" not in k]
+    assert not missing, missing
+    groups = {"rgbhead.": 0.0, "sigmahead.out_geometry_fc": 0.0, "sigmahead.c.": 0.0, "sigmahead.xyzc_attn.w_": 0.0,
+              "sigmahead.xyzc_net": 0.0, "encoder.layer2": 0.0, "encoder.conv1": 0.0}
+    for k, p in r.named_parameters():
+        for g in groups:
+            if g in k:
+                groups[g] += float(p.grad.abs().sum())
+    assert all(v > 0.0 for v in groups.values()), groups
+
+    # head gradients against torch autograd through the oracle on the same products and the same jitter
+    with torch.no_grad():
+        torch.manual_seed(11)
+        fm = trainmode.encoder_forward(r.encoder, batch["src_imgs"].squeeze(0))
+        sh = r.nerfhead.sigmahead
+        cams = r._pack_cameras(batch, batch["src_imgs"].shape[-2:], DEV)
+        xyz = batch["feature"][..., :3].float()
+        smpl_xyz = torch.bmm(xyz, batch["Rh"].float().transpose(1, 2)) + batch["Th"].float()
+        feats = trainmode.smpl_features(smpl_xyz, cams, fm).flatten(0, 1)
+        code = sh.c(torch.arange(6890, device=DEV))
+        fused = trainmode.attention_forward(sh.xyzc_attn, code.unsqueeze(1), feats).squeeze(1)
+        mom = [m.momentum for m in sh.xyzc_net.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+        for m in sh.xyzc_net.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.momentum = 0.0                              # the comparison pass must not move the running statistics
+        rows, dims = trainmode.pyramid_forward(sh.xyzc_net, fused, batch["coord"].reshape(-1, 3),
+                                               [int(v) for v in scene["out_sh"][0]])
+        for m, mo in zip([m for m in sh.xyzc_net.modules() if isinstance(m, torch.nn.BatchNorm1d)], mom):
+            m.momentum = mo
+        levels = [trainmode.rows_to_dense(a, c, d).cpu() for (a, c), d in zip(rows, dims)]
+        t_rand = torch.rand((1, R, 16))[0]
+    w_c = {k: p.detach().cpu().clone().requires_grad_(True) for k, p in r.nerfhead.named_parameters()
+           if k.startswith("rgbhead.") or k.startswith("sigmahead.out_geometry_fc")}
+    rays = tuple(batch[k][0].cpu() for k in ("ray_o", "ray_d", "near", "far"))
+    outs_c = _oracle_dense_differentiable(scene, w_c, rays, 16, t_rand, levels, fm.cpu())
+    loss_c = torch.mean((outs_c[0] - batch["rgb"][0].cpu()) ** 2)
+    loss_c.backward()
+    assert abs(float(loss_c) - float(loss0)) < 1e-4 * max(1.0, float(loss_c)), (float(loss_c), float(loss0))
+    for k, p in r.nerfhead.named_parameters():
+        if k in w_c:
+            want, got = w_c[k].grad, p.grad.cpu()
+            scale = max(float(want.abs().max()), 1e-7)
+            assert float((got - want).abs().max()) <= 5e-3 * scale + 1e-8, (k, float((got - want).abs().max()), scale)
+    opt.step()
+    losses = [float(loss0)]
+    for _ in range(5):                                        # a few more trainer iterations
+        torch.manual_seed(11)
+        loss = criterion(r.render(batch), batch)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
