@@ -27,23 +27,10 @@
 // results (which points exist) were fixed upstream by the exact K1/K2 kernels.
 // 256 threads, 2 CTAs/SM: one CTA's gather overlaps the other's MMA/epilogue.
 #include <stdlib.h>
+#include <string.h>
 #include "tc_heads.cuh"
 
 namespace gpnerf {
-
-struct FusedArgs {
-  const __half* lv[GPNERF_N_LEVELS];
-  const __half* feat;            // [V][fh+2][fw+2][32]
-  const float4* rgbx;            // [V][H+2][W+2] (r,g,b,·) in [0,1]
-  const int32_t* valid;
-  const float *rays_o, *rays_d, *z_vals;
-  const int32_t* counters;
-  const uint8_t* image;          // packed weights
-  float* sigma;
-  uint4* rec;
-  float* alpha;              // optional: K4's α = 1 − exp(−σ) …
-  uint32_t* alpha_words;     // … and its survivor flags (one ballot word per 32 points), written here
-};
 
 struct FusedSmem {
   static constexpr uint32_t IMG = 0;
@@ -420,6 +407,8 @@ int gpnerf_color_mlp_tc_any(const float* rgb_feat, const float* meanvar, const v
                             const gpnerf_head_weights_t* w, int n_views, int n_points_max,
                             const int32_t* count_ptr, float* rgb, cudaStream_t st);
 
+int launch_fused_ws(const gpnerf::FusedArgs& a, const gpnerf_frame_t* f, int n_points_max, cudaStream_t st);
+
 template <int V>
 static int launch_fused(const FusedArgs& a, const gpnerf_frame_t* f, int n_points_max, cudaStream_t st) {
   static bool attr_set = false;
@@ -467,6 +456,10 @@ int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], 
   a.alpha = alpha;
   a.alpha_words = alpha ? carve_workspace(k4_workspace, n_points_max).words : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  // GPNERF_FUSED_IMPL=monolithic selects the round-1 kernel (one 256-thread CTA does plan → gather → 4 MMA rounds
+  // serially, two CTAs per SM); the default is the warp-specialised kernel of k23_fused_ws.cu
+  static const bool monolithic = getenv("GPNERF_FUSED_IMPL") && !strcmp(getenv("GPNERF_FUSED_IMPL"), "monolithic");
+  if (!monolithic) return launch_fused_ws(a, f, n_points_max, st);
   switch (f->n_views) {
     case 1: return launch_fused<1>(a, f, n_points_max, st);
     case 2: return launch_fused<2>(a, f, n_points_max, st);

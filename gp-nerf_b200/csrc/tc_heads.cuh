@@ -76,6 +76,20 @@ constexpr uint32_t kImageBytes = kColImgOffset + ((ColImg<4>::BYTES + 127) / 128
 // point: the G tile's 9 non-zero chunks followed by 5 non-zero chunks per view.
 __host__ __device__ constexpr int rec_chunks(int V) { return 9 + 5 * V; }
 
+struct FusedArgs {
+  const __half* lv[GPNERF_N_LEVELS];
+  const __half* feat;            // [V][fh+2][fw+2][32]
+  const float4* rgbx;            // [V][H+2][W+2] (r,g,b,·) in [0,1]
+  const int32_t* valid;
+  const float *rays_o, *rays_d, *z_vals;
+  const int32_t* counters;
+  const uint8_t* image;          // packed weights
+  float* sigma;
+  uint4* rec;
+  float* alpha;              // optional: K4's α = 1 − exp(−σ) …
+  uint32_t* alpha_words;     // … and its survivor flags (one ballot word per 32 points), written here
+};
+
 // ---------------------------------------------------------------------------
 // epilogue helpers
 // ---------------------------------------------------------------------------

@@ -529,8 +529,9 @@ def test_renderer_from_images_only(V, H):
         sc_r = synth.make_scene("zju", H=H, W=H, V=V, seed=13, with_rays=True)
         rays = {k: sc_r[k][:, :300].to(DEV) for k in ("ray_o", "ray_d", "near", "far")}
     rd = Renderer(enc, head, is_train=False, n_samples=16, progressive=False, precision=PREC_BF16)
-    d1 = rd.render({**base, **rays})
-    d2 = rd.render({**base, **rays, "featmaps": fm})
+    with torch.no_grad():                 # validation runs under no_grad (BaseTrainer.py:209-217): the inference kernels
+        d1 = rd.render({**base, **rays})
+        d2 = rd.render({**base, **rays, "featmaps": fm})
     assert d1["rgb_map"].shape == (1, 300, 3) and bool(torch.isfinite(d1["rgb_map"]).all())
     assert torch.equal(d1["rgb_map"], d2["rgb_map"]) and float(d1["acc_map"].max()) > 0.0
     # the same through render_stream from host batches: a sweep of target views, producers run per frame on the
