@@ -105,6 +105,8 @@ _SIGNATURES = {
     "gpnerf_k23_gather_density_tc": ([C.POINTER(_P), _P, _P, _P, _P, _P, _P, C.POINTER(Frame), C.POINTER(HeadWeights),
                                       _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "gpnerf_k3_color_mlp_records": ([_P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _P], C.c_int),
+    "gpnerf_k3_color_gather_tc": ([_P, _P, _P, _P, _P, _P, _P, C.POINTER(Frame), C.POINTER(HeadWeights), _I, _P, _I, _P, _P,
+                                   _P], C.c_int),
     "gpnerf_k2_gather_volume_bwd": ([C.POINTER(_P), _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),
     "gpnerf_k2_project_gather_bwd": ([_P, _I, _P, _P, _P, _P, _P, C.POINTER(Frame), _I, _P, _P, _P], C.c_int),
     "gpnerf_k6_linear": ([_P, _I, _I, C.c_float, _P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I,

@@ -438,7 +438,7 @@ int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], 
                                  const gpnerf_head_weights_t* w, int n_points_max, const int32_t* counters,
                                  float* sigma, void* records, float* alpha, void* k4_workspace, void* stream) {
   GPNERF_REQUIRE(levels_f16 && featmaps_f16 && images_rgbx && valid && rays_o && rays_d && z_vals && f && w &&
-                 counters && sigma && records && n_points_max > 0);
+                 counters && sigma && n_points_max > 0);        // records may be NULL (no colour records)
   GPNERF_REQUIRE(w->tc_image != nullptr && f->n_samples > 0 && f->src_w > 1 && f->src_h > 1);
   FusedArgs a;
   for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
@@ -460,6 +460,7 @@ int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], 
   // serially, two CTAs per SM); the default is the warp-specialised kernel of k23_fused_ws.cu
   static const bool monolithic = getenv("GPNERF_FUSED_IMPL") && !strcmp(getenv("GPNERF_FUSED_IMPL"), "monolithic");
   if (!monolithic) return launch_fused_ws(a, f, n_points_max, st);
+  GPNERF_REQUIRE(records != nullptr);       // the round-1 kernel always writes its colour records
   switch (f->n_views) {
     case 1: return launch_fused<1>(a, f, n_points_max, st);
     case 2: return launch_fused<2>(a, f, n_points_max, st);

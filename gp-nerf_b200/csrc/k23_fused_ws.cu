@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
       uint32_t e2m_ph[kChains] = {0, 0};
       bool done[kChains] = {false, false};
       uint32_t idle = 0;
+      int next_start = 0;          // tiles start strictly in order (a parity wait tells only consecutive phases apart)
       while (!(done[0] && done[1])) {
         bool progressed = false;
 #pragma unroll
@@ -429,6 +430,7 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
           const uint32_t acc = tmem + c * 128, act = tmem + c * 128 + 64;
           if (step[c] == 0) {
             // chain free (the final epilogue of its previous tile has read the accumulator) and stage full
+            if (i != next_start) continue;
             if (i >= kChains && !mbar_test(e2m + c, e2m_ph[c])) continue;
             if (!mbar_test(full + s, (i / kStages) & 1)) continue;
             if (i >= kChains) e2m_ph[c] ^= 1u;
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
             umma_bf16(acc, ones_d, bdesc(DenImg::Wg, 8, 144), id64, 1u);
             umma_commit(m2e + c);
             step[c] = 1;
+            ++next_start;
           } else {
             if (!mbar_test(e2m + c, e2m_ph[c])) continue;
             e2m_ph[c] ^= 1u;

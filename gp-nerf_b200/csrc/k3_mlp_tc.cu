@@ -78,9 +78,17 @@ __device__ void pack_color(uint8_t* c, const RawW& w) {
   pack_operand(c + I::Wv1, w.vis_w[1], w.vis_b[1], 32, 32, 48, 1.0f, 0, 0, IdBiasMap{32});
   pack_operand(c + I::Wr0, w.rgb_w[0], w.rgb_b[0], 32, 32 * V, 32 * V + 16, 1.0f, 0, 0, IdBiasMap{32 * V});
   pack_operand(c + I::Wr1, w.rgb_w[1], w.rgb_b[1], 16, 32, 48, 1.0f, 0, 0, IdBiasMap{32});
+  for (int v = 0; v < V; ++v)
+    pack_operand(c + I::Wb0r + v * op_bytes(64, 16), w.base_w[0], nullptr, 64, 105, 16, kLog2e, 0, 0,
+                 [v](int j) { return (j >= 3 * v && j < 3 * v + 3) ? 70 + (j - 3 * v) : kZero; });
+  pack_operand(c + I::Wr0x, w.rgb_w[0], nullptr, 32, 32 * V, 32 * V, (float)V, 0, 0, [](int j) { return j; });
   float* f = reinterpret_cast<float*>(c + I::F32);
   pack_floats(f + I::rw2, w.rgb_w[2], 48, 1.0f / kLog2e);
   pack_floats(f + I::rb2, w.rgb_b[2], 3, 1.0f);
+  pack_floats(f + I::rb0c, w.rgb_b[0], 32, kLog2e);
+  pack_floats(f + I::w1f, w.rgb_w[1], 512, 1.0f / kLog2e);
+  pack_floats(f + I::b1f, w.rgb_b[1], 16, 1.0f);
+  pack_floats(f + I::rw2u, w.rgb_w[2], 48, 1.0f);
 }
 
 __global__ void pack_weights_kernel(RawW w, int V, uint8_t* image) {

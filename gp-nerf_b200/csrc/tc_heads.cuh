@@ -64,8 +64,17 @@ struct ColImg {   // colour head; base_fc.0 split into its [mean|var] (G order) 
   static constexpr uint32_t Wv1 = Wv0 + op_bytes(32, 48);           // [32 x 48]
   static constexpr uint32_t Wr0 = Wv1 + op_bytes(32, 48);           // [32 x (32V+16)]
   static constexpr uint32_t Wr1 = Wr0 + op_bytes(32, 32 * V + 16);  // [16 x 48]
-  static constexpr uint32_t F32 = Wr1 + op_bytes(16, 48);
-  static constexpr int rw2 = 0, rb2 = 48, NF = 52;                  // rgb_fc.4 weights / c, bias
+  // warp-specialised colour head (k3_color_ws.cu): the per-view RGB inputs of base_fc.0 sit in ONE shared
+  // [128 x 16] operand (column 3v + c = channel c of view v), so every view has its own [64 x 16] weight block that
+  // picks its three columns; and rgb_fc.0's residual input x_v is fed as x_v / V (the vis_fc input that is in TMEM
+  // anyway) against weights scaled by V
+  static constexpr uint32_t Wb0r = Wr1 + op_bytes(16, 48);          // V x [64 x 16]  c·W[:, 70 + c] in columns 3v + c
+  static constexpr uint32_t Wr0x = Wb0r + V * op_bytes(64, 16);     // [32 x 32V]    V · rgb_fc.0.weight
+  static constexpr uint32_t F32 = Wr0x + op_bytes(32, 32 * V);
+  static constexpr int rw2 = 0, rb2 = 48;                           // rgb_fc.4 weights / c, bias
+  // CUDA-core tail of the warp-specialised colour head: c·rgb_fc.0.bias (added in the epilogue), rgb_fc.2 as fp32
+  // weights / c [16][32] + bias, rgb_fc.4 weights unscaled [3][16]
+  static constexpr int rb0c = 52, w1f = 84, b1f = 596, rw2u = 612, NF = 660;
   static constexpr uint32_t BYTES = F32 + NF * 4;
 };
 

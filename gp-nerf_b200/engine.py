@@ -34,7 +34,7 @@ KERNELS_PER_CALL = {
     "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 5, "k2_occupancy_compact": 4,
     "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,   # 3 when fused
     "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1, "peer_wait": 1,
-    "k23_gather_density_tc": 1, "k3_color_mlp_records": 1,
+    "k23_gather_density_tc": 1, "k3_color_mlp_records": 1, "k3_color_gather_tc": 1,
 }
 
 
@@ -137,8 +137,13 @@ class Engine:
             # tensor-core path: gathered features stay on chip; one bf16 record per point for the colour head
             if not 1 <= self.V <= 4:
                 raise _lib.GpnerfError("the bf16 tensor-core path supports 1..4 source views")
+            # GPNERF_COLOR_IMPL=records: round 1's colour head, fed from one 16(9+5V)-byte record per P1 point that
+            # the fused kernel writes; default: the colour head gathers its own inputs for the survivors only
+            import os
+            self.use_records = os.environ.get("GPNERF_COLOR_IMPL", "") == "records"
             self.rec_bytes = int(self.lib.gpnerf_k23_record_bytes(self.V))
-            self.rec = torch.empty(self.max_pts * self.rec_bytes, dtype=torch.uint8, device=dev)
+            self.rec = torch.empty(self.max_pts * self.rec_bytes, dtype=torch.uint8, device=dev) if self.use_records else None
+            self.rgb_in = None       # per-view RGB taps [P1][V][3], dense path only (allocated on first use)
             self.vol_feat = self.rgb_feat = self.mask = self.meanvar = None
         else:
             self.rec = None
@@ -479,7 +484,7 @@ class Engine:
         # tensor-core path: α and the survivor flags were written by the fused kernel's epilogue
         self._run("k4_compact_alpha", L.gpnerf_k4_compact_alpha, None if self.bf16 else ptr(self.sigma), self.max_pts,
                   ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
-        self._color(ptr(self.valid1), self.max_pts, CNT_P2)
+        self._color(ptr(self.valid1), self.max_pts, CNT_P2, frame)
         ex = self.exchange
         self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.alpha), ptr(self.rgb), ptr(self.ray_pix),
                   ptr(self.tile_ray_begin), ptr(self.ray_pt_begin), fr, C.c_float(self.t_min), ptr(self.rgb_map),
@@ -492,9 +497,13 @@ class Engine:
             self._toc(ev)
             self.launches += 1
 
-    def _color(self, valid1_ptr, n_pts_max, slot):
+    def _color(self, valid1_ptr, n_pts_max, slot, frame=None, rgb_in=None):
         L, st = self.lib, self._stream()
-        if self.bf16:
+        if self.bf16 and not self.use_records:
+            self._run("k3_color_gather_tc", L.gpnerf_k3_color_gather_tc, ptr(self.featmaps_cl), ptr(self.images_rgbx),
+                      ptr(self.valid), valid1_ptr, ptr(self.rays_o), ptr(self.rays_d), ptr(self.z_vals), C.byref(frame),
+                      C.byref(self._weights), n_pts_max, ptr(self.counters), slot, ptr(self.rgb), ptr(rgb_in), st)
+        elif self.bf16:
             self._run("k3_color_mlp_records", L.gpnerf_k3_color_mlp_records, ptr(self.rec), valid1_ptr,
                       C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), slot, ptr(self.rgb), st)
         else:
@@ -514,7 +523,7 @@ class Engine:
             self._run("k23_gather_density_tc", L.gpnerf_k23_gather_density_tc, ptr_array(self.levels_cl),
                       ptr(self.featmaps_cl), ptr(self.images_rgbx), ptr(self.valid), ptr(self.rays_o),
                       ptr(self.rays_d), ptr(self.z_vals), fr, C.byref(self._weights), n_pts_max,
-                      ptr(self.counters), ptr(self.sigma), ptr(self.rec),
+                      ptr(self.counters), ptr(self.sigma), ptr(self.rec) if self.use_records else None,
                       ptr(self.alpha) if fuse_alpha else None, ptr(self.workspace) if fuse_alpha else None, st)
             return
         self._run("k2_gather_volume", L.gpnerf_k2_gather_volume, ptr_array(self.levels_cl), 0, ptr(self.valid),
@@ -549,9 +558,16 @@ class Engine:
         self._heads(frame, masks3d=None, t_rand=tr, n_rays_max=R)
         n = R * self.S
         # colour head on every point (valid1 = NULL → all rows in order)
-        self._color(None, n, CNT_P1)
+        if self.bf16 and not self.use_records:
+            if self.rgb_in is None or self.rgb_in.numel() < n * self.V * 3:
+                self.rgb_in = torch.empty(self.max_pts * self.V * 3, dtype=torch.float32, device=dev)
+            self._color(None, n, CNT_P1, frame, self.rgb_in)
+        else:
+            self._color(None, n, CNT_P1, frame)
         raw = torch.cat([self.rgb[: n * 3].view(n, 3), self.sigma[:n].view(n, 1)], 1).contiguous()
-        if self.bf16:     # per-view RGB sits in chunk 4 of each view block of the record
+        if self.bf16 and not self.use_records:
+            rgb_in = self.rgb_in[: n * self.V * 3].view(n, self.V, 3)
+        elif self.bf16:     # per-view RGB sits in chunk 4 of each view block of the record
             rc = self.rec_bytes // 2
             recs = self.rec[: n * self.rec_bytes].view(torch.bfloat16).view(n, rc)
             cols = [(9 + 5 * v + 4) * 8 + c for v in range(self.V) for c in range(3)]

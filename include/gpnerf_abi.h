@@ -319,6 +319,21 @@ int gpnerf_k3_color_mlp_records(const void *records, const int32_t *valid1,
                                 int n_points_max, const int32_t *counters, int counter_slot,
                                 float *rgb, void *stream);
 
+/* Colour trunk (trainhead.py:85-100, 118-145) for the points listed in valid1 (indices into
+ * the P1 arrays; NULL = all P1 points in order), gathering its own inputs: the V-view
+ * pixel-aligned features and RGB taps (BaseRender.py:283-363) and their mean / variance
+ * (trainhead.py:20-24) from the fp16 channel-last zero-bordered feature maps and the padded
+ * RGBx images of K0 – no per-point record is written upstream of the progressive step.
+ * rgb float[P1][3] is written at the P1 index of every processed point; rgb_in (may be
+ * NULL) float[P1][V][3] receives the per-view RGB taps (BaseRender's rgb_in_map input).
+ * Count = counters[counter_slot].  n_views in 1..4. */
+int gpnerf_k3_color_gather_tc(const void *featmaps_f16, const float *images_rgbx, const int32_t *valid,
+                              const int32_t *valid1, const float *rays_o, const float *rays_d,
+                              const float *z_vals, const gpnerf_frame_t *frame_host,
+                              const gpnerf_head_weights_t *weights_host, int n_points_max,
+                              const int32_t *counters, int counter_slot, float *rgb, float *rgb_in,
+                              void *stream);
+
 /* ---- K7: the sparse-conv geometry encoder -------------- */
 /* libs/nerfheads/networks/SparseConvNet.py:21-124 without spconv (1.2.1 @ abf0acf3, not in the reference tree,
  * does not build for sm_100): SubMConv3d / SparseConv3d(3, 2, padding 1) as their published semantics – a dense
