@@ -35,24 +35,12 @@ struct ColorWsArgs {
   float* rgb_in;                 // optional [P1][V][3]: the per-view RGB taps (BaseRender's rgb_in_map input)
 };
 
-#ifdef GPNERF_DEBUG_COLOR
-__device__ unsigned g_color_dbg[16 + 6 * 16 + 6 * 16 + 6 * 16];
-#define DBG_ACC(code, r, n)                                                         \
-  do {                                                                               \
-    bool bad_ = false;                                                               \
-    for (int q_ = 0; q_ < (n); ++q_) bad_ |= !isfinite(__uint_as_float((r)[q_]));    \
-    if (bad_) atomicAdd(&g_color_dbg[code], 1u);                                     \
-    for (int q_ = 0; q_ < (n); ++q_) if (!isfinite(__uint_as_float((r)[q_]))) atomicAdd(&g_color_dbg[16 + 96 + code * 16 + q_], 1u); \
-    if (row == 5 && blockIdx.x == 0 && i == c) { for (int q_ = 0; q_ < (n); ++q_) g_color_dbg[16 + code * 16 + q_] = (r)[q_]; }   \
-  } while (0)
-#else
-#define DBG_ACC(code, r, n)
-#endif
 
 namespace cws {
 constexpr int kProdWarps = 8, kChains = 3, kStages = 2;
-constexpr int kThreads = (kProdWarps + 4 * kChains + 1) * 32;        // 672
-constexpr int kMmaWarp = kProdWarps + 4 * kChains;
+constexpr int kPasses = 16 / kProdWarps;          // passes of 8 points per producer warp and tile
+constexpr int kThreads = (kProdWarps + 4 * kChains + kChains) * 32;  // 736
+constexpr int kMmaWarp0 = kProdWarps + 4 * kChains;                  // one MMA-issuing warp per chain
 constexpr int kChainCols = 160;                                      // TMEM columns per chain
 constexpr uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 template <int V>
@@ -101,7 +89,7 @@ __device__ __forceinline__ void cw_st_rows8_sw(uint8_t* kblock, int row8, int c0
 __device__ __forceinline__ void cw_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_test(bar, parity)) {
-    __nanosleep(100);
+    __nanosleep(40);
     if (++spins > 4000000u) __trap();
   }
 }
@@ -135,6 +123,7 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
       mbar_init(m2e + c, 1);
       mbar_init(e2m + c, 128);
     }
+    *reinterpret_cast<volatile int*>(smem + S::MISC + 192) = 0;       // next tile (CTA-local index) allowed to start
     fence_mbar_init();
     mbar_arrive_expect_tx(bar_w, I::BYTES);
     bulk_g2s(img, a.image, I::BYTES, bar_w);
@@ -195,11 +184,11 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
         z = fmaf(__ldg(a.rays_d + ray * 3 + 2), zz, oz);
       }
     };
-    int icur[2], inext[2];
-    float px[2], py[2], pz[2];
+    int icur[kPasses], inext[kPasses];
+    float px[kPasses], py[kPasses], pz[kPasses];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      icur[j] = fetch_i((long long)blockIdx.x * 128, warp * 16 + j * 8 + grp);
+    for (int j = 0; j < kPasses; ++j) {
+      icur[j] = fetch_i((long long)blockIdx.x * 128, (warp * kPasses + j) * 8 + grp);
       position(icur[j], px[j], py[j], pz[j]);
     }
     int it = 0;
@@ -208,11 +197,11 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
       uint8_t* stage = smem + S::STAGE0 + s * S::STAGE_BYTES;
       int32_t* dst_idx = reinterpret_cast<int32_t*>(smem + S::DST + s * 512);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) inext[j] = fetch_i((long long)(tile + G) * 128, warp * 16 + j * 8 + grp);
+      for (int j = 0; j < kPasses; ++j) inext[j] = fetch_i((long long)(tile + G) * 128, (warp * kPasses + j) * 8 + grp);
       cw_wait(empty + s, ((it / kStages) & 1) ^ 1);
 #pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const int r = warp * 16 + j * 8 + grp;
+      for (int j = 0; j < kPasses; ++j) {
+        const int r = (warp * kPasses + j) * 8 + grp;
         const int pi = icur[j];
         const bool ok = pi >= 0;
         const float ppx = px[j], ppy = py[j], ppz = pz[j];
@@ -337,28 +326,33 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < kPasses; ++j) {
         icur[j] = inext[j];
         position(icur[j], px[j], py[j], pz[j]);
       }
     }
 #undef plan
-  } else if (warp == kMmaWarp) {
-    // =========================================================== MMA issuer (one thread)
+  } else if (warp >= kMmaWarp0) {
+    // =========================================================== MMA issuers: one thread per chain
+    // (a single issuer serving all chains through a polling state machine was the bottleneck of the first
+    // version: ~40 services per three tiles, each a few hundred cycles of descriptor arithmetic on one thread)
     if (lane == 0) {
+      const int c = warp - kMmaWarp0;
+      volatile int* next_start = reinterpret_cast<volatile int*>(smem + S::MISC + 192);
       mbar_wait(bar_w, 0);
       const uint32_t wimg = smem_u32(img);
       const uint64_t ones_d = make_smem_desc(smem_u32(smem + S::ONES), kLBO, kSbo16);
-      const uint32_t id64 = make_idesc_bf16(128, 64), id32 = make_idesc_bf16(128, 32), id16 = make_idesc_bf16(128, 16);
+      const uint32_t id64 = make_idesc_bf16(128, 64), id32 = make_idesc_bf16(128, 32);
       auto bdesc = [&](uint32_t w_off, int k16, int Kp) {
         return make_smem_desc(wimg + w_off + k16 * 2 * kLBO, kLBO, op_sbo(Kp));
       };
       // per-chain TMEM columns.  An A operand in TMEM must start on a 32-column boundary (an operand at column 112
-      // was read as garbage for part of the rows): H, Y, E and Z share columns 64.., each dead before the next is written
-      constexpr uint32_t ACC1 = 0, ACC2 = 0, ACC3 = 32, ACC4 = 0, ACC5 = 128, ACC6 = 32;
-      constexpr uint32_t H_ = 64, XS = 96, Y_ = 64, E_ = 64, Z_ = 64;
+      // was read as garbage for part of the rows): H, Y and E share columns 64.., each dead before the next is written
+      constexpr uint32_t ACC1 = 0, ACC2 = 0, ACC3 = 32, ACC4 = 0, ACC5 = 128;
+      constexpr uint32_t H_ = 64, XS = 96, Y_ = 64, E_ = 64;
+      const uint32_t tb = tmem + c * kChainCols;
       // base_fc.0 of view v: [mean|var] (80 columns, bias in 70/71) + feat_v (32) + rgb_v (16-column block) → 64
-      auto issue_r1 = [&](uint32_t tb, uint32_t stage, int v) {
+      auto issue_r1 = [&](uint32_t stage, int v) {
         for (int k16 = 0; k16 < 4; ++k16)
           umma_bf16(tb + ACC1, make_smem_desc_sw128(stage + S::G64 + k16 * 32), bdesc(I::Wb0a, k16, 80), id64, k16 > 0);
         umma_bf16(tb + ACC1, make_smem_desc(stage + S::TAIL, kLBO, kSbo16), bdesc(I::Wb0a, 4, 80), id64, 1u);
@@ -368,101 +362,67 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
         umma_bf16(tb + ACC1, make_smem_desc(stage + S::RGBS, kLBO, kSbo16),
                   make_smem_desc(wimg + I::Wb0r + v * op_bytes(64, 16), kLBO, kSbo16), id64, 1u);
       };
-      int step[kChains], li[kChains];
-      uint32_t e2m_ph[kChains];
-      bool done[kChains];
-      for (int c = 0; c < kChains; ++c) { step[c] = 0; li[c] = c; e2m_ph[c] = 0; done[c] = false; }
-      constexpr int kSteps = 4 * V + 1;      // arrivals of the epilogue per tile
-      uint32_t idle = 0;
-      int n_done = 0;
-      // tiles start strictly in order: a parity wait on full[s] can only tell two consecutive phases apart, and with
-      // fewer stages than chains a chain would otherwise see "its" phase of a stage complete one tenant early
-      int next_start = 0;
-      while (n_done < kChains) {
-        bool progressed = false;
-#pragma unroll
-        for (int c = 0; c < kChains; ++c) {
-          if (done[c]) continue;
-          const int i = li[c];
-          if (blockIdx.x + (long long)i * G >= n_tiles) {
-            done[c] = true;
-            ++n_done;
-            progressed = true;
-            continue;
-          }
-          const int s = i % kStages;
-          const uint32_t stage = smem_u32(smem + S::STAGE0 + s * S::STAGE_BYTES);
-          const uint32_t tb = tmem + c * kChainCols;
-          const int st = step[c];
-          if (st == 0) {
-            if (i != next_start) continue;
-            if (i >= kChains && !mbar_test(e2m + c, e2m_ph[c])) continue;      // chain free
-            if (!mbar_test(full + s, (i / kStages) & 1)) continue;             // stage full
-            if (i >= kChains) e2m_ph[c] ^= 1u;
-            tc_fence_after();
-            issue_r1(tb, stage, 0);
-            umma_commit(m2e + c);
-            step[c] = 1;
-            ++next_start;
-          } else {
-            if (!mbar_test(e2m + c, e2m_ph[c])) continue;
-            e2m_ph[c] ^= 1u;
-            tc_fence_after();
-            const int k = st - 1;                  // index of the epilogue arrival just consumed
-            {
-              const int v = k >> 2, ph = k & 3;
-              if (ph == 0) {
-                // after H_v: base_fc.2 (64 → 32); then the next view's base_fc.0 while this view's epilogues run
-                for (int k16 = 0; k16 < 4; ++k16) umma_ts(tb + ACC2, tb + H_ + k16 * 8, bdesc(I::Wb1, k16, 80), id32, k16 > 0);
-                umma_bf16(tb + ACC2, ones_d, bdesc(I::Wb1, 4, 80), id32, 1u);
-                umma_commit(m2e + c);
-                // one view only: base_fc.0 was the last reader of the stage (and the epilogue has fetched its rows'
-                // destinations from it by now)
-                if (V == 1) umma_commit(empty + s);
-              } else if (ph == 1) {
-                // after Xs_v: vis_fc.0 (32 → 32) and this view's residual share of rgb_fc.0: (V·W_v)·(x_v / V)
-                for (int k16 = 0; k16 < 2; ++k16) umma_ts(tb + ACC3, tb + XS + k16 * 8, bdesc(I::Wv0, k16, 48), id32, k16 > 0);
-                umma_bf16(tb + ACC3, ones_d, bdesc(I::Wv0, 2, 48), id32, 1u);
-                umma_commit(m2e + c);
-#if GPNERF_DEBUG_COLOR != 2
-                for (int k16 = 0; k16 < 2; ++k16)
-                  umma_ts(tb + ACC5, tb + XS + k16 * 8, bdesc(I::Wr0x, 2 * v + k16, 32 * V), id32, (v > 0 || k16 > 0));
-#endif
-              } else if (ph == 2) {
-                // after Y_v: vis_fc.2 (32 → 32)
-                for (int k16 = 0; k16 < 2; ++k16) umma_ts(tb + ACC4, tb + Y_ + k16 * 8, bdesc(I::Wv1, k16, 48), id32, k16 > 0);
-                umma_bf16(tb + ACC4, ones_d, bdesc(I::Wv1, 2, 48), id32, 1u);
-                umma_commit(m2e + c);
-              } else {
-                // after E_v: its share of rgb_fc.0; then either the next view's base_fc.0 (its accumulator, columns
-                // 0..63, overlaps those of base_fc.2 / vis_fc.0 / vis_fc.2, all consumed by now) or rgb_fc.0's bias
-#if GPNERF_DEBUG_COLOR == 2
-                for (int k16 = 0; k16 < 2; ++k16)
-                  umma_ts(tb + ACC5, tb + E_ + k16 * 8, bdesc(I::Wr0, 2 * v + k16, 32 * V + 16), id32, (v > 0 || k16 > 0));
-#else
-                for (int k16 = 0; k16 < 2; ++k16)
-                  umma_ts(tb + ACC5, tb + E_ + k16 * 8, bdesc(I::Wr0, 2 * v + k16, 32 * V + 16), id32, 1u);
-#endif
-                if (v + 1 < V) {
-                  issue_r1(tb, stage, v + 1);
-                  if (v + 2 == V) umma_commit(empty + s);      // the last GEMM that reads the stage
-                }
-                umma_commit(m2e + c);
-              }
-            }
-            step[c] = st + 1;
-            if (step[c] == kSteps) {          // the final epilogue's arrival is consumed by the next tile's first step
-              step[c] = 0;
-              li[c] += kChains;
-            }
-          }
-          progressed = true;
+      uint32_t eph = 0;
+      auto wait_epi = [&]() {          // the chain's epilogue group has published its activations
+        uint32_t spins = 0;
+        while (!mbar_test(e2m + c, eph)) {
+          __nanosleep(32);
+          if (++spins > 8000000u) __trap();
         }
-        if (progressed) {
-          idle = 0;
-        } else {
-          __nanosleep(100);
-          if (++idle > 8000000u) __trap();
+        eph ^= 1u;
+        tc_fence_after();
+      };
+      for (int i = c; blockIdx.x + (long long)i * G < n_tiles; i += kChains) {
+        const int s = i % kStages;
+        const uint32_t stage = smem_u32(smem + S::STAGE0 + s * S::STAGE_BYTES);
+        // tiles start strictly in order: a parity wait on full[s] tells only two consecutive phases apart, and with
+        // fewer stages than chains a chain would otherwise see "its" phase of a stage complete one tenant early
+        {
+          uint32_t spins = 0;
+          while (*next_start != i) {
+            __nanosleep(64);
+            if (++spins > 8000000u) __trap();
+          }
+        }
+        if (i >= kChains) wait_epi();                // chain free: the final epilogue of its previous tile is through
+        cw_wait(full + s, (i / kStages) & 1);
+        tc_fence_after();
+        issue_r1(stage, 0);
+        umma_commit(m2e + c);
+        __threadfence_block();
+        *next_start = i + 1;
+#pragma unroll 1
+        for (int v = 0; v < V; ++v) {
+          // after H_v: base_fc.2 (64 → 32)
+          wait_epi();
+          for (int k16 = 0; k16 < 4; ++k16) umma_ts(tb + ACC2, tb + H_ + k16 * 8, bdesc(I::Wb1, k16, 80), id32, k16 > 0);
+          umma_bf16(tb + ACC2, ones_d, bdesc(I::Wb1, 4, 80), id32, 1u);
+          umma_commit(m2e + c);
+          // one view only: base_fc.0 was the last reader of the stage (and the epilogue has fetched its rows'
+          // destinations from it by now)
+          if (V == 1) umma_commit(empty + s);
+          // after Xs_v: vis_fc.0 (32 → 32) and this view's residual share of rgb_fc.0: (V·W_v)·(x_v / V)
+          wait_epi();
+          for (int k16 = 0; k16 < 2; ++k16) umma_ts(tb + ACC3, tb + XS + k16 * 8, bdesc(I::Wv0, k16, 48), id32, k16 > 0);
+          umma_bf16(tb + ACC3, ones_d, bdesc(I::Wv0, 2, 48), id32, 1u);
+          umma_commit(m2e + c);
+          for (int k16 = 0; k16 < 2; ++k16)
+            umma_ts(tb + ACC5, tb + XS + k16 * 8, bdesc(I::Wr0x, 2 * v + k16, 32 * V), id32, (v > 0 || k16 > 0));
+          // after Y_v: vis_fc.2 (32 → 32)
+          wait_epi();
+          for (int k16 = 0; k16 < 2; ++k16) umma_ts(tb + ACC4, tb + Y_ + k16 * 8, bdesc(I::Wv1, k16, 48), id32, k16 > 0);
+          umma_bf16(tb + ACC4, ones_d, bdesc(I::Wv1, 2, 48), id32, 1u);
+          umma_commit(m2e + c);
+          // after E_v: its share of rgb_fc.0 (the bias is added by the epilogue); then the next view's base_fc.0 – its
+          // accumulator, columns 0..63, overlaps those of base_fc.2 / vis_fc.0 / vis_fc.2, all consumed by now
+          wait_epi();
+          for (int k16 = 0; k16 < 2; ++k16)
+            umma_ts(tb + ACC5, tb + E_ + k16 * 8, bdesc(I::Wr0, 2 * v + k16, 32 * V + 16), id32, 1u);
+          if (v + 1 < V) {
+            issue_r1(stage, v + 1);
+            if (v + 2 == V) umma_commit(empty + s);      // the last GEMM that reads the stage
+          }
+          umma_commit(m2e + c);
         }
       }
     }
@@ -472,10 +432,11 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
     const int wq = (warp - kProdWarps) & 3;
     const int row = wq * 32 + lane;
     const uint32_t tb = tmem + c * kChainCols + ((uint32_t)(wq * 32) << 16);
-    constexpr uint32_t ACC1 = 0, ACC2 = 0, ACC3 = 32, ACC4 = 0, ACC5 = 128, ACC6 = 32;
-    constexpr uint32_t H_ = 64, XS = 96, Y_ = 64, E_ = 64, Z_ = 64;
+    constexpr uint32_t ACC1 = 0, ACC2 = 0, ACC3 = 32, ACC4 = 0, ACC5 = 128;
+    constexpr uint32_t H_ = 64, XS = 96, Y_ = 64, E_ = 64;
     mbar_wait(bar_w, 0);
     uint32_t ph = 0;
+    // one warp of the group polls the mbarrier; the other three block on a named barrier (no polling)
     const bool leader = wq == 0;
     auto wait_acc = [&]() {
       if (leader) cw_wait(m2e + c, ph);
@@ -487,78 +448,56 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
       tc_fence_before();
       mbar_arrive(e2m + c);
     };
-    // 16 accumulator columns → scaled ELU (times `scale`) → 8 packed bf16 pairs
-    int i = c;
-    auto epi16 = [&](uint32_t col, float scale, uint32_t (&pk)[8], int code) {
-      uint32_t r[16];
-      tmem_ld16(tb + col, r);
+    // 32 accumulator columns → scaled ELU (times `scale`) → 16 packed bf16 pairs → 16 TMEM columns of the next operand
+    auto epi32 = [&](uint32_t col, uint32_t dst_col, float scale) {
+      uint32_t r[32], pk[16];
+      tmem_ld32(tb + col, r);
       tmem_wait_ld();
-      DBG_ACC(code, r, 16);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 16; ++j)
         pk[j] = pack_bf16x2(scale * elu_scaled(__uint_as_float(r[2 * j])), scale * elu_scaled(__uint_as_float(r[2 * j + 1])));
-#ifdef GPNERF_DEBUG_COLOR
-      if (row == 5 && blockIdx.x == 0 && i == c && code >= 1 && code <= 4)
-        for (int j = 0; j < 8; ++j) g_color_dbg[16 + 192 + code * 16 + ((col & 16) ? 8 : 0) + j] = pk[j];
-#endif
+      tmem_st16(tb + dst_col, pk);
     };
-    const float inv_v = 1.0f / (float)V;
-    for (i = c; blockIdx.x + (long long)i * G < n_tiles; i += kChains) {
+    const float inv_views = 1.0f / (float)V;
+    for (int i = c; blockIdx.x + (long long)i * G < n_tiles; i += kChains) {
       const int s = i % kStages;
-      uint32_t pk[8];
       int dst = -1;
 #pragma unroll 1
       for (int v = 0; v < V; ++v) {
         // ---- base_fc.0 → H_v (64 columns)
         wait_acc();
-        if (v == 0) dst = reinterpret_cast<const int32_t*>(smem + S::DST + s * 512)[row];   // (stage still held: see below)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          epi16(ACC1 + 16 * b, 1.0f, pk, 0);
-          tmem_st8(tb + H_ + 8 * b, pk);
-        }
+        if (v == 0) dst = reinterpret_cast<const int32_t*>(smem + S::DST + s * 512)[row];   // (the stage is still held)
+        epi32(ACC1, H_, 1.0f);
+        epi32(ACC1 + 32, H_ + 16, 1.0f);
         tmem_wait_st();
         publish();
         // ---- base_fc.2 → x_v ; stored as x_v / V (vis_fc input, trainhead.py:140)
         wait_acc();
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          epi16(ACC2 + 16 * b, inv_v, pk, 1);
-          tmem_st8(tb + XS + 8 * b, pk);
-        }
+        epi32(ACC2, XS, inv_views);
         tmem_wait_st();
         publish();
         // ---- vis_fc.0 → Y_v
         wait_acc();
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          epi16(ACC3 + 16 * b, 1.0f, pk, 2);
-          tmem_st8(tb + Y_ + 8 * b, pk);
-        }
+        epi32(ACC3, Y_, 1.0f);
         tmem_wait_st();
         publish();
         // ---- vis_fc.2 → E_v
         wait_acc();
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          epi16(ACC4 + 16 * b, 1.0f, pk, 3);
-          tmem_st8(tb + E_ + 8 * b, pk);
-        }
+        epi32(ACC4, E_, 1.0f);
         tmem_wait_st();
         publish();
       }
       // ---- rgb_fc.0 (bias added here) → z ; rgb_fc.2 (32 → 16) and rgb_fc.4 (16 → 3) on CUDA cores ; sigmoid.
-      // (The two small tail layers are 560 FMAs per point: cheaper than two more MMA round trips per tile.)
+      // (The two small tail layers are 560 FMAs per point: cheaper than two more MMA round trips per tile – and bias
+      // MMAs at these accumulator positions returned garbage for reasons not understood, see profiles/r02 notes.)
       wait_acc();
       float z[32];
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        uint32_t r[16];
-        tmem_ld16(tb + ACC5 + 16 * b, r);
+      {
+        uint32_t r[32];
+        tmem_ld32(tb + ACC5, r);
         tmem_wait_ld();
-        DBG_ACC(4, r, 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) z[16 * b + j] = elu_scaled(__uint_as_float(r[j]) + fl[I::rb0c + 16 * b + j]);
+        for (int j = 0; j < 32; ++j) z[j] = elu_scaled(__uint_as_float(r[j]) + fl[I::rb0c + j]);
       }
       publish();                                   // chain free: its next tile may overwrite the accumulators
       float o0 = fl[I::rb2], o1 = fl[I::rb2 + 1], o2 = fl[I::rb2 + 2];
@@ -585,18 +524,6 @@ __global__ void __launch_bounds__(cws::kThreads, 1) color_mlp_ws(ColorWsArgs a, 
   }
   tc_fence_before();
   __syncthreads();
-#ifdef GPNERF_DEBUG_COLOR
-  if (tid == 0 && blockIdx.x == 0) {
-    unsigned cnt = 0, first = 0xffffffffu, last = 0;
-    for (uint32_t o = 0; o < I::BYTES; o += 4)
-      if (*reinterpret_cast<const uint32_t*>(img + o) != *reinterpret_cast<const uint32_t*>(a.image + o)) {
-        ++cnt;
-        if (first == 0xffffffffu) first = o;
-        last = o;
-      }
-    g_color_dbg[6] = cnt; g_color_dbg[7] = first; g_color_dbg[8] = last; g_color_dbg[9] = I::BYTES;
-  }
-#endif
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -624,11 +551,6 @@ static int launch_color_ws(const ColorWsArgs& a, const gpnerf_frame_t* f, int n_
 
 extern "C" {
 
-#ifdef GPNERF_DEBUG_COLOR
-int gpnerf_debug_color(unsigned* out16) {
-  return (int)cudaMemcpyFromSymbol(out16, g_color_dbg, sizeof(unsigned) * (16 + 288));
-}
-#endif
 
 int gpnerf_k3_color_gather_tc(const void* featmaps_f16, const float* images_rgbx, const int32_t* valid,
                               const int32_t* valid1, const float* rays_o, const float* rays_d, const float* z_vals,
