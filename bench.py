@@ -44,6 +44,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "rays/s"
+WORKLOAD = ("zju-like synthetic frame 512x512, V=3, S=64 (BASELINE configs[1], trainzju_valzju inference shape), "
+            "progressive path")
 SWEEP_STEP_DEG = 2.0          # angular step between the frames of the N-view sweep (frames mode)
 S_SAMPLES = 64
 VIEWS = 3
@@ -64,6 +66,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="render", choices=["render", "train"],
+                    help="render: the progressive frame (BASELINE configs[1], the default); train: configs[3], one "
+                         "4096-ray forward+backward step through Renderer.render + MSE + one flat gradient all-reduce")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (tiles) sub-record")
     return ap.parse_args()
 
 
@@ -131,9 +137,14 @@ class ClockSampler:
 
 
 # per-point algorithmic work of each stage (SURVEY.md §8d / DESIGN.md)
-def stage_work(counts, n_level_elems, V):
+def stage_work(counts, n_level_elems, V, n_map_elems=0, n_img_px=0):
+    """Algorithmic work per launch.  Bandwidth-bound stages: COMPULSORY bytes – every distinct input
+    byte once plus the outputs – so that achieved / peak is a physical HBM fraction (the gathers re-request the
+    L2-resident volumes many times over; that re-request rate is reported separately as `requested_gbs`)."""
     P, P1, P2 = counts["n_rays"] * S_SAMPLES, counts["P1"], counts["P2"]
+    fused_compulsory = 2.0 * n_level_elems / 4 + 2.0 * n_map_elems + 16.0 * n_img_px + 20.0 * P1
     return {
+        "k3_color_gather_tc": ("tensor", 72160.0 * P2, "72,160 FLOP per surviving point (colour trunk)"),
         "k0_level_to_channels_last": ("hbm", 8.0 * n_level_elems / 4, "all 4 calls: 4 B read + 4 B written per element"),
         "k0_products_to_f16": ("hbm", 6.0 * n_level_elems / 4 + 4.0 * n_level_elems / 4 / 32,
                                "4 B read + 2 B written per element, 4 B channel sum per voxel"),
@@ -144,9 +155,10 @@ def stage_work(counts, n_level_elems, V):
         "k3_color_mlp": ("tensor", 72160.0 * P2, "72,160 FLOP per point"),
         # bf16 path: gathers (bf16 storage: 4 levels x 8 corners x 64 B + V x 4 x (64 B + 16 B RGBx)) fused
         # with the density head; 16*(9+5V) B record written per point
-        "k23_gather_density_tc": ("hbm", (2048.0 + V * 320.0 + 16.0 * (9 + 5 * V)) * P1,
-                                  "gather-bound fused kernel: 2,048 B volume + 320 B/view images read, "
-                                  "16(9+5V) B record written per point (bf16 storage); also 38,688 FLOP/point"),
+        "k23_gather_density_tc": ("hbm", fused_compulsory,
+                                  "compulsory bytes: the fp16 volumes, feature maps and RGBx images once (they are L2 "
+                                  "resident), 12 B read + 8 B written per P1 point; the kernel REQUESTS 2,048 B volume + "
+                                  "320 B/view per point from L1/L2 and runs 38,688 FLOP/point on the tensor pipe"),
         "k3_color_mlp_records": ("tensor", 72160.0 * P2, "72,160 FLOP per point"),
         "k4_compact_alpha": ("hbm", 8.0 * P1, "4 B read + 4 B written per point"),
         "k5_composite": ("hbm", 16.0 * P1, "16 B per surviving sample"),
@@ -162,7 +174,7 @@ def cpu_reference_frames(scene, weights, min_seconds, max_frames):
     t_all = time.perf_counter()
     while len(times) < max_frames and (time.perf_counter() - t_all < min_seconds or not times):
         t0 = time.perf_counter()
-        out = orc.render_progressive(scene, weights, S=S_SAMPLES, chunk=131072)
+        out = orc.render_progressive(scene, weights, S=S_SAMPLES, chunk=131072, keep=True)
         times.append(time.perf_counter() - t0)
     return times, out
 
@@ -194,8 +206,7 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": len(times) / total,
-        "config": {"workload": f"zju-like synthetic frame, {RES}x{RES}, V={VIEWS}, S={S_SAMPLES} (BASELINE configs[1])",
-                   "rays": rays, "P1": out["P1"], "P2": out["P2"]},
+        "config": {"workload": WORKLOAD, "rays": rays, "P1": out["P1"], "P2": out["P2"]},
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": "every step = the full frame through oracle/gpnerf_oracle.py "
                                    "(torch CPU restatement of the reference; chunk 131072 points)"},
@@ -203,6 +214,149 @@ def run_reference(args, rank):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_train(args, rank, world, local_rank):
+    """--mode train: BASELINE configs[3] – one training step = 4096 rays x 64 samples split evenly over the ranks,
+    forward + backward through the hot path's K6 kernels (TF32 tcgen05 heads), MSE against random targets, head
+    gradients averaged with ONE flat all-reduce (train.GradBucket, NCCL over NVLink), AdamW step.  `value` = rays/s
+    with the upstream products (levels, feature maps) resident – the hot path of SURVEY §8; `full_pipeline` repeats
+    the step through `Renderer.render(batch)` from the source images (encoder + SMPL attention + sparse-conv
+    pyramid in their training form, trainmode.py), i.e. the exact sequence of BaseTrainer.train."""
+    import torch.distributed as dist
+    import gpnerf_b200  # noqa: F401
+    from gpnerf_b200 import synth, train
+    from gpnerf_b200.encoder import ResUNet
+    from gpnerf_b200.engine import Engine
+    from gpnerf_b200.nerfhead import NeRFHead
+    from gpnerf_b200.render import Renderer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("GPNERF_NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    n_rays_total, S, V = 4096, S_SAMPLES, VIEWS
+    R = n_rays_total // world
+    scene = synth.make_scene("zju", H=RES, W=RES, V=V, seed=42, with_rays=True)
+    w0 = synth.make_head_weights(V=V, seed=42, random_bias=True)
+    n_all = scene["ray_o"].shape[1]
+    sel = ((torch.arange(n_rays_total) * max(1, n_all // n_rays_total)) % n_all)[rank * R:(rank + 1) * R]
+    rays = tuple(scene[k][0][sel].to(dev) for k in ("ray_o", "ray_d", "near", "far"))
+    eng = Engine(RES, RES, S, V, device=dev, max_rays=R)
+    w_g = {k: torch.nn.Parameter(v.clone().to(dev)) for k, v in w0.items()}
+    lv = [t.to(dev) for t in scene["levels"]]
+    fm, im = scene["featmaps"].to(dev), scene["src_imgs"].to(dev)
+    eng.set_weights(w0)
+    eng.upload_products(lv, fm, im)
+    frame = eng.make_frame(scene)
+    target = torch.rand(R, 3, device=dev)
+    bucket = train.GradBucket(w_g.values())
+    opt = torch.optim.AdamW(list(w_g.values()), lr=1e-4)
+    gen = torch.Generator().manual_seed(rank)
+    t_pin = torch.empty(R, S).pin_memory()
+
+    def step():
+        bucket.zero()
+        t_pin.copy_(torch.rand(R, S, generator=gen))                 # the jitter is drawn on the host (BaseRender.py:40-47)
+        out = train.render_dense_autograd(eng, frame, rays, lv, fm, im, w_g, t_rand=t_pin.to(dev, non_blocking=True),
+                                          precision=train.PREC_TRAIN_TF32)
+        loss = ((out["rgb_map"] - target) ** 2).mean()
+        loss.backward()
+        bucket.all_reduce_mean()
+        opt.step()
+        return loss
+
+    def time_steps(fn, k):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / k, 1e3 * wall / k], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    wall0 = time.perf_counter()
+    ms_dev, ms_wall = time_steps(step, args.steps)
+    clocks = sampler.stop(wall0, time.perf_counter()) if rank == 0 else None
+    chk = bucket.flat.double().sum().reshape(1)
+    same = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool((hi - lo).abs() <= 1e-9 * hi.abs().clamp_min(1e-30))
+    # ---- the same step through the plugin API from the source images (BaseTrainer._forward's sequence)
+    full = None
+    try:
+        torch.manual_seed(42)
+        head = NeRFHead(code_dim=16, n_views=V).to(dev)
+        sd = head.state_dict()
+        for k, v in w0.items():
+            if k in sd and sd[k].shape == v.shape:
+                sd[k].copy_(v)
+        for k, v in sd.items():
+            if "xyzc_net" in k and (k.endswith(".1.weight") or k.endswith(".4.weight")):
+                v.fill_(3.0)
+        head.load_state_dict(sd)
+        enc = synth.fill_encoder_params(ResUNet(), seed=42).to(dev)
+        r = Renderer(enc, head, is_train=True, n_samples=S, progressive=False).to(dev).train()
+        batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in scene.items() if k not in ("levels", "featmaps")}
+        for k in ("ray_o", "ray_d", "near", "far"):
+            batch[k] = batch[k][:, sel.to(dev)]
+        bucket2 = train.GradBucket(r.parameters())
+        opt2 = torch.optim.AdamW(list(r.parameters()), lr=1e-4)
+
+        def step_full():
+            bucket2.zero()
+            ret = r.render(batch)
+            loss = ((ret["rgb_map"][0] - target) ** 2).mean()
+            loss.backward()
+            bucket2.all_reduce_mean()
+            opt2.step()
+        for _ in range(3):
+            step_full()
+        f_dev, f_wall = time_steps(step_full, max(3, args.steps // 2))
+        full = {"ms_per_step": f_wall, "device_ms_per_step": f_dev, "value": n_rays_total * 1e3 / f_wall, "unit": "rays/s",
+                "trainable_values_all_reduced": int(bucket2.flat.numel()),
+                "what": "Renderer.render(batch) from the source images + SMPL fit, training mode: encoder, SMPL attention "
+                        "and sparse-conv pyramid in training form (torch autograd ops, batch-statistics BatchNorm), "
+                        "hot path in the K6 kernels; MSE; one flat all-reduce over ALL parameters; AdamW"}
+    except Exception as exc:                # the hot-path number stands on its own
+        full = {"error": repr(exc)[:300]}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    emit({
+        "metric": METRIC, "value": n_rays_total * 1e3 / ms_wall, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_wall, "device_ms_per_step": ms_dev, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "mode": "train",
+        "config": {"workload": "training step, 4096 rays x 64 samples per step split evenly over the ranks, forward + backward "
+                               "through gathers, both heads and raw2outputs (BASELINE configs[3]); zju-like synthetic "
+                               "scene 512x512, V=3; products resident, head parameters trainable",
+                   "rays_per_gpu": R, "l2": "working set ≈10 GB of activations per step ≫ 126 MB L2",
+                   "collective": "one flat all-reduce of the head gradients per step (train.GradBucket)" if world > 1 else "none",
+                   "grad_values_all_reduced": int(bucket.flat.numel()), "grads_identical_on_all_ranks": same},
+        "clocks": clocks, "full_pipeline": full, "gpu_launches": None,
+        "e2e": {"value": n_rays_total * 1e3 / ms_wall, "unit": "rays/s", "h2d_bytes_per_step": int(R * S * 4),
+                "d2h_bytes_per_step": 0, "what": "host wall clock around the steps; the per-step jitter is uploaded from pinned memory"},
+    })
 
 
 _JSON_FD = None
@@ -236,6 +390,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.mode == "train":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        run_train(args, rank, world, local_rank)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -321,6 +480,8 @@ def main():
         torch.cuda.synchronize(dev)
     counts = eng.read_counters()
     ref_image = eng.result_image().cpu().clone()
+    ref_hit = eng.result_hit_mask().cpu().clone()
+    ref_valid1 = eng.valid1[: counts["P2"]].cpu().clone()
     if world > 1:
         tot = torch.tensor([counts["n_rays"], counts["P1"], counts["P2"]], device=dev)
         dist.all_reduce(tot)
@@ -420,6 +581,64 @@ def main():
         dist.all_gather(allr, mine)
         per_rank = [{"rays": int(t[0]), "P1": int(t[1]), "P2": int(t[2]), "stages_ms_sum": round(float(t[3]), 4),
                      "peer_wait_ms": round(float(t[4]), 4)} for t in allr]
+
+    # ---- strong scaling of ONE frame (north_star: "rays are sharded evenly across the GPUs"): the frame's pixel tiles
+    #      dealt over the ranks (shard.py), every rank ends with the full image.  Two frames: the headline one and
+    #      BASELINE configs[4]'s shape (1024², S=128, V=4).  At N=1 the same code gives the single-GPU reference, so the
+    #      per-N records of a scaling run can be divided directly.
+    strong = None
+    if not args.no_strong and prec == PREC_BF16 and not args.no_graph:
+        strong = {}
+        for tag, res, views, samples in (("zju512_v3_s64", RES, VIEWS, S_SAMPLES), ("zju1024_v4_s128", 1024, 4, 128)):
+            sc = synth.make_scene("zju", H=res, W=res, V=views, seed=42)
+            wts = synth.make_head_weights(V=views, seed=42)
+            hd = NeRFHead(code_dim=32, n_views=views, precision=prec)
+            sdd = hd.state_dict()
+            sdd.update({k: v for k, v in wts.items()})
+            hd.load_state_dict(sdd)
+            rt = Renderer(None, hd.to(dev), is_train=False, n_samples=samples, progressive=True, precision=prec,
+                          rank=rank, world=world, tile_px=args.tile_px, shard="tiles", collective=args.collective)
+            et = rt.engine_for(res, res, views, dev)
+            et.set_weights(hd.hot_path_state())
+            lv_t = [t.to(dev) for t in sc["levels"]]
+            fm_t, im_t = sc["featmaps"].to(dev), sc["src_imgs"].to(dev)
+            et.set_static_inputs(lv_t, fm_t, im_t)
+            et.upload_products(lv_t, fm_t, im_t)
+            fr_t = et.make_frame(sc)
+
+            def step_t():
+                et.run_progressive_graphed(fr_t)
+                if world > 1 and et.exchange is None:
+                    return shard.gather_frame(et.pred_img.view(res * res, 3), res, args.tile_px)
+                return et.result_image()
+            for _ in range(3):
+                flush.zero_()
+                step_t()
+            torch.cuda.synchronize(dev)
+            evt = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            if world > 1:
+                dist.barrier()
+            for a, b in evt:
+                flush.zero_()
+                a.record()
+                step_t()
+                b.record()
+            torch.cuda.synchronize(dev)
+            ms_t = torch.tensor([sum(a.elapsed_time(b) for a, b in evt) / args.steps], device=dev)
+            ct = et.read_counters()
+            tot_t = torch.tensor([ct["n_rays"], ct["P1"], ct["P2"]], device=dev)
+            if world > 1:
+                dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tot_t)
+            hits = int(et.result_hit_mask().sum())
+            strong[tag] = {"ms_per_frame": float(ms_t), "rays": int(tot_t[0]), "P1": int(tot_t[1]), "P2": int(tot_t[2]),
+                           "value": int(tot_t[0]) / (float(ms_t) * 1e-3), "unit": "rays/s", "frames_per_s": 1e3 / float(ms_t),
+                           "full_image_on_every_rank": bool(hits == int(tot_t[0])),
+                           "sharding": f"pixel tiles of {args.tile_px} dealt diagonally over {world} rank(s); " +
+                                       ("K5 writes every tile into all ranks' images over NVLink (peer memory)"
+                                        if et.exchange is not None else "one NCCL all_gather" if world > 1 else "single GPU")}
+            del rt, et, lv_t, fm_t, im_t
+            torch.cuda.empty_cache()
 
     # ---- e2e: Renderer.render(batch) with pinned host inputs, image read back
     e2e = None
@@ -594,34 +813,65 @@ def main():
     # ---- roofline of the dominant kernel (this rank's share of the work)
     pk = peaks()
     n_level_elems = sum(t.numel() for t in scene["levels"]) * 4
-    work = stage_work(counts, n_level_elems, VIEWS)
+    n_map_elems = scene["featmaps"].numel()
+    n_img_px = VIEWS * (RES + 2) * (RES + 2)
+    work = stage_work(counts, n_level_elems, VIEWS, n_map_elems, n_img_px)
     timed = {k: v for k, v in stage_ms.items() if k in work}
     top = max(timed, key=timed.get) if timed else None
-    roofline = None
-    if top:
-        bound, amount, what = work[top]
-        n_calls = 4 if top == "k0_level_to_channels_last" else 1
-        dur_s = timed[top] * n_calls * 1e-3
+    tj = {}
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            tj["_file"] = name
+            break
+    flops_of = {"k23_gather_density_tc": 38688.0 * counts["P1"], "k3_color_gather_tc": 72160.0 * counts["P2"],
+                "k3_color_mlp_records": 72160.0 * counts["P2"]}
+    requested_of = {"k23_gather_density_tc": (2048.0 + VIEWS * 320.0) * counts["P1"],
+                    "k3_color_gather_tc": VIEWS * 320.0 * counts["P2"]}
+
+    def kernel_roofline(name):
+        """The contract's roofline object for one kernel: `achieved` = algorithmic (compulsory) bytes or FLOPs per
+        launch / its CUDA-event duration; beside it the other physical fractions and what ncu names as the busiest
+        unit, so that a latency- or L1-bound kernel is not mistaken for an HBM-bound one."""
+        bound, amount, what = work[name]
+        n_calls = 4 if name == "k0_level_to_channels_last" else 1
+        dur_s = timed[name] * n_calls * 1e-3
         if bound == "hbm":
             ach, peak, unit = amount / dur_s / 1e9, pk["hbm_gbs"], "GB/s"
         else:
             ach, peak, unit = amount / dur_s / 1e12, pk["bf16_tflops"], "TFLOP/s"
-        traffic, traffic_src, ncu_units = None, None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and world == 1:
-            tj = json.load(open(tpath))
-            if top in tj:
-                traffic, traffic_src = tj[top], "ncu --set full, same workload (profiles/r01_final_ncu_summary.md)"
-                ncu_units = tj.get("ncu", {}).get(top)
-        roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic": what,
-                    "algorithmic_bytes_or_flops": amount, "launch_ms": timed[top] * n_calls,
-                    "peak_source": pk["source"], "ncu": ncu_units,
-                    "note": "achieved counts REQUESTED gather bytes (SURVEY §8d per-point figure, 16-bit storage); the "
-                            "volumes/maps are L2-resident, so it can exceed the HBM copy peak while DRAM traffic "
-                            "(`traffic`) stays far below it.  What binds the kernel is the L1 data pipe (`ncu`): one "
-                            "128-byte wavefront per 64-byte corner fetch"
-                    if bound == "hbm" else None}
+        traffic = tj.get(name) if world == 1 else None
+        r = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+             "traffic": traffic,
+             "traffic_source": (f"ncu --set full, same workload (profiles/{tj.get('_file')})" if traffic else None),
+             "algorithmic": what, "algorithmic_bytes_or_flops": amount, "launch_ms": timed[name] * n_calls,
+             "peak_source": pk["source"], "ncu": tj.get("ncu", {}).get(name)}
+        if traffic:
+            r["frac_dram"] = traffic / dur_s / 1e9 / pk["hbm_gbs"]
+        if name in flops_of:
+            r["tflops"] = flops_of[name] / dur_s / 1e12
+            r["frac_tensor"] = r["tflops"] / pk["bf16_tflops"]
+        if name in requested_of:
+            r["requested_gbs"] = requested_of[name] / dur_s / 1e9
+            r["binding_unit"] = ("L1 data pipe: one 128-byte wavefront per 64-byte corner fetch, L2-resident operands "
+                                 "(`ncu`); neither HBM nor the tensor pipe bounds this kernel"
+                                 if name == "k23_gather_density_tc" else
+                                 "latency of the 4V+1 dependent MMA → epilogue rounds of a tile (three chains per SM); "
+                                 "MUFU (528 exponentials per point) and the MMA operand fetch are the next limits")
+        return r
+    roofline = kernel_roofline(top) if top else None
+    if roofline is not None:
+        others = [k for k in ("k23_gather_density_tc", "k3_color_gather_tc") if k in timed and k != top]
+        roofline["other_head_kernels"] = [kernel_roofline(k) for k in others]
+        # the whole frame against both roofs: every distinct input byte once + the image, and the heads' FLOPs
+        frame_bytes = (6.0 * n_level_elems / 4 + 6.0 * n_map_elems + 28.0 * n_img_px + 36.0 * counts["n_rays"] * S_SAMPLES +
+                       40.0 * counts["P1"] + 16.0 * RES * RES)
+        frame_flops = 38688.0 * counts["P1"] + 72160.0 * counts["P2"]
+        roofline["frame"] = {"compulsory_dram_bytes": frame_bytes, "flops": frame_flops, "ms": ms_per_step,
+                             "frac_hbm": frame_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             "frac_tensor": frame_flops / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                             "lower_bound_ms": max(frame_bytes / (pk["hbm_gbs"] * 1e9), frame_flops / (pk["bf16_tflops_sustained"] * 1e12)) * 1e3}
     stages_out = {}
     for k, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
         ent = {"ms": round(ms * (4 if k == "k0_level_to_channels_last" else 1), 4)}
@@ -634,7 +884,7 @@ def main():
                 ent["TFLOP/s"] = round(amount / dur / 1e12, 2); ent["frac_bf16"] = round(amount / dur / 1e12 / pk["bf16_tflops"], 4)
         stages_out[k] = ent
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if not args.no_cpu_baseline:
         times, o = cpu_reference_frames(scene, weights, min_seconds=10.0, max_frames=3)
         cpu_baseline = {"value": o["n_rays"] * len(times) / sum(times), "unit": "rays/s",
@@ -642,6 +892,23 @@ def main():
                         "sample": f"{len(times)} full frame(s) of the same scene through oracle/gpnerf_oracle.py "
                                   f"({sum(times):.1f} s of CPU work)",
                         "s_per_frame": sum(times) / len(times)}
+        # the benchmarked (tensor-core) frame against the oracle frame just rendered, over the mask_at_box pixels
+        # only (libs/evaluators/if_nerf.py:49-57)
+        if world == 1:
+            import numpy as np
+            m = o["mask_at_box"].reshape(-1).bool()
+            a = ref_image.reshape(-1, 3)[m].double()
+            b = o["pred_img"].reshape(-1, 3)[m].double()
+            mse = float(((a - b) ** 2).mean()) if a.numel() else 0.0
+            xor = np.setxor1d(ref_valid1.numpy(), o["valid1"].numpy())
+            parity = {"against": "oracle/gpnerf_oracle.py (fp32, CPU) on the same scene and weights",
+                      "pixels": "mask_at_box only", "n_px": int(m.sum()),
+                      "psnr_mask": 10.0 * __import__("math").log10(1.0 / max(mse, 1e-20)),
+                      "max_abs": float((a - b).abs().max()) if a.numel() else 0.0, "rms": mse ** 0.5,
+                      "rays_equal": bool(counts["n_rays"] == o["n_rays"]), "P1_equal": bool(counts["P1"] == o["P1"]),
+                      "hit_mask_equal": bool(torch.equal(ref_hit.bool(), o["mask_at_box"].reshape(-1).bool())),
+                      "valid1_xor": int(len(xor)), "P2_oracle": int(o["P2"]),
+                      "valid1_xor_max_abs_sigma": float(o["sigma"][torch.from_numpy(xor).long()].abs().max()) if len(xor) else 0.0}
 
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -650,9 +917,7 @@ def main():
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "frames_per_s": (world if frames_mode else 1) * 1e3 / ms_per_step,
         "pixel_rays_per_s": (world if frames_mode else 1) * n_px * 1e3 / ms_per_step,
-        "config": {"workload": f"zju-like synthetic frame {RES}x{RES}, V={VIEWS}, S={S_SAMPLES} "
-                               "(BASELINE configs[1], trainzju_valzju inference shape), progressive path",
-                   "rays": g_rays, "points": g_rays * S_SAMPLES, "P1": g_p1, "P2": g_p2,
+        "config": {"workload": WORKLOAD, "rays": g_rays, "points": g_rays * S_SAMPLES, "P1": g_p1, "P2": g_p2,
                    "l2": "256 MB flush between timed steps; inputs 135 MB > 126 MB L2",
                    "sharding": ("single GPU" if world == 1 else
                                 (f"one frame per GPU and step ({world} consecutive frames of an orbit sweep, {SWEEP_STEP_DEG}° apart), "
@@ -668,7 +933,7 @@ def main():
                    "stages_ms_from": "eager re-issue of the same steps with CUDA events around every stage",
                    "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-        "sparse_levels_device": sparse_dev,
+        "sparse_levels_device": sparse_dev, "strong": strong, "parity": parity,
         "stages_ms": stages_out, "cpu_baseline": cpu_baseline,
     }
     emit(line)

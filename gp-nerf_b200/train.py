@@ -336,18 +336,34 @@ class GradBucket:
         dev, dt = self.params[0].device, torch.float32
         self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=dt, device=dev)
         self.group = group
+        self._views = []
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self._views.append(self.flat[off:off + n].view_as(p))
+            p.grad = self._views[-1]
             off += n
 
     def zero(self):
         self.flat.zero_()
+        self._reattach()
+
+    def _reattach(self):
+        """`optimizer.zero_grad()` (set_to_none=True by default) or an optimizer that replaces `.grad` breaks the
+        aliasing between `param.grad` and the flat buffer: gradients that were accumulated elsewhere are copied in
+        and the views are attached again, so the all-reduce never runs on stale values."""
+        for p, v in zip(self.params, self._views):
+            g = p.grad
+            if g is None:
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+                p.grad = v
 
     def all_reduce_mean(self):
         """Average the bucket over the ranks (no-op without a process group)."""
         import torch.distributed as dist
+        self._reattach()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.div_(dist.get_world_size(self.group))
