@@ -734,7 +734,15 @@ def main():
                         n_out[0] += int(out["mask_at_box"].sum() > 0)
                 run_stream_sparse(8)
                 et_s = timed(lambda: run_stream_sparse(args.steps), "sparse_levels")
+                def blocking_sparse():
+                    b = dict(sbatch)
+                    b["src_imgs"] = sbatch["src_imgs"].to(dev, non_blocking=True)
+                    return renderer.render(b)
+                for _ in range(4):
+                    blocking_sparse()
+                et_sb = timed(lambda: [blocking_sparse() for _ in range(args.steps)], "sparse_levels_blocking_call")
                 e2e_sparse = {"ms_per_step": 1e3 * et_s / args.steps, "value": g_rays * args.steps / et_s,
+                              "blocking_call_ms_per_step": 1e3 * et_sb / args.steps,
                               "unit": "rays/s", "h2d_bytes_per_step": int(h2d_s),
                               "what": "render_stream with the 4 levels as sparse rows (features + indices) instead of "
                                       "dense NCDHW tensors"}
@@ -791,13 +799,22 @@ def main():
                                   "image encoder, SMPL-code attention, sparse-conv pyramid and K1..K5 all inside the "
                                   "call; random-init producers, so the ray count differs from the synthetic-volume frame; "
                                   "stream_* = the same batches through Renderer.render_stream"}
-        e2e = {"value": g_rays * args.steps / et, "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(n_px * 3 * 4 + n_px + 32), "ms_per_step": 1e3 * et / args.steps,
-               "frames_per_s": args.steps * (world if frames_mode else 1) / et,
-               "api": ("gpnerf_b200.render.Renderer.render_stream(batches) – levels/featmaps/src_imgs of every frame in "
-                       "pinned host memory, uploads of the following frames overlapped with the render, every image "
-                       "read back to the host") if stream_ok else
+        # headline: the levels handed over as the sparse-conv net holds them (active rows) – what the upstream producer
+        # owns before `.dense()`; the dense NCDHW hand-off (119 MB of >95 % zeros per frame over PCIe) stays beside it
+        dense_leg = {"value": g_rays * args.steps / et, "ms_per_step": 1e3 * et / args.steps, "h2d_bytes_per_step": int(h2d),
+                     "what": "the same stream with the 4 levels as dense NCDHW fp32 tensors (SparseConvTensor.dense() layout)"}
+        if e2e_sparse is not None:
+            et_head, h2d_head = e2e_sparse["ms_per_step"] * 1e-3 * args.steps, e2e_sparse["h2d_bytes_per_step"]
+        else:
+            et_head, h2d_head = et, h2d
+        e2e = {"value": g_rays * args.steps / et_head, "unit": "rays/s", "h2d_bytes_per_step": int(h2d_head),
+               "d2h_bytes_per_step": int(n_px * 3 * 4 + n_px + 32), "ms_per_step": 1e3 * et_head / args.steps,
+               "frames_per_s": args.steps * (world if frames_mode else 1) / et_head,
+               "api": ("gpnerf_b200.render.Renderer.render_stream(batches) – sparse level rows / featmaps / src_imgs of "
+                       "every frame in pinned host memory, uploads of the following frames overlapped with the render, "
+                       "every image read back to the host") if stream_ok else
                       "gpnerf_b200.render.Renderer.render(batch) – levels/featmaps/src_imgs in pinned host memory",
+               "dense_levels": dense_leg,
                "blocking_call_ms_per_step": 1e3 * et_sync / args.steps,
                "blocking_call_api": "gpnerf_b200.render.Renderer.render(batch), one blocking call per frame",
                "sparse_levels": e2e_sparse, "from_images": e2e_images,

@@ -356,8 +356,23 @@ class Engine:
     def upload_frame(self, frame):
         """Refresh the device copy of the frame constants (pinned host → device,
         on the current stream).  Every render entry point calls it first."""
-        C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
-        self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
+        # four pinned staging slots in rotation, each guarded by an event: a second frame queued while the GPU is
+        # still behind must not overwrite constants whose host→device copy has not executed yet
+        slots = getattr(self, "_frame_slots", None)
+        if slots is None:
+            slots = self._frame_slots = [[torch.empty(C.sizeof(Frame), dtype=torch.uint8).pin_memory(), None]
+                                         for _ in range(4)]
+            self._frame_slot_i = 0
+        slot = slots[self._frame_slot_i]
+        self._frame_slot_i = (self._frame_slot_i + 1) % len(slots)
+        if slot[1] is not None:
+            slot[1].synchronize()
+        C.memmove(slot[0].data_ptr(), C.addressof(frame), C.sizeof(Frame))
+        self.frame_dev.copy_(slot[0], non_blocking=True)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        if not torch.cuda.is_current_stream_capturing():
+            slot[1].record(torch.cuda.current_stream(self.device))
 
     def attach_exchange(self, exchange):
         """Publish the rendered tiles through peer memory (peer.PeerExchange)

@@ -41,6 +41,27 @@ def level_to_channels_last(level):
     return out, cs
 
 
+def sparse_levels_to_channels_last(levels_sparse, level_dims, n_rows_dev=None):
+    """The pyramid's levels as active rows (features [N,32], indices [N,3|4] with (d,h,w) last; what a
+    SparseConvTensor holds before `.dense()`, SparseConvNet.py:110) → the 4 fp32 channel-last volumes
+    [D·H·W·32] that `gather_volume` reads (gpnerf_k0_sparse_to_f32: one scatter, no dense NCDHW tensor)."""
+    lib = _lib.load()
+    feats = [_c(f.to(torch.float32)) for f, _ in levels_sparse]
+    idxs = [i.detach().to(torch.int32).contiguous() for _, i in levels_sparse]
+    _need_cuda(*feats, *idxs)
+    dev = feats[0].device
+    dims = [tuple(int(v) for v in d) for d in level_dims]
+    cols = int(idxs[0].shape[1])
+    out = [torch.empty(d * h * w * 32, dtype=torch.float32, device=dev) for d, h, w in dims]
+    sums = [torch.empty(d * h * w, dtype=torch.float32, device=dev) for d, h, w in dims]
+    dims_c = ((C.c_int32 * 3) * 4)(*[(C.c_int32 * 3)(*d) for d in dims])
+    n_rows = (C.c_int32 * 4)(*[int(f.shape[0]) for f in feats])
+    nrd = None if n_rows_dev is None else _lib.ptr_array([t.view(1) for t in n_rows_dev])
+    check(lib.gpnerf_k0_sparse_to_f32(_lib.ptr_array(feats), _lib.ptr_array(idxs), n_rows, nrd, cols, dims_c,
+                                      _lib.ptr_array(out), _lib.ptr_array(sums), _stream(dev)), "k0_sparse_to_f32")
+    return out, dims
+
+
 def featmaps_to_channels_last(featmaps):
     _need_cuda(featmaps)
     lib = _lib.load()

@@ -200,6 +200,7 @@ class Renderer(nn.Module):
         """demo_render.Renderer.render: returns numpy rgb_map [R,3], pred_img
         [H,W,3] (float64), mask_at_box [H*W] bool, time_slots, etime, rtime."""
         device = batch["src_imgs"].device
+        t_host0 = time.perf_counter()
         # etime / rtime (demo_render.py:98-101, 442-447) from stream events instead of two device-wide
         # synchronisations: the host keeps queueing while the producers run
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -207,6 +208,7 @@ class Renderer(nn.Module):
         # queued, each of these tiny copies would wait for the encoder and the pyramid
         hostc = {k: batch[k].detach().cpu() for k in _HOST_KEYS if k in batch and torch.is_tensor(batch[k]) and batch[k].is_cuda}
         batch = {**batch, **hostc}               # (a copy: the caller's dict is never modified)
+        t_host = time.perf_counter() - t_host0
         ev[0].record(torch.cuda.current_stream(device))
         featmaps, levels = self._upstream(batch)
         ev[1].record(torch.cuda.current_stream(device))
@@ -214,12 +216,17 @@ class Renderer(nn.Module):
         V = batch["src_imgs"].shape[1]
         eng = self.engine_for(int(H), int(W), int(V), device)
         self._sync_weights(eng)
+        detail = bool(getattr(self, "time_slots_detail", False))
+        eng.timing = detail
+        if detail:
+            eng.stage_events = {}
+        use_graph = self.use_cuda_graph and not detail
         if levels is None:
             # sparse levels: scatter the active rows (no dense volume, no K0 transposition), then K1…K5
             eng.upload_products_sparse(batch["levels_sparse"], batch["level_dims"], featmaps, batch["src_imgs"],
                                        n_rows_dev=batch.get("levels_sparse_rows"))
             frame = eng.make_frame(batch, neg_ray=self._neg_ray(batch))
-            if self.use_cuda_graph:
+            if use_graph:
                 if getattr(self, "_frame_pinned", None) is None:
                     import ctypes as C
                     from ._lib import Frame
@@ -227,7 +234,7 @@ class Renderer(nn.Module):
                 eng.run_progressive_graphed(frame, with_k0=False, frame_src=self._frame_pinned)
             else:
                 eng.render_progressive(frame)
-        elif self.use_cuda_graph:
+        elif use_graph:
             # inputs land in static device buffers; the whole frame is one graph launch
             eng.copy_into_static_inputs(levels, featmaps, batch["src_imgs"],
                                         sharded_upload=self.world > 1 and self.shard == "tiles" and self._dist_ready())
@@ -251,17 +258,52 @@ class Renderer(nn.Module):
             both = torch.cat([img_d, hit_d.view(-1, 1).float()], 1)
             both = shard.gather_frame(both, int(W), self.tile_px)
             img_d, hit_d = both[:, :3].contiguous(), both[:, 3] > 0.5
-        cnt = eng.read_counters()                     # the frame's single host sync
-        pred_img = img_d.view(H, W, 3).cpu().numpy().astype(np.float64)
-        mask_at_box = hit_d.cpu().numpy().astype(bool)
-        if tiled:
-            rgb_map = pred_img.reshape(-1, 3)[mask_at_box].astype(np.float32)   # ascending pixel order
-        else:
-            n = cnt["n_rays"]
-            rgb_map = eng.rgb_map[: n * 3].view(n, 3).cpu().numpy()
+        # the frame's single host sync: image, hit mask and counters travel together through pinned staging (one
+        # event wait; a pageable `.cpu()` per tensor costs three synchronous copies at a third of the bandwidth)
+        pin = getattr(self, "_out_pinned", None)
+        n_px = int(H) * int(W)
+        if pin is None or pin[0].numel() != n_px * 3:
+            pin = self._out_pinned = (torch.empty(n_px * 3, dtype=torch.float32).pin_memory(),
+                                      torch.empty(n_px, dtype=torch.uint8).pin_memory(),
+                                      torch.empty(_lib.N_COUNTERS, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        pin[0].copy_(img_d.reshape(-1), non_blocking=True)
+        pin[1].copy_(hit_d.reshape(-1).to(torch.uint8), non_blocking=True)
+        pin[2].copy_(eng.counters, non_blocking=True)
+        pin[3].record(torch.cuda.current_stream(device))
+        pin[3].synchronize()
+        c = pin[2].tolist()
+        cnt = {"n_pix": c[_lib.CNT_PIX], "n_rays": c[_lib.CNT_RAYS], "P1": c[_lib.CNT_P1], "P2": c[_lib.CNT_P2]}
+        img32 = pin[0].numpy().reshape(-1, 3)
+        mask_at_box = pin[1].numpy().astype(bool)
+        rgb_map = img32[np.flatnonzero(mask_at_box)]             # ascending pixel order = the reference's ray order
+        pred_img = img32.reshape(H, W, 3).astype(np.float64)     # (fresh arrays: the staging buffers are reused)
         etime, rtime = ev[0].elapsed_time(ev[1]) * 1e-3, ev[1].elapsed_time(ev[2]) * 1e-3
         return {"rgb_map": rgb_map, "pred_img": pred_img, "mask_at_box": mask_at_box,
-                "time_slots": {"bc_render": rtime}, "etime": etime, "rtime": rtime, "counts": cnt}
+                "time_slots": self._time_slots(eng, etime, rtime, t_host), "etime": etime, "rtime": rtime, "counts": cnt}
+
+    def _time_slots(self, eng, etime, rtime, t_host):
+        """The ten keys of demo_render.render_rays' `time_slots` (demo_render.py:97-357), in seconds.  The reference
+        brackets each stage with two device-wide synchronisations; here a frame is one CUDA-graph launch, so by
+        default only what stream events can separate without stalling the pipeline is non-zero: `bc_time` (host set-up),
+        `sp_encode` (all upstream producers: encoder, SMPL gather, attention, pyramid) and `bc_render` (K1…K5).  With
+        `renderer.time_slots_detail = True` the frame is issued kernel by kernel with events around every stage and the
+        path's own keys are filled in: `bf_sigma` (layout, pixel mask, rays, sampling, occupancy compaction),
+        `sigma_f` (gathers + density head), `bf_rgb` (α + second compaction), `rgb_f` (colour head), `bc_render`
+        (compositing)."""
+        ts = {k: 0.0 for k in ("bc_time", "sigma_c", "bc_attn", "sigma_attn", "sp_encode", "bf_sigma", "sigma_f",
+                               "bf_rgb", "rgb_f", "bc_render")}
+        ts["bc_time"], ts["sp_encode"], ts["bc_render"] = t_host, etime, rtime
+        if getattr(self, "time_slots_detail", False) and eng.stage_events:
+            st = eng.stage_times_ms()
+            g = lambda *keys: sum(st.get(k, 0.0) for k in keys) * 1e-3        # noqa: E731
+            ts["bf_sigma"] = g("k0_products_to_f16", "k0_sparse_to_f16", "k0_level_to_channels_last",
+                               "k0_featmaps_to_channels_last", "k0_images_to_rgbx", "k0_build_masks3d", "k1_voxel_pixel_mask",
+                               "k1_rays_bbox", "k2_occupancy_compact")
+            ts["sigma_f"] = g("k23_gather_density_tc", "k2_gather_volume", "k2_project_gather_meanvar", "k3_density_mlp")
+            ts["bf_rgb"] = g("k4_compact_alpha")
+            ts["rgb_f"] = g("k3_color_gather_tc", "k3_color_mlp_records", "k3_color_mlp")
+            ts["bc_render"] = g("k5_composite", "peer_wait")
+        return ts
 
     @torch.no_grad()
     def render_stream(self, batches, depth=3):
@@ -444,22 +486,25 @@ class Renderer(nn.Module):
         (marching cubes stays their job, as in the reference).  Gathers and the head
         run in the library's kernels at explicit points (no rays, no compaction)."""
         device = batch["src_imgs"].device
+        batch = dict(batch)                     # _upstream may add the produced rows: never to the caller's dict
         featmaps, levels = self._upstream(batch)
-        if levels is None:
-            raise _lib.GpnerfError("render_mesh takes dense levels")
         src = batch["src_imgs"]
         H, W = int(src.shape[-2]), int(src.shape[-1])
         V = int(src.shape[1])
         from .engine import frame_from_batch
-        lv = [t.to(device) for t in levels]
         fm = featmaps.to(device)
-        dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
+        if levels is None:                      # sparse rows (from the batch or from the sigma head's own producers)
+            rows = [(f.to(device), i.to(device)) for f, i in batch["levels_sparse"]]
+            levels_cl, dims = ops.sparse_levels_to_channels_last(rows, batch["level_dims"], batch.get("levels_sparse_rows"))
+        else:
+            lv = [t.to(device) for t in levels]
+            dims = [tuple(int(v) for v in t.shape[-3:]) for t in lv]
+            levels_cl = [ops.level_to_channels_last(t)[0] for t in lv]
         frame = frame_from_batch(batch, H=H, W=W, n_views=V, n_samples=1, level_dims=dims, src_hw=(H, W),
                                  feat_hw=tuple(int(v) for v in fm.shape[-2:]),
                                  voxel_size=tuple(float(v) for v in self.voxel_size), neg_ray=self._neg_ray(batch))
         hw, _keep = ops.pack_head_weights(self.nerfhead.hot_path_state(), device, V,
                                           tensor_core_image=self.precision != PREC_FP32)
-        levels_cl = [ops.level_to_channels_last(t)[0] for t in lv]
         fm_cl = ops.featmaps_to_channels_last(fm)
         rgbx = ops.images_to_rgbx(src[0] if src.dim() == 5 else src, unnormalize=True)
         inside = batch["inside"][0].bool()

@@ -312,6 +312,15 @@ def test_mesh_branch_cube_vs_oracle():
     assert got.shape == want.shape and got.dtype == np.float64
     assert float(np.abs(got - want).max()) < TOL and float(want.max()) > 0.1
     assert float(np.abs(got[:10]).max()) == 0.0           # the 10-voxel pad
+    # the same from the levels as sparse rows (what a dataset batch leads to: the pyramid never builds a dense volume)
+    lv_s, dims_s = synth.sparsify_levels(scene["levels"])
+    b2 = {k: v for k, v in b.items() if k != "levels"}
+    b2.update(levels_sparse=[(f.to(DEV), i.to(DEV)) for f, i in lv_s], level_dims=dims_s)
+    got2 = r.render_mesh(b2)["cube"]
+    assert np.array_equal(got2, got)
+    ts = _renderer_for(w, 3, 16, PREC_FP32).render(dict(b, src_imgs=scene["src_imgs"].to(DEV)))["time_slots"]
+    assert sorted(ts) == sorted(["bc_time", "sigma_c", "bc_attn", "sigma_attn", "sp_encode", "bf_sigma", "sigma_f", "bf_rgb",
+                                 "rgb_f", "bc_render"])          # demo_render.py:97-357
 
 
 @pytest.mark.parametrize("in_dim,precision", [(16, "tf32x3"), (32, "tf32x3"), (16, "fp32"), (32, "fp32")])

@@ -16,7 +16,12 @@ head = NeRFHead(code_dim=32, n_views=3, precision=PREC_BF16)
 sd = head.state_dict(); sd.update(w); head.load_state_dict(sd)
 r = Renderer(None, head.to(dev), is_train=False, n_samples=64, progressive=True, precision=PREC_BF16)
 batch = {k: v for k, v in scene.items() if torch.is_tensor(v)}
-batch["levels"] = [t.pin_memory() for t in scene["levels"]]
+if os.environ.get("SPARSE", "1") == "1":          # levels as sparse rows (4 MB) instead of dense NCDHW tensors (119 MB)
+    lv_s, dims_s = synth.sparsify_levels(scene["levels"])
+    batch["levels_sparse"] = [(f.pin_memory(), i.pin_memory()) for f, i in lv_s]
+    batch["level_dims"] = dims_s
+else:
+    batch["levels"] = [t.pin_memory() for t in scene["levels"]]
 batch["featmaps"] = scene["featmaps"].pin_memory()
 batch["src_imgs"] = scene["src_imgs"].pin_memory()
 
