@@ -482,9 +482,10 @@ class Renderer(nn.Module):
         demo_render.py:249-268, 366-376): σ of the density head at the grid points
         `batch['pts']` [1,X,Y,Z,3] selected by `batch['inside']` [1,X,Y,Z], α = 1 - exp(-σ)
         scattered into the grid, zero-padded by 10 → ret['cube'] (float64 numpy, as
-        the reference builds it); ret['mesh'] when mcubes + trimesh are importable
-        (marching cubes stays their job, as in the reference).  Gathers and the head
-        run in the library's kernels at explicit points (no rays, no compaction)."""
+        the reference builds it); ret['vertices'] / ret['triangles'] / ret['mesh'] from
+        PyMCubes + trimesh when importable (as the reference does), else from this
+        package's marching tetrahedra (isosurface.py).  Gathers and the head run in
+        the library's kernels at explicit points (no rays, no compaction)."""
         device = batch["src_imgs"].device
         batch = dict(batch)                     # _upstream may add the produced rows: never to the caller's dict
         featmaps, levels = self._upstream(batch)
@@ -521,13 +522,19 @@ class Renderer(nn.Module):
         cube[inside.cpu().numpy()] = alpha.cpu().numpy()
         cube = np.pad(cube, 10, mode="constant")
         ret = {"cube": cube}
-        try:
+        try:                                    # the reference's own path (BaseRender.py:270-272), when its packages exist
             import mcubes
-            import trimesh
             vertices, triangles = mcubes.marching_cubes(cube, self.mesh_th)
+        except ImportError:                     # PyMCubes is not part of the reference tree: marching tetrahedra on the GPU
+            from .isosurface import marching_tetrahedra
+            vertices, triangles = marching_tetrahedra(torch.from_numpy(cube).to(device), float(self.mesh_th))
+        ret["vertices"], ret["triangles"] = vertices, triangles
+        try:
+            import trimesh
             ret["mesh"] = trimesh.Trimesh(vertices, triangles)
         except ImportError:
-            pass
+            from types import SimpleNamespace
+            ret["mesh"] = SimpleNamespace(vertices=vertices, faces=triangles)
         return ret
 
     def _wants_grad(self):

@@ -35,6 +35,27 @@ import torch.nn.functional as F
 # --------------------------------------------------------------------------
 
 
+# SURVEY §8c, second mode: the reference really runs these chains with torch on the GPU – cuBLAS for the K = 3 / 4
+# matmuls, ATen's CUDA kernels for norm and grid_sample – whose rounding differs from ATen-CPU's (to which the
+# bit-exact pins above are tied).  Inside `with native_ops("cuda:0"):` the three primitives every integer result
+# depends on (small matmul, 3-vector norm, grid_sample) are executed by torch on that device exactly as the reference
+# issues them; everything else stays as is.  tests/test_gpu_parity.py reports how many integer results move.
+_NATIVE = {"device": None}
+
+
+class native_ops:
+    def __init__(self, device):
+        self.device = device
+
+    def __enter__(self):
+        self.prev, _NATIVE["device"] = _NATIVE["device"], self.device
+        return self
+
+    def __exit__(self, *exc):
+        _NATIVE["device"] = self.prev
+        return False
+
+
 def _fma(a, b, c):
     """round_fp32(a*b + c) with one rounding (the product of two fp32 is exact
     in fp64; the fp64 sum is then rounded once more to fp32 – double rounding
@@ -45,6 +66,8 @@ def _fma(a, b, c):
 def mm_seqfma(A, B):
     """A[..., M, K] @ B[..., K, N] as ATen's CPU sgemm rounds it for tiny K:
     acc = a0*b0 (rounded); acc = fma(ak, bk, acc) for k = 1..K-1."""
+    if _NATIVE["device"] is not None:
+        return torch.matmul(A.to(_NATIVE["device"]), B.to(_NATIVE["device"])).cpu()
     K = A.shape[-1]
     acc = A[..., :, 0:1] * B[..., 0:1, :]
     for k in range(1, K):
@@ -57,6 +80,8 @@ def norm3(x):
     rounded, two FMAs, then a correctly rounded sqrt (taken in fp64 and rounded
     once more – torch.sqrt's vectorised fp32 kernel is NOT correctly rounded,
     torch.norm's is)."""
+    if _NATIVE["device"] is not None:
+        return torch.norm(x.to(_NATIVE["device"]), dim=-1).cpu()
     acc = x[..., 0] * x[..., 0]
     acc = _fma(x[..., 1], x[..., 1], acc)
     acc = _fma(x[..., 2], x[..., 2], acc)
@@ -208,7 +233,11 @@ def grid_coords_of(pts_smpl, bounds, out_sh_dhw, voxel=0.005):
 
 def trilinear(vol, grid):
     """vol [C,D,H,W], grid [P,3] (x,y,z) → [P,C]; align_corners, zeros padding."""
-    out = F.grid_sample(vol[None], grid[None, None, None], padding_mode="zeros", align_corners=True)
+    if _NATIVE["device"] is not None:
+        d = _NATIVE["device"]
+        out = F.grid_sample(vol[None].to(d), grid[None, None, None].to(d), padding_mode="zeros", align_corners=True).cpu()
+    else:
+        out = F.grid_sample(vol[None], grid[None, None, None], padding_mode="zeros", align_corners=True)
     return out[0, :, 0, 0].permute(1, 0)
 
 
@@ -266,8 +295,13 @@ def projector_compute(xyz, src_imgs01, cams, featmaps, neg_ray=False):
     pix, in_front = project(xyz, cams, neg_ray)
     resize = torch.stack([w - 1.0, h - 1.0])[None, None]
     norm = 2 * pix / resize - 1.0                                       # [V,P,2]
-    rgb = F.grid_sample(src_imgs01, norm[:, :, None], align_corners=True)[..., 0]      # [V,3,P]
-    feat = F.grid_sample(featmaps, norm[:, :, None], align_corners=True)[..., 0]       # [V,C,P]
+    if _NATIVE["device"] is not None:
+        d = _NATIVE["device"]
+        rgb = F.grid_sample(src_imgs01.to(d), norm[:, :, None].to(d), align_corners=True)[..., 0].cpu()
+        feat = F.grid_sample(featmaps.to(d), norm[:, :, None].to(d), align_corners=True)[..., 0].cpu()
+    else:
+        rgb = F.grid_sample(src_imgs01, norm[:, :, None], align_corners=True)[..., 0]      # [V,3,P]
+        feat = F.grid_sample(featmaps, norm[:, :, None], align_corners=True)[..., 0]       # [V,C,P]
     rgb_feat = torch.cat([rgb, feat], 1).permute(2, 0, 1).contiguous()                # [P,V,3+C]
     inbound = ((pix[..., 0] <= w - 1.0) & (pix[..., 0] >= 0)
                & (pix[..., 1] <= h - 1.0) & (pix[..., 1] >= 0))

@@ -225,3 +225,28 @@ def test_build_render_plugin_entry_points():
     assert "nerfhead.rgbhead.rgb_fc.4.bias" in keys and "nerfhead.sigmahead.c.weight" in keys
     with pytest.raises(Exception):
         r.render({"src_imgs": torch.zeros(1, 3, 3, 64, 64)})          # CPU tensors: no fallback
+
+
+def test_isosurface_marching_tetrahedra_closed_and_accurate():
+    """Row f4: the mesh extraction that stands in for PyMCubes (absent).  A sphere's signed distance: the surface must
+    be closed (every edge in exactly two triangles, traversed in opposite directions), consistently oriented
+    outwards, and sit on the sphere."""
+    import numpy as np
+    from gpnerf_b200.isosurface import marching_tetrahedra
+    n, r, c = 36, 11.3, np.array([17.3, 18.1, 16.7])
+    g = np.stack(np.meshgrid(*[np.arange(n)] * 3, indexing="ij"), -1).astype(np.float64)
+    v, f = marching_tetrahedra(r - np.linalg.norm(g - c, axis=-1), 0.0)
+    assert v.dtype == np.float64 and f.shape[1] == 3 and len(f) > 1000
+    assert np.abs(np.linalg.norm(v - c, axis=1) - r).max() < 0.05
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    und = np.sort(e, 1)
+    _, cnt = np.unique(und[:, 0] * len(v) + und[:, 1], return_counts=True)
+    assert (cnt == 2).all()
+    assert len(np.unique(e[:, 0] * len(v) + e[:, 1])) == len(e)
+    p0, p1, p2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    nrm = np.cross(p1 - p0, p2 - p0)
+    assert ((nrm * (p0 - c)).sum(1) > 0).all()
+    assert abs(0.5 * np.linalg.norm(nrm, axis=1).sum() / (4 * np.pi * r * r) - 1) < 0.01
+    assert abs((p0 * nrm).sum() / 6 / (4 / 3 * np.pi * r ** 3) - 1) < 0.01
+    v0, f0 = marching_tetrahedra(np.zeros((5, 5, 5)), 0.5)
+    assert v0.shape == (0, 3) and f0.shape == (0, 3)

@@ -308,7 +308,11 @@ def test_mesh_branch_cube_vs_oracle():
     b = {k: v for k, v in scene.items() if torch.is_tensor(v)}
     b.update(levels=scene["levels"], featmaps=scene["featmaps"], src_imgs=scene["src_imgs"].to(DEV),
              pts=pts[None], inside=inside[None])
-    got = r.render_mesh(b)["cube"]
+    r.mesh_th = 0.3
+    ret = r.render_mesh(b)
+    got = ret["cube"]
+    assert ret["triangles"].shape[1] == 3 and len(ret["triangles"]) > 100       # the iso-surface at α = 0.3
+    assert float(ret["vertices"].min()) >= 0.0 and ret["vertices"].shape[1] == 3
     assert got.shape == want.shape and got.dtype == np.float64
     assert float(np.abs(got - want).max()) < TOL and float(want.max()) > 0.1
     assert float(np.abs(got[:10]).max()) == 0.0           # the 10-voxel pad
@@ -1133,3 +1137,136 @@ def test_plugin_trains_under_the_reference_trainer_sequence():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+def test_same_gpu_torch_ops_oracle_reports_mismatch_counts():
+    """SURVEY §8c, second mode.  The bit-exact pins are tied to ATen-CPU rounding (the only way the reference's code
+    runs in the build container); the reference itself runs on the GPU, where cuBLAS (K = 3 / 4 matmuls), torch.norm
+    and grid_sample round differently.  The oracle's `native_ops` mode executes those primitives with torch on this
+    GPU exactly as the reference issues them; this test records how many integer results move between the two
+    roundings – an intrinsic property of the reference, not of this library – and checks that the library's exact
+    path sits within that band of the GPU-rounded oracle."""
+    scene = synth.make_scene("zju", H=160, W=160, V=3, seed=23)
+    w = synth.make_head_weights(V=3, seed=123, random_bias=True)
+    S = 48
+    o_cpu = orc.render_progressive(scene, w, S=S, keep=True)
+    with orc.native_ops(DEV):
+        o_gpu = orc.render_progressive(scene, w, S=S, keep=True)
+    rep = {"rays_cpu": o_cpu["n_rays"], "rays_gpu_ops": o_gpu["n_rays"],
+           "ray_pix_xor": stages.xor_count(o_cpu["ray_pix"], o_gpu["ray_pix"]),
+           "P1_cpu": o_cpu["P1"], "P1_gpu_ops": o_gpu["P1"]}
+    common = np.intersect1d(o_cpu["ray_pix"].numpy(), o_gpu["ray_pix"].numpy())
+    # sample ids are (ray, sample): compare through (pixel, sample) keys so that a moved ray does not shift everything
+    def keys(o):
+        ray = torch.div(o["valid"], S, rounding_mode="floor")
+        return (o["ray_pix"][ray].long() * S + (o["valid"] - ray * S)).numpy()
+    rep["valid_xor"] = int(len(np.setxor1d(keys(o_cpu), keys(o_gpu))))
+    img_c, img_g = o_cpu["pred_img"], o_gpu["pred_img"]
+    rep["image_max_abs"] = float((img_c - img_g).abs().max())
+    eng, _ = stages.run_engine_progressive(scene, w, S)
+    img_k = eng.pred_img.cpu().view(160, 160, 3).double()
+    rep["kernels_vs_cpu_rounding"] = float((img_k - img_c).abs().max())
+    rep["kernels_vs_gpu_rounding"] = float((img_k - img_g).abs().max())
+    print("same-GPU torch-ops oracle vs CPU-rounding oracle:", rep)
+    assert len(common) >= 0.99 * o_cpu["n_rays"]
+    assert rep["valid_xor"] <= 0.01 * o_cpu["P1"] + 16
+    assert rep["kernels_vs_cpu_rounding"] < TOL
+    # a ray or sample that exists under one rounding only changes a pixel by its full contribution: bound the damage
+    # by the count, not by a per-pixel tolerance
+    assert rep["ray_pix_xor"] <= 0.01 * o_cpu["n_rays"] + 4
+
+
+def test_sparse_conv_kernels_vs_hand_derived_spconv_cases():
+    """Row f1, the pin the dense emulation cannot give: spconv 1.2.1 (abf0acf3, absent here) semantics stated directly
+    and evaluated by explicit loops over sites – no convolution routine involved.
+      * `SubMConv3d(k=3)` ("submanifold", spconv README / Graham et al. 2017 §2): the output site set IS the input
+        site set; out[p] = Σ_{Δ∈{-1,0,1}³} W[Δ+1]ᵀ · in[p+Δ] over the ACTIVE input sites p+Δ only.
+      * `SparseConv3d(k=3, stride=2, padding=1)`: output site q (grid ⌊(D-1)/2⌋+1 …) is active iff some active input
+        site p satisfies 2q-1 ≤ p ≤ 2q+1 on every axis; out[q] = Σ_Δ W[Δ+1]ᵀ · in[2q+Δ].
+      * weight layout [kd, kh, kw, in, out] (SparseConvNet.py:21-87 hands spconv exactly these modules), no bias.
+      * duplicate input coordinates: one site (this library: the smallest row id owns it – spconv's hash insert is
+        implementation-defined).
+    Integer-valued features and weights make every sum exact, so the comparison is bit for bit."""
+    import ctypes as C
+    lib = _lib.load()
+    ptr = _lib.ptr
+    st = C.c_void_p(torch.cuda.current_stream(torch.device(DEV)).cuda_stream)
+    g = torch.Generator().manual_seed(5)
+    D, H, W = 6, 7, 5
+    # 40 random voxels (some duplicated on purpose) + a far corner site with no neighbours at all
+    coords = torch.stack([torch.randint(0, D - 1, (40,), generator=g), torch.randint(0, H - 1, (40,), generator=g),
+                          torch.randint(0, W - 1, (40,), generator=g)], 1).int()
+    coords = torch.cat([coords, coords[:5], torch.tensor([[D - 1, H - 1, W - 1]], dtype=torch.int32)])
+    n = coords.shape[0]
+    feat = torch.randint(-3, 4, (n, 16), generator=g).float()
+    w_subm = torch.randint(-2, 3, (3, 3, 3, 16, 16), generator=g).float()
+    w_down = torch.randint(-2, 3, (3, 3, 3, 16, 32), generator=g).float()
+    # ---------------- hand evaluation (dicts keyed by voxel)
+    owner = {}
+    for i, c in enumerate(coords.tolist()):
+        owner.setdefault(tuple(c), i)                       # smallest row id owns a duplicated voxel
+    sites = sorted(owner, key=owner.get)                     # level 0: sites in the order of their owning input rows
+    x_in = {p: feat[owner[p]] for p in sites}
+
+    def conv_at(inp, wt, centre):
+        acc = torch.zeros(wt.shape[-1])
+        for kd in range(3):
+            for kh in range(3):
+                for kw in range(3):
+                    p = (centre[0] - 1 + kd, centre[1] - 1 + kh, centre[2] - 1 + kw)
+                    if p in inp:
+                        acc += inp[p] @ wt[kd, kh, kw]
+        return acc
+    want_subm = {p: torch.relu(conv_at(x_in, w_subm, p)) for p in sites}
+    Do, Ho, Wo = (D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out_sites = sorted({(q0, q1, q2) for q0 in range(Do) for q1 in range(Ho) for q2 in range(Wo)
+                        if any((2 * q0 + a, 2 * q1 + b, 2 * q2 + c) in want_subm
+                               for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1))})
+    want_down = {q: torch.relu(conv_at(want_subm, w_down, (2 * q[0], 2 * q[1], 2 * q[2]))) for q in out_sites}
+    # ---------------- the library's kernels
+    i32 = dict(dtype=torch.int32, device=DEV)
+    ws = torch.empty(int(lib.gpnerf_workspace_bytes(max(D * H * W, n))), dtype=torch.uint8, device=DEV)
+    idx0, owners, c0, n0 = torch.empty(D * H * W, **i32), torch.empty(n, **i32), torch.empty(n * 3, **i32), torch.zeros(1, **i32)
+    _lib.check(lib.gpnerf_sc_index_input(ptr(coords.to(DEV).contiguous()), 3, n, D, H, W, ptr(idx0), ptr(owners), ptr(c0), ptr(n0),
+                                         ptr(ws), st), "sc_index_input")
+    ns = int(n0.item())
+    assert ns == len(sites)
+    assert [tuple(r) for r in c0[: ns * 3].view(ns, 3).cpu().tolist()] == sites
+    assert owners[:ns].cpu().tolist() == [owner[p] for p in sites]
+    x0 = torch.empty(n * 16, dtype=torch.float32, device=DEV)
+    _lib.check(lib.gpnerf_sc_gather_rows(ptr(feat.to(DEV).contiguous()), 16, ptr(owners), ptr(n0), n, ptr(x0), st), "sc_gather_rows")
+    ones16, zeros16 = torch.ones(16, device=DEV), torch.zeros(16, device=DEV)
+    ones32, zeros32 = torch.ones(32, device=DEV), torch.zeros(32, device=DEV)
+    nbr = torch.empty(27 * n, **i32)
+    _lib.check(lib.gpnerf_sc_neighbours(ptr(c0), ptr(n0), n, 1, ptr(idx0), D, H, W, ptr(n0), ptr(nbr), st), "sc_neighbours")
+    y0 = torch.empty(n * 16, dtype=torch.float32, device=DEV)
+    _lib.check(lib.gpnerf_sc_conv(ptr(x0), 16, ptr(nbr), ptr(n0), n, ptr(w_subm.to(DEV).contiguous()), ptr(ones16), ptr(zeros16), 16,
+                                  ptr(y0), st), "sc_conv subm")
+    got_subm = y0[: ns * 16].view(ns, 16).cpu()
+    for j, p in enumerate(sites):                            # SubM: same sites, exact sums
+        assert torch.equal(got_subm[j], want_subm[p]), (p, got_subm[j], want_subm[p])
+    cap1 = 8 * n
+    lin, c1 = torch.empty(cap1, **i32), torch.empty(cap1 * 3, **i32)
+    idx1, n1 = torch.empty(Do * Ho * Wo, **i32), torch.zeros(1, **i32)
+    _lib.check(lib.gpnerf_sc_strided_sites(ptr(c0), ptr(n0), n, Do, Ho, Wo, ptr(lin), ptr(c1), ptr(idx1), ptr(n1), ptr(ws), st),
+               "sc_strided_sites")
+    no = int(n1.item())
+    assert [tuple(r) for r in c1[: no * 3].view(no, 3).cpu().tolist()] == out_sites       # the strided site rule
+    nbr1 = torch.empty(27 * cap1, **i32)
+    _lib.check(lib.gpnerf_sc_neighbours(ptr(c1), ptr(n1), cap1, 2, ptr(idx0), D, H, W, ptr(n0), ptr(nbr1), st), "sc_neighbours s2")
+    y1 = torch.empty(cap1 * 32, dtype=torch.float32, device=DEV)
+    _lib.check(lib.gpnerf_sc_conv(ptr(y0), 16, ptr(nbr1), ptr(n1), cap1, ptr(w_down.to(DEV).contiguous()), ptr(ones32), ptr(zeros32),
+                                  32, ptr(y1), st), "sc_conv down")
+    got_down = y1[: no * 32].view(no, 32).cpu()
+    for j, q in enumerate(out_sites):
+        assert torch.equal(got_down[j], want_down[q]), (q, got_down[j], want_down[q])
+    # weight layout: a single non-zero tap (kd, kh, kw) = (2, 0, 1) with W = I moves features by exactly (+1, -1, 0)
+    w_one = torch.zeros(3, 3, 3, 16, 16)
+    w_one[2, 0, 1] = torch.eye(16)
+    _lib.check(lib.gpnerf_sc_conv(ptr(x0), 16, ptr(nbr), ptr(n0), n, ptr(w_one.to(DEV).contiguous()), ptr(ones16), ptr(zeros16), 16,
+                                  ptr(y0), st), "sc_conv one tap")
+    got_one = y0[: ns * 16].view(ns, 16).cpu()
+    for j, p in enumerate(sites):
+        src = (p[0] + 1, p[1] - 1, p[2])
+        want = torch.relu(x_in[src]) if src in x_in else torch.zeros(16)
+        assert torch.equal(got_one[j], want), (p, src)
