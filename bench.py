@@ -161,6 +161,7 @@ def stage_work(counts, n_level_elems, V, n_map_elems=0, n_img_px=0):
                                   "320 B/view per point from L1/L2 and runs 38,688 FLOP/point on the tensor pipe"),
         "k3_color_mlp_records": ("tensor", 72160.0 * P2, "72,160 FLOP per point"),
         "k4_compact_alpha": ("hbm", 8.0 * P1, "4 B read + 4 B written per point"),
+        "k4_compact_alpha_fused": ("hbm", 0.125 * P1 + 4.0 * P2, "1 flag bit read per point, 4 B written per survivor"),
         "k5_composite": ("hbm", 16.0 * P1, "16 B per surviving sample"),
     }
 

@@ -2,6 +2,7 @@
 // stream-compaction passes shared by K1 (pixels→rays), K2 (occupancy) and K4
 // (density).  HBM-bound integer work: 1 bit/item in, 4 B/survivor out.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -168,6 +169,113 @@ __global__ void __launch_bounds__(kTileWords) compact_expand(const uint32_t* __r
   }
 }
 
+// --- single pass: tile popcount, decoupled look-back over the tile prefixes, expansion ----------------------
+// One launch instead of three (tile sums → single-CTA scan → expand): a tile (kTileWords words = 8,192 items) is
+// claimed through a ticket, so tiles are processed in an order in which every predecessor has been started; the CTA
+// publishes its aggregate, looks back over its predecessors' descriptors ((status << 32) | value: 1 = aggregate,
+// 2 = inclusive prefix) until it meets an inclusive prefix, publishes its own and expands its words into ascending
+// indices.  Descriptors and the ticket live in the workspace (tile_sums | tile_offs as one uint64 array) and are
+// cleared by a memset node in front of every launch.
+__global__ void __launch_bounds__(kTileWords) compact_single_pass(const uint32_t* __restrict__ words,
+                                                                  unsigned long long* __restrict__ desc, int* __restrict__ ticket,
+                                                                  const int32_t* n_src, int mult, long long n_const,
+                                                                  int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count,
+                                                                  int row_len, int32_t* __restrict__ row_begin) {
+  const long long n_items = live_count(n_src, mult, n_const);
+  const long long n_words = (n_items + 31) >> 5;
+  const int n_tiles = (int)((n_words + kTileWords - 1) / kTileWords);
+  constexpr int NW = kTileWords / 32;
+  __shared__ int word_off[kTileWords];
+  __shared__ uint32_t word_bits[kTileWords];
+  __shared__ int warp_tot[NW];
+  __shared__ int tile_s, excl_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (n_tiles == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      *out_count = 0;
+      if (row_begin != nullptr) row_begin[0] = 0;
+    }
+    return;
+  }
+  for (;;) {
+    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tile = tile_s;
+    if (tile >= n_tiles) return;
+    const long long w = (long long)tile * kTileWords + threadIdx.x;
+    const uint32_t bits = (w < n_words) ? __ldg(words + w) : 0u;
+    const int cnt = __popc(bits);
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int k = 0; k < NW; ++k) {
+      if (k < wid) wbase += warp_tot[k];
+      total += warp_tot[k];
+    }
+    // ---- publish the aggregate, look back (warp 0), publish the inclusive prefix
+    if (wid == 0) {
+      volatile unsigned long long* vd = desc;
+      if (lane == 0) {
+        const unsigned long long mine = ((unsigned long long)(tile == 0 ? 2u : 1u) << 32) | (unsigned)total;
+        atomicExch(desc + tile, mine);
+      }
+      int excl = 0;
+      if (tile > 0) {
+        int look = tile - 1;
+        for (;;) {          // 32 predecessors at a time, nearest first
+          const int t = look - lane;
+          unsigned long long d = 0;
+          if (t >= 0) {
+            do {
+              d = vd[t];
+            } while ((d >> 32) == 0ull);
+          } else {
+            d = 2ull << 32;               // before tile 0: an empty inclusive prefix
+          }
+          const unsigned full = __ballot_sync(0xffffffffu, (d >> 32) == 2ull);
+          const int first_full = full ? (__ffs(full) - 1) : 32;
+          int v = (lane <= first_full) ? (int)(unsigned)d : 0;
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          excl += v;
+          if (full) break;
+          look -= 32;
+        }
+        if (lane == 0) {
+          __threadfence();
+          atomicExch(desc + tile, (2ull << 32) | (unsigned)(excl + total));
+        }
+      }
+      if (lane == 0) {
+        excl_s = excl;
+        if (tile == n_tiles - 1) {
+          *out_count = excl + total;
+          if (row_begin != nullptr) row_begin[(n_items + row_len - 1) / row_len] = excl + total;   // CSR sentinel
+        }
+      }
+    }
+    word_off[threadIdx.x] = wbase + incl - cnt;
+    word_bits[threadIdx.x] = bits;
+    __syncthreads();
+    const int tile_off = excl_s;
+    // ---- expansion: a warp expands one word at a time (coalesced index writes)
+    for (int wl = wid; wl < kTileWords; wl += NW) {
+      const uint32_t b = word_bits[wl];
+      const unsigned item = (unsigned)(((long long)tile * kTileWords + wl) * 32 + lane);     // item counts stay below 2^31
+      const int rank = __popc(b & ((1u << lane) - 1u));
+      if (row_begin != nullptr && item < (unsigned)n_items && item % (unsigned)row_len == 0u)
+        row_begin[item / (unsigned)row_len] = tile_off + word_off[wl] + rank;
+      if (b == 0u) continue;
+      if ((b >> lane) & 1u) out_idx[tile_off + word_off[wl] + rank] = (int32_t)item;
+    }
+    __syncthreads();
+  }
+}
+
 int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t n_const,
                    int64_t n_items_max, int32_t* out_idx, int32_t* out_count, cudaStream_t st, int row_len,
                    int32_t* row_begin) {
@@ -179,10 +287,25 @@ int compact_launch(const CompactWs& ws, const int32_t* n_src, int mult, int64_t 
   int64_t n_words = div_up(n_items_max, 32);
   int64_t n_tiles = div_up(n_words, kTileWords);
   int grid = (int)(n_tiles < (int64_t)sm_count() * 8 ? (n_tiles > 0 ? n_tiles : 1) : sm_count() * 8);
-  compact_tile_sums<<<grid, kTileWords, 0, st>>>(ws.words, n_src, mult, n_const, ws.tile_sums);
-  compact_scan<<<1, 1024, 0, st>>>(ws.tile_sums, n_src, mult, n_const, ws.tile_offs, out_count, row_len, row_begin);
-  compact_expand<<<grid, kTileWords, 0, st>>>(ws.words, ws.tile_offs, n_src, mult, n_const, out_idx, row_len,
-                                              row_begin);
+  static const bool three_pass = getenv("GPNERF_COMPACT_IMPL") && !strcmp(getenv("GPNERF_COMPACT_IMPL"), "three_pass");
+  if (three_pass) {
+    compact_tile_sums<<<grid, kTileWords, 0, st>>>(ws.words, n_src, mult, n_const, ws.tile_sums);
+    compact_scan<<<1, 1024, 0, st>>>(ws.tile_sums, n_src, mult, n_const, ws.tile_offs, out_count, row_len, row_begin);
+    compact_expand<<<grid, kTileWords, 0, st>>>(ws.words, ws.tile_offs, n_src, mult, n_const, out_idx, row_len,
+                                                row_begin);
+    return check_launch("compact");
+  }
+  // descriptors (one uint64 per tile, in the tile_sums | tile_offs area) + the ticket behind them
+  const int64_t n_pad = div_up(n_tiles, 64) * 64;
+  unsigned long long* desc = reinterpret_cast<unsigned long long*>(ws.tile_sums);
+  int* ticket = reinterpret_cast<int*>(desc + n_pad);
+  cudaError_t e = cudaMemsetAsync(desc, 0, (size_t)n_pad * 8 + 64, st);
+  if (e != cudaSuccess) {
+    set_error("memset compaction descriptors", e);
+    return GPNERF_E_CUDA;
+  }
+  compact_single_pass<<<grid, kTileWords, 0, st>>>(ws.words, desc, ticket, n_src, mult, n_const, out_idx, out_count, row_len,
+                                                   row_begin);
   return check_launch("compact");
 }
 
@@ -206,7 +329,7 @@ int64_t gpnerf_workspace_bytes(int64_t n_items) {
   if (n_items < 0) return GPNERF_E_ARG;
   int64_t n_words = gpnerf::div_up(n_items, 32);
   int64_t n_tiles = gpnerf::div_up(n_words, gpnerf::kTileWords);
-  return (gpnerf::div_up(n_words, 64) * 64 + 2 * gpnerf::div_up(n_tiles, 64) * 64 + 64) * 4;
+  return (gpnerf::div_up(n_words, 64) * 64 + 2 * gpnerf::div_up(n_tiles, 64) * 64 + 64 + 64) * 4;
 }
 
 }  // extern "C"

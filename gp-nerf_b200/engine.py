@@ -31,8 +31,9 @@ HEAD_KEYS = {
 KERNELS_PER_CALL = {
     "k0_level_to_channels_last": 1, "k0_featmaps_to_channels_last": 1, "k0_images_to_rgbx": 1,
     "k0_products_to_f16": 1, "k0_sparse_to_f16": 1,
-    "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 5, "k2_occupancy_compact": 4,
-    "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 4,   # 3 when fused
+    "k0_build_masks3d": 1, "k1_voxel_pixel_mask": 3, "k1_rays_bbox": 3, "k2_occupancy_compact": 2,
+    "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 2,
+    "k4_compact_alpha_fused": 1,      # α and the flags come from the fused kernel: the single-pass compaction only
     "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1, "peer_wait": 1,
     "k23_gather_density_tc": 1, "k3_color_mlp_records": 1, "k3_color_gather_tc": 1,
 }
@@ -497,7 +498,8 @@ class Engine:
                   ptr(self.counters), ptr(self.workspace), ptr(self.tile_ray_begin), st)
         self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays, fuse_alpha=True)
         # tensor-core path: α and the survivor flags were written by the fused kernel's epilogue
-        self._run("k4_compact_alpha", L.gpnerf_k4_compact_alpha, None if self.bf16 else ptr(self.sigma), self.max_pts,
+        self._run("k4_compact_alpha_fused" if self.bf16 else "k4_compact_alpha", L.gpnerf_k4_compact_alpha,
+                  None if self.bf16 else ptr(self.sigma), self.max_pts,
                   ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
         self._color(ptr(self.valid1), self.max_pts, CNT_P2, frame)
         ex = self.exchange

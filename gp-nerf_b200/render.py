@@ -300,7 +300,7 @@ class Renderer(nn.Module):
                                "k0_featmaps_to_channels_last", "k0_images_to_rgbx", "k0_build_masks3d", "k1_voxel_pixel_mask",
                                "k1_rays_bbox", "k2_occupancy_compact")
             ts["sigma_f"] = g("k23_gather_density_tc", "k2_gather_volume", "k2_project_gather_meanvar", "k3_density_mlp")
-            ts["bf_rgb"] = g("k4_compact_alpha")
+            ts["bf_rgb"] = g("k4_compact_alpha", "k4_compact_alpha_fused")
             ts["rgb_f"] = g("k3_color_gather_tc", "k3_color_mlp_records", "k3_color_mlp")
             ts["bc_render"] = g("k5_composite", "peer_wait")
         return ts
