@@ -104,6 +104,10 @@ _SIGNATURES = {
     "gpnerf_k23_record_bytes": ([_I], C.c_int64),
     "gpnerf_k23_gather_density_tc": ([C.POINTER(_P), _P, _P, _P, _P, _P, _P, C.POINTER(Frame), C.POINTER(HeadWeights),
                                       _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k23_tile_record_bytes": ([_I], C.c_int64),
+    "gpnerf_k23_gather_density_tiles_tc": ([C.POINTER(_P), _P, _P, _P, _P, _P, _P, C.POINTER(Frame),
+                                            C.POINTER(HeadWeights), _I, _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "gpnerf_k3_color_tiles_tc": ([_P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _P], C.c_int),
     "gpnerf_k3_color_mlp_records": ([_P, _P, C.POINTER(HeadWeights), _I, _I, _P, _I, _P, _P], C.c_int),
     "gpnerf_k3_color_gather_tc": ([_P, _P, _P, _P, _P, _P, _P, C.POINTER(Frame), C.POINTER(HeadWeights), _I, _P, _I, _P, _P,
                                    _P], C.c_int),

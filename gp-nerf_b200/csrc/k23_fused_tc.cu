@@ -432,15 +432,13 @@ extern "C" {
 
 int64_t gpnerf_k23_record_bytes(int n_views) { return 16ll * rec_chunks(n_views); }
 
-int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], const void* featmaps_f16,
-                                 const float* images_rgbx, const int32_t* valid, const float* rays_o,
-                                 const float* rays_d, const float* z_vals, const gpnerf_frame_t* f,
-                                 const gpnerf_head_weights_t* w, int n_points_max, const int32_t* counters,
-                                 float* sigma, void* records, float* alpha, void* k4_workspace, void* stream) {
+static int fused_args(FusedArgs& a, const void* const levels_f16[GPNERF_N_LEVELS], const void* featmaps_f16,
+                      const float* images_rgbx, const int32_t* valid, const float* rays_o, const float* rays_d,
+                      const float* z_vals, const gpnerf_frame_t* f, const gpnerf_head_weights_t* w, int n_points_max,
+                      const int32_t* counters, float* sigma, float* alpha, void* k4_workspace) {
   GPNERF_REQUIRE(levels_f16 && featmaps_f16 && images_rgbx && valid && rays_o && rays_d && z_vals && f && w &&
-                 counters && sigma && n_points_max > 0);        // records may be NULL (no colour records)
+                 counters && sigma && n_points_max > 0);
   GPNERF_REQUIRE(w->tc_image != nullptr && f->n_samples > 0 && f->src_w > 1 && f->src_h > 1);
-  FusedArgs a;
   for (int l = 0; l < GPNERF_N_LEVELS; ++l) {
     GPNERF_REQUIRE(levels_f16[l] != nullptr);
     a.lv[l] = reinterpret_cast<const __half*>(levels_f16[l]);
@@ -451,15 +449,33 @@ int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], 
   a.counters = counters;
   a.image = reinterpret_cast<const uint8_t*>(w->tc_image);
   a.sigma = sigma;
-  a.rec = reinterpret_cast<uint4*>(records);
+  a.rec = nullptr;
+  a.rec_tiles = nullptr;
+  a.rgb_in = nullptr;
+  static const int dbg = getenv("GPNERF_FUSED_DEBUG") ? atoi(getenv("GPNERF_FUSED_DEBUG")) : 0;
+  a.debug = dbg;
   GPNERF_REQUIRE((alpha == nullptr) == (k4_workspace == nullptr));
   a.alpha = alpha;
   a.alpha_words = alpha ? carve_workspace(k4_workspace, n_points_max).words : nullptr;
+  return GPNERF_OK;
+}
+
+int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], const void* featmaps_f16,
+                                 const float* images_rgbx, const int32_t* valid, const float* rays_o,
+                                 const float* rays_d, const float* z_vals, const gpnerf_frame_t* f,
+                                 const gpnerf_head_weights_t* w, int n_points_max, const int32_t* counters,
+                                 float* sigma, void* records, float* alpha, void* k4_workspace, void* stream) {
+  FusedArgs a;
+  int rc = fused_args(a, levels_f16, featmaps_f16, images_rgbx, valid, rays_o, rays_d, z_vals, f, w, n_points_max,
+                      counters, sigma, alpha, k4_workspace);
+  if (rc != GPNERF_OK) return rc;
+  a.rec = reinterpret_cast<uint4*>(records);
   cudaStream_t st = (cudaStream_t)stream;
-  // GPNERF_FUSED_IMPL=monolithic selects the round-1 kernel (one 256-thread CTA does plan → gather → 4 MMA rounds
-  // serially, two CTAs per SM); the default is the warp-specialised kernel of k23_fused_ws.cu
+  // Per-point records (round 1's hand-off to gpnerf_k3_color_mlp_records) are written by round 1's kernel only: one
+  // 256-thread CTA does plan → gather → 4 MMA rounds serially, two CTAs per SM.  GPNERF_FUSED_IMPL=monolithic selects
+  // it without records as well; the default is the warp-specialised kernel of k23_fused_ws.cu.
   static const bool monolithic = getenv("GPNERF_FUSED_IMPL") && !strcmp(getenv("GPNERF_FUSED_IMPL"), "monolithic");
-  if (!monolithic) return launch_fused_ws(a, f, n_points_max, st);
+  if (!monolithic && records == nullptr) return launch_fused_ws(a, f, n_points_max, st);
   GPNERF_REQUIRE(records != nullptr);       // the round-1 kernel always writes its colour records
   switch (f->n_views) {
     case 1: return launch_fused<1>(a, f, n_points_max, st);
@@ -470,6 +486,22 @@ int gpnerf_k23_gather_density_tc(const void* const levels_f16[GPNERF_N_LEVELS], 
       set_error("fused tcgen05 path supports 1..4 source views", cudaSuccess);
       return GPNERF_E_UNSUPPORTED;
   }
+}
+
+int gpnerf_k23_gather_density_tiles_tc(const void* const levels_f16[GPNERF_N_LEVELS], const void* featmaps_f16,
+                                       const float* images_rgbx, const int32_t* valid, const float* rays_o,
+                                       const float* rays_d, const float* z_vals, const gpnerf_frame_t* f,
+                                       const gpnerf_head_weights_t* w, int n_points_max, const int32_t* counters,
+                                       float* sigma, void* tile_records, float* rgb_in, float* alpha,
+                                       void* k4_workspace, void* stream) {
+  FusedArgs a;
+  int rc = fused_args(a, levels_f16, featmaps_f16, images_rgbx, valid, rays_o, rays_d, z_vals, f, w, n_points_max,
+                      counters, sigma, alpha, k4_workspace);
+  if (rc != GPNERF_OK) return rc;
+  GPNERF_REQUIRE(tile_records != nullptr);
+  a.rec_tiles = reinterpret_cast<uint8_t*>(tile_records);
+  a.rgb_in = rgb_in;
+  return launch_fused_ws(a, f, n_points_max, (cudaStream_t)stream);
 }
 
 int gpnerf_k3_color_mlp_records(const void* records, const int32_t* valid1, const gpnerf_head_weights_t* w,

@@ -20,8 +20,10 @@
 // While chain 0's tile waits for a GEMM, chain 1's tile is in its epilogue and the producers are two tiles ahead:
 // the gather (L1-bound) never waits for the head (latency-bound) as it did in the monolithic kernel
 // (k23_fused_tc.cu, kept behind GPNERF_FUSED_IMPL=monolithic).
-// No colour record is written unless `rec` is given (the record-fed colour head of round 1); the colour head of
-// k3_color_ws.cu gathers its own inputs for the survivors of the progressive step only.
+// With `rec_tiles` the producers also leave the colour head's inputs behind, one block per tile in the colour head's
+// own operand layouts (RecTile<V>, tc_heads.cuh; consumed by k3_color_tiles.cu with one bulk copy per tile): the
+// per-view features are gathered once per point and frame.  Without it nothing is written per point but σ / α
+// (k3_color_ws.cu then gathers the colour head's inputs again for the survivors of the progressive step).
 #include <stdlib.h>
 #include "tc_heads.cuh"
 
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
     const float wm1 = (float)(f.src_w - 1), hm1 = (float)(f.src_h - 1);
     const int img_stride_p = (f.src_h + 2) * (f.src_w + 2);          // padded image, float4 units
     const int map_stride_q = (f.feat_h + 2) * (f.feat_w + 2) * 4;    // padded map, uint4 units
-    constexpr int RC = rec_chunks(V);
+    using RT = RecTile<V>;
     auto fetch_q = [&](long long first_row, int r) -> int {
       return (first_row + r < n) ? __ldg(a.valid + first_row + r) : -1;
     };
@@ -192,12 +194,14 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
       const int n_valid = min(128, n - (int)first);
       const int s = it % kStages;
       uint8_t* stage = smem + Smem::STAGE0 + s * Smem::STAGE_BYTES;
+      // colour-stage record of this tile (tc_heads.cuh): written with streaming stores, read back by one bulk copy
+      uint8_t* rt = a.rec_tiles ? a.rec_tiles + (size_t)tile * RT::BYTES : nullptr;
 #pragma unroll
       for (int j = 0; j < kPasses; ++j) qn[j] = fetch_q((long long)(tile + G) * 128, (warp * kPasses + j) * 8 + grp);
       // the stage is free once the second GEMM of its previous tenant has completed
       ws_wait(empty + s, ((it / kStages) & 1) ^ 1);
 #pragma unroll 1
-      for (int j = 0; j < kPasses; ++j) {
+      for (int j = 0; j < ((a.debug & 1) ? 0 : kPasses); ++j) {
         const int r = (warp * kPasses + j) * 8 + grp;
         const bool ok = r < n_valid;
         const float ppx = px[j], ppy = py[j], ppz = pz[j];
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
             fv[v][2 * jj] = t.x;
             fv[v][2 * jj + 1] = t.y;
           }
-          if (a.rec != nullptr && ok) a.rec[(first + r) * RC + 9 + v * 5 + sub] = ws_pack8(fv[v]);
+          if (rt != nullptr) __stcs(reinterpret_cast<uint4*>(rt + RT::ff_off(v, r, sub)), ws_pack8(fv[v]));
         }
         // ---- RGB taps: lane `sub` takes view `sub` (fp32 images, fp32 arithmetic)
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -323,9 +327,9 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
           c0 = fmaf(t3.x, w3, fmaf(t2.x, w2, fmaf(t1.x, w1, t0.x * w0)));
           c1 = fmaf(t3.y, w3, fmaf(t2.y, w2, fmaf(t1.y, w1, t0.y * w0)));
           c2 = fmaf(t3.z, w3, fmaf(t2.z, w2, fmaf(t1.z, w1, t0.z * w0)));
-          if (a.rec != nullptr && ok) {
-            const float t[8] = {c0, c1, c2, 0.f, 0.f, 0.f, 0.f, 0.f};
-            a.rec[(first + r) * RC + 9 + sub * 5 + 4] = ws_pack8(t);
+          if (a.rgb_in != nullptr && ok) {
+            float* o = a.rgb_in + ((first + r) * V + sub) * 3;
+            o[0] = c0; o[1] = c1; o[2] = c2;
           }
         }
         {
@@ -346,35 +350,44 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
           const uint4 qm = ws_pack8(mean), qv = ws_pack8(var);
           ws_st_rows8_sw(stage + Smem::G64, r & ~7, 0, qm, lane);
           ws_st_rows8_sw(stage + Smem::G64, r & ~7, 4, qv, lane);
-          if (a.rec != nullptr && ok) {
-            uint4* rp = a.rec + (first + r) * RC;
-            rp[sub] = qm;
-            rp[4 + sub] = qv;
+          if (rt != nullptr) {
+            __stcs(reinterpret_cast<uint4*>(rt + RT::G64 + sw128_off(r, sub)), qm);
+            __stcs(reinterpret_cast<uint4*>(rt + RT::G64 + sw128_off(r, 4 + sub)), qv);
           }
-          // RGB mean / variance over the views: butterfly over the point's 4 lanes (lanes >= V hold 0)
-          float m0 = c0, m1 = c1, m2 = c2;
+          // RGB mean / variance over the views: lane 0 of the point collects (r,g,b) of the V views from lanes 0..V-1
+          float rgbv[12];
 #pragma unroll
-          for (int o = 1; o < 4; o <<= 1) {
-            m0 += __shfl_xor_sync(0xffffffffu, m0, o);
-            m1 += __shfl_xor_sync(0xffffffffu, m1, o);
-            m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-          }
-          m0 *= inv_v; m1 *= inv_v; m2 *= inv_v;
-          const bool mine = sub < V;
-          float s0 = mine ? (c0 - m0) * (c0 - m0) : 0.f, s1 = mine ? (c1 - m1) * (c1 - m1) : 0.f;
-          float s2 = mine ? (c2 - m2) * (c2 - m2) : 0.f;
-#pragma unroll
-          for (int o = 1; o < 4; o <<= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          for (int v = 0; v < 4; ++v) {
+            rgbv[3 * v + 0] = __shfl_sync(0xffffffffu, c0, (lane & ~3) + v);
+            rgbv[3 * v + 1] = __shfl_sync(0xffffffffu, c1, (lane & ~3) + v);
+            rgbv[3 * v + 2] = __shfl_sync(0xffffffffu, c2, (lane & ~3) + v);
           }
           if (sub == 0) {
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) { m0 += rgbv[3 * v]; m1 += rgbv[3 * v + 1]; m2 += rgbv[3 * v + 2]; }
+            m0 *= inv_v; m1 *= inv_v; m2 *= inv_v;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              s0 = fmaf(rgbv[3 * v] - m0, rgbv[3 * v] - m0, s0);
+              s1 = fmaf(rgbv[3 * v + 1] - m1, rgbv[3 * v + 1] - m1, s1);
+              s2 = fmaf(rgbv[3 * v + 2] - m2, rgbv[3 * v + 2] - m2, s2);
+            }
             // columns 70, 71 of the [mean|var] operand are the constant 1.0 that carries the layer's bias
             const float t[8] = {m0, m1, m2, s0 * inv_v, s1 * inv_v, s2 * inv_v, 1.0f, 1.0f};
             const uint4 qc = ws_pack8(t);
             *reinterpret_cast<uint4*>(stage + Smem::TAIL + chunk_off(r, 0, kTailSbo)) = qc;
-            if (a.rec != nullptr && ok) a.rec[(first + r) * RC + 8] = qc;
+            if (rt != nullptr) {
+              __stcs(reinterpret_cast<uint4*>(rt + RT::TAIL + chunk_off(r, 0, kTailSbo)), qc);
+              // per-view RGB block of base_fc.0's input: column 3v + c = channel c of view v
+              const float u0[8] = {rgbv[0], rgbv[1], rgbv[2], rgbv[3], rgbv[4], rgbv[5], rgbv[6], rgbv[7]};
+              __stcs(reinterpret_cast<uint4*>(rt + RT::RGBS + chunk_off(r, 0, kTailSbo)), ws_pack8(u0));
+              if (V > 2) {
+                const float u1[8] = {rgbv[8], V > 3 ? rgbv[9] : 0.f, V > 3 ? rgbv[10] : 0.f, V > 3 ? rgbv[11] : 0.f, 0.f, 0.f, 0.f, 0.f};
+                __stcs(reinterpret_cast<uint4*>(rt + RT::RGBS + chunk_off(r, 1, kTailSbo)), ws_pack8(u1));
+              }
+            }
           }
         }
         __syncwarp();               // the next pass rewrites this warp's plan scratch
@@ -414,6 +427,13 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
       bool done[kChains] = {false, false};
       uint32_t idle = 0;
       int next_start = 0;          // tiles start strictly in order (a parity wait tells only consecutive phases apart)
+      if (a.debug & 2) {           // profiling experiment: no head at all, stages handed straight back
+        for (int i = 0; blockIdx.x + (long long)i * G < n_tiles; ++i) {
+          ws_wait(full + i % kStages, (i / kStages) & 1);
+          mbar_arrive(empty + i % kStages);
+        }
+        done[0] = done[1] = true;
+      }
       while (!(done[0] && done[1])) {
         bool progressed = false;
 #pragma unroll
@@ -509,7 +529,7 @@ __global__ void __launch_bounds__(ws::kThreads, 1) gather_density_ws(FusedArgs a
       for (int j = 0; j < 16; ++j)
         pk[j] = pack_bf16x2(elu_scaled(__uint_as_float(r[2 * j])), elu_scaled(__uint_as_float(r[2 * j + 1])));
     };
-    for (int i = c; blockIdx.x + (long long)i * G < n_tiles; i += kChains) {
+    for (int i = c; blockIdx.x + (long long)i * G < n_tiles && !(a.debug & 2); i += kChains) {
       const long long first = ((long long)blockIdx.x + (long long)i * G) * 128;
       const int n_valid = min(128, n - (int)first);
       const int s = i % kStages;

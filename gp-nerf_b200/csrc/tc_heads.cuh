@@ -85,6 +85,33 @@ constexpr uint32_t kImageBytes = kColImgOffset + ((ColImg<4>::BYTES + 127) / 128
 // point: the G tile's 9 non-zero chunks followed by 5 non-zero chunks per view.
 __host__ __device__ constexpr int rec_chunks(int V) { return 9 + 5 * V; }
 
+// Colour-stage tile record (round 2, tile hand-off): what the fused gather → density kernel leaves behind for
+// the colour head, one block per 128-point tile of the P1 list, laid out exactly as the colour head's shared-
+// memory stage (tcgen05 operand layouts), so that the colour head fetches a tile with ONE bulk copy
+// (cp.async.bulk) and feeds it to the tensor core untouched:
+//   G64   [128 x 64] bf16  mean_feat | var_feat                  K-major SWIZZLE_128B
+//   FF    views 2j, 2j+1 share a [128 x 64] SWIZZLE_128B block (view v at columns 32 (v % 2) …); an odd last view
+//         has a [128 x 32] block in the unswizzled core-matrix layout (8 KB)
+//   TAIL  [128 x 16] bf16  mean rgb 3, var rgb 3, 1, 1 | 0 x 8   core-matrix layout
+//   RGBS  [128 x 16] bf16  column 3v + c = channel c of view v   core-matrix layout
+// Columns that no view owns are never written: the buffer must be zero-filled once by whoever allocates it.
+template <int V>
+struct RecTile {
+  static constexpr uint32_t G64 = 0;
+  static constexpr uint32_t FF = 16384;
+  static constexpr uint32_t FF_ODD = FF + (V / 2) * 16384;            // the odd last view's block
+  static constexpr uint32_t TAIL = FF_ODD + (V & 1) * 8192;
+  static constexpr uint32_t RGBS = TAIL + 4096;
+  static constexpr uint32_t BYTES = RGBS + 4096;                      // V = 1..4: 32, 40, 48, 56 KB
+  static constexpr uint32_t kOddSbo = op_sbo(32);
+  // byte offset (inside the tile) of 16-byte chunk c (0..3) of view v's 32 features of row r
+  __device__ __forceinline__ static uint32_t ff_off(int v, int r, int c) {
+    if ((V & 1) && v == V - 1) return FF_ODD + chunk_off(r, c, kOddSbo);
+    return FF + (uint32_t)(v >> 1) * 16384u + sw128_off(r, (v & 1) * 4 + c);
+  }
+};
+__host__ __device__ constexpr uint32_t rec_tile_bytes(int V) { return 16384u + (V / 2) * 16384u + (V & 1) * 8192u + 8192u; }
+
 struct FusedArgs {
   const __half* lv[GPNERF_N_LEVELS];
   const __half* feat;            // [V][fh+2][fw+2][32]
@@ -97,6 +124,9 @@ struct FusedArgs {
   uint4* rec;
   float* alpha;              // optional: K4's α = 1 − exp(−σ) …
   uint32_t* alpha_words;     // … and its survivor flags (one ballot word per 32 points), written here
+  uint8_t* rec_tiles;        // optional: colour-stage tile records (RecTile<V>), one per 128 points
+  float* rgb_in;             // optional [P1][V][3]: the per-view RGB taps (BaseRender's rgb_in_map input)
+  int debug;                 // profiling experiments only (GPNERF_FUSED_DEBUG): 1 = producers skip the gathers
 };
 
 // ---------------------------------------------------------------------------

@@ -35,7 +35,7 @@ KERNELS_PER_CALL = {
     "k2_gather_volume": 1, "k2_project_gather_meanvar": 1, "k3_density_mlp": 1, "k4_compact_alpha": 2,
     "k4_compact_alpha_fused": 1,      # α and the flags come from the fused kernel: the single-pass compaction only
     "k3_color_mlp": 1, "k5_composite": 1, "k5_raw2outputs": 1, "peer_wait": 1,
-    "k23_gather_density_tc": 1, "k3_color_mlp_records": 1, "k3_color_gather_tc": 1,
+    "k23_gather_density_tc": 1, "k3_color_mlp_records": 1, "k3_color_gather_tc": 1, "k3_color_tiles_tc": 1,
 }
 
 
@@ -138,16 +138,28 @@ class Engine:
             # tensor-core path: gathered features stay on chip; one bf16 record per point for the colour head
             if not 1 <= self.V <= 4:
                 raise _lib.GpnerfError("the bf16 tensor-core path supports 1..4 source views")
-            # GPNERF_COLOR_IMPL=records: round 1's colour head, fed from one 16(9+5V)-byte record per P1 point that
-            # the fused kernel writes; default: the colour head gathers its own inputs for the survivors only
+            # Hand-off from the fused gather → density kernel to the colour head (GPNERF_COLOR_IMPL):
+            #   tiles   (default) one block per 128-point tile of the P1 list in the colour head's own operand
+            #           layouts, fetched with one bulk copy per tile: the per-view features are gathered once
+            #   gather  nothing is handed over; the colour head gathers its inputs again for the survivors
+            #   records round 1: one 16(9+5V)-byte record per P1 point, written by round 1's monolithic kernel
             import os
-            self.use_records = os.environ.get("GPNERF_COLOR_IMPL", "") == "records"
+            impl = os.environ.get("GPNERF_COLOR_IMPL", "") or "tiles"
+            if impl not in ("tiles", "gather", "records"):
+                raise _lib.GpnerfError(f"GPNERF_COLOR_IMPL={impl!r}: expected tiles, gather or records")
+            self.color_impl = impl
+            self.use_records = impl == "records"
             self.rec_bytes = int(self.lib.gpnerf_k23_record_bytes(self.V))
             self.rec = torch.empty(self.max_pts * self.rec_bytes, dtype=torch.uint8, device=dev) if self.use_records else None
+            # tile records: zero-filled once (columns no view owns are never written)
+            self.tile_rec_bytes = int(self.lib.gpnerf_k23_tile_record_bytes(self.V))
+            self.rec_tiles = (torch.zeros(((self.max_pts + 127) // 128) * self.tile_rec_bytes, dtype=torch.uint8, device=dev)
+                              if impl == "tiles" else None)
             self.rgb_in = None       # per-view RGB taps [P1][V][3], dense path only (allocated on first use)
             self.vol_feat = self.rgb_feat = self.mask = self.meanvar = None
         else:
-            self.rec = None
+            self.rec = self.rec_tiles = None
+            self.color_impl = None
             self.vol_feat = buf(self.max_pts * 128)
             self.rgb_feat = buf(self.max_pts * self.V * 35)
             self.mask = buf(self.max_pts * self.V)
@@ -501,7 +513,12 @@ class Engine:
         self._run("k4_compact_alpha_fused" if self.bf16 else "k4_compact_alpha", L.gpnerf_k4_compact_alpha,
                   None if self.bf16 else ptr(self.sigma), self.max_pts,
                   ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
-        self._color(ptr(self.valid1), self.max_pts, CNT_P2, frame)
+        if self.bf16 and self.color_impl == "tiles":
+            # every tile of the P1 list that has a survivor (K5 ignores the colour of a culled point)
+            self._run("k3_color_tiles_tc", L.gpnerf_k3_color_tiles_tc, ptr(self.rec_tiles), ptr(self.workspace),
+                      C.byref(self._weights), self.V, self.max_pts, ptr(self.counters), CNT_P1, ptr(self.rgb), st)
+        else:
+            self._color(ptr(self.valid1), self.max_pts, CNT_P2, frame)
         ex = self.exchange
         self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.alpha), ptr(self.rgb), ptr(self.ray_pix),
                   ptr(self.tile_ray_begin), ptr(self.ray_pt_begin), fr, C.c_float(self.t_min), ptr(self.rgb_map),
@@ -528,7 +545,7 @@ class Engine:
                       C.byref(self._weights), self.V, n_pts_max, ptr(self.counters), slot, ptr(self.rgb),
                       self.precision, st)
 
-    def _heads(self, frame, masks3d, t_rand, n_rays_max, fuse_alpha=False):
+    def _heads(self, frame, masks3d, t_rand, n_rays_max, fuse_alpha=False, rgb_in=None):
         """occupancy (or identity) compaction → gathers → density head."""
         L, st, fr = self.lib, self._stream(), C.byref(frame)
         n_pts_max = n_rays_max * self.S
@@ -536,6 +553,13 @@ class Engine:
                   ptr(self.rays_d), ptr(self.near), ptr(self.far), ptr(self.t_vals), ptr(t_rand), fr, n_rays_max,
                   ptr(self.valid), ptr(self.z_vals), ptr(self.counters), ptr(self.workspace),
                   ptr(self.ray_pt_begin), st)
+        if self.bf16 and self.color_impl == "tiles":
+            self._run("k23_gather_density_tc", L.gpnerf_k23_gather_density_tiles_tc, ptr_array(self.levels_cl),
+                      ptr(self.featmaps_cl), ptr(self.images_rgbx), ptr(self.valid), ptr(self.rays_o),
+                      ptr(self.rays_d), ptr(self.z_vals), fr, C.byref(self._weights), n_pts_max,
+                      ptr(self.counters), ptr(self.sigma), ptr(self.rec_tiles), ptr(rgb_in),
+                      ptr(self.alpha) if fuse_alpha else None, ptr(self.workspace) if fuse_alpha else None, st)
+            return
         if self.bf16:
             self._run("k23_gather_density_tc", L.gpnerf_k23_gather_density_tc, ptr_array(self.levels_cl),
                       ptr(self.featmaps_cl), ptr(self.images_rgbx), ptr(self.valid), ptr(self.rays_o),
@@ -572,12 +596,16 @@ class Engine:
         self.far[:R].copy_(_f32(far, dev).reshape(-1), non_blocking=True)
         self.counters[CNT_RAYS] = R
         tr = None if t_rand is None else _f32(t_rand, dev).reshape(-1)
-        self._heads(frame, masks3d=None, t_rand=tr, n_rays_max=R)
         n = R * self.S
+        if self.bf16 and not self.use_records and (self.rgb_in is None or self.rgb_in.numel() < n * self.V * 3):
+            self.rgb_in = torch.empty(self.max_pts * self.V * 3, dtype=torch.float32, device=dev)
+        tiles = self.bf16 and self.color_impl == "tiles"
+        self._heads(frame, masks3d=None, t_rand=tr, n_rays_max=R, rgb_in=self.rgb_in if tiles else None)
         # colour head on every point (valid1 = NULL → all rows in order)
-        if self.bf16 and not self.use_records:
-            if self.rgb_in is None or self.rgb_in.numel() < n * self.V * 3:
-                self.rgb_in = torch.empty(self.max_pts * self.V * 3, dtype=torch.float32, device=dev)
+        if tiles:
+            self._run("k3_color_tiles_tc", L.gpnerf_k3_color_tiles_tc, ptr(self.rec_tiles), None,
+                      C.byref(self._weights), self.V, n, ptr(self.counters), CNT_P1, ptr(self.rgb), st)
+        elif self.bf16 and not self.use_records:
             self._color(None, n, CNT_P1, frame, self.rgb_in)
         else:
             self._color(None, n, CNT_P1, frame)

@@ -313,6 +313,31 @@ int gpnerf_k23_gather_density_tc(const void *const levels_f16[GPNERF_N_LEVELS],
 /* With alpha / k4_workspace (both or neither) the kernel also writes K4's
  * α = 1-exp(-σ) and its survivor flags straight into the compaction workspace:
  * follow with gpnerf_k4_compact_alpha(sigma = NULL, …). */
+/* Tile hand-off to the colour head (the default of the tensor-core path): the same kernel, which additionally
+ * leaves the colour head's inputs behind – per 128-point tile of the P1 list one block of
+ * gpnerf_k23_tile_record_bytes(V) bytes, already in the tcgen05 operand layouts of
+ * gpnerf_k3_color_tiles_tc (mean|var features, the V per-view feature rows, RGB mean/var, per-view RGB:
+ * BaseRender.py:283-363, trainhead.py:20-24), so that a point's pixel-aligned features are gathered once per
+ * frame.  tile_records: ceil(n_points_max / 128) blocks, 1024-byte aligned, ZERO-FILLED ONCE by the caller
+ * (columns no view owns are never written).  rgb_in (may be NULL) float[P1][V][3] receives the per-view RGB
+ * taps (BaseRender's rgb_in_map input).  alpha / k4_workspace as above. */
+int64_t gpnerf_k23_tile_record_bytes(int n_views);
+int gpnerf_k23_gather_density_tiles_tc(const void *const levels_f16[GPNERF_N_LEVELS],
+                                       const void *featmaps_f16, const float *images_rgbx,
+                                       const int32_t *valid, const float *rays_o, const float *rays_d,
+                                       const float *z_vals, const gpnerf_frame_t *frame_host,
+                                       const gpnerf_head_weights_t *weights_host, int n_points_max,
+                                       const int32_t *counters, float *sigma, void *tile_records,
+                                       float *rgb_in, float *alpha, void *k4_workspace, void *stream);
+/* Colour trunk (trainhead.py:85-100, 118-145) on the tiles of the P1 list, fed from the tile records above
+ * (one bulk copy per tile; no gather).  rgb float[P1][3] is written for every point of every processed tile.
+ * k4_workspace (may be NULL): the workspace gpnerf_k23_gather_density_tiles_tc wrote the progressive step's
+ * survivor flags into – tiles without a survivor are skipped (demo_render.py:312-333: colour only for the
+ * survivors; here at tile granularity, K5 ignores the colour of a culled point).  Count =
+ * counters[counter_slot] (the P1 count).  n_views in 1..4. */
+int gpnerf_k3_color_tiles_tc(const void *tile_records, const void *k4_workspace,
+                             const gpnerf_head_weights_t *weights_host, int n_views, int n_points_max,
+                             const int32_t *counters, int counter_slot, float *rgb, void *stream);
 /* Colour trunk (trainhead.py:128-145) on the record rows listed in valid1. */
 int gpnerf_k3_color_mlp_records(const void *records, const int32_t *valid1,
                                 const gpnerf_head_weights_t *weights_host, int n_views,
