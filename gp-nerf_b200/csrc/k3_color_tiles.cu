@@ -30,6 +30,7 @@ struct ColorTilesArgs {
   const uint8_t* rec;            // [tiles] RecTile<V>
   const uint32_t* alive_words;   // optional: the progressive step's survivor flags, 4 words per tile (all zero = skip)
   const int32_t* count_ptr;      // number of P1 points
+  int32_t* counters;             // with alive_words: counters[P2] receives the number of survivors (slots 6, 7: scratch)
   const uint8_t* image;          // packed colour weights (ColImg<V>)
   float* rgb;                    // [P1][3]
 };
@@ -132,6 +133,25 @@ __global__ void __launch_bounds__(ctl::kThreads, 1) color_tiles_ws(ColorTilesArg
         mbar_arrive_expect_tx(full + s, R::BYTES);
         bulk_g2s(smem + S::STAGE0 + s * S::STAGE_BYTES, a.rec + (size_t)tile * R::BYTES, R::BYTES, full + s);
         ++i;
+      }
+    } else if (lane >= 4 && lane < 8 && a.alive_words != nullptr && a.counters != nullptr) {
+      // the progressive step's survivor count (counters[P2], demo_render.py:312-317) without a compaction pass: four
+      // idle lanes count the flag bits of this CTA's tiles; the last CTA to finish publishes the total and re-arms
+      // the two scratch slots (zero at allocation, zero again when the kernel ends)
+      int cnt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += G) cnt += __popc(__ldg(a.alive_words + tile * 4 + (lane - 4)));
+      cnt += __shfl_xor_sync(0xf0u, cnt, 1);
+      cnt += __shfl_xor_sync(0xf0u, cnt, 2);
+      if (lane == 4) {
+        int* acc = a.counters + GPNERF_N_COUNTERS - 2;
+        int* ticket = a.counters + GPNERF_N_COUNTERS - 1;
+        atomicAdd(acc, cnt);
+        __threadfence();
+        if (atomicAdd(ticket, 1) == G - 1) {
+          __threadfence();
+          a.counters[GPNERF_CNT_P2] = atomicExch(acc, 0);
+          *ticket = 0;
+        }
       }
     }
   } else {
@@ -367,7 +387,7 @@ int64_t gpnerf_k23_tile_record_bytes(int n_views) {
 }
 
 int gpnerf_k3_color_tiles_tc(const void* tile_records, const void* k4_workspace, const gpnerf_head_weights_t* w,
-                             int n_views, int n_points_max, const int32_t* counters, int counter_slot, float* rgb,
+                             int n_views, int n_points_max, int32_t* counters, int counter_slot, float* rgb,
                              void* stream) {
   GPNERF_REQUIRE(tile_records && w && counters && rgb);
   GPNERF_REQUIRE(n_points_max > 0 && counter_slot >= 0 && counter_slot < GPNERF_N_COUNTERS);
@@ -376,6 +396,7 @@ int gpnerf_k3_color_tiles_tc(const void* tile_records, const void* k4_workspace,
   a.rec = reinterpret_cast<const uint8_t*>(tile_records);
   a.alive_words = k4_workspace ? carve_workspace(const_cast<void*>(k4_workspace), n_points_max).words : nullptr;
   a.count_ptr = counters + counter_slot;
+  a.counters = counters;
   a.image = reinterpret_cast<const uint8_t*>(w->tc_image) + kColImgOffset;
   a.rgb = rgb;
   cudaStream_t st = (cudaStream_t)stream;

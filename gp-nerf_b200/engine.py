@@ -488,6 +488,8 @@ class Engine:
             self.exchange.next_frame()       # one more K5 launch queued (its frame counter lives on the device)
         g.replay()
         self.launches += n_launch
+        if self.bf16 and self.color_impl == "tiles":
+            self._valid1_pending = True
 
     # --------------------------------------------------------------- launches
     def build_occupancy(self, frame):
@@ -509,15 +511,19 @@ class Engine:
                   ptr(self.ray_pix), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near), ptr(self.far),
                   ptr(self.counters), ptr(self.workspace), ptr(self.tile_ray_begin), st)
         self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays, fuse_alpha=True)
-        # tensor-core path: α and the survivor flags were written by the fused kernel's epilogue
-        self._run("k4_compact_alpha_fused" if self.bf16 else "k4_compact_alpha", L.gpnerf_k4_compact_alpha,
-                  None if self.bf16 else ptr(self.sigma), self.max_pts,
-                  ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
         if self.bf16 and self.color_impl == "tiles":
-            # every tile of the P1 list that has a survivor (K5 ignores the colour of a culled point)
+            # tile hand-off: the colour head takes every tile of the P1 list that has a survivor (K5 ignores the
+            # colour of a culled point) and counts the survivors; the ordered survivor list (valid1) is not on the
+            # frame's path any more – survivor_list() / read_counters() produce it on demand from the flags the
+            # fused kernel left in the workspace
             self._run("k3_color_tiles_tc", L.gpnerf_k3_color_tiles_tc, ptr(self.rec_tiles), ptr(self.workspace),
                       C.byref(self._weights), self.V, self.max_pts, ptr(self.counters), CNT_P1, ptr(self.rgb), st)
+            self._valid1_pending = True
         else:
+            # tensor-core path: α and the survivor flags were written by the fused kernel's epilogue
+            self._run("k4_compact_alpha_fused" if self.bf16 else "k4_compact_alpha", L.gpnerf_k4_compact_alpha,
+                      None if self.bf16 else ptr(self.sigma), self.max_pts,
+                      ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
             self._color(ptr(self.valid1), self.max_pts, CNT_P2, frame)
         ex = self.exchange
         self._run("k5_composite", L.gpnerf_k5_composite, ptr(self.alpha), ptr(self.rgb), ptr(self.ray_pix),
@@ -629,7 +635,18 @@ class Engine:
         out["raw"] = raw.view(R, self.S, 4)
         return out
 
+    def survivor_list(self):
+        """The progressive step's ordered survivor list (demo_render.py:312-317) of the last frame: fills
+        self.valid1[:P2].  With the tile hand-off it is not needed to render and is produced here, on demand,
+        from the flag words of the fused kernel (still in the workspace until the next frame)."""
+        if getattr(self, "_valid1_pending", False):
+            self._valid1_pending = False
+            self._run("k4_compact_alpha_fused", self.lib.gpnerf_k4_compact_alpha, None, self.max_pts,
+                      ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), self._stream())
+        return self.valid1
+
     def read_counters(self):
-        """One device→host sync: (n_pix, n_rays, P1, P2)."""
+        """One device→host sync: (n_pix, n_rays, P1, P2).  Also brings valid1 up to date (survivor_list)."""
+        self.survivor_list()
         c = self.counters.cpu().tolist()
         return {"n_pix": c[CNT_PIX], "n_rays": c[CNT_RAYS], "P1": c[CNT_P1], "P2": c[CNT_P2]}

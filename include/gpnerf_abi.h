@@ -337,7 +337,10 @@ int gpnerf_k23_gather_density_tiles_tc(const void *const levels_f16[GPNERF_N_LEV
  * counters[counter_slot] (the P1 count).  n_views in 1..4. */
 int gpnerf_k3_color_tiles_tc(const void *tile_records, const void *k4_workspace,
                              const gpnerf_head_weights_t *weights_host, int n_views, int n_points_max,
-                             const int32_t *counters, int counter_slot, float *rgb, void *stream);
+                             int32_t *counters, int counter_slot, float *rgb, void *stream);
+/* With k4_workspace the kernel also leaves the progressive step's survivor count in counters[GPNERF_CNT_P2]
+ * (popcount of the flags; the ordered list itself – gpnerf_k4_compact_alpha(sigma = NULL) – is only needed by
+ * callers that want valid1).  counters[6], counters[7] are scratch: zero before the first call, zero after each. */
 /* Colour trunk (trainhead.py:128-145) on the record rows listed in valid1. */
 int gpnerf_k3_color_mlp_records(const void *records, const int32_t *valid1,
                                 const gpnerf_head_weights_t *weights_host, int n_views,
