@@ -186,8 +186,7 @@ __global__ void __launch_bounds__(ctl::kThreads, 1) color_tiles_ws(ColorTilesArg
     // the chain's GEMMs of this round have completed: the leader polls the mbarrier, the other three warps block
     // on a named barrier (a poll is a shared-memory access; a parked warp costs nothing)
     auto wait_acc = [&]() {
-      if (leader) wait_backoff(m2e + c, ph);
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * c) : "memory");
+      mbar_wait(m2e + c, ph);          // mbarrier.try_wait with a suspend-time hint: the warp sleeps in hardware
       ph ^= 1u;
       tc_fence_after();
     };
