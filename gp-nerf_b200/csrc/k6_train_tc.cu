@@ -77,24 +77,123 @@ struct LinTcArgs {
   int add_pre, add_post;
   long long P;
   int Kp, Np;      // K rounded up to 8, N rounded up to 16
+  int nbuf;        // X tiles in flight (2..4)
+  int vec_y;       // Y (and aux) rows are 16-byte aligned and N % 4 == 0: float4 epilogue
 };
 
+// ---- asynchronous copies global → shared (LDGSTS): no registers held while the data is in flight, so a thread
+// keeps a whole tile (or several) in flight; src-size 0 writes zeros (rows beyond P, padding columns)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {      // at most n groups still pending
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+
+// Y[P x N] = epi(in_scale · (X ⊙ ELU'(in_aux)) · B + bias), one 128-row tile per round, persistent CTAs.
+// Streaming kernel (≈100 B read + ≈100 B written per point and layer, a few hundred FLOP): what matters is bytes in
+// flight.  The X tiles go global → shared with cp.async straight into the tcgen05 operand layout, `nbuf` − 1 tiles
+// ahead of the one being multiplied; the accumulator is double buffered in TMEM, so the epilogue of tile i − 1
+// (TMEM → registers → global) overlaps the GEMM of tile i and the loads of tiles i + 1 …
+// VEC: X rows (and in_aux rows) are 16-byte aligned and K % 4 == 0 – 16-byte copies (one core-matrix row each).
+template <bool VEC>
 __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int Kp = a.Kp, Np = a.Np, K = a.K, N = a.N;
+  const int Kp = a.Kp, Np = a.Np, K = a.K, N = a.N, nbuf = a.nbuf;
   const uint32_t sbo = (uint32_t)(Kp / 4) * kLBO;          // both operands are [rows x Kp]
+  const uint32_t tile_bytes = 16 * sbo;
   uint8_t* Bt = smem;                                       // [Np x Kp]
-  uint8_t* At = smem + (size_t)(Np / 8) * sbo;              // [128 x Kp]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(At + 16 * sbo);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* At = smem + (size_t)(Np / 8) * sbo;              // nbuf x [128 x Kp]
+  uint8_t* Xt = At + (size_t)nbuf * tile_bytes;             // nbuf x [128 x Kp]: in_aux tiles (only with in_aux)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Xt + (a.in_aux ? (size_t)nbuf * tile_bytes : 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ncols = tmem_cols_for(Np);
+  const uint32_t acc_cols = tmem_cols_for(Np);
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
     fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(tmem_slot, ncols);
+  if (warp == 0) tmem_alloc(tmem_slot, 2 * acc_cols);
+  const long long n_tiles = (a.P + 127) / 128;
+  const uint32_t a_addr = smem_u32(At), x_addr = smem_u32(Xt), b_addr = smem_u32(Bt);
+  // all copies of tile `t` into buffer `b` (rows beyond P and columns beyond K are zero-filled)
+  auto issue_loads = [&](long long t, int b) {
+    const long long first = t * 128;
+    const uint32_t ab = a_addr + (uint32_t)b * tile_bytes, xb = x_addr + (uint32_t)b * tile_bytes;
+    if (VEC) {
+      const int r8 = lane & 7, kq = lane >> 3;
+      for (int rg = warp; rg < 16; rg += 8) {
+        const long long p = first + rg * 8 + r8;
+        const bool okp = p < a.P;
+        const float* xr = a.X + (okp ? p : 0) * a.ldx;
+        const float* ar = a.in_aux ? a.in_aux + (okp ? p : 0) * a.ld_in_aux : nullptr;
+        const uint32_t off = (uint32_t)rg * sbo + (uint32_t)r8 * 16;
+        for (int kc = kq; kc < Kp / 4; kc += 4) {
+          const bool ok = okp && 4 * kc < K;
+          cp_async16(ab + off + (uint32_t)kc * kLBO, xr + (ok ? 4 * kc : 0), ok);
+          if (ar) cp_async16(xb + off + (uint32_t)kc * kLBO, ar + (ok ? 4 * kc : 0), ok);
+        }
+      }
+    } else {
+      const int r8 = lane >> 2, e = lane & 3;
+      for (int rg = warp; rg < 16; rg += 8) {
+        const long long p = first + rg * 8 + r8;
+        const bool okp = p < a.P;
+        const float* xr = a.X + (okp ? p : 0) * a.ldx;
+        const float* ar = a.in_aux ? a.in_aux + (okp ? p : 0) * a.ld_in_aux : nullptr;
+        const uint32_t off = (uint32_t)rg * sbo + (uint32_t)r8 * 16 + (uint32_t)e * 4;
+        for (int kc = 0; kc < Kp / 4; ++kc) {
+          const int k = 4 * kc + e;
+          const bool ok = okp && k < K;
+          cp_async4(ab + off + (uint32_t)kc * kLBO, xr + (ok ? k : 0), ok);
+          if (ar) cp_async4(xb + off + (uint32_t)kc * kLBO, ar + (ok ? k : 0), ok);
+        }
+      }
+    }
+  };
+  // X ⊙ ELU'(in_aux) on the elements this thread copied itself (visible to it after its own wait_group)
+  auto scale_by_aux = [&](int b) {
+    uint8_t* ab = At + (size_t)b * tile_bytes;
+    const uint8_t* xb = Xt + (size_t)b * tile_bytes;
+    if (VEC) {
+      const int r8 = lane & 7, kq = lane >> 3;
+      for (int rg = warp; rg < 16; rg += 8) {
+        const uint32_t off = (uint32_t)rg * sbo + (uint32_t)r8 * 16;
+        for (int kc = kq; kc < Kp / 4; kc += 4) {
+          float4 x = *reinterpret_cast<float4*>(ab + off + (uint32_t)kc * kLBO);
+          const float4 h = *reinterpret_cast<const float4*>(xb + off + (uint32_t)kc * kLBO);
+          x.x *= delu_from_out(h.x); x.y *= delu_from_out(h.y); x.z *= delu_from_out(h.z); x.w *= delu_from_out(h.w);
+          *reinterpret_cast<float4*>(ab + off + (uint32_t)kc * kLBO) = x;
+        }
+      }
+    } else {
+      const int r8 = lane >> 2, e = lane & 3;
+      for (int rg = warp; rg < 16; rg += 8) {
+        const uint32_t off = (uint32_t)rg * sbo + (uint32_t)r8 * 16 + (uint32_t)e * 4;
+        for (int kc = 0; kc < Kp / 4; ++kc) {
+          float* x = reinterpret_cast<float*>(ab + off + (uint32_t)kc * kLBO);
+          *x *= delu_from_out(*reinterpret_cast<const float*>(xb + off + (uint32_t)kc * kLBO));
+        }
+      }
+    }
+  };
+  auto tile_of = [&](int i) { return (long long)blockIdx.x + (long long)i * gridDim.x; };
+  // the first nbuf − 1 tiles are requested before anything else (the weights below are staged while they fly)
+  for (int j = 0; j < nbuf - 1; ++j) {
+    if (tile_of(j) < n_tiles) issue_loads(tile_of(j), j);
+    cp_async_commit();
+  }
   // B[n][k] = W^T or W, zero padded
   for (int i = tid; i < Np * Kp; i += blockDim.x) {
     const int n = i / Kp, k = i - n * Kp;
@@ -107,51 +206,41 @@ __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t a_addr = smem_u32(At), b_addr = smem_u32(Bt);
   const int row = tid & 127, half = tid >> 7;
-  const int r8 = lane >> 2, e = lane & 3;
-  uint32_t phase = 0;
-  const long long n_tiles = (a.P + 127) / 128;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long first = tile * 128;
-    // ---- stage the X tile (input scaling / ELU' of the saved activation applied on the way)
-    for (int rg = warp; rg < 16; rg += 8) {
-      const long long p = first + rg * 8 + r8;
-      const bool okp = p < a.P;
-      const float* xr = a.X + p * a.ldx;
-      const float* ar = a.in_aux ? a.in_aux + p * a.ld_in_aux : nullptr;
-      uint8_t* dst = At + (uint32_t)rg * sbo + (uint32_t)r8 * 16 + (uint32_t)e * 4;
-      // batches of 8 independent loads before their stores (the loop is latency bound otherwise)
-      for (int kc0 = 0; kc0 < Kp / 4; kc0 += 8) {
-        float x[8], h[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = 4 * (kc0 + j) + e;
-          const bool ok = okp && k < K;
-          x[j] = ok ? __ldg(xr + k) : 0.0f;
-          h[j] = (ok && ar) ? __ldg(ar + k) : 1.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (kc0 + j < Kp / 4)
-            *reinterpret_cast<float*>(dst + (uint32_t)(kc0 + j) * kLBO) = x[j] * a.in_scale * delu_from_out(h[j]);
-      }
-    }
-    sync_round();
-    if (tid == 0) issue_gemm_tf32(a_addr, sbo, b_addr, sbo, Kp, Np, tmem, false, bar);
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    // ---- epilogue: thread (row, half) takes the 16-column blocks half, half+2, …
-    const long long p = first + row;
+  uint32_t ph[2] = {0u, 0u};
+
+  auto epilogue = [&](long long tile, int ab) {
+    const long long p = tile * 128 + row;
+    const uint32_t t_acc = t_row + (uint32_t)ab * acc_cols;
     for (int c0 = half * 16; c0 < Np; c0 += 32) {
       uint32_t r[16];
-      tmem_ld16(t_row + c0, r);
+      tmem_ld16(t_acc + c0, r);
       tmem_wait_ld();
-      if (p < a.P) {
-        float* y = a.Y + p * a.ldy;
-        const float* ax = a.aux ? a.aux + p * a.ld_aux : nullptr;
-        const bool rd_y = a.add_pre || a.add_post;
+      if (p >= a.P) continue;
+      float* y = a.Y + p * a.ldy;
+      const float* ax = a.aux ? a.aux + p * a.ld_aux : nullptr;
+      const bool rd_y = a.add_pre || a.add_post;
+      if (a.vec_y) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = c0 + 4 * q;
+          if (col >= N) break;
+          float4 yv = make_float4(0.f, 0.f, 0.f, 0.f), av = yv, bv = yv;
+          if (rd_y) yv = *reinterpret_cast<const float4*>(y + col);
+          if (ax) av = __ldg(reinterpret_cast<const float4*>(ax + col));
+          if (a.bias) bv = make_float4(__ldg(a.bias + col), __ldg(a.bias + col + 1), __ldg(a.bias + col + 2), __ldg(a.bias + col + 3));
+          float v[4] = {fmaf(__uint_as_float(r[4 * q]), a.in_scale, bv.x), fmaf(__uint_as_float(r[4 * q + 1]), a.in_scale, bv.y),
+                        fmaf(__uint_as_float(r[4 * q + 2]), a.in_scale, bv.z), fmaf(__uint_as_float(r[4 * q + 3]), a.in_scale, bv.w)};
+          const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (a.add_pre) v[j] += yy[j];
+            v[j] = tce_apply(v[j], a.epi, aa[j]);
+            if (a.add_post) v[j] += yy[j];
+          }
+          *reinterpret_cast<float4*>(y + col) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
         float yv[16], av[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {           // all loads before the first store to y
@@ -163,7 +252,7 @@ __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
         for (int j = 0; j < 16; ++j) {
           const int col = c0 + j;
           if (col < N) {
-            float v = __uint_as_float(r[j]) + (a.bias ? __ldg(a.bias + col) : 0.0f);
+            float v = fmaf(__uint_as_float(r[j]), a.in_scale, a.bias ? __ldg(a.bias + col) : 0.0f);
             if (a.add_pre) v += yv[j];
             v = tce_apply(v, a.epi, av[j]);
             if (a.add_post) v += yv[j];
@@ -172,11 +261,38 @@ __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
         }
       }
     }
-    // TMEM reads of this tile are ordered before the next tile's MMAs by the next sync_round
+  };
+
+  int i = 0;
+  for (; tile_of(i) < n_tiles; ++i) {
+    const int b = i % nbuf, ab = i & 1;
+    if (i >= 1) {                      // GEMM of tile i − 1 done: its X buffer is free, its accumulator is complete
+      mbar_wait(bar + (ab ^ 1), ph[ab ^ 1]);
+      ph[ab ^ 1] ^= 1u;
+      tc_fence_after();
+    }
+    {
+      const int j = i + nbuf - 1;      // (its buffer is the one tile i − 1 has just released)
+      if (tile_of(j) < n_tiles) issue_loads(tile_of(j), j % nbuf);
+      cp_async_commit();
+    }
+    cp_async_wait_pending(nbuf - 1);   // this thread's copies of tile i have landed
+    if (a.in_aux) scale_by_aux(b);
+    sync_round();
+    if (tid == 0)
+      issue_gemm_tf32(a_addr + (uint32_t)b * tile_bytes, sbo, b_addr, sbo, Kp, Np, tmem + (uint32_t)ab * acc_cols, false, bar + ab);
+    if (i >= 1) epilogue(tile_of(i - 1), ab ^ 1);
   }
+  if (i >= 1) {
+    const int ab = (i - 1) & 1;
+    mbar_wait(bar + ab, ph[ab]);
+    tc_fence_after();
+    epilogue(tile_of(i - 1), ab);
+  }
+  cp_async_wait_pending(0);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, ncols);
+  if (warp == 0) tmem_dealloc(tmem, 2 * acc_cols);
 }
 
 struct GwTcArgs {
@@ -185,16 +301,21 @@ struct GwTcArgs {
   const float* dy_aux; int ld_dy_aux;
   float* dW; int ldw; float* db; long long P;
   int Kp;          // (K + 1 "ones" row for the bias gradient) rounded up to 16
+  int nbuf;        // operand chunks in flight (2..3)
 };
 constexpr int GPT = 64;      // points per chunk = contraction length per round
 
+// dW[N x K] += in_scale · (dY ⊙ ELU'(dy_aux))ᵀ · X, db[N] += Σ_p dY ⊙ ELU'(dy_aux): contraction over the points,
+// 64 per round, accumulated in ONE TMEM accumulator over all rounds of the CTA and added to dW / db with atomics
+// at the end.  Both operands are staged transposed (feature-major) with 4-byte cp.async copies straight into the
+// tcgen05 operand layout – any row stride works – `nbuf` − 1 chunks ahead of the one being multiplied.
 __global__ void __launch_bounds__(256, 2) grad_weights_tc(GwTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int Kp = a.Kp, K = a.K, N = a.N;
+  const int Kp = a.Kp, K = a.K, N = a.N, nbuf = a.nbuf;
   constexpr uint32_t sbo = (uint32_t)(GPT / 4) * kLBO;      // operands are [rows x GPT points]
-  uint8_t* At = smem;                                       // dY^T : [128 x GPT] (rows >= N stay zero)
-  uint8_t* Bt = smem + 16 * sbo;                            // X^T  : [Kp x GPT] (row K = ones)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Bt + (size_t)(Kp / 8) * sbo);
+  const uint32_t a_bytes = 16 * sbo, b_bytes = (uint32_t)(Kp / 8) * sbo, h_bytes = a.dy_aux ? a_bytes : 0u;
+  const uint32_t buf_bytes = a_bytes + b_bytes + h_bytes;   // dY^T [128 x GPT] | X^T [Kp x GPT] (row K = ones) | aux^T
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)nbuf * buf_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tmem_cols_for(Kp);
@@ -204,60 +325,99 @@ __global__ void __launch_bounds__(256, 2) grad_weights_tc(GwTcArgs a) {
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, ncols);
-  for (int i = tid; i < (int)(16 * sbo / 16); i += blockDim.x) reinterpret_cast<uint4*>(At)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // rows >= N of every dY^T tile stay zero
+  for (int b = 0; b < nbuf; ++b)
+    for (int i = tid; i < (int)(a_bytes / 16); i += blockDim.x)
+      reinterpret_cast<uint4*>(smem + (size_t)b * buf_bytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const int f8 = lane >> 2, e = lane & 3;                   // feature within its group of 8, point within its group of 4
+  const int nA = (N + 7) / 8, nB = Kp / 8;                  // feature groups of the two operands, dealt to the warps together
+  const long long n_chunks = (a.P + GPT - 1) / GPT;
+  auto chunk_of = [&](int i) { return (long long)blockIdx.x + (long long)i * gridDim.x; };
+  const uint32_t s_addr = smem_u32(smem);
+  auto issue_loads = [&](long long ch, int b) {
+    const long long first = ch * GPT;
+    const uint32_t base = s_addr + (uint32_t)b * buf_bytes;
+    for (int t = warp; t < nA + nB; t += 8) {
+      if (t < nA) {
+        const int n = 8 * t + f8;
+        const uint32_t dst = base + (uint32_t)t * sbo + (uint32_t)f8 * 16 + (uint32_t)e * 4;
+#pragma unroll 4
+        for (int pc = 0; pc < GPT / 4; ++pc) {
+          const long long p = first + 4 * pc + e;
+          const bool ok = p < a.P && n < N;
+          cp_async4(dst + (uint32_t)pc * kLBO, a.dY + (ok ? p * a.ldy + n : 0), ok);
+          if (a.dy_aux) cp_async4(dst + a_bytes + b_bytes + (uint32_t)pc * kLBO, a.dy_aux + (ok ? p * a.ld_dy_aux + n : 0), ok);
+        }
+      } else {
+        const int g = t - nA, k = 8 * g + f8;
+        const uint32_t dst = base + a_bytes + (uint32_t)g * sbo + (uint32_t)f8 * 16 + (uint32_t)e * 4;
+        if (k == K) continue;                                // the ones row is written after the wait (plain stores)
+#pragma unroll 4
+        for (int pc = 0; pc < GPT / 4; ++pc) {
+          const long long p = first + 4 * pc + e;
+          const bool ok = p < a.P && k < K;
+          cp_async4(dst + (uint32_t)pc * kLBO, a.X + (ok ? p * a.ldx + k : 0), ok);
+        }
+      }
+    }
+  };
+  // what cp.async cannot do, on the elements this thread owns: the ones row of X^T and dY ⊙ ELU'(dy_aux)
+  auto fix_up = [&](long long ch, int b) {
+    const long long first = ch * GPT;
+    uint8_t* base = smem + (size_t)b * buf_bytes;
+    for (int t = warp; t < nA + nB; t += 8) {
+      if (t < nA) {
+        if (!a.dy_aux) continue;
+        uint8_t* dst = base + (uint32_t)t * sbo + (uint32_t)f8 * 16 + (uint32_t)e * 4;
+        for (int pc = 0; pc < GPT / 4; ++pc) {
+          float* d = reinterpret_cast<float*>(dst + (uint32_t)pc * kLBO);
+          *d *= delu_from_out(*reinterpret_cast<const float*>(dst + a_bytes + b_bytes + (uint32_t)pc * kLBO));
+        }
+      } else {
+        const int g = t - nA, k = 8 * g + f8;
+        if (k != K) continue;
+        uint8_t* dst = base + a_bytes + (uint32_t)g * sbo + (uint32_t)f8 * 16 + (uint32_t)e * 4;
+        for (int pc = 0; pc < GPT / 4; ++pc)
+          *reinterpret_cast<float*>(dst + (uint32_t)pc * kLBO) = (first + 4 * pc + e < a.P) ? 1.0f : 0.0f;
+      }
+    }
+  };
+  for (int j = 0; j < nbuf - 1; ++j) {
+    if (chunk_of(j) < n_chunks) issue_loads(chunk_of(j), j);
+    cp_async_commit();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t a_addr = smem_u32(At), b_addr = smem_u32(Bt);
-  const int f8 = lane >> 2, e = lane & 3;                   // feature within its group of 8, point within its group of 4
   uint32_t phase = 0;
-  bool any = false;
-  const long long n_chunks = (a.P + GPT - 1) / GPT;
-  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-    const long long first = ch * GPT;
-    // ---- dY^T: feature groups over the warps, 16 point-quads each
-    for (int g = warp; g < (N + 7) / 8; g += 8) {
-      const int n = 8 * g + f8;
-      uint8_t* dst = At + (uint32_t)g * sbo + (uint32_t)f8 * 16 + (uint32_t)e * 4;
-      float d[GPT / 4], h[GPT / 4];
-#pragma unroll
-      for (int pc = 0; pc < GPT / 4; ++pc) {       // all loads of the group first
-        const long long p = first + 4 * pc + e;
-        const bool ok = p < a.P && n < N;
-        d[pc] = ok ? __ldg(a.dY + p * a.ldy + n) : 0.0f;
-        h[pc] = (ok && a.dy_aux) ? __ldg(a.dy_aux + p * a.ld_dy_aux + n) : 1.0f;
-      }
-#pragma unroll
-      for (int pc = 0; pc < GPT / 4; ++pc)
-        *reinterpret_cast<float*>(dst + (uint32_t)pc * kLBO) = d[pc] * delu_from_out(h[pc]);
+  int i = 0;
+  for (; chunk_of(i) < n_chunks; ++i) {
+    const int b = i % nbuf;
+    if (i >= 1) {                      // GEMM of chunk i − 1 done: its buffer is free
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc_fence_after();
     }
-    // ---- X^T (+ the ones row that yields db)
-    for (int g = warp; g < Kp / 8; g += 8) {
-      const int k = 8 * g + f8;
-      uint8_t* dst = Bt + (uint32_t)g * sbo + (uint32_t)f8 * 16 + (uint32_t)e * 4;
-      float x[GPT / 4];
-#pragma unroll
-      for (int pc = 0; pc < GPT / 4; ++pc) {
-        const long long p = first + 4 * pc + e;
-        x[pc] = 0.0f;
-        if (p < a.P) {
-          if (k < K) x[pc] = __ldg(a.X + p * a.ldx + k) * a.in_scale;
-          else if (k == K) x[pc] = 1.0f;
-        }
-      }
-#pragma unroll
-      for (int pc = 0; pc < GPT / 4; ++pc) *reinterpret_cast<float*>(dst + (uint32_t)pc * kLBO) = x[pc];
+    {
+      const int j = i + nbuf - 1;
+      if (chunk_of(j) < n_chunks) issue_loads(chunk_of(j), j % nbuf);
+      cp_async_commit();
     }
+    cp_async_wait_pending(nbuf - 1);
+    fix_up(chunk_of(i), b);
     sync_round();
-    if (tid == 0) issue_gemm_tf32(a_addr, sbo, b_addr, sbo, GPT, Kp, tmem, any, bar);
-    any = true;
-    mbar_wait(bar, phase);      // the operand tiles are rewritten next round
-    phase ^= 1u;
-    tc_fence_after();
+    if (tid == 0) {
+      const uint32_t base = s_addr + (uint32_t)b * buf_bytes;
+      issue_gemm_tf32(base, sbo, base + a_bytes, sbo, GPT, Kp, tmem, i > 0, bar);
+    }
   }
-  if (any) {
+  cp_async_wait_pending(0);
+  if (i >= 1) {
+    mbar_wait(bar, phase);
+    tc_fence_after();
     const int n = tid & 127, half = tid >> 7;
     for (int c0 = half * 16; c0 < Kp; c0 += 32) {
       uint32_t r[16];
@@ -267,7 +427,7 @@ __global__ void __launch_bounds__(256, 2) grad_weights_tc(GwTcArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = c0 + j;
-          if (k < K) atomicAdd(a.dW + (long long)n * a.ldw + k, __uint_as_float(r[j]));
+          if (k < K) atomicAdd(a.dW + (long long)n * a.ldw + k, __uint_as_float(r[j]) * a.in_scale);
           else if (k == K && a.db != nullptr) atomicAdd(a.db + n, __uint_as_float(r[j]));
         }
       }
@@ -278,45 +438,79 @@ __global__ void __launch_bounds__(256, 2) grad_weights_tc(GwTcArgs a) {
   if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
-static int grid_for_tiles(long long tiles) {
-  const long long cap = 2ll * sm_count();
-  return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
-}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int linear_tc_launch(const float* X, int ldx, int K, float in_scale, const float* in_aux, int ld_in_aux,
                      const float* W, int ldw, int w_is_kn, int N, const float* bias, int epilogue, const float* aux,
                      int ld_aux, float* Y, int ldy, int add_pre, int add_post, long long P, cudaStream_t st) {
   LinTcArgs a{X, ldx, K, in_scale, in_aux, ld_in_aux, W, ldw, w_is_kn, N, bias, epilogue, aux, ld_aux, Y, ldy,
-              add_pre, add_post, P, (K + 7) & ~7, (N + 15) & ~15};
-  const size_t smem = (size_t)(a.Np + 128) * a.Kp * 4 + 64;
+              add_pre, add_post, P, (K + 7) & ~7, (N + 15) & ~15, 2, 0};
+  const bool vec_x = aligned16(X) && ldx % 4 == 0 && K % 4 == 0 &&
+                     (in_aux == nullptr || (aligned16(in_aux) && ld_in_aux % 4 == 0));
+  a.vec_y = aligned16(Y) && ldy % 4 == 0 && N % 4 == 0 && (aux == nullptr || (aligned16(aux) && ld_aux % 4 == 0)) &&
+            (bias == nullptr || true);
+  // shared memory: weights + nbuf X tiles (+ nbuf in_aux tiles); two CTAs per SM when at least two tiles each fit
+  const size_t tile = (size_t)128 * a.Kp * 4 * (in_aux ? 2 : 1), wb = (size_t)a.Np * a.Kp * 4;
+  const size_t budget = 220 * 1024;
+  int ctas = 2;
+  long long nbuf = ((long long)(budget / 2) - (long long)wb - 256) / (long long)tile;
+  if (nbuf < 2) {
+    ctas = 1;
+    nbuf = ((long long)budget - (long long)wb - 256) / (long long)tile;
+  }
+  if (nbuf < 2) {
+    set_error("k6_linear (tcgen05 tf32): K too large for two X tiles in shared memory", cudaSuccess);
+    return GPNERF_E_UNSUPPORTED;
+  }
+  a.nbuf = (int)(nbuf > 4 ? 4 : nbuf);
+  const size_t smem = wb + (size_t)a.nbuf * tile + 64;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(linear_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
       set_error("linear_tc smem attribute", e);
       return GPNERF_E_CUDA;
     }
     set = true;
   }
-  linear_tc<<<grid_for_tiles((P + 127) / 128), 256, smem, st>>>(a);
+  const long long tiles = (P + 127) / 128, cap = (long long)ctas * sm_count();
+  const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+  if (vec_x) linear_tc<true><<<grid, 256, smem, st>>>(a);
+  else linear_tc<false><<<grid, 256, smem, st>>>(a);
   return check_launch("k6_linear (tcgen05 tf32)");
 }
 
 int grad_weights_tc_launch(const float* X, int ldx, int K, float in_scale, const float* dY, int ldy, int N,
                            const float* dy_aux, int ld_dy_aux, float* dW, int ldw, float* db, long long P,
                            cudaStream_t st) {
-  GwTcArgs a{X, ldx, K, in_scale, dY, ldy, N, dy_aux, ld_dy_aux, dW, ldw, db, P, (K + 1 + 15) & ~15};
-  const size_t smem = (size_t)(128 + a.Kp) * GPT * 4 + 64;
+  GwTcArgs a{X, ldx, K, in_scale, dY, ldy, N, dy_aux, ld_dy_aux, dW, ldw, db, P, (K + 1 + 15) & ~15, 2};
+  const size_t buf = (size_t)(128 + a.Kp + (dy_aux ? 128 : 0)) * GPT * 4;
+  const size_t budget = 220 * 1024;
+  int ctas = 2;
+  long long nbuf = ((long long)(budget / 2) - 256) / (long long)buf;
+  if (nbuf < 2) {
+    ctas = 1;
+    nbuf = ((long long)budget - 256) / (long long)buf;
+  }
+  if (nbuf < 2) {
+    set_error("k6_grad_weights (tcgen05 tf32): K too large for two operand chunks in shared memory", cudaSuccess);
+    return GPNERF_E_UNSUPPORTED;
+  }
+  a.nbuf = (int)(nbuf > 3 ? 3 : nbuf);
+  const size_t smem = (size_t)a.nbuf * buf + 64;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(grad_weights_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(grad_weights_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
       set_error("grad_weights_tc smem attribute", e);
       return GPNERF_E_CUDA;
     }
     set = true;
   }
-  grad_weights_tc<<<grid_for_tiles((P + GPT - 1) / GPT), 256, smem, st>>>(a);
+  const long long chunks = (P + GPT - 1) / GPT, cap = (long long)ctas * sm_count();
+  const int grid = (int)(chunks < cap ? (chunks > 0 ? chunks : 1) : cap);
+  grad_weights_tc<<<grid, 256, smem, st>>>(a);
   return check_launch("k6_grad_weights (tcgen05 tf32)");
 }
 
