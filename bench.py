@@ -145,6 +145,7 @@ def stage_work(counts, n_level_elems, V, n_map_elems=0, n_img_px=0):
     fused_compulsory = 2.0 * n_level_elems / 4 + 2.0 * n_map_elems + 16.0 * n_img_px + 20.0 * P1
     return {
         "k3_color_gather_tc": ("tensor", 72160.0 * P2, "72,160 FLOP per surviving point (colour trunk)"),
+        "k3_color_tiles_tc": ("tensor", 72160.0 * P1, "72,160 FLOP per P1 point (colour trunk on every tile that has a survivor; tile hand-off)"),
         "k0_level_to_channels_last": ("hbm", 8.0 * n_level_elems / 4, "all 4 calls: 4 B read + 4 B written per element"),
         "k0_products_to_f16": ("hbm", 6.0 * n_level_elems / 4 + 4.0 * n_level_elems / 4 / 32,
                                "4 B read + 2 B written per element, 4 B channel sum per voxel"),
@@ -844,7 +845,15 @@ def main():
             tj["_file"] = name
             break
     flops_of = {"k23_gather_density_tc": 38688.0 * counts["P1"], "k3_color_gather_tc": 72160.0 * counts["P2"],
-                "k3_color_mlp_records": 72160.0 * counts["P2"]}
+                "k3_color_mlp_records": 72160.0 * counts["P2"], "k3_color_tiles_tc": 72160.0 * counts["P1"]}
+    binding = {
+        "k23_gather_density_tc": "the producers' gathers: load latency x loads in flight (16 warps x 8 x 16 B per lane; long-scoreboard "
+                                 "stall 4.9 warps per issue cycle) with the L1 data pipe at 73 % - what-if runs: producers only 0.28 ms, "
+                                 "head only 0.125 ms (profiles/r02_ncu_summary.md section 8); neither HBM nor the tensor pipe bounds this kernel",
+        "k3_color_gather_tc": "latency of the 4V+1 dependent MMA -> epilogue rounds of a tile (three chains per SM) and the re-gather",
+        "k3_color_tiles_tc": "latency of the 4V+1 dependent MMA -> epilogue rounds of a tile, four chains per SM (TMEM: 4 x 128 columns); "
+                             "floors: tensor pipe 0.124 ms (69 MMAs of ~75 cycles per tile), MUFU 0.10 ms, issue slots 0.094 ms",
+    }
     requested_of = {"k23_gather_density_tc": (2048.0 + VIEWS * 320.0) * counts["P1"],
                     "k3_color_gather_tc": VIEWS * 320.0 * counts["P2"]}
 
@@ -872,15 +881,12 @@ def main():
             r["frac_tensor"] = r["tflops"] / pk["bf16_tflops"]
         if name in requested_of:
             r["requested_gbs"] = requested_of[name] / dur_s / 1e9
-            r["binding_unit"] = ("L1 data pipe: one 128-byte wavefront per 64-byte corner fetch, L2-resident operands "
-                                 "(`ncu`); neither HBM nor the tensor pipe bounds this kernel"
-                                 if name == "k23_gather_density_tc" else
-                                 "latency of the 4V+1 dependent MMA → epilogue rounds of a tile (three chains per SM); "
-                                 "MUFU (528 exponentials per point) and the MMA operand fetch are the next limits")
+        if name in binding:
+            r["binding_unit"] = binding[name]
         return r
     roofline = kernel_roofline(top) if top else None
     if roofline is not None:
-        others = [k for k in ("k23_gather_density_tc", "k3_color_gather_tc") if k in timed and k != top]
+        others = [k for k in ("k23_gather_density_tc", "k3_color_gather_tc", "k3_color_tiles_tc") if k in timed and k != top]
         roofline["other_head_kernels"] = [kernel_roofline(k) for k in others]
         # the whole frame against both roofs: every distinct input byte once + the image, and the heads' FLOPs
         frame_bytes = (6.0 * n_level_elems / 4 + 6.0 * n_map_elems + 28.0 * n_img_px + 36.0 * counts["n_rays"] * S_SAMPLES +

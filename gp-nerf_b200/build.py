@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libgpnerf_b200.so")
 SOURCES = ["abi.cu", "k0_layout.cu", "k1_rays.cu", "k2_gather.cu", "k3_mlp_fp32.cu", "k3_mlp_tc.cu", "k23_fused_tc.cu", "k23_fused_ws.cu", "k3_color_ws.cu", "k3_color_tiles.cu",
            "k4_k5_progressive.cu", "k6_train.cu", "k6_train_tc.cu", "k7_sparseconv.cu", "k7_sparseconv_tc.cu", "k8_attention.cu", "k9_instnorm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("GPNERF_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

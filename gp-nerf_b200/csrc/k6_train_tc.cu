@@ -57,6 +57,16 @@ __device__ __forceinline__ float tce_apply(float v, int epi, float aux) {
     default: return v;
   }
 }
+// branch-free forms for the epilogues (a per-element switch compiles to an indirect branch plus out-of-line
+// expm1f / expf calls: ≈400 cycles per element, the whole epilogue of a tile 12 k cycles)
+template <int EPI>
+__device__ __forceinline__ float tce_apply_t(float v, float aux) {
+  if (EPI == TCE_ELU) return v > 0.0f ? v : ex2_ftz(v * kLog2e) - 1.0f;
+  if (EPI == TCE_RELU) return fmaxf(v, 0.0f);
+  if (EPI == TCE_SIGMOID) return __fdividef(1.0f, 1.0f + ex2_ftz(-v * kLog2e));
+  if (EPI == TCE_MUL_DELU) return v * delu_from_out(aux);
+  return v;
+}
 __device__ __forceinline__ void sync_round() {
   fence_proxy_async_smem();
   tc_fence_before();
@@ -64,6 +74,8 @@ __device__ __forceinline__ void sync_round() {
   tc_fence_after();
 }
 __host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct LinTcArgs {
   const float* X; int ldx; int K; float in_scale;
@@ -81,6 +93,15 @@ struct LinTcArgs {
   int vec_y;       // Y (and aux) rows are 16-byte aligned and N % 4 == 0: float4 epilogue
 };
 
+#ifdef GPNERF_K6_TRACE
+__device__ long long g_k6_trace[2048];
+__device__ int g_k6_trace_n;
+__device__ unsigned long long g_k6_span[1024];
+__device__ __forceinline__ unsigned long long k6_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define K6_STAMP() do { if (tid == 0 && blockIdx.x == 0 && g_k6_trace_n < 2040) g_k6_trace[g_k6_trace_n++] = clock64(); } while (0)
+#else
+#define K6_STAMP() do {} while (0)
+#endif
 // ---- asynchronous copies global → shared (LDGSTS): no registers held while the data is in flight, so a thread
 // keeps a whole tile (or several) in flight; src-size 0 writes zeros (rows beyond P, padding columns)
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
@@ -105,7 +126,9 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {      // at most n
 // ahead of the one being multiplied; the accumulator is double buffered in TMEM, so the epilogue of tile i − 1
 // (TMEM → registers → global) overlaps the GEMM of tile i and the loads of tiles i + 1 …
 // VEC: X rows (and in_aux rows) are 16-byte aligned and K % 4 == 0 – 16-byte copies (one core-matrix row each).
-template <bool VEC>
+constexpr int kStgStride = 20;        // floats per patch row (16 + 4: conflict-free 16-byte row writes)
+constexpr size_t kStgBytes = 8 * 32 * kStgStride * 4;
+template <bool VEC, int EPI>
 __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Kp = a.Kp, Np = a.Np, K = a.K, N = a.N, nbuf = a.nbuf;
@@ -114,10 +137,15 @@ __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
   uint8_t* Bt = smem;                                       // [Np x Kp]
   uint8_t* At = smem + (size_t)(Np / 8) * sbo;              // nbuf x [128 x Kp]
   uint8_t* Xt = At + (size_t)nbuf * tile_bytes;             // nbuf x [128 x Kp]: in_aux tiles (only with in_aux)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Xt + (a.in_aux ? (size_t)nbuf * tile_bytes : 0));
+  float* stg = reinterpret_cast<float*>(Xt + (a.in_aux ? (size_t)nbuf * tile_bytes : 0));      // 8 warps x [32 x 16] patches
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stg + 8 * 32 * kStgStride);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t acc_cols = tmem_cols_for(Np);
+  K6_STAMP();
+#ifdef GPNERF_K6_TRACE
+  if (tid == 0 && blockIdx.x < 512) g_k6_span[2 * blockIdx.x] = k6_gtime();
+#endif
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
@@ -189,75 +217,108 @@ __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
     }
   };
   auto tile_of = [&](int i) { return (long long)blockIdx.x + (long long)i * gridDim.x; };
-  // the first nbuf − 1 tiles are requested before anything else (the weights below are staged while they fly)
+  // B[n][k] = W^T or W, zero padded: asynchronous copies as well (a loop of dependent load → store pairs cost
+  // 19 k cycles per CTA here), in the same group as the first X tile
+  for (int i = tid; i < Np * Kp; i += blockDim.x) {
+    const int n = i / Kp, k = i - n * Kp;
+    const bool ok = n < N && k < K;
+    const float* src = a.W;
+    if (ok) src = a.w_is_kn ? a.W + (long long)k * a.ldw + n : a.W + (long long)n * a.ldw + k;
+    cp_async4(b_addr + off32(n, k, sbo), src, ok);
+  }
+  // the first nbuf − 1 tiles are requested before anything else
   for (int j = 0; j < nbuf - 1; ++j) {
     if (tile_of(j) < n_tiles) issue_loads(tile_of(j), j);
     cp_async_commit();
-  }
-  // B[n][k] = W^T or W, zero padded
-  for (int i = tid; i < Np * Kp; i += blockDim.x) {
-    const int n = i / Kp, k = i - n * Kp;
-    float v = 0.0f;
-    if (n < N && k < K) v = __ldg(a.w_is_kn ? a.W + (long long)k * a.ldw + n : a.W + (long long)n * a.ldw + k);
-    *reinterpret_cast<float*>(Bt + off32(n, k, sbo)) = v;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  K6_STAMP();
   const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int row = tid & 127, half = tid >> 7;
   uint32_t ph[2] = {0u, 0u};
 
   auto epilogue = [&](long long tile, int ab) {
-    const long long p = tile * 128 + row;
     const uint32_t t_acc = t_row + (uint32_t)ab * acc_cols;
     for (int c0 = half * 16; c0 < Np; c0 += 32) {
       uint32_t r[16];
+      K6_STAMP();
       tmem_ld16(t_acc + c0, r);
       tmem_wait_ld();
-      if (p >= a.P) continue;
-      float* y = a.Y + p * a.ldy;
-      const float* ax = a.aux ? a.aux + p * a.ld_aux : nullptr;
+      K6_STAMP();
       const bool rd_y = a.add_pre || a.add_post;
       if (a.vec_y) {
+        // Thread = row holds 16 consecutive columns; written like that, a warp store touches 32 different lines (32 L1
+        // wavefronts for 512 bytes).  The warp's [32 x 16] block goes through a private shared-memory patch instead
+        // and leaves – and its aux / y operands arrive – as 4 instructions of 8 rows x 64 contiguous bytes.
+        float* patch = stg + warp * (32 * kStgStride);
+        __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col = c0 + 4 * q;
-          if (col >= N) break;
-          float4 yv = make_float4(0.f, 0.f, 0.f, 0.f), av = yv, bv = yv;
-          if (rd_y) yv = *reinterpret_cast<const float4*>(y + col);
-          if (ax) av = __ldg(reinterpret_cast<const float4*>(ax + col));
-          if (a.bias) bv = make_float4(__ldg(a.bias + col), __ldg(a.bias + col + 1), __ldg(a.bias + col + 2), __ldg(a.bias + col + 3));
-          float v[4] = {fmaf(__uint_as_float(r[4 * q]), a.in_scale, bv.x), fmaf(__uint_as_float(r[4 * q + 1]), a.in_scale, bv.y),
-                        fmaf(__uint_as_float(r[4 * q + 2]), a.in_scale, bv.z), fmaf(__uint_as_float(r[4 * q + 3]), a.in_scale, bv.w)};
-          const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, aa[4] = {av.x, av.y, av.z, av.w};
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias && col < N) bv = make_float4(__ldg(a.bias + col), __ldg(a.bias + col + 1), __ldg(a.bias + col + 2), __ldg(a.bias + col + 3));
+          *reinterpret_cast<float4*>(patch + lane * kStgStride + 4 * q) =
+              make_float4(fmaf(__uint_as_float(r[4 * q]), a.in_scale, bv.x), fmaf(__uint_as_float(r[4 * q + 1]), a.in_scale, bv.y),
+                          fmaf(__uint_as_float(r[4 * q + 2]), a.in_scale, bv.z), fmaf(__uint_as_float(r[4 * q + 3]), a.in_scale, bv.w));
+        }
+        __syncwarp();
+        const int col = c0 + 4 * (lane & 3);
+        const long long p0 = tile * 128 + (warp & 3) * 32 + (lane >> 2);
+        float4 yv[4], av[4];
+#pragma unroll
+        for (int sI = 0; sI < 4; ++sI) {          // all operand loads first
+          const long long pp = p0 + 8 * sI;
+          const bool ok = pp < a.P && col < N;
+          yv[sI] = av[sI] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && rd_y) yv[sI] = *reinterpret_cast<const float4*>(a.Y + pp * a.ldy + col);
+          if (ok && a.aux) av[sI] = __ldg(reinterpret_cast<const float4*>(a.aux + pp * a.ld_aux + col));
+        }
+#pragma unroll
+        for (int sI = 0; sI < 4; ++sI) {
+          const long long pp = p0 + 8 * sI;
+          if (!(pp < a.P && col < N)) continue;
+          const float4 t = *reinterpret_cast<const float4*>(patch + (8 * sI + (lane >> 2)) * kStgStride + 4 * (lane & 3));
+          float v[4] = {t.x, t.y, t.z, t.w};
+          const float yy[4] = {yv[sI].x, yv[sI].y, yv[sI].z, yv[sI].w}, aa[4] = {av[sI].x, av[sI].y, av[sI].z, av[sI].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (a.add_pre) v[j] += yy[j];
-            v[j] = tce_apply(v[j], a.epi, aa[j]);
+            v[j] = tce_apply_t<EPI>(v[j], aa[j]);
             if (a.add_post) v[j] += yy[j];
           }
-          *reinterpret_cast<float4*>(y + col) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(a.Y + pp * a.ldy + col) = make_float4(v[0], v[1], v[2], v[3]);
         }
       } else {
-        float yv[16], av[16];
+        // rows of Y that are not 16-byte aligned (the 70- / 35-float gather gradients): same patch, read back as
+        // 16 instructions of 2 rows x 16 consecutive floats
+        float* patch = stg + warp * (32 * kStgStride);
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {           // all loads before the first store to y
-          const int col = c0 + j;
-          yv[j] = (rd_y && col < N) ? y[col] : 0.0f;
-          av[j] = (ax && col < N) ? __ldg(ax + col) : 0.0f;
+        for (int q = 0; q < 4; ++q) {
+          float b4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b4[j] = (a.bias && c0 + 4 * q + j < N) ? __ldg(a.bias + c0 + 4 * q + j) : 0.0f;
+          *reinterpret_cast<float4*>(patch + lane * kStgStride + 4 * q) =
+              make_float4(fmaf(__uint_as_float(r[4 * q]), a.in_scale, b4[0]), fmaf(__uint_as_float(r[4 * q + 1]), a.in_scale, b4[1]),
+                          fmaf(__uint_as_float(r[4 * q + 2]), a.in_scale, b4[2]), fmaf(__uint_as_float(r[4 * q + 3]), a.in_scale, b4[3]));
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          if (col < N) {
-            float v = fmaf(__uint_as_float(r[j]), a.in_scale, a.bias ? __ldg(a.bias + col) : 0.0f);
-            if (a.add_pre) v += yv[j];
-            v = tce_apply(v, a.epi, av[j]);
-            if (a.add_post) v += yv[j];
-            y[col] = v;
-          }
+        __syncwarp();
+        const int col = c0 + (lane & 15);
+        const long long p0 = tile * 128 + (warp & 3) * 32 + (lane >> 4);
+#pragma unroll 4
+        for (int sI = 0; sI < 16; ++sI) {
+          const long long pp = p0 + 2 * sI;
+          if (!(pp < a.P && col < N)) continue;
+          float v = patch[(2 * sI + (lane >> 4)) * kStgStride + (lane & 15)];
+          const float yy = rd_y ? a.Y[pp * a.ldy + col] : 0.0f;
+          const float aa = a.aux ? __ldg(a.aux + pp * a.ld_aux + col) : 0.0f;
+          if (a.add_pre) v += yy;
+          v = tce_apply_t<EPI>(v, aa);
+          if (a.add_post) v += yy;
+          a.Y[pp * a.ldy + col] = v;
         }
       }
     }
@@ -266,22 +327,28 @@ __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
   int i = 0;
   for (; tile_of(i) < n_tiles; ++i) {
     const int b = i % nbuf, ab = i & 1;
+    K6_STAMP();
     if (i >= 1) {                      // GEMM of tile i − 1 done: its X buffer is free, its accumulator is complete
       mbar_wait(bar + (ab ^ 1), ph[ab ^ 1]);
       ph[ab ^ 1] ^= 1u;
       tc_fence_after();
     }
+    K6_STAMP();
     {
       const int j = i + nbuf - 1;      // (its buffer is the one tile i − 1 has just released)
       if (tile_of(j) < n_tiles) issue_loads(tile_of(j), j % nbuf);
       cp_async_commit();
     }
+    K6_STAMP();
     cp_async_wait_pending(nbuf - 1);   // this thread's copies of tile i have landed
+    K6_STAMP();
     if (a.in_aux) scale_by_aux(b);
     sync_round();
+    K6_STAMP();
     if (tid == 0)
       issue_gemm_tf32(a_addr + (uint32_t)b * tile_bytes, sbo, b_addr, sbo, Kp, Np, tmem + (uint32_t)ab * acc_cols, false, bar + ab);
     if (i >= 1) epilogue(tile_of(i - 1), ab ^ 1);
+    K6_STAMP();
   }
   if (i >= 1) {
     const int ab = (i - 1) & 1;
@@ -290,9 +357,14 @@ __global__ void __launch_bounds__(256, 2) linear_tc(LinTcArgs a) {
     epilogue(tile_of(i - 1), ab);
   }
   cp_async_wait_pending(0);
+  K6_STAMP();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 2 * acc_cols);
+  K6_STAMP();
+#ifdef GPNERF_K6_TRACE
+  if (tid == 0 && blockIdx.x < 512) g_k6_span[2 * blockIdx.x + 1] = k6_gtime();
+#endif
 }
 
 struct GwTcArgs {
@@ -438,8 +510,6 @@ __global__ void __launch_bounds__(256, 2) grad_weights_tc(GwTcArgs a) {
   if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
 int linear_tc_launch(const float* X, int ldx, int K, float in_scale, const float* in_aux, int ld_in_aux,
                      const float* W, int ldw, int w_is_kn, int N, const float* bias, int epilogue, const float* aux,
                      int ld_aux, float* Y, int ldy, int add_pre, int add_post, long long P, cudaStream_t st) {
@@ -453,38 +523,185 @@ int linear_tc_launch(const float* X, int ldx, int K, float in_scale, const float
   const size_t tile = (size_t)128 * a.Kp * 4 * (in_aux ? 2 : 1), wb = (size_t)a.Np * a.Kp * 4;
   const size_t budget = 220 * 1024;
   int ctas = 2;
-  long long nbuf = ((long long)(budget / 2) - (long long)wb - 256) / (long long)tile;
+  const long long fixed = (long long)wb + (long long)kStgBytes + 256;
+  long long nbuf = ((long long)(budget / 2) - fixed) / (long long)tile;
   if (nbuf < 2) {
     ctas = 1;
-    nbuf = ((long long)budget - (long long)wb - 256) / (long long)tile;
+    nbuf = ((long long)budget - fixed) / (long long)tile;
   }
   if (nbuf < 2) {
     set_error("k6_linear (tcgen05 tf32): K too large for two X tiles in shared memory", cudaSuccess);
     return GPNERF_E_UNSUPPORTED;
   }
   a.nbuf = (int)(nbuf > 4 ? 4 : nbuf);
-  const size_t smem = wb + (size_t)a.nbuf * tile + 64;
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e != cudaSuccess) {
-      set_error("linear_tc smem attribute", e);
-      return GPNERF_E_CUDA;
-    }
-    set = true;
-  }
+  const size_t smem = wb + (size_t)a.nbuf * tile + kStgBytes + 64;
   const long long tiles = (P + 127) / 128, cap = (long long)ctas * sm_count();
   const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
-  if (vec_x) linear_tc<true><<<grid, 256, smem, st>>>(a);
-  else linear_tc<false><<<grid, 256, smem, st>>>(a);
+  using Kern = void (*)(LinTcArgs);
+  static const Kern kerns[2][5] = {
+      {linear_tc<false, 0>, linear_tc<false, 1>, linear_tc<false, 2>, linear_tc<false, 3>, linear_tc<false, 4>},
+      {linear_tc<true, 0>, linear_tc<true, 1>, linear_tc<true, 2>, linear_tc<true, 3>, linear_tc<true, 4>}};
+  static bool set = false;
+  if (!set) {
+    for (int v = 0; v < 2; ++v)
+      for (int e = 0; e < 5; ++e) {
+        cudaError_t err = cudaFuncSetAttribute(kerns[v][e], cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (err != cudaSuccess) {
+          set_error("linear_tc smem attribute", err);
+          return GPNERF_E_CUDA;
+        }
+      }
+    set = true;
+  }
+  if (epilogue < 0 || epilogue > 4) {
+    set_error("k6_linear: unknown epilogue", cudaSuccess);
+    return GPNERF_E_ARG;
+  }
+  kerns[vec_x ? 1 : 0][epilogue]<<<grid, 256, smem, st>>>(a);
   return check_launch("k6_linear (tcgen05 tf32)");
+}
+
+// Same contraction for 16-byte aligned operands (the activations and their gradients: every layer but the ones that
+// read the 70- / 35-float gather outputs): 4-byte cp.async copies cost the LSU ≈30 cycles per 128 bytes, so the
+// operands are fetched with 16-byte loads into registers – one chunk ahead of the chunk being multiplied – and
+// scattered into the transposed operand layout with 4-byte shared-memory stores; dY ⊙ ELU'(dy_aux) is applied in
+// registers.  Two operand buffers, two barriers: the GEMM of chunk i − 1 overlaps the staging of chunk i.
+__global__ void __launch_bounds__(256, 2) grad_weights_vec(GwTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int Kp = a.Kp, K = a.K, N = a.N;
+  constexpr uint32_t sbo = (uint32_t)(GPT / 4) * kLBO;
+  const uint32_t a_bytes = 16 * sbo, b_bytes = (uint32_t)(Kp / 8) * sbo, buf_bytes = a_bytes + b_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)buf_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t ncols = tmem_cols_for(Kp);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
+  // rows >= N of dY^T and rows >= K of X^T stay zero (row K, the ones row, is rewritten per chunk)
+  for (int i = tid; i < (int)(2 * buf_bytes / 16); i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  const long long n_chunks = (a.P + GPT - 1) / GPT;
+  auto chunk_of = [&](int i) { return (long long)blockIdx.x + (long long)i * gridDim.x; };
+  const int qa = N / 4, qb = K / 4;                         // 16-byte pieces per point of dY and of X
+  const int na = (GPT * qa + 255) / 256, nb = (GPT * qb + 255) / 256;        // pieces per thread: <= 4, <= 8
+  float4 dyv[4], hv[4], xv[8];
+  auto load_regs = [&](long long ch) {
+    const long long first = ch * GPT;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + 256 * it, pl = idx / qa, q = idx - pl * qa;
+      dyv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (it < na && pl < GPT && first + pl < a.P) {
+        dyv[it] = __ldg(reinterpret_cast<const float4*>(a.dY + (first + pl) * a.ldy) + q);
+        if (a.dy_aux) hv[it] = __ldg(reinterpret_cast<const float4*>(a.dy_aux + (first + pl) * a.ld_dy_aux) + q);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + 256 * it, pl = idx / qb, q = idx - pl * qb;
+      xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (it < nb && pl < GPT && first + pl < a.P) xv[it] = __ldg(reinterpret_cast<const float4*>(a.X + (first + pl) * a.ldx) + q);
+    }
+  };
+  auto store_regs = [&](long long ch, int b) {
+    uint8_t* At = smem + (size_t)b * buf_bytes;
+    uint8_t* Bt = At + a_bytes;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + 256 * it, pl = idx / qa, q = idx - pl * qa;
+      if (it < na && pl < GPT) {
+        const float v[4] = {dyv[it].x * delu_from_out(hv[it].x), dyv[it].y * delu_from_out(hv[it].y),
+                            dyv[it].z * delu_from_out(hv[it].z), dyv[it].w * delu_from_out(hv[it].w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float*>(At + off32(4 * q + j, pl, sbo)) = v[j];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + 256 * it, pl = idx / qb, q = idx - pl * qb;
+      if (it < nb && pl < GPT) {
+        const float v[4] = {xv[it].x, xv[it].y, xv[it].z, xv[it].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float*>(Bt + off32(4 * q + j, pl, sbo)) = v[j];
+      }
+    }
+    if (tid < GPT) *reinterpret_cast<float*>(Bt + off32(K, tid, sbo)) = (ch * GPT + tid < a.P) ? 1.0f : 0.0f;   // ones row → db
+  };
+  if (chunk_of(0) < n_chunks) load_regs(chunk_of(0));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t s_addr = smem_u32(smem);
+  uint32_t ph[2] = {0u, 0u};
+  int i = 0;
+  for (; chunk_of(i) < n_chunks; ++i) {
+    const int b = i & 1;
+    if (i >= 2) {                      // GEMM of chunk i − 2 done: its buffer is free
+      mbar_wait(bar + b, ph[b]);
+      ph[b] ^= 1u;
+    }
+    store_regs(chunk_of(i), b);
+    if (chunk_of(i + 1) < n_chunks) load_regs(chunk_of(i + 1));      // in flight while this chunk is multiplied
+    sync_round();
+    if (tid == 0) {
+      const uint32_t base = s_addr + (uint32_t)b * buf_bytes;
+      issue_gemm_tf32(base, sbo, base + a_bytes, sbo, GPT, Kp, tmem, i > 0, bar + b);
+    }
+  }
+  if (i >= 1) {
+    // everything issued has completed when the last commit has arrived (tcgen05.commit covers all earlier MMAs)
+    const int b = (i - 1) & 1;
+    mbar_wait(bar + b, ph[b]);
+    tc_fence_after();
+    const int n = tid & 127, half = tid >> 7;
+    for (int c0 = half * 16; c0 < Kp; c0 += 32) {
+      uint32_t r[16];
+      tmem_ld16(t_row + c0, r);
+      tmem_wait_ld();
+      if (n < N) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = c0 + j;
+          if (k < K) atomicAdd(a.dW + (long long)n * a.ldw + k, __uint_as_float(r[j]) * a.in_scale);
+          else if (k == K && a.db != nullptr) atomicAdd(a.db + n, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
 int grad_weights_tc_launch(const float* X, int ldx, int K, float in_scale, const float* dY, int ldy, int N,
                            const float* dy_aux, int ld_dy_aux, float* dW, int ldw, float* db, long long P,
                            cudaStream_t st) {
   GwTcArgs a{X, ldx, K, in_scale, dY, ldy, N, dy_aux, ld_dy_aux, dW, ldw, db, P, (K + 1 + 15) & ~15, 2};
+  const bool vec = aligned16(X) && ldx % 4 == 0 && K % 4 == 0 && K <= 128 && aligned16(dY) && ldy % 4 == 0 && N % 4 == 0 &&
+                   N <= 64 && (dy_aux == nullptr || (aligned16(dy_aux) && ld_dy_aux % 4 == 0));
+  if (vec) {
+    const size_t smem_v = 2 * (size_t)(128 + a.Kp) * GPT * 4 + 64;
+    static bool set_v = false;
+    if (!set_v) {
+      cudaError_t e = cudaFuncSetAttribute(grad_weights_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+      if (e != cudaSuccess) {
+        set_error("grad_weights_vec smem attribute", e);
+        return GPNERF_E_CUDA;
+      }
+      set_v = true;
+    }
+    const long long chunks_v = (P + GPT - 1) / GPT, cap_v = (smem_v <= 110 * 1024 ? 2ll : 1ll) * sm_count();
+    const int grid_v = (int)(chunks_v < cap_v ? (chunks_v > 0 ? chunks_v : 1) : cap_v);
+    grad_weights_vec<<<grid_v, 256, smem_v, st>>>(a);
+    return check_launch("k6_grad_weights (tcgen05 tf32, vector staging)");
+  }
   const size_t buf = (size_t)(128 + a.Kp + (dy_aux ? 128 : 0)) * GPT * 4;
   const size_t budget = 220 * 1024;
   int ctas = 2;
@@ -513,5 +730,18 @@ int grad_weights_tc_launch(const float* X, int ldx, int K, float in_scale, const
   grad_weights_tc<<<grid, 256, smem, st>>>(a);
   return check_launch("k6_grad_weights (tcgen05 tf32)");
 }
+
+#ifdef GPNERF_K6_TRACE
+extern "C" int gpnerf_debug_k6_trace(long long* out, int reset) {
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, g_k6_trace_n, sizeof(int));
+  if (out) cudaMemcpyFromSymbol(out, g_k6_trace, sizeof(long long) * 2048);
+  if (reset) { int z = 0; cudaMemcpyToSymbol(g_k6_trace_n, &z, sizeof(int)); }
+  return n;
+}
+extern "C" int gpnerf_debug_k6_span(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_k6_span, sizeof(unsigned long long) * 1024);
+}
+#endif
 
 }  // namespace gpnerf
