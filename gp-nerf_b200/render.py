@@ -301,7 +301,7 @@ class Renderer(nn.Module):
                                "k1_rays_bbox", "k2_occupancy_compact")
             ts["sigma_f"] = g("k23_gather_density_tc", "k2_gather_volume", "k2_project_gather_meanvar", "k3_density_mlp")
             ts["bf_rgb"] = g("k4_compact_alpha", "k4_compact_alpha_fused")
-            ts["rgb_f"] = g("k3_color_gather_tc", "k3_color_mlp_records", "k3_color_mlp")
+            ts["rgb_f"] = g("k3_color_gather_tc", "k3_color_tiles_tc", "k3_color_mlp_records", "k3_color_mlp")
             ts["bc_render"] = g("k5_composite", "peer_wait")
         return ts
 
@@ -331,7 +331,14 @@ class Renderer(nn.Module):
         # the host-side tail of a frame (wait for its event, fp32 → float64 image, boolean mask, the
         # compact rgb_map) runs on two worker threads – numpy releases the GIL – while the main thread queues
         # the next frames; results are still yielded in order
-        pool = ThreadPoolExecutor(max_workers=2)
+        # (the pool and the staging sets below – pinned host buffers, device buffers, a copy stream, events – are
+        # kept on the Renderer between calls: allocating them cost 5-20 ms per call, more than ten frames)
+        pool = getattr(self, "_stream_pool", None)
+        if pool is None:
+            pool = self._stream_pool = ThreadPoolExecutor(max_workers=2)
+        cache = getattr(self, "_stream_cache", None)
+        if cache is None:
+            cache = self._stream_cache = {}
 
         def host_tail(slot, H, W, t_start):
             st["done"][slot].synchronize()
@@ -360,9 +367,17 @@ class Renderer(nn.Module):
             eng = self.engine_for(H, W, V, device)
             self._sync_weights(eng)
             if st is None:
+                key = (H, W, V, str(device), depth, sparse, produce, need_fm,
+                       None if (sparse or produce) else tuple(tuple(t.shape) for t in batch["levels"]),
+                       None if need_fm else tuple(batch["featmaps"].shape))
+                st = cache.get(key)
+                if st is not None:          # (a previous stream that was abandoned half way may still have work queued)
+                    st["copy"].synchronize()
+                    torch.cuda.current_stream(device).synchronize()
+            if st is None:
                 mk = lambda t: torch.empty(t.shape, dtype=torch.float32, device=device)     # noqa: E731
                 im0 = src[0] if src.dim() == 5 else src
-                st = {
+                st = cache[key] = {
                     "copy": torch.cuda.Stream(device),
                     "stage": [([] if (sparse or produce) else [mk(t) for t in batch["levels"]],
                                None if need_fm else mk(batch["featmaps"]), mk(im0)) for _ in range(depth)],
@@ -468,7 +483,6 @@ class Renderer(nn.Module):
             pending.append(pool.submit(host_tail, slot, H, W, t_start))
         while pending:
             yield finalize(pending.popleft())
-        pool.shutdown(wait=True)
 
     def _stream_device(self, batch):
         src = batch["src_imgs"]
