@@ -253,13 +253,12 @@ def run_train(args, rank, world, local_rank):
     frame = eng.make_frame(scene)
     target = torch.rand(R, 3, device=dev)
     bucket = train.GradBucket(w_g.values())
-    opt = torch.optim.AdamW(list(w_g.values()), lr=1e-4)
+    opt = torch.optim.AdamW(list(w_g.values()), lr=1e-4, capturable=True)
     gen = torch.Generator().manual_seed(rank)
     t_pin = torch.empty(R, S).pin_memory()
 
-    def step():
+    def device_step():
         bucket.zero()
-        t_pin.copy_(torch.rand(R, S, generator=gen))                 # the jitter is drawn on the host (BaseRender.py:40-47)
         out = train.render_dense_autograd(eng, frame, rays, lv, fm, im, w_g, t_rand=t_pin.to(dev, non_blocking=True),
                                           precision=train.PREC_TRAIN_TF32)
         loss = ((out["rgb_map"] - target) ** 2).mean()
@@ -267,6 +266,19 @@ def run_train(args, rank, world, local_rank):
         bucket.all_reduce_mean()
         opt.step()
         return loss
+    # the whole step as one CUDA graph (train.GraphedStep); --no-graph launches the kernels one by one
+    graphed, graph_note = None, "kernels launched one by one (--no-graph)"
+    if not args.no_graph:
+        try:
+            t_pin.copy_(torch.rand(R, S, generator=gen))
+            graphed = train.GraphedStep(device_step, dev)
+            graph_note = "forward + backward + all-reduce + AdamW replayed as one CUDA graph per step (train.GraphedStep)"
+        except Exception as e:       # noqa: BLE001 - report and fall back to eager launches
+            graphed, graph_note = None, f"CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches"
+
+    def step():
+        t_pin.copy_(torch.rand(R, S, generator=gen))                 # the jitter is drawn on the host (BaseRender.py:40-47)
+        return graphed() if graphed is not None else device_step()
 
     def time_steps(fn, k):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
@@ -354,7 +366,8 @@ def run_train(args, rank, world, local_rank):
                                "scene 512x512, V=3; products resident, head parameters trainable",
                    "rays_per_gpu": R, "l2": "working set ≈10 GB of activations per step ≫ 126 MB L2",
                    "collective": "one flat all-reduce of the head gradients per step (train.GradBucket)" if world > 1 else "none",
-                   "grad_values_all_reduced": int(bucket.flat.numel()), "grads_identical_on_all_ranks": same},
+                   "grad_values_all_reduced": int(bucket.flat.numel()), "grads_identical_on_all_ranks": same,
+                   "launch": graph_note},
         "clocks": clocks, "full_pipeline": full, "gpu_launches": None,
         "e2e": {"value": n_rays_total * 1e3 / ms_wall, "unit": "rays/s", "h2d_bytes_per_step": int(R * S * 4),
                 "d2h_bytes_per_step": 0, "what": "host wall clock around the steps; the per-step jitter is uploaded from pinned memory"},

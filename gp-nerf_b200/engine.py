@@ -371,6 +371,15 @@ class Engine:
         on the current stream).  Every render entry point calls it first."""
         # four pinned staging slots in rotation, each guarded by an event: a second frame queued while the GPU is
         # still behind must not overwrite constants whose host→device copy has not executed yet
+        raw = C.string_at(C.addressof(frame), C.sizeof(Frame))
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture (train.GraphedStep) nothing may wait on an event, and a copy node would
+            # re-read a pinned slot that later frames overwrite: the constants must already be on the device
+            if raw != getattr(self, "_frame_bytes", None):
+                raise _lib.GpnerfError("upload_frame during CUDA-graph capture: run one step with these frame "
+                                       "constants before capturing")
+            return
+        self._frame_bytes = raw
         slots = getattr(self, "_frame_slots", None)
         if slots is None:
             slots = self._frame_slots = [[torch.empty(C.sizeof(Frame), dtype=torch.uint8).pin_memory(), None]
@@ -600,7 +609,7 @@ class Engine:
         self.rays_d[: R * 3].copy_(_f32(ray_d, dev).reshape(-1), non_blocking=True)
         self.near[:R].copy_(_f32(near, dev).reshape(-1), non_blocking=True)
         self.far[:R].copy_(_f32(far, dev).reshape(-1), non_blocking=True)
-        self.counters[CNT_RAYS] = R
+        self.counters[CNT_RAYS:CNT_RAYS + 1].fill_(R)
         tr = None if t_rand is None else _f32(t_rand, dev).reshape(-1)
         n = R * self.S
         if self.bf16 and not self.use_records and (self.rgb_in is None or self.rgb_in.numel() < n * self.V * 3):

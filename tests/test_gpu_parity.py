@@ -1270,3 +1270,66 @@ def test_sparse_conv_kernels_vs_hand_derived_spconv_cases():
         src = (p[0] + 1, p[1] - 1, p[2])
         want = torch.relu(x_in[src]) if src in x_in else torch.zeros(16)
         assert torch.equal(got_one[j], want), (p, src)
+
+
+@pytest.mark.gpu
+def test_training_step_as_one_cuda_graph_matches_eager_launches():
+    """train.GraphedStep: forward + backward + AdamW captured once and replayed must leave the same parameters
+    behind as the same steps launched kernel by kernel (same inputs, same jitter)."""
+    from gpnerf_b200 import train
+    R, S, V = 256, 64, 3
+    scene = synth.make_scene("zju", H=72, W=72, V=V, seed=7, with_rays=True)
+    w0 = synth.make_head_weights(V=V, seed=7, random_bias=True)
+    sel = torch.arange(R) % scene["ray_o"].shape[1]
+    rays = tuple(scene[k][0][sel].to(DEV) for k in ("ray_o", "ray_d", "near", "far"))
+    lv = [t.to(DEV) for t in scene["levels"]]
+    fm, im = scene["featmaps"].to(DEV), scene["src_imgs"].to(DEV)
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+    jit = [torch.rand(R, S, generator=torch.Generator().manual_seed(10 + i)) for i in range(3)]
+
+    def run(graph):
+        eng = Engine(72, 72, S, V, device=DEV, max_rays=R)
+        eng.set_weights(w0)
+        eng.upload_products(lv, fm, im)
+        frame = eng.make_frame(scene)
+        params = {k: torch.nn.Parameter(v.clone().to(DEV)) for k, v in w0.items()}
+        opt = torch.optim.AdamW(list(params.values()), lr=1e-3, capturable=True)
+        bucket = train.GradBucket(params.values())
+        t_pin = torch.empty(R, S).pin_memory()
+
+        def step():
+            bucket.zero()
+            out = train.render_dense_autograd(eng, frame, rays, lv, fm, im, params, t_rand=t_pin.to(DEV, non_blocking=True),
+                                              precision=train.PREC_TRAIN_TF32)
+            loss = ((out["rgb_map"] - target) ** 2).mean()
+            loss.backward()
+            bucket.all_reduce_mean()
+            opt.step()
+            return loss
+        snap = {k: p.detach().clone() for k, p in params.items()}
+        st0 = None
+        if graph:
+            t_pin.copy_(jit[0])
+            g = train.GraphedStep(step, DEV, warmup=2)          # the warm-up and capture steps moved the parameters:
+            with torch.no_grad():                               # rewind parameters and optimizer state
+                for k, p in params.items():
+                    p.copy_(snap[k])
+                for stt in opt.state.values():
+                    for v in stt.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            fn = g
+        else:
+            fn = step
+        losses = []
+        for j in jit:
+            t_pin.copy_(j)
+            losses.append(float(fn()))
+        torch.cuda.synchronize()
+        return losses, {k: p.detach().clone() for k, p in params.items()}
+
+    l_e, p_e = run(False)
+    l_g, p_g = run(True)
+    assert all(abs(a - b) <= 1e-5 * max(1.0, abs(a)) for a, b in zip(l_e, l_g)), (l_e, l_g)
+    for k in p_e:
+        assert float((p_e[k] - p_g[k]).abs().max()) <= 2e-5 * max(1.0, float(p_e[k].abs().max())), k
