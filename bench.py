@@ -497,6 +497,11 @@ def main():
             flush.zero_()
             step_device()
         torch.cuda.synchronize(dev)
+    counts = eng.read_counters()       # (also settles the engine's auto hand-off to the colour head: tiles / gather)
+    for _ in range(2):                 # untimed: a changed hand-off is a new CUDA graph, captured here
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize(dev)
     counts = eng.read_counters()
     ref_image = eng.result_image().cpu().clone()
     ref_hit = eng.result_hit_mask().cpu().clone()
@@ -631,6 +636,12 @@ def main():
                     return shard.gather_frame(et.pred_img.view(res * res, 3), res, args.tile_px)
                 return et.result_image()
             for _ in range(3):
+                flush.zero_()
+                step_t()
+            # auto hand-off to the colour head: the engine settles on tiles / gather from this frame's survivor ratio
+            # (every rank of a tiles-mode frame decides from its own share); the steps after it are still warm-up
+            et.read_counters()
+            for _ in range(2):
                 flush.zero_()
                 step_t()
             torch.cuda.synchronize(dev)

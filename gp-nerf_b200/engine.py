@@ -143,11 +143,16 @@ class Engine:
             #           layouts, fetched with one bulk copy per tile: the per-view features are gathered once
             #   gather  nothing is handed over; the colour head gathers its inputs again for the survivors
             #   records round 1: one 16(9+5V)-byte record per P1 point, written by round 1's monolithic kernel
+            # Unset = auto: tiles, re-decided from the survivor ratio of the frames rendered so far (note_counts):
+            # the tile-fed head processes every tile that has a survivor, i.e. ≈P1 points, the gathering head P2; on
+            # the benchmark frame (P2 / P1 = 0.90) tiles win by 0.03 ms, on the 1024² S=128 frame (0.14) they lose 2 ms
             import os
-            impl = os.environ.get("GPNERF_COLOR_IMPL", "") or "tiles"
-            if impl not in ("tiles", "gather", "records"):
-                raise _lib.GpnerfError(f"GPNERF_COLOR_IMPL={impl!r}: expected tiles, gather or records")
-            self.color_impl = impl
+            impl = os.environ.get("GPNERF_COLOR_IMPL", "") or "auto"
+            if impl not in ("auto", "tiles", "gather", "records"):
+                raise _lib.GpnerfError(f"GPNERF_COLOR_IMPL={impl!r}: expected auto, tiles, gather or records")
+            self.color_impl_auto = impl == "auto"
+            self.color_impl = "tiles" if impl == "auto" else impl
+            impl = self.color_impl
             self.use_records = impl == "records"
             self.rec_bytes = int(self.lib.gpnerf_k23_record_bytes(self.V))
             self.rec = torch.empty(self.max_pts * self.rec_bytes, dtype=torch.uint8, device=dev) if self.use_records else None
@@ -155,11 +160,12 @@ class Engine:
             self.tile_rec_bytes = int(self.lib.gpnerf_k23_tile_record_bytes(self.V))
             self.rec_tiles = (torch.zeros(((self.max_pts + 127) // 128) * self.tile_rec_bytes, dtype=torch.uint8, device=dev)
                               if impl == "tiles" else None)
+            self.tiles_min_survival = 0.85
             self.rgb_in = None       # per-view RGB taps [P1][V][3], dense path only (allocated on first use)
             self.vol_feat = self.rgb_feat = self.mask = self.meanvar = None
         else:
             self.rec = self.rec_tiles = None
-            self.color_impl = None
+            self.color_impl, self.color_impl_auto = None, False
             self.vol_feat = buf(self.max_pts * 128)
             self.rgb_feat = buf(self.max_pts * self.V * 35)
             self.mask = buf(self.max_pts * self.V)
@@ -465,16 +471,17 @@ class Engine:
                        be queued ahead of the GPU (Renderer.render_stream)."""
         if with_k0 and self._static_inputs is None:
             raise _lib.GpnerfError("set_static_inputs() first")
-        key = (tuple(self.level_dims or ()), getattr(self, "src_hw", None), getattr(self, "feat_hw", None), with_k0)
+        impl = self.color_impl              # read once: note_counts may change it from a worker thread
+        key = (tuple(self.level_dims or ()), getattr(self, "src_hw", None), getattr(self, "feat_hw", None), with_k0, impl)
         graphs = self._graphs
         if key not in graphs:
             timing, self.timing = self.timing, False
             if with_k0:
                 lv, fm, im = self._static_inputs
                 self.upload_products(lv, fm, im)             # eager warm-up: allocations, func attributes
-            self.render_progressive(frame)
+            self.render_progressive(frame, impl=impl)
             torch.cuda.synchronize(self.device)
-            key = (tuple(self.level_dims), self.src_hw, self.feat_hw, with_k0)
+            key = (tuple(self.level_dims), self.src_hw, self.feat_hw, with_k0, impl)
             C.memmove(self.frame_pinned.data_ptr(), C.addressof(frame), C.sizeof(Frame))
             g = torch.cuda.CUDAGraph()
             l0 = self.launches
@@ -482,7 +489,7 @@ class Engine:
                 if with_k0:
                     self.frame_dev.copy_(self.frame_pinned, non_blocking=True)
                     self.upload_products(lv, fm, im)
-                self.render_progressive(frame, upload=False)
+                self.render_progressive(frame, upload=False, impl=impl)
             graphs[key] = (g, self.launches - l0)
             self.timing = timing
         g, n_launch = graphs[key]
@@ -497,7 +504,7 @@ class Engine:
             self.exchange.next_frame()       # one more K5 launch queued (its frame counter lives on the device)
         g.replay()
         self.launches += n_launch
-        if self.bf16 and self.color_impl == "tiles":
+        if self.bf16 and impl == "tiles":
             self._valid1_pending = True
 
     # --------------------------------------------------------------- launches
@@ -505,12 +512,13 @@ class Engine:
         self._run("k0_build_masks3d", self.lib.gpnerf_k0_build_masks3d, ptr_array(self.chan_sums),
                   C.byref(frame), ptr(self.masks3d), self._stream())
 
-    def render_progressive(self, frame, t_rand=None, upload=True):
+    def render_progressive(self, frame, t_rand=None, upload=True, impl=None):
         """demo_render.Renderer.render_rays downstream of the producers.
         Leaves results in self.{rgb_map,pred_img,hit_mask,counters,...}."""
         if self._weights is None:
             raise _lib.GpnerfError("set_weights() has not been called")
         L, st, fr = self.lib, self._stream(), C.byref(frame)
+        impl = self._impl_now = impl or self.color_impl      # one hand-off per frame, whatever note_counts does meanwhile
         if upload:
             self.upload_frame(frame)
         self.build_occupancy(frame)
@@ -520,7 +528,7 @@ class Engine:
                   ptr(self.ray_pix), ptr(self.rays_o), ptr(self.rays_d), ptr(self.near), ptr(self.far),
                   ptr(self.counters), ptr(self.workspace), ptr(self.tile_ray_begin), st)
         self._heads(frame, masks3d=self.masks3d, t_rand=t_rand, n_rays_max=self.max_rays, fuse_alpha=True)
-        if self.bf16 and self.color_impl == "tiles":
+        if self.bf16 and impl == "tiles":
             # tile hand-off: the colour head takes every tile of the P1 list that has a survivor (K5 ignores the
             # colour of a culled point) and counts the survivors; the ordered survivor list (valid1) is not on the
             # frame's path any more – survivor_list() / read_counters() produce it on demand from the flags the
@@ -530,6 +538,7 @@ class Engine:
             self._valid1_pending = True
         else:
             # tensor-core path: α and the survivor flags were written by the fused kernel's epilogue
+            self._valid1_pending = False
             self._run("k4_compact_alpha_fused" if self.bf16 else "k4_compact_alpha", L.gpnerf_k4_compact_alpha,
                       None if self.bf16 else ptr(self.sigma), self.max_pts,
                       ptr(self.counters), ptr(self.alpha), ptr(self.valid1), ptr(self.workspace), st)
@@ -568,7 +577,10 @@ class Engine:
                   ptr(self.rays_d), ptr(self.near), ptr(self.far), ptr(self.t_vals), ptr(t_rand), fr, n_rays_max,
                   ptr(self.valid), ptr(self.z_vals), ptr(self.counters), ptr(self.workspace),
                   ptr(self.ray_pt_begin), st)
-        if self.bf16 and self.color_impl == "tiles":
+        if self.bf16 and self._impl_now == "tiles":
+            if self.rec_tiles is None:          # (auto mode that started on another hand-off)
+                self.rec_tiles = torch.zeros(((self.max_pts + 127) // 128) * self.tile_rec_bytes, dtype=torch.uint8,
+                                             device=self.device)
             self._run("k23_gather_density_tc", L.gpnerf_k23_gather_density_tiles_tc, ptr_array(self.levels_cl),
                       ptr(self.featmaps_cl), ptr(self.images_rgbx), ptr(self.valid), ptr(self.rays_o),
                       ptr(self.rays_d), ptr(self.z_vals), fr, C.byref(self._weights), n_pts_max,
@@ -614,7 +626,9 @@ class Engine:
         n = R * self.S
         if self.bf16 and not self.use_records and (self.rgb_in is None or self.rgb_in.numel() < n * self.V * 3):
             self.rgb_in = torch.empty(self.max_pts * self.V * 3, dtype=torch.float32, device=dev)
-        tiles = self.bf16 and self.color_impl == "tiles"
+        # dense render: every sample goes through both heads – the tile hand-off unless another one was asked for
+        self._impl_now = "tiles" if self.color_impl_auto else self.color_impl
+        tiles = self.bf16 and self._impl_now == "tiles"
         self._heads(frame, masks3d=None, t_rand=tr, n_rays_max=R, rgb_in=self.rgb_in if tiles else None)
         # colour head on every point (valid1 = NULL → all rows in order)
         if tiles:
@@ -644,6 +658,12 @@ class Engine:
         out["raw"] = raw.view(R, self.S, 4)
         return out
 
+    def note_counts(self, p1, p2):
+        """Auto hand-off (GPNERF_COLOR_IMPL unset): pick the colour head for the next frames from the survivor
+        ratio of a frame just rendered."""
+        if self.bf16 and self.color_impl_auto and p1 > 0:
+            self.color_impl = "tiles" if p2 >= self.tiles_min_survival * p1 else "gather"
+
     def survivor_list(self):
         """The progressive step's ordered survivor list (demo_render.py:312-317) of the last frame: fills
         self.valid1[:P2].  With the tile hand-off it is not needed to render and is produced here, on demand,
@@ -658,4 +678,5 @@ class Engine:
         """One device→host sync: (n_pix, n_rays, P1, P2).  Also brings valid1 up to date (survivor_list)."""
         self.survivor_list()
         c = self.counters.cpu().tolist()
+        self.note_counts(c[CNT_P1], c[CNT_P2])
         return {"n_pix": c[CNT_PIX], "n_rays": c[CNT_RAYS], "P1": c[CNT_P1], "P2": c[CNT_P2]}

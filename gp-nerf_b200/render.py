@@ -273,6 +273,7 @@ class Renderer(nn.Module):
         pin[3].synchronize()
         c = pin[2].tolist()
         cnt = {"n_pix": c[_lib.CNT_PIX], "n_rays": c[_lib.CNT_RAYS], "P1": c[_lib.CNT_P1], "P2": c[_lib.CNT_P2]}
+        eng.note_counts(cnt["P1"], cnt["P2"])          # auto hand-off: the colour head of the next frames
         img32 = pin[0].numpy().reshape(-1, 3)
         mask_at_box = pin[1].numpy().astype(bool)
         rgb_map = img32[np.flatnonzero(mask_at_box)]             # ascending pixel order = the reference's ray order
@@ -343,6 +344,7 @@ class Renderer(nn.Module):
         def host_tail(slot, H, W, t_start):
             st["done"][slot].synchronize()
             cnt = dict(zip(("n_pix", "n_rays", "P1", "P2"), st["cnt"][slot][:4].tolist()))
+            eng.note_counts(cnt["P1"], cnt["P2"])      # auto hand-off: the colour head of the frames queued from now on
             img32 = st["img"][slot].numpy().reshape(-1, 3)
             mask_at_box = st["hit"][slot].numpy().astype(bool)
             rgb_map = img32[np.flatnonzero(mask_at_box)]                  # ascending pixel order, fp32

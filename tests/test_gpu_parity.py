@@ -1333,3 +1333,38 @@ def test_training_step_as_one_cuda_graph_matches_eager_launches():
     assert all(abs(a - b) <= 1e-5 * max(1.0, abs(a)) for a, b in zip(l_e, l_g)), (l_e, l_g)
     for k in p_e:
         assert float((p_e[k] - p_g[k]).abs().max()) <= 2e-5 * max(1.0, float(p_e[k].abs().max())), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V", [3, 4])
+def test_colour_hand_offs_agree(V, monkeypatch):
+    """The three ways the fused kernel hands its gathers to the colour head – tile records + bulk copies (tiles), a
+    second gather for the survivors (gather), round 1's per-point records (records) – and the auto choice must
+    render the same frame: identical rays / survivors (integer work), images within bf16 noise of each other and
+    of the oracle.  Also: with the tile hand-off the survivor count comes from the colour head and the ordered list
+    on demand."""
+    scene = synth.make_scene("zju", H=96, W=96, V=V, seed=23)
+    w = synth.make_head_weights(V=V, seed=23, random_bias=True)
+    o = orc.render_progressive(scene, w, S=48, keep=True)
+    d = stages.to_dev(scene, DEV)
+    imgs, lists = {}, {}
+    for impl in ("tiles", "gather", "records", ""):
+        monkeypatch.setenv("GPNERF_COLOR_IMPL", impl)
+        eng = Engine(96, 96, 48, V, device=DEV, precision=1)
+        assert eng.color_impl == (impl or "tiles") and eng.color_impl_auto == (impl == "")
+        eng.set_weights(w)
+        eng.upload_products(d["levels"], d["featmaps"], d["src_imgs"])
+        fr = eng.make_frame(scene)
+        for _ in range(3 if impl == "" else 1):       # auto: first frame on tiles, then whatever the ratio says
+            eng.render_progressive(fr)
+            c = eng.read_counters()
+        assert c["n_rays"] == o["n_rays"] and c["P1"] == o["P1"]
+        lists[impl] = eng.valid1[: c["P2"]].cpu().clone()
+        imgs[impl] = eng.pred_img.cpu().view(96, 96, 3).double()
+        st = stages.masked_image_stats(imgs[impl], o["pred_img"], o["mask_at_box"])
+        assert st["max_abs"] < BF16_MAX_ABS and st["psnr_mask"] > BF16_PSNR_MASK_MIN, (impl, st)
+        if impl == "":
+            assert eng.color_impl == ("tiles" if c["P2"] >= 0.85 * c["P1"] else "gather")
+    for impl in ("gather", "records", ""):
+        assert torch.equal(lists[impl], lists["tiles"]), impl           # same σ kernel, same flags
+        assert float((imgs[impl] - imgs["tiles"]).abs().max()) < 0.02, impl
