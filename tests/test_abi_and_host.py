@@ -250,3 +250,12 @@ def test_isosurface_marching_tetrahedra_closed_and_accurate():
     assert abs((p0 * nrm).sum() / 6 / (4 / 3 * np.pi * r ** 3) - 1) < 0.01
     v0, f0 = marching_tetrahedra(np.zeros((5, 5, 5)), 0.5)
     assert v0.shape == (0, 3) and f0.shape == (0, 3)
+
+
+def test_tile_record_sizes_are_host_arithmetic():
+    """gpnerf_k23_tile_record_bytes: [mean|var] 16 KB + one 16 KB block per view pair (8 KB for an odd last view) +
+    two 4 KB 16-column tiles; 1024-byte multiples so that consecutive tiles keep the SWIZZLE_128B alignment."""
+    from gpnerf_b200 import _lib
+    lib = _lib.load()
+    assert [int(lib.gpnerf_k23_tile_record_bytes(v)) for v in (1, 2, 3, 4)] == [32768, 40960, 49152, 57344]
+    assert int(lib.gpnerf_k23_tile_record_bytes(5)) < 0
