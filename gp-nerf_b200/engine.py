@@ -143,15 +143,17 @@ class Engine:
             #           layouts, fetched with one bulk copy per tile: the per-view features are gathered once
             #   gather  nothing is handed over; the colour head gathers its inputs again for the survivors
             #   records round 1: one 16(9+5V)-byte record per P1 point, written by round 1's monolithic kernel
-            # Unset = auto: tiles, re-decided from the survivor ratio of the frames rendered so far (note_counts):
-            # the tile-fed head processes every tile that has a survivor, i.e. ≈P1 points, the gathering head P2; on
-            # the benchmark frame (P2 / P1 = 0.90) tiles win by 0.03 ms, on the 1024² S=128 frame (0.14) they lose 2 ms
+            # Unset = auto: starts on gather and is re-decided from the survivor ratio of the frames rendered so far
+            # (note_counts): the tile-fed head processes every tile that has a survivor, i.e. ≈P1 points, the
+            # gathering head P2; on the benchmark frame (P2 / P1 = 0.90) tiles win by 0.03 ms, on the 1024² S=128
+            # frame (0.14) they lose 2 ms – and their record buffer (384 B per point of capacity) is only
+            # allocated once a frame asks for it
             import os
             impl = os.environ.get("GPNERF_COLOR_IMPL", "") or "auto"
             if impl not in ("auto", "tiles", "gather", "records"):
                 raise _lib.GpnerfError(f"GPNERF_COLOR_IMPL={impl!r}: expected auto, tiles, gather or records")
             self.color_impl_auto = impl == "auto"
-            self.color_impl = "tiles" if impl == "auto" else impl
+            self.color_impl = "gather" if impl == "auto" else impl
             impl = self.color_impl
             self.use_records = impl == "records"
             self.rec_bytes = int(self.lib.gpnerf_k23_record_bytes(self.V))

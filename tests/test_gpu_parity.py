@@ -1351,11 +1351,11 @@ def test_colour_hand_offs_agree(V, monkeypatch):
     for impl in ("tiles", "gather", "records", ""):
         monkeypatch.setenv("GPNERF_COLOR_IMPL", impl)
         eng = Engine(96, 96, 48, V, device=DEV, precision=1)
-        assert eng.color_impl == (impl or "tiles") and eng.color_impl_auto == (impl == "")
+        assert eng.color_impl == (impl or "gather") and eng.color_impl_auto == (impl == "")
         eng.set_weights(w)
         eng.upload_products(d["levels"], d["featmaps"], d["src_imgs"])
         fr = eng.make_frame(scene)
-        for _ in range(3 if impl == "" else 1):       # auto: first frame on tiles, then whatever the ratio says
+        for _ in range(3 if impl == "" else 1):       # auto: first frame re-gathers, then whatever the ratio says
             eng.render_progressive(fr)
             c = eng.read_counters()
         assert c["n_rays"] == o["n_rays"] and c["P1"] == o["P1"]
